@@ -1,0 +1,124 @@
+"""ctypes loader for the C oracle (oracle/flip_oracle.c) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module;
+the product package never does (tests/test_layout.py enforces it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libflip_oracle.so")
+_lib = None
+
+FLIP, APIC = 0, 1
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc, seconds). Returns the .so path."""
+    src = os.path.join(_HERE, "flip_oracle.c")
+    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(
+        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "flip_oracle.h")))
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "oracle"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=C.c_float):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def mac_shapes(I, J, K):
+    """C-order [K,J,I] shapes of the x-fastest u, v, w arrays (macvelocityfield.cpp:46-54)."""
+    return (K, J, I + 1), (K, J + 1, I), (K + 1, J, I)
+
+
+def bin_sort(I, J, K, dx, pos):
+    pos = _f32(pos)
+    n = pos.shape[0]
+    cell = np.empty(n, np.int32)
+    hkey = np.empty(n, np.uint32)
+    perm = np.empty(n, np.uint32)
+    lib().flip_oracle_bin_sort(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_int(n), _p(pos),
+                               _p(cell, C.c_int32), _p(hkey, C.c_uint32), _p(perm, C.c_uint32))
+    return cell, hkey, perm
+
+
+def p2g(I, J, K, dx, radius, method, pos, vel, affx=None, affy=None, affz=None, with_wsum=False):
+    pos, vel, affx, affy, affz = map(_f32, (pos, vel, affx, affy, affz))
+    n = pos.shape[0]
+    su, sv, sw = mac_shapes(I, J, K)
+    u, v, w = np.zeros(su, np.float32), np.zeros(sv, np.float32), np.zeros(sw, np.float32)
+    vu, vv, vw = np.zeros(su, np.uint8), np.zeros(sv, np.uint8), np.zeros(sw, np.uint8)
+    wu, wv, ww = np.zeros(su, np.float32), np.zeros(sv, np.float32), np.zeros(sw, np.float32)
+    lib().flip_oracle_p2g_w(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius), C.c_int(method),
+                            C.c_int(n), _p(pos), _p(vel), _p(affx), _p(affy), _p(affz), _p(u), _p(v), _p(w),
+                            _p(vu, C.c_uint8), _p(vv, C.c_uint8), _p(vw, C.c_uint8), _p(wu), _p(wv), _p(ww))
+    if with_wsum:
+        return (u, v, w), (vu, vv, vw), (wu, wv, ww)
+    return (u, v, w), (vu, vv, vw)
+
+
+def g2p_flip(I, J, K, dx, pos, vel, mac, saved, ratio):
+    pos = _f32(pos)
+    out = _f32(vel).copy()
+    u, v, w = map(_f32, mac)
+    su, sv, sw = map(_f32, saved)
+    lib().flip_oracle_g2p_flip(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_int(pos.shape[0]), _p(pos),
+                               _p(out), _p(u), _p(v), _p(w), _p(su), _p(sv), _p(sw), C.c_double(ratio))
+    return out
+
+
+def g2p_apic(I, J, K, dx, pos, mac):
+    pos = _f32(pos)
+    n = pos.shape[0]
+    u, v, w = map(_f32, mac)
+    vel = np.zeros((n, 3), np.float32)
+    ax, ay, az = (np.zeros((n, 3), np.float32) for _ in range(3))
+    lib().flip_oracle_g2p_apic(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_int(n), _p(pos), _p(vel),
+                               _p(ax), _p(ay), _p(az), _p(u), _p(v), _p(w))
+    return vel, ax, ay, az
+
+
+def mac_sample(I, J, K, dx, pos, mac):
+    pos = _f32(pos)
+    u, v, w = map(_f32, mac)
+    out = np.zeros_like(pos)
+    lib().flip_oracle_mac_sample(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_int(pos.shape[0]), _p(pos),
+                                 _p(out), _p(u), _p(v), _p(w))
+    return out
+
+
+def near_dims(I, J, K, dx):
+    gi, gj, gk = C.c_int(), C.c_int(), C.c_int()
+    lib().flip_oracle_near_dims(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.byref(gi), C.byref(gj),
+                                C.byref(gk))
+    return gi.value, gj.value, gk.value
+
+
+def advect(I, J, K, dx, pos, mac, phi, near, dt, cfl=5.0, collide=True):
+    pos = _f32(pos)
+    u, v, w = map(_f32, mac)
+    phi = _f32(phi)
+    near = np.ascontiguousarray(near, dtype=np.uint8)
+    out = np.zeros_like(pos)
+    lib().flip_oracle_advect(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_int(pos.shape[0]), _p(pos),
+                             _p(out), _p(u), _p(v), _p(w), _p(phi), _p(near, C.c_uint8), C.c_double(dt),
+                             C.c_double(cfl), C.c_int(1 if collide else 0))
+    return out

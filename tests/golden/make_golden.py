@@ -1,0 +1,165 @@
+"""Generate the golden fixtures in tests/golden/*.npz from the UNMODIFIED reference engine.
+
+Run in the build container only (needs /root/reference to build oracle/_ref):
+
+    make -C oracle -j8 all && python tests/golden/make_golden.py
+
+Every array in the fixtures is an output of oracle/_ref/ref_harness, i.e. of the reference's
+own VelocityAdvector::advect, _updateMarkerParticleVelocitiesThread and
+_advanceMarkerParticlesThread compiled from /root/reference/src/engine (v1.8.5). The reference
+ships no tests or golden vectors of its own, so these are the pin for
+oracle/flip_oracle.c and, through it, for the CUDA path. Inputs are seeded numpy arrays
+(blender_flip_fluids_b200/scenes.py) so the script is reproducible.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from blender_flip_fluids_b200 import scenes  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def run(mode, workdir, **kw):
+    cmd = [HARNESS, mode, workdir] + [f"{k}={v!r}" if isinstance(v, float) else f"{k}={v}" for k, v in kw.items()]
+    r = subprocess.run(cmd, capture_output=True, text=True, check=True)
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def save_inputs(d, **arrs):
+    for k, a in arrs.items():
+        if a is not None:
+            np.save(os.path.join(d, f"in_{k}.npy"), a)
+
+
+def load_all(d, prefix):
+    out = {}
+    for f in sorted(os.listdir(d)):
+        if f.startswith(prefix) and f.endswith(".npy"):
+            out[f[:-4]] = np.load(os.path.join(d, f))
+    return out
+
+
+def seeded_particles(I, J, K, dx, rng, apic):
+    """Ragged blob with a free surface, spanning the 10-node block seams, 8-ish ppc."""
+    sc = scenes.dam_break(max(I, J, K), apic=apic, seed=int(rng.integers(1 << 30)), dx=dx, vel="random", v0=1.0,
+                          dims=(I, J, K))
+    keep = rng.random(sc.n) < 0.85                       # knock holes in it: ragged fringe faces
+    pos, vel = sc.pos[keep], sc.vel[keep]
+    aff = [a[keep] for a in (sc.affx, sc.affy, sc.affz)] if apic else [None] * 3
+    return pos, vel, aff
+
+
+def seam_particles(I, J, K, dx, rng, count=600):
+    """Adversarial positions: within a few ulps / 1e-6 of block seams (10*dx multiples, with
+    and without the half-cell stagger) and of the 'simple vs overlapping' threshold
+    seam -+ (radius + 1e-6) (velocityadvector.cpp:306-320), plus cell boundaries."""
+    r = 0.5 * dx * math.sqrt(3.0)
+    pts = []
+    seams = [10 * dx * m for m in range(1, max(I, J, K) // 10 + 1)]
+    for _ in range(count):
+        p = np.array([rng.uniform(3, I - 3), rng.uniform(3, J - 3), rng.uniform(3, K - 3)]) * dx
+        ax = int(rng.integers(3))
+        s = seams[int(rng.integers(len(seams)))]
+        if s >= (I, J, K)[ax] * dx - 3 * dx:
+            s = seams[0]
+        kind = int(rng.integers(6))
+        off = [0.0, 0.5 * dx][int(rng.integers(2))]
+        base = {0: s, 1: s - (r + 1e-6), 2: s + (r + 1e-6), 3: s - r, 4: s + r,
+                5: dx * int(rng.integers(4, (I, J, K)[ax] - 4))}[kind] + off
+        p[ax] = base + rng.choice([0.0, 1e-7, -1e-7, 3e-8, -3e-8, 1e-6, -1e-6, 1e-9]) * (1.0 if rng.random() < 0.5 else dx)
+        pts.append(p)
+    return np.asarray(pts, np.float32)
+
+
+def fixture_scene(name, I, J, K, dx, method, warm, obstacle, dt, seed):
+    rng = np.random.default_rng(seed)
+    apic = method == "apic"
+    pos, vel, aff = seeded_particles(I, J, K, dx, rng, apic)
+    vel = (vel * 0.4).astype(np.float32)
+    d = tempfile.mkdtemp(prefix="ffgold_")
+    save_inputs(d, pos=pos, vel=vel, affx=aff[0], affy=aff[1], affz=aff[2])
+    info = run("scene", d, I=I, J=J, K=K, dx=float(dx), method=method, warm=warm, obstacle=obstacle, dt=float(dt))
+    arrs = load_all(d, "s")
+    shutil.rmtree(d)
+    meta = dict(I=I, J=J, K=K, dx=dx, method=method, dt=dt, ratio=info["ratio"], cfl=info["cfl"],
+                radius=info["radius"], warm=warm, obstacle=obstacle, particles=info["particles"])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), **arrs)
+    print(name, meta)
+
+
+def fixture_p2g(name, I, J, K, dx, method, seed, radius_scale=1.0):
+    rng = np.random.default_rng(seed)
+    apic = method == "apic"
+    pos, vel, aff = seeded_particles(I, J, K, dx, rng, apic)
+    sp = seam_particles(I, J, K, dx, rng)
+    pos = np.concatenate([pos, sp]).astype(np.float32)
+    perm = rng.permutation(pos.shape[0])                 # seam particles interleaved in index order
+    pos = pos[perm]
+    vel = np.concatenate([vel, rng.uniform(-1, 1, size=sp.shape).astype(np.float32)])[perm]
+    if apic:
+        aff = [np.concatenate([a, (rng.uniform(-1, 1, size=sp.shape) * 0.1 / dx).astype(np.float32)])[perm] for a in aff]
+    radius = 0.5 * dx * math.sqrt(3.0) * radius_scale
+    d = tempfile.mkdtemp(prefix="ffgold_")
+    save_inputs(d, pos=pos, vel=vel, affx=aff[0], affy=aff[1], affz=aff[2])
+    run("p2g", d, I=I, J=J, K=K, dx=float(dx), method=method, radius=float(radius), threads=3)
+    arrs = load_all(d, "out_")
+    arrs.update(load_all(d, "in_"))
+    shutil.rmtree(d)
+    meta = dict(I=I, J=J, K=K, dx=dx, method=method, radius=radius, particles=int(pos.shape[0]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), **arrs)
+    print(name, meta)
+
+
+def fixture_advect(name, scene_npz, seed, cells_per_step=4.0):
+    """Collision-heavy advection: the reference's own solid SDF / near-solid grid from a scene
+    fixture, and a coherent velocity field that drives particles into walls and obstacle."""
+    z = np.load(os.path.join(OUT, scene_npz + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    rng = np.random.default_rng(seed)
+    dt = 1.0 / 30.0
+    vmag = cells_per_step * dx / dt
+    shp = [(K, J, I + 1), (K, J + 1, I), (K + 1, J, I)]
+    zz, yy, xx = np.meshgrid(np.arange(K + 1), np.arange(J + 1), np.arange(I + 1), indexing="ij")
+    base = [np.sin(0.4 * yy + 0.3 * zz), -np.cos(0.35 * xx + 0.2 * zz) - 0.5, np.sin(0.5 * xx - 0.3 * yy)]
+    mac = []
+    for c, s in enumerate(shp):
+        f = base[c][: s[0], : s[1], : s[2]] * vmag + rng.uniform(-0.3, 0.3, size=s) * vmag
+        mac.append(f.astype(np.float32))
+    pos = z["s0_pos"]
+    d = tempfile.mkdtemp(prefix="ffgold_")
+    save_inputs(d, pos=pos, vel=np.zeros_like(pos), u=mac[0], v=mac[1], w=mac[2], phi=z["s2_phi"], near=z["s2_near"])
+    run("advect", d, I=I, J=J, K=K, dx=float(dx), dt=float(dt), cfl=5)
+    out = np.load(os.path.join(d, "out_pos.npy"))
+    shutil.rmtree(d)
+    m2 = dict(I=I, J=J, K=K, dx=dx, dt=dt, cfl=5.0, particles=int(pos.shape[0]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), in_pos=pos, in_u=mac[0], in_v=mac[1],
+                        in_w=mac[2], in_phi=z["s2_phi"], in_near=z["s2_near"], out_pos=out)
+    print(name, m2, "moved", int((out != pos).any(axis=1).sum()))
+
+
+if __name__ == "__main__":
+    if not os.path.exists(HARNESS):
+        sys.exit("build oracle/_ref first: make -C oracle -j8 all")
+    # whole-substep chains (reference-produced velocities, SDF, near-solid grid)
+    fixture_scene("scene_flip_24x20x22_nondyadic", 24, 20, 22, 0.01, "flip", 2, "sphere:0.12,0.05,0.11,0.035", 1 / 60, 11)
+    fixture_scene("scene_apic_22x24x20_dyadic", 22, 24, 20, 1.0 / 16.0, "apic", 1, "none", 1 / 60, 12)
+    # stage-level P2G with seam-adversarial particles
+    fixture_p2g("p2g_flip_23x21x25_seams", 23, 21, 25, 0.004, "flip", 21)
+    fixture_p2g("p2g_apic_23x21x25_seams", 23, 21, 25, 0.004, "apic", 22)
+    fixture_p2g("p2g_apic_20x20x20_dyadic", 20, 20, 20, 0.125, "apic", 23)
+    fixture_p2g("p2g_flip_21x20x22_radius2", 21, 20, 22, 0.01, "flip", 24, radius_scale=2.0)
+    # collision-heavy advection
+    fixture_advect("advect_collide_24x20x22", "scene_flip_24x20x22_nondyadic", 31)

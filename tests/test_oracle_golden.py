@@ -1,0 +1,88 @@
+"""CPU suite: the C oracle (oracle/flip_oracle.c) against the reference-generated golden
+fixtures in tests/golden/ (tests/golden/make_golden.py). Everything is bit-exact: the oracle
+repeats the reference's float/double operation order (no tolerance anywhere in this file).
+"""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, load_golden
+
+P2G_FIXTURES = ["p2g_flip_23x21x25_seams", "p2g_apic_23x21x25_seams", "p2g_apic_20x20x20_dyadic",
+                "p2g_flip_21x20x22_radius2"]
+SCENES = ["scene_flip_24x20x22_nondyadic", "scene_apic_22x24x20_dyadic"]
+
+
+def _method(oracle, meta):
+    return oracle.APIC if meta["method"] == "apic" else oracle.FLIP
+
+
+@pytest.mark.parametrize("name", P2G_FIXTURES)
+def test_p2g_stage_fixture(oracle, name):
+    meta, g = load_golden(name)
+    aff = [g.get("in_aff" + c) for c in "xyz"]
+    (u, v, w), (vu, vv, vw) = oracle.p2g(meta["I"], meta["J"], meta["K"], meta["dx"], meta["radius"],
+                                         _method(oracle, meta), g["in_pos"], g["in_vel"], *aff)
+    for got, key in ((u, "out_u"), (v, "out_v"), (w, "out_w")):
+        assert bits_equal(got, g[key]), key
+    for got, key in ((vu, "out_validu"), (vv, "out_validv"), (vw, "out_validw")):
+        assert np.array_equal(got, g[key]), key
+    assert vu.sum() > 0 and vu.sum() < vu.size          # ragged: both valid and invalid faces exist
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_scene_chain(oracle, name):
+    meta, g = load_golden(name)
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    apic = meta["method"] == "apic"
+    aff = [g.get("s0_aff" + c) for c in "xyz"]
+    (u, v, w), (vu, vv, vw) = oracle.p2g(I, J, K, dx, meta["radius"], _method(oracle, meta), g["s0_pos"], g["s0_vel"],
+                                         *aff)
+    assert bits_equal(u, g["s1_u"]) and bits_equal(v, g["s1_v"]) and bits_equal(w, g["s1_w"])
+    assert np.array_equal(vu, g["s1_validu"]) and np.array_equal(vv, g["s1_validv"]) and np.array_equal(vw, g["s1_validw"])
+    mac = (g["s2_u"], g["s2_v"], g["s2_w"])
+    if apic:
+        vel, ax, ay, az = oracle.g2p_apic(I, J, K, dx, g["s0_pos"], mac)
+        assert bits_equal(ax, g["s3_affx"]) and bits_equal(ay, g["s3_affy"]) and bits_equal(az, g["s3_affz"])
+    else:
+        vel = oracle.g2p_flip(I, J, K, dx, g["s0_pos"], g["s0_vel"], mac, (g["s2_su"], g["s2_sv"], g["s2_sw"]),
+                              meta["ratio"])
+    assert bits_equal(vel, g["s3_vel"])
+    out = oracle.advect(I, J, K, dx, g["s0_pos"], mac, g["s2_phi"], g["s2_near"], meta["dt"], meta["cfl"])
+    assert bits_equal(out, g["s4_pos"])
+
+
+def test_advect_collision_fixture(oracle):
+    meta, g = load_golden("advect_collide_24x20x22")
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    mac = (g["in_u"], g["in_v"], g["in_w"])
+    out = oracle.advect(I, J, K, dx, g["in_pos"], mac, g["in_phi"], g["in_near"], meta["dt"], meta["cfl"])
+    assert bits_equal(out, g["out_pos"])
+    free = oracle.advect(I, J, K, dx, g["in_pos"], mac, g["in_phi"], g["in_near"], meta["dt"], meta["cfl"],
+                         collide=False)
+    collided = (free != out).any(axis=1).sum()
+    assert collided > 0.05 * len(out)                   # the fixture really exercises _resolveCollision
+
+
+def test_bin_sort_properties(oracle):
+    meta, g = load_golden("p2g_flip_23x21x25_seams")
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    pos = g["in_pos"].copy()
+    pos[:5] = [[-1e-3, 0.01, 0.01], [0.01, (J + 1) * dx, 0.01], [0.01, 0.01, K * dx + 1], [(I + 0.5) * dx, 0.0, 0.0], [0, 0, 0]]
+    cell, hkey, perm = oracle.bin_sort(I, J, K, dx, pos)
+    inv = 1.0 / dx
+    ci = np.floor(pos.astype(np.float64) * inv).astype(np.int64)           # grid3d.h:55-60
+    ok = ((ci >= 0) & (ci < [I, J, K])).all(axis=1)
+    want = np.where(ok, ci[:, 0] + I * (ci[:, 1] + J * ci[:, 2]), -1)
+    assert np.array_equal(cell, want)
+    assert list(ok[:5]) == [False, False, False, False, True]
+    # half-cell keys refine the cell index exactly
+    hk = hkey[ok].astype(np.int64)
+    hi, hj, hk2 = hk % (2 * I), (hk // (2 * I)) % (2 * J), hk // (4 * I * J)
+    assert np.array_equal((hi >> 1) + I * ((hj >> 1) + J * (hk2 >> 1)), cell[ok])
+    assert (hkey[~ok] == 8 * I * J * K).all()
+    # stable order: keys ascending, ties by ascending particle index
+    ks = hkey[perm]
+    assert (np.diff(ks.astype(np.int64)) >= 0).all()
+    same = np.diff(ks.astype(np.int64)) == 0
+    assert (np.diff(perm.astype(np.int64))[same] > 0).all()
+    assert np.array_equal(np.sort(perm), np.arange(len(pos)))
