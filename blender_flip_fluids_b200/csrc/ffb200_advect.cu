@@ -1,0 +1,236 @@
+// ffb200_advect.cu -- marker-particle advection on the sorted SoA streams.
+//
+//   _RK3                         fluidsimulation.cpp:7616-7623  (Ralston RK3 through the MAC field)
+//   _resolveCollision            fluidsimulation.cpp:7646-7721  (march + SDF projection)
+//   _getBoundaryAABB             fluidsimulation.cpp:5175-5180
+//   AABB::{expand,isPointInside,getNearestPointInsideAABB}   aabb.cpp:122-133, 493-518
+//   Interpolation::trilinearInterpolate(vec3, dx, grid)      interpolation.cpp:72-112
+//   Interpolation::trilinearInterpolateGradient              interpolation.cpp:197-259
+//
+// One thread per particle. The arithmetic repeats the reference's float/double mix operation
+// for operation, so positions are bit-identical on identical inputs. The collision march is
+// the data-dependent slow path: sorted particles share their 3dx near-solid flag with their
+// neighbours, which keeps warps mostly convergent on the gate.
+#include "ffb200_ctx.h"
+
+namespace ffb200 {
+
+namespace {
+
+struct Box {
+    float px, py, pz;       // AABB::position (floats)
+    double w, h, d;         // AABB::width/height/depth (doubles)
+};
+
+struct AdvectParams {
+    GridDesc g;
+    MacView mac;
+    const float *phi;       // (I+1)(J+1)(kloc+1), first stored node plane = kbase
+    const uint8_t *near_solid;
+    int ni, nj, nk;
+    double inv_near;        // 1.0 / (3*dx)
+    Box box;
+    float *px, *py, *pz;
+    float c2, c3, c9;       // (float)(0.5dt), (float)(0.75dt), (float)(dt/9.0f)
+    float step;             // _markerParticleStepDistanceFactor * (float)_dx
+    float maxdist;          // (float)(_CFLConditionNumber * _dx)
+    double buffer;          // (double)_solidBufferWidth * _dx
+    int collide;
+    int n;
+};
+
+__device__ __forceinline__ bool box_inside(const Box &b, float x, float y, float z) {
+    return x >= b.px && y >= b.py && z >= b.pz && (double)x < (double)b.px + b.w && (double)y < (double)b.py + b.h &&
+           (double)z < (double)b.pz + b.d;
+}
+
+__device__ __forceinline__ void box_nearest_inside(const Box &b, float &x, float &y, float &z) {
+    if (box_inside(b, x, y, z)) return;
+    const double eps = 1e-6;
+    const float mx = b.px + (float)b.w, my = b.py + (float)b.h, mz = b.pz + (float)b.d;
+    x = fmaxf(x, b.px); y = fmaxf(y, b.py); z = fmaxf(z, b.pz);
+    x = (float)fmin((double)x, (double)mx - eps);
+    y = (float)fmin((double)y, (double)my - eps);
+    z = (float)fmin((double)z, (double)mz - eps);
+}
+
+struct SdfCell {
+    double ix, iy, iz;
+    float v[8];             // 000,100,010,001,101,011,110,111 (the reference's corner order)
+};
+
+__device__ __forceinline__ void sdf_cell(const AdvectParams &P, float x, float y, float z, SdfCell &c) {
+    const GridDesc &g = P.g;
+    const int w = g.I + 1, h = g.J + 1, d = g.K + 1;
+    const int i = pos2idx(x, g.inv_dx), j = pos2idx(y, g.inv_dx), k = pos2idx(z, g.inv_dx);
+    c.ix = (double)(x - idx2posf(i, g.dx)) * g.inv_dx;
+    c.iy = (double)(y - idx2posf(j, g.dx)) * g.inv_dx;
+    c.iz = (double)(z - idx2posf(k, g.dx)) * g.inv_dx;
+    const bool i0 = (unsigned)i < (unsigned)w, i1 = (unsigned)(i + 1) < (unsigned)w;
+    const bool j0 = (unsigned)j < (unsigned)h, j1 = (unsigned)(j + 1) < (unsigned)h;
+    const bool k0 = (unsigned)k < (unsigned)d, k1 = (unsigned)(k + 1) < (unsigned)d;
+    const long long sj = w, sk = (long long)w * h;
+    const long long base = (long long)i + sj * j + sk * (long long)(k - g.kbase);
+    const float *f = P.phi;
+    c.v[0] = (i0 && j0 && k0) ? __ldg(f + base) : 0.0f;
+    c.v[1] = (i1 && j0 && k0) ? __ldg(f + base + 1) : 0.0f;
+    c.v[2] = (i0 && j1 && k0) ? __ldg(f + base + sj) : 0.0f;
+    c.v[3] = (i0 && j0 && k1) ? __ldg(f + base + sk) : 0.0f;
+    c.v[4] = (i1 && j0 && k1) ? __ldg(f + base + sk + 1) : 0.0f;
+    c.v[5] = (i0 && j1 && k1) ? __ldg(f + base + sk + sj) : 0.0f;
+    c.v[6] = (i1 && j1 && k0) ? __ldg(f + base + sj + 1) : 0.0f;
+    c.v[7] = (i1 && j1 && k1) ? __ldg(f + base + sk + sj + 1) : 0.0f;
+}
+
+__device__ __forceinline__ float sdf_sample(const AdvectParams &P, float x, float y, float z) {
+    SdfCell c;
+    sdf_cell(P, x, y, z, c);
+    double p[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) p[q] = (double)c.v[q];
+    return (float)trilerp8(p, c.ix, c.iy, c.iz);
+}
+
+__device__ __forceinline__ double bilerp(double v00, double v10, double v01, double v11, double ix, double iy) {
+    const double l1 = (1 - ix) * v00 + ix * v10;
+    const double l2 = (1 - ix) * v01 + ix * v11;
+    return (1 - iy) * l1 + iy * l2;
+}
+
+__device__ __forceinline__ void sdf_gradient(const AdvectParams &P, float x, float y, float z, float &gx, float &gy, float &gz) {
+    SdfCell c;
+    sdf_cell(P, x, y, z, c);
+    const float v000 = c.v[0], v100 = c.v[1], v010 = c.v[2], v001 = c.v[3], v101 = c.v[4], v011 = c.v[5], v110 = c.v[6],
+                v111 = c.v[7];
+    const float ddx00 = v100 - v000, ddx10 = v110 - v010, ddx01 = v101 - v001, ddx11 = v111 - v011;
+    gx = (float)bilerp(ddx00, ddx10, ddx01, ddx11, c.iy, c.iz);
+    const float ddy00 = v010 - v000, ddy10 = v110 - v100, ddy01 = v011 - v001, ddy11 = v111 - v101;
+    gy = (float)bilerp(ddy00, ddy10, ddy01, ddy11, c.ix, c.iz);
+    const float ddz00 = v001 - v000, ddz10 = v101 - v100, ddz01 = v011 - v010, ddz11 = v111 - v110;
+    gz = (float)bilerp(ddz00, ddz10, ddz01, ddz11, c.ix, c.iy);
+}
+
+__device__ __forceinline__ bool near_solid(const AdvectParams &P, float x, float y, float z) {
+    const int i = pos2idx(x, P.inv_near), j = pos2idx(y, P.inv_near), k = pos2idx(z, P.inv_near);
+    // unchecked Array3d<bool> read in the reference (:7654-7656); out of range -> "near"
+    if (!in_range3(i, j, k, P.ni, P.nj, P.nk)) return true;
+    return P.near_solid[i + P.ni * (j + P.nj * k)] != 0;
+}
+
+__device__ __noinline__ void resolve_collision(const AdvectParams &P, float ox, float oy, float oz, float &nx, float &ny,
+                                               float &nz) {
+    const GridDesc &g = P.g;
+    const int gi = pos2idx(nx, g.inv_dx), gj = pos2idx(ny, g.inv_dx), gk = pos2idx(nz, g.inv_dx);
+    if (!in_range3(gi, gj, gk, g.I, g.J, g.K)) box_nearest_inside(P.box, nx, ny, nz);
+    if (!near_solid(P, ox, oy, oz) && !near_solid(P, nx, ny, nz)) return;
+
+    const float eps = 1e-6f;
+    const float dxx = nx - ox, dyy = ny - oy, dzz = nz - oz;
+    const float travel = vlen3(dxx, dyy, dzz);
+    if (travel < eps) return;
+    const int nsteps = (int)ceilf(travel / P.step);
+    const float invlen = finv(travel);
+    const float dirx = dxx * invlen, diry = dyy * invlen, dirz = dzz * invlen;
+
+    float lx = ox, ly = oy, lz = oz;
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;
+    bool found = false;
+    float cphi = 0.0f;
+    for (int st = 0; st < nsteps; st++) {
+        if (st == nsteps - 1) {
+            cx = nx; cy = ny; cz = nz;
+        } else {
+            const float t = (float)(st + 1) * P.step;
+            cx = ox + dirx * t; cy = oy + diry * t; cz = oz + dirz * t;
+        }
+        const float phi = sdf_sample(P, cx, cy, cz);
+        if (phi < 0.0f || !box_inside(P.box, cx, cy, cz)) {
+            cphi = phi;
+            found = true;
+            break;
+        }
+        lx = cx; ly = cy; lz = cz;
+    }
+    if (!found) return;
+
+    float rx, ry, rz;
+    float gx, gy, gz;
+    sdf_gradient(P, cx, cy, cz, gx, gy, gz);
+    const float glen = vlen3(gx, gy, gz);
+    if (glen > eps) {
+        const float ginv = finv(glen);
+        gx *= ginv; gy *= ginv; gz *= ginv;
+        const float push = (float)((double)cphi - P.buffer);
+        rx = cx - gx * push; ry = cy - gy * push; rz = cz - gz * push;
+        const float rphi = sdf_sample(P, rx, ry, rz);
+        const float rdist = vlen3(rx - cx, ry - cy, rz - cz);
+        if (rphi < 0 || rdist > P.maxdist) { rx = lx; ry = ly; rz = lz; }
+    } else {
+        rx = lx; ry = ly; rz = lz;
+    }
+    if (!box_inside(P.box, rx, ry, rz)) {
+        const float qx = rx, qy = ry, qz = rz;
+        box_nearest_inside(P.box, rx, ry, rz);
+        const float rphi = sdf_sample(P, rx, ry, rz);
+        const float rdist = vlen3(rx - qx, ry - qy, rz - qz);
+        if (rphi < 0.0f || rdist > P.maxdist) { rx = lx; ry = ly; rz = lz; }
+    }
+    nx = rx; ny = ry; nz = rz;
+}
+
+__global__ void __launch_bounds__(256) k_advect(AdvectParams P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
+    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
+    mac_eval(P.g, P.mac, x0, y0, z0, k1x, k1y, k1z);
+    mac_eval(P.g, P.mac, x0 + k1x * P.c2, y0 + k1y * P.c2, z0 + k1z * P.c2, k2x, k2y, k2z);
+    mac_eval(P.g, P.mac, x0 + k2x * P.c3, y0 + k2y * P.c3, z0 + k2z * P.c3, k3x, k3y, k3z);
+    float x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
+    float y1 = y0 + ((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * P.c9;
+    float z1 = z0 + ((k1z * 2.0f + k2z * 3.0f) + k3z * 4.0f) * P.c9;
+    if (P.collide) resolve_collision(P, x0, y0, z0, x1, y1, z1);
+    P.px[j] = x1; P.py[j] = y1; P.pz[j] = z1;
+}
+
+void box_expand(Box &b, double v) {                     // aabb.cpp:122-128
+    const double hh = 0.5 * v;
+    const float hf = (float)hh;
+    b.px -= hf; b.py -= hf; b.pz -= hf;
+    b.w += v; b.h += v; b.d += v;
+}
+
+}  // namespace
+
+int launch_advect(Context &c, double dt, double cfl, int collide) {
+    if (c.n == 0) return 0;
+    if (collide && !c.has_solid) throw CudaError("ffb200_advect: collision resolution needs ffb200_set_solid first");
+    ParticleSoA &s = c.soa[c.cur];
+    const GridDesc &g = c.g;
+    AdvectParams P;
+    P.g = g;
+    P.mac = MacView{c.face[0].vel, c.face[1].vel, c.face[2].vel};
+    P.phi = c.phi;
+    P.near_solid = c.near_solid;
+    P.ni = c.ni; P.nj = c.nj; P.nk = c.nk;
+    P.inv_near = 1.0 / (3 * g.dx);                      // _nearSolidGridCellSizeFactor * _dx
+    P.box.px = P.box.py = P.box.pz = 0.0f;              // _getBoundaryAABB
+    P.box.w = g.I * g.dx; P.box.h = g.J * g.dx; P.box.d = g.K * g.dx;
+    box_expand(P.box, -3 * g.dx - 1e-4);
+    box_expand(P.box, -0.2f * g.dx);                    // boundary.expand(-_solidBufferWidth * _dx)
+    P.px = s.p[0]; P.py = s.p[1]; P.pz = s.p[2];
+    P.c2 = (float)(0.5 * dt);
+    P.c3 = (float)(0.75 * dt);
+    P.c9 = (float)(dt / 9.0f);
+    P.step = 0.1f * (float)g.dx;
+    P.maxdist = (float)(cfl * g.dx);
+    P.buffer = (double)0.2f * g.dx;
+    P.collide = collide;
+    P.n = c.n;
+    k_advect<<<(c.n + 255) / 256, 256, 0, c.stream>>>(P);
+    FFB_CUDA(cudaGetLastError());
+    c.sorted = false;                                   // positions moved: bins are stale
+    return 1;
+}
+
+}  // namespace ffb200

@@ -1,0 +1,524 @@
+// ffb200_api.cu -- the extern "C" layer of libffb200.so (include/ffb200.h) and device memory
+// management. No kernels here; see ffb200_{sort,p2g,g2p,advect}.cu.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <exception>
+#include <limits>
+#include <new>
+
+#include "ffb200_ctx.h"
+
+using namespace ffb200;
+
+namespace {
+
+// One global message buffer, like the reference's c_bindings/cbindings.cpp:37-47.
+char g_error[4096] = "";
+
+void set_error(const char *fn, const char *what) { snprintf(g_error, sizeof(g_error), "%s - %s", fn, what); }
+
+template <class F>
+int guarded(const char *fn, ffb200_context *ctx, F &&body) {
+    try {
+        if (!ctx) throw std::invalid_argument("null context");
+        Context &c = *reinterpret_cast<Context *>(ctx);
+        FFB_CUDA(cudaSetDevice(c.device));
+        body(c);
+        return FFB200_SUCCESS;
+    } catch (const std::exception &e) {
+        set_error(fn, e.what());
+    } catch (...) {
+        set_error(fn, "unknown exception");
+    }
+    return FFB200_FAIL;
+}
+
+template <class T>
+void dev_alloc(T *&p, size_t count) {
+    FFB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), (count ? count : 1) * sizeof(T)));
+}
+
+template <class T>
+void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+enum Stage { kSort = 0, kP2G, kG2P, kAdvect, kH2D, kD2H, kNumStages };
+
+struct StageEvents {
+    cudaEvent_t start[kNumStages] = {}, stop[kNumStages] = {};
+    bool used[kNumStages] = {};
+};
+
+// Context plus the bookkeeping that only this file needs.
+struct ContextImpl : Context {
+    StageEvents evs;
+    int launches[kNumStages] = {};
+};
+
+struct StageTimer {
+    ContextImpl &c;
+    Stage s;
+    StageTimer(ContextImpl &ctx, Stage st) : c(ctx), s(st) {
+        FFB_CUDA(cudaEventRecord(c.evs.start[s], c.stream));
+    }
+    void done(int launched) {
+        FFB_CUDA(cudaEventRecord(c.evs.stop[s], c.stream));
+        c.evs.used[s] = true;
+        c.launches[s] = launched;
+    }
+};
+
+void free_particles(ContextImpl &c) {
+    for (int b = 0; b < 2; b++) {
+        for (int q = 0; q < 3; q++) { dev_free(c.soa[b].p[q]); dev_free(c.soa[b].v[q]); }
+        for (int q = 0; q < 9; q++) dev_free(c.soa[b].a[q]);
+        dev_free(c.soa[b].orig);
+        dev_free(c.sort.key[b]);
+        dev_free(c.sort.val[b]);
+    }
+    dev_free(c.sort.seam);
+    dev_free(c.aos_stage);
+    c.cap = 0;
+}
+
+void ensure_affine(ContextImpl &c) {
+    if (c.soa[0].a[0]) return;
+    for (int b = 0; b < 2; b++)
+        for (int q = 0; q < 9; q++) {
+            dev_alloc(c.soa[b].a[q], (size_t)c.cap);
+            FFB_CUDA(cudaMemsetAsync(c.soa[b].a[q], 0, (size_t)c.cap * sizeof(float), c.stream));
+        }
+}
+
+void ensure_capacity(ContextImpl &c, int n, bool affine) {
+    if (n > c.cap) {
+        const bool had_affine = c.soa[0].a[0] != nullptr;
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+        free_particles(c);
+        c.cap = n + n / 8 + 1024;
+        for (int b = 0; b < 2; b++) {
+            for (int q = 0; q < 3; q++) { dev_alloc(c.soa[b].p[q], (size_t)c.cap); dev_alloc(c.soa[b].v[q], (size_t)c.cap); }
+            dev_alloc(c.soa[b].orig, (size_t)c.cap);
+            dev_alloc(c.sort.key[b], (size_t)c.cap);
+            dev_alloc(c.sort.val[b], (size_t)c.cap);
+        }
+        dev_alloc(c.sort.seam, (size_t)c.cap * 3);
+        dev_alloc(c.aos_stage, (size_t)c.cap * 3);
+        if (had_affine) ensure_affine(c);
+    }
+    if (affine) ensure_affine(c);
+}
+
+void destroy_impl(ContextImpl *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_particles(*c);
+    dev_free(c->sort.tile_hist);
+    dev_free(c->sort.bin_start);
+    dev_free(c->sort.scan_partials);
+    for (int d = 0; d < 3; d++) {
+        FaceGrid &f = c->face[d];
+        dev_free(f.vel); dev_free(f.saved); dev_free(f.wsum); dev_free(f.valid); dev_free(f.home); dev_free(f.active);
+    }
+    dev_free(c->phi);
+    dev_free(c->near_solid);
+    for (int s = 0; s < kNumStages; s++) {
+        if (c->evs.start[s]) cudaEventDestroy(c->evs.start[s]);
+        if (c->evs.stop[s]) cudaEventDestroy(c->evs.stop[s]);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int create_impl(ffb200_context **out, int I, int J, int K, double dx, int device, int k_begin, int k_end, int halo) {
+    ContextImpl *c = nullptr;
+    try {
+        if (!out) throw std::invalid_argument("null output pointer");
+        *out = nullptr;
+        if (I <= 0 || J <= 0 || K <= 0 || !(dx > 0.0)) throw std::domain_error("grid dimensions and dx must be positive");
+        if (k_begin < 0 || k_end > K || k_begin >= k_end || halo < 0) throw std::domain_error("invalid z-slab range");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw CudaError(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                            "); libffb200 has no CPU fallback");
+        if (device < 0 || device >= ndev) throw std::domain_error("CUDA device ordinal out of range");
+        FFB_CUDA(cudaSetDevice(device));
+        c = new ContextImpl();
+        c->device = device;
+        c->k_own_begin = k_begin; c->k_own_end = k_end; c->halo = halo;
+        GridDesc &g = c->g;
+        g.I = I; g.J = J; g.K = K;
+        g.kbase = k_begin - halo < 0 ? 0 : k_begin - halo;
+        const int ktop = k_end + halo > K ? K : k_end + halo;
+        g.kloc = ktop - g.kbase;
+        g.dx = dx;
+        g.inv_dx = 1.0 / dx;
+        g.inv_2dx = 2.0 * g.inv_dx;
+        g.HX = 2 * I + 2 * kApron; g.HY = 2 * J + 2 * kApron; g.HZ = 2 * g.kloc + 2 * kApron;
+        const unsigned long long nb = (unsigned long long)g.HX * g.HY * g.HZ;
+        if (nb >= 0xfffffff0ull) throw std::domain_error("grid too large for 32-bit bin keys");
+        g.nbins = (uint32_t)nb;
+        FFB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        for (int s = 0; s < kNumStages; s++) {
+            FFB_CUDA(cudaEventCreate(&c->evs.start[s]));
+            FFB_CUDA(cudaEventCreate(&c->evs.stop[s]));
+        }
+        dev_alloc(c->sort.bin_start, (size_t)g.nbins + 2);
+        for (int d = 0; d < 3; d++) {
+            FaceGrid &f = c->face[d];
+            f.gi = I + (d == 0); f.gj = J + (d == 1); f.gk = K + (d == 2);
+            f.bi = (f.gi + kChunk - 1) / kChunk; f.bj = (f.gj + kChunk - 1) / kChunk; f.bk = (f.gk + kChunk - 1) / kChunk;
+            f.kstore = g.kloc + (d == 2);
+            f.count = (size_t)f.gi * f.gj * f.kstore;
+            dev_alloc(f.vel, f.count); dev_alloc(f.saved, f.count); dev_alloc(f.wsum, f.count); dev_alloc(f.valid, f.count);
+            dev_alloc(f.home, (size_t)f.bi * f.bj * f.bk); dev_alloc(f.active, (size_t)f.bi * f.bj * f.bk);
+            FFB_CUDA(cudaMemsetAsync(f.vel, 0, f.count * 4, c->stream));
+            FFB_CUDA(cudaMemsetAsync(f.saved, 0, f.count * 4, c->stream));
+            FFB_CUDA(cudaMemsetAsync(f.wsum, 0, f.count * 4, c->stream));
+            FFB_CUDA(cudaMemsetAsync(f.valid, 0, f.count, c->stream));
+        }
+        const double cell = 3 * dx;                         // fluidsimulation.cpp:5448-5451
+        c->ni = (int)std::ceil(I * dx / cell); c->nj = (int)std::ceil(J * dx / cell); c->nk = (int)std::ceil(K * dx / cell);
+        dev_alloc(c->phi, (size_t)(I + 1) * (J + 1) * (g.kloc + 1));
+        dev_alloc(c->near_solid, (size_t)c->ni * c->nj * c->nk);
+        FFB_CUDA(cudaStreamSynchronize(c->stream));
+        *out = reinterpret_cast<ffb200_context *>(static_cast<Context *>(c));
+        return FFB200_SUCCESS;
+    } catch (const std::exception &e) {
+        set_error("ffb200_create", e.what());
+    } catch (...) {
+        set_error("ffb200_create", "unknown exception");
+    }
+    destroy_impl(c);
+    return FFB200_FAIL;
+}
+
+ContextImpl &impl(Context &c) { return static_cast<ContextImpl &>(c); }
+
+void upload_attr(ContextImpl &c, const float *host, float *const dst[3], int n) {
+    FFB_CUDA(cudaMemcpyAsync(c.aos_stage, host, (size_t)n * 12, cudaMemcpyHostToDevice, c.stream));
+    launch_unpack_aos(c, c.aos_stage, dst, n);
+}
+
+void download_attr(ContextImpl &c, const float *const src[3], float *host, int n) {
+    launch_pack_aos(c, src, c.soa[c.cur].orig, c.aos_stage, n);
+    FFB_CUDA(cudaMemcpyAsync(host, c.aos_stage, (size_t)n * 12, cudaMemcpyDeviceToHost, c.stream));
+}
+
+void set_particles_impl(ContextImpl &c, int n, const float *pos, const float *vel, const float *affx, const float *affy,
+                        const float *affz) {
+    if (n < 0) throw std::domain_error("negative particle count");
+    if (n > 0 && (!pos || !vel)) throw std::invalid_argument("positions and velocities are required");
+    const bool affine = affx && affy && affz;
+    ensure_capacity(c, n, affine);
+    c.n = n;
+    c.has_affine = affine;
+    c.sorted = false;
+    if (n == 0) return;
+    StageTimer t(c, kH2D);
+    ParticleSoA &s = c.soa[c.cur];
+    upload_attr(c, pos, s.p, n);
+    upload_attr(c, vel, s.v, n);
+    if (affine) {
+        upload_attr(c, affx, s.a + 0, n);
+        upload_attr(c, affy, s.a + 3, n);
+        upload_attr(c, affz, s.a + 6, n);
+    }
+    launch_iota(c, s.orig, n);
+    t.done(0);
+}
+
+void get_particles_impl(ContextImpl &c, float *pos, float *vel, float *affx, float *affy, float *affz) {
+    const int n = c.n;
+    if (n > 0) {
+        StageTimer t(c, kD2H);
+        ParticleSoA &s = c.soa[c.cur];
+        if (pos) download_attr(c, s.p, pos, n);
+        if (vel) download_attr(c, s.v, vel, n);
+        if (affx || affy || affz) {
+            if (!s.a[0]) throw std::logic_error("no affine data on the device");
+            if (affx) download_attr(c, s.a + 0, affx, n);
+            if (affy) download_attr(c, s.a + 3, affy, n);
+            if (affz) download_attr(c, s.a + 6, affz, n);
+        }
+        t.done(0);
+    }
+    FFB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+void sort_impl(ContextImpl &c) {
+    if (c.sorted) return;
+    StageTimer t(c, kSort);
+    int l = launch_sort(c);
+    t.done(l);
+}
+
+// Host grids are full-size reference arrays; a slab context copies its stored planes.
+void upload_field(ContextImpl &c, bool saved, const float *u, const float *v, const float *w) {
+    const float *h[3] = {u, v, w};
+    for (int d = 0; d < 3; d++) {
+        if (!h[d]) throw std::invalid_argument("null velocity field pointer");
+        FaceGrid &f = c.face[d];
+        const size_t off = (size_t)f.gi * f.gj * c.g.kbase;
+        FFB_CUDA(cudaMemcpyAsync(saved ? f.saved : f.vel, h[d] + off, f.count * 4, cudaMemcpyHostToDevice, c.stream));
+    }
+}
+
+void set_solid_impl(ContextImpl &c, const float *phi, const uint8_t *near_solid) {
+    if (!phi || !near_solid) throw std::invalid_argument("null solid SDF / near-solid pointer");
+    const GridDesc &g = c.g;
+    const size_t plane = (size_t)(g.I + 1) * (g.J + 1);
+    FFB_CUDA(cudaMemcpyAsync(c.phi, phi + plane * g.kbase, plane * (g.kloc + 1) * 4, cudaMemcpyHostToDevice, c.stream));
+    FFB_CUDA(cudaMemcpyAsync(c.near_solid, near_solid, (size_t)c.ni * c.nj * c.nk, cudaMemcpyHostToDevice, c.stream));
+    c.has_solid = true;
+}
+
+void p2g_impl(ContextImpl &c, double radius, int method) {
+    if (method != FFB200_TRANSFER_FLIP && method != FFB200_TRANSFER_APIC) throw std::domain_error("unknown transfer method");
+    if (!(radius > 0.0)) throw std::domain_error("particle radius must be positive");
+    if (method == FFB200_TRANSFER_APIC && !c.has_affine) throw std::logic_error("APIC transfer needs affine particle data");
+    sort_impl(c);
+    StageTimer t(c, kP2G);
+    int l = launch_p2g(c, radius, method);
+    t.done(l);
+}
+
+void g2p_impl(ContextImpl &c, int method, double ratio) {
+    if (method != FFB200_TRANSFER_FLIP && method != FFB200_TRANSFER_APIC) throw std::domain_error("unknown transfer method");
+    if (method == FFB200_TRANSFER_APIC) {
+        ensure_capacity(c, c.n, true);
+        c.has_affine = true;
+    }
+    StageTimer t(c, kG2P);
+    int l = launch_g2p(c, method, ratio);
+    t.done(l);
+}
+
+void advect_impl(ContextImpl &c, double dt, double cfl, int collide) {
+    StageTimer t(c, kAdvect);
+    int l = launch_advect(c, dt, cfl, collide);
+    t.done(l);
+}
+
+void get_field_impl(ContextImpl &c, float *u, float *v, float *w, uint8_t *vu, uint8_t *vv, uint8_t *vw) {
+    float *h[3] = {u, v, w};
+    uint8_t *hv[3] = {vu, vv, vw};
+    StageTimer t(c, kD2H);
+    for (int d = 0; d < 3; d++) {
+        FaceGrid &f = c.face[d];
+        const size_t off = (size_t)f.gi * f.gj * c.g.kbase;
+        if (h[d]) FFB_CUDA(cudaMemcpyAsync(h[d] + off, f.vel, f.count * 4, cudaMemcpyDeviceToHost, c.stream));
+        if (hv[d]) FFB_CUDA(cudaMemcpyAsync(hv[d] + off, f.valid, f.count, cudaMemcpyDeviceToHost, c.stream));
+    }
+    t.done(0);
+    FFB_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ffb200_create(ffb200_context **ctx, int isize, int jsize, int ksize, double dx, int device) {
+    return create_impl(ctx, isize, jsize, ksize, dx, device, 0, ksize, 0);
+}
+
+int ffb200_create_slab(ffb200_context **ctx, int isize, int jsize, int ksize, double dx, int device, int k_begin,
+                       int k_end, int halo) {
+    return create_impl(ctx, isize, jsize, ksize, dx, device, k_begin, k_end, halo);
+}
+
+void ffb200_destroy(ffb200_context *ctx) {
+    if (ctx) destroy_impl(static_cast<ContextImpl *>(reinterpret_cast<Context *>(ctx)));
+}
+
+const char *ffb200_get_error_message(void) { return g_error; }
+
+int ffb200_get_version(int *major, int *minor, int *revision) {
+    if (major) *major = 0;
+    if (minor) *minor = 1;
+    if (revision) *revision = 0;
+    return FFB200_SUCCESS;
+}
+
+int ffb200_set_stream(ffb200_context *ctx, void *cuda_stream) {
+    return guarded("ffb200_set_stream", ctx, [&](Context &c) {
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+        c.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c.own_stream;
+    });
+}
+
+int ffb200_synchronize(ffb200_context *ctx) {
+    return guarded("ffb200_synchronize", ctx, [&](Context &c) { FFB_CUDA(cudaStreamSynchronize(c.stream)); });
+}
+
+int ffb200_get_timing(ffb200_context *ctx, ffb200_timing *out) {
+    return guarded("ffb200_get_timing", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (!out) throw std::invalid_argument("null output pointer");
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+        float ms[kNumStages] = {};
+        for (int s = 0; s < kNumStages; s++)
+            if (c.evs.used[s]) FFB_CUDA(cudaEventElapsedTime(&ms[s], c.evs.start[s], c.evs.stop[s]));
+        out->sort_ms = ms[kSort]; out->p2g_ms = ms[kP2G]; out->g2p_ms = ms[kG2P]; out->advect_ms = ms[kAdvect];
+        out->h2d_ms = ms[kH2D]; out->d2h_ms = ms[kD2H];
+        out->sort_launches = c.launches[kSort]; out->p2g_launches = c.launches[kP2G];
+        out->g2p_launches = c.launches[kG2P]; out->advect_launches = c.launches[kAdvect];
+    });
+}
+
+int ffb200_set_valid_guard(ffb200_context *ctx, float abs_tol, float per_contrib_tol) {
+    return guarded("ffb200_set_valid_guard", ctx, [&](Context &c) {
+        c.guard_abs = abs_tol;
+        c.guard_per = per_contrib_tol;
+    });
+}
+
+int ffb200_set_particles(ffb200_context *ctx, int n, const float *pos, const float *vel, const float *affx,
+                         const float *affy, const float *affz) {
+    return guarded("ffb200_set_particles", ctx, [&](Context &c) { set_particles_impl(impl(c), n, pos, vel, affx, affy, affz); });
+}
+
+int ffb200_get_particles(ffb200_context *ctx, float *pos, float *vel, float *affx, float *affy, float *affz) {
+    return guarded("ffb200_get_particles", ctx, [&](Context &c) { get_particles_impl(impl(c), pos, vel, affx, affy, affz); });
+}
+
+int ffb200_get_num_particles(ffb200_context *ctx, int *n) {
+    return guarded("ffb200_get_num_particles", ctx, [&](Context &c) {
+        if (!n) throw std::invalid_argument("null output pointer");
+        *n = c.n;
+    });
+}
+
+int ffb200_sort_particles(ffb200_context *ctx) {
+    return guarded("ffb200_sort_particles", ctx, [&](Context &c) { sort_impl(impl(c)); });
+}
+
+int ffb200_get_binning(ffb200_context *ctx, int32_t *cell, uint32_t *hkey, uint32_t *perm) {
+    return guarded("ffb200_get_binning", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (!cell || !hkey || !perm) throw std::invalid_argument("null output pointer");
+        sort_impl(c);
+        const int n = c.n;
+        if (n == 0) return;
+        // key/val scratch is free after the sort: reuse it for the dump
+        int32_t *d_cell = reinterpret_cast<int32_t *>(c.sort.key[1]);
+        uint32_t *d_hkey = c.sort.val[1], *d_perm = reinterpret_cast<uint32_t *>(c.aos_stage);
+        launch_binning_dump(c, d_cell, d_hkey, d_perm);
+        FFB_CUDA(cudaMemcpyAsync(cell, d_cell, (size_t)n * 4, cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaMemcpyAsync(hkey, d_hkey, (size_t)n * 4, cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaMemcpyAsync(perm, d_perm, (size_t)n * 4, cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int ffb200_set_velocity_field(ffb200_context *ctx, const float *u, const float *v, const float *w) {
+    return guarded("ffb200_set_velocity_field", ctx, [&](Context &c) { upload_field(impl(c), false, u, v, w); });
+}
+
+int ffb200_set_saved_velocity_field(ffb200_context *ctx, const float *u, const float *v, const float *w) {
+    return guarded("ffb200_set_saved_velocity_field", ctx, [&](Context &c) { upload_field(impl(c), true, u, v, w); });
+}
+
+int ffb200_get_velocity_field(ffb200_context *ctx, float *u, float *v, float *w, uint8_t *validu, uint8_t *validv,
+                              uint8_t *validw) {
+    return guarded("ffb200_get_velocity_field", ctx,
+                   [&](Context &c) { get_field_impl(impl(c), u, v, w, validu, validv, validw); });
+}
+
+int ffb200_get_weight_sums(ffb200_context *ctx, float *wu, float *wv, float *ww) {
+    return guarded("ffb200_get_weight_sums", ctx, [&](Context &c) {
+        float *h[3] = {wu, wv, ww};
+        for (int d = 0; d < 3; d++) {
+            FaceGrid &f = c.face[d];
+            const size_t off = (size_t)f.gi * f.gj * c.g.kbase;
+            if (h[d]) FFB_CUDA(cudaMemcpyAsync(h[d] + off, f.wsum, f.count * 4, cudaMemcpyDeviceToHost, c.stream));
+        }
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int ffb200_save_velocity_field(ffb200_context *ctx) {
+    return guarded("ffb200_save_velocity_field", ctx, [&](Context &c) {
+        for (int d = 0; d < 3; d++)
+            FFB_CUDA(cudaMemcpyAsync(c.face[d].saved, c.face[d].vel, c.face[d].count * 4, cudaMemcpyDeviceToDevice, c.stream));
+    });
+}
+
+int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid) {
+    return guarded("ffb200_set_solid", ctx, [&](Context &c) { set_solid_impl(impl(c), phi, near_solid); });
+}
+
+int ffb200_p2g(ffb200_context *ctx, double particle_radius, int transfer_method) {
+    return guarded("ffb200_p2g", ctx, [&](Context &c) { p2g_impl(impl(c), particle_radius, transfer_method); });
+}
+
+int ffb200_g2p(ffb200_context *ctx, int transfer_method, double ratio_pic_flip) {
+    return guarded("ffb200_g2p", ctx, [&](Context &c) { g2p_impl(impl(c), transfer_method, ratio_pic_flip); });
+}
+
+int ffb200_advect(ffb200_context *ctx, double dt, double cfl_condition_number, int resolve_collisions) {
+    return guarded("ffb200_advect", ctx,
+                   [&](Context &c) { advect_impl(impl(c), dt, cfl_condition_number, resolve_collisions); });
+}
+
+int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos, const float *vel, const float *affx,
+                                    const float *affy, const float *affz, double particle_radius, int transfer_method,
+                                    float *u, float *v, float *w, uint8_t *validu, uint8_t *validv, uint8_t *validw) {
+    return guarded("ffb200_velocity_advector_advect", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        set_particles_impl(c, n, pos, vel, affx, affy, affz);
+        p2g_impl(c, particle_radius, transfer_method);
+        get_field_impl(c, u, v, w, validu, validv, validw);
+    });
+}
+
+int ffb200_update_marker_particle_velocities(ffb200_context *ctx, int n, const float *pos, float *vel, float *affx,
+                                             float *affy, float *affz, const float *u, const float *v, const float *w,
+                                             const float *su, const float *sv, const float *sw, int transfer_method,
+                                             double ratio_pic_flip) {
+    return guarded("ffb200_update_marker_particle_velocities", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        const bool apic = transfer_method == FFB200_TRANSFER_APIC;
+        if (apic && (!affx || !affy || !affz)) throw std::invalid_argument("APIC needs affine output buffers");
+        if (!apic && (!su || !sv || !sw)) throw std::invalid_argument("FLIP needs the saved velocity field");
+        set_particles_impl(c, n, pos, vel, nullptr, nullptr, nullptr);
+        upload_field(c, false, u, v, w);
+        if (!apic) upload_field(c, true, su, sv, sw);
+        sort_impl(c);                                          // spatial order for the gathers
+        g2p_impl(c, transfer_method, ratio_pic_flip);
+        get_particles_impl(c, nullptr, vel, apic ? affx : nullptr, apic ? affy : nullptr, apic ? affz : nullptr);
+    });
+}
+
+int ffb200_advance_marker_particles(ffb200_context *ctx, int n, float *pos, const float *u, const float *v,
+                                    const float *w, const float *phi, const uint8_t *near_solid, double dt,
+                                    double cfl_condition_number) {
+    return guarded("ffb200_advance_marker_particles", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (n > 0 && !pos) throw std::invalid_argument("null position pointer");
+        // velocities are not needed by advection: upload positions twice is avoided by a zero-copy alias
+        ensure_capacity(c, n, false);
+        c.n = n;
+        c.has_affine = false;
+        c.sorted = false;
+        if (n > 0) {
+            StageTimer t(c, kH2D);
+            upload_attr(c, pos, c.soa[c.cur].p, n);
+            launch_iota(c, c.soa[c.cur].orig, n);
+            t.done(0);
+        }
+        upload_field(c, false, u, v, w);
+        if (phi && near_solid) set_solid_impl(c, phi, near_solid);
+        sort_impl(c);
+        advect_impl(c, dt, cfl_condition_number, 1);
+        get_particles_impl(c, pos, nullptr, nullptr, nullptr, nullptr);
+    });
+}
+
+}  // extern "C"

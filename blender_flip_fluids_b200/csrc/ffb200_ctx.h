@@ -1,0 +1,104 @@
+// ffb200_ctx.h -- host-side context and the launch functions each .cu file provides.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "../../include/ffb200.h"
+#include "ffb200_common.cuh"
+
+namespace ffb200 {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define FFB_CUDA(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            throw ffb200::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) +  \
+                                    " (" __FILE__ ":" + std::to_string(__LINE__) + ")");          \
+    } while (0)
+
+// Particle attributes on the device, struct-of-arrays, one float stream per component.
+struct ParticleSoA {
+    float *p[3] = {nullptr, nullptr, nullptr};       // position
+    float *v[3] = {nullptr, nullptr, nullptr};       // velocity
+    float *a[9] = {};                                // AFFINEX.xyz, AFFINEY.xyz, AFFINEZ.xyz
+    uint32_t *orig = nullptr;                        // original (host) index of the particle in this slot
+};
+
+// Per direction (U, V, W): face grid + the reference's 10^3-node block grid.
+struct FaceGrid {
+    int gi = 0, gj = 0, gk = 0;   // global face dims
+    int bi = 0, bj = 0, bk = 0;   // block dims, blockarray3d.h:66-70
+    int kstore = 0;               // stored face planes (kloc, or kloc+1 for w)
+    size_t count = 0;             // gi*gj*kstore
+    float *vel = nullptr;         // current field component
+    float *saved = nullptr;       // _savedVelocityField component
+    float *wsum = nullptr;        // weight sums of the last P2G
+    uint8_t *valid = nullptr;
+    uint8_t *home = nullptr, *active = nullptr;   // block masks (bi*bj*bk)
+};
+
+struct SortScratch {
+    uint32_t *key[2] = {nullptr, nullptr};
+    uint32_t *val[2] = {nullptr, nullptr};
+    uint32_t *tile_hist = nullptr;       // digits x tiles, digit-major
+    size_t tile_hist_cap = 0;
+    uint32_t *bin_start = nullptr;       // nbins + 2 entries
+    uint32_t *scan_partials = nullptr;   // block sums for the scans
+    size_t scan_partials_cap = 0;
+    uint32_t *seam = nullptr;            // 3 words per slot [dir*cap + slot]: 10^3-block membership
+};
+
+struct Context {
+    GridDesc g;
+    int device = 0;
+    int k_own_begin = 0, k_own_end = 0, halo = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int n = 0, cap = 0;
+    bool has_affine = false;
+    bool sorted = false;                 // soa[cur] is in (hkey, orig) order and bin_start is valid
+    int cur = 0;
+    ParticleSoA soa[2];
+    float *aos_stage = nullptr;          // device staging for AoS <-> SoA transposes (cap*3 floats)
+    void *h_stage = nullptr;             // pinned host staging
+    size_t h_stage_bytes = 0;
+    SortScratch sort;
+    FaceGrid face[3];
+
+    float *phi = nullptr;                // (I+1)(J+1)(kloc+1) node-centred solid SDF
+    uint8_t *near_solid = nullptr;       // ni*nj*nk
+    int ni = 0, nj = 0, nk = 0;
+    bool has_solid = false;
+
+    float guard_abs = -1.f, guard_per = -1.f;
+    ffb200_timing timing = {};
+};
+
+// ---- launchers (each returns the number of kernels it launched) -------------------------------
+
+// ffb200_sort.cu
+int launch_unpack_aos(Context &c, const float *aos, float *const dst[3], int n);
+int launch_pack_aos(Context &c, const float *const src[3], const uint32_t *orig, float *aos, int n);
+int launch_iota(Context &c, uint32_t *dst, int n);
+int launch_sort(Context &c);             // keys -> radix sort -> bin table -> reorder; flips c.cur
+int launch_binning_dump(Context &c, int32_t *cell, uint32_t *hkey, uint32_t *perm);   // device outputs
+
+// ffb200_p2g.cu
+int launch_p2g(Context &c, double radius, int method);
+
+// ffb200_g2p.cu
+int launch_g2p(Context &c, int method, double ratio);
+
+// ffb200_advect.cu
+int launch_advect(Context &c, double dt, double cfl, int collide);
+
+}  // namespace ffb200

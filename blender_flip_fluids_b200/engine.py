@@ -1,0 +1,272 @@
+"""ctypes host side of libffb200.so -- mirrors how the reference's ``ffengine`` package binds
+its library (src/engine/ffengine/pybindings.py:26-60: argtypes, an error flag, ``RuntimeError``
+raised with the library's message).
+
+``FlipContext`` holds one device context (grid + resident particles/fields). The three
+reference-named operators take and return HOST numpy arrays in the reference's layouts and
+are what the parity tests and the e2e benchmark call:
+
+    velocity_advector_advect            <- VelocityAdvector::advect          (velocityadvector.cpp:38)
+    update_marker_particle_velocities   <- _updateMarkerParticleVelocitiesThread (fluidsimulation.cpp:6845)
+    advance_marker_particles            <- _advanceMarkerParticles RK3+collide   (fluidsimulation.cpp:7853)
+
+There is no CPU fallback: if the CUDA library is missing or no device is present the
+constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+FLIP, APIC = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffb200.so")
+_lib = None
+
+_f32p = C.POINTER(C.c_float)
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_i32p = C.POINTER(C.c_int32)
+
+
+class Timing(C.Structure):
+    _fields_ = [("sort_ms", C.c_float), ("p2g_ms", C.c_float), ("g2p_ms", C.c_float), ("advect_ms", C.c_float),
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("sort_launches", C.c_int), ("p2g_launches", C.c_int),
+                ("g2p_launches", C.c_int), ("advect_launches", C.c_int)]
+
+
+# name -> argtypes; every entry point of include/ffb200.h (tests/test_abi.py checks the list
+# against the header and the built library).
+SIGNATURES = {
+    "ffb200_create": [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int],
+    "ffb200_create_slab": [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int],
+    "ffb200_destroy": [C.c_void_p],
+    "ffb200_get_error_message": [],
+    "ffb200_get_version": [C.POINTER(C.c_int)] * 3,
+    "ffb200_set_stream": [C.c_void_p, C.c_void_p],
+    "ffb200_synchronize": [C.c_void_p],
+    "ffb200_get_timing": [C.c_void_p, C.POINTER(Timing)],
+    "ffb200_set_valid_guard": [C.c_void_p, C.c_float, C.c_float],
+    "ffb200_set_particles": [C.c_void_p, C.c_int] + [_f32p] * 5,
+    "ffb200_get_particles": [C.c_void_p] + [_f32p] * 5,
+    "ffb200_get_num_particles": [C.c_void_p, C.POINTER(C.c_int)],
+    "ffb200_sort_particles": [C.c_void_p],
+    "ffb200_get_binning": [C.c_void_p, _i32p, _u32p, _u32p],
+    "ffb200_set_velocity_field": [C.c_void_p] + [_f32p] * 3,
+    "ffb200_set_saved_velocity_field": [C.c_void_p] + [_f32p] * 3,
+    "ffb200_get_velocity_field": [C.c_void_p] + [_f32p] * 3 + [_u8p] * 3,
+    "ffb200_get_weight_sums": [C.c_void_p] + [_f32p] * 3,
+    "ffb200_save_velocity_field": [C.c_void_p],
+    "ffb200_set_solid": [C.c_void_p, _f32p, _u8p],
+    "ffb200_p2g": [C.c_void_p, C.c_double, C.c_int],
+    "ffb200_g2p": [C.c_void_p, C.c_int, C.c_double],
+    "ffb200_advect": [C.c_void_p, C.c_double, C.c_double, C.c_int],
+    "ffb200_velocity_advector_advect": [C.c_void_p, C.c_int] + [_f32p] * 5 + [C.c_double, C.c_int] + [_f32p] * 3 + [_u8p] * 3,
+    "ffb200_update_marker_particle_velocities": [C.c_void_p, C.c_int] + [_f32p] * 11 + [C.c_int, C.c_double],
+    "ffb200_advance_marker_particles": [C.c_void_p, C.c_int] + [_f32p] * 5 + [_u8p, C.c_double, C.c_double],
+}
+
+
+def load_library():
+    """Load libffb200.so (built in-tree by build.py). Raises if it is missing: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: run `python -m blender_flip_fluids_b200.build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.ffb200_destroy.restype = None
+    lib.ffb200_get_error_message.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(ok, name):
+    if ok != 1:                                           # FFB200_SUCCESS
+        msg = load_library().ffb200_get_error_message().decode("utf-8", "replace")
+        raise RuntimeError(msg if msg else name)
+
+
+def _f32(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _ptr(a, t=_f32p):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+def mac_shapes(I, J, K):
+    return (K, J, I + 1), (K, J + 1, I), (K + 1, J, I)
+
+
+class FlipContext:
+    def __init__(self, isize, jsize, ksize, dx, device=0, slab=None):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.I, self.J, self.K, self.dx = int(isize), int(jsize), int(ksize), float(dx)
+        if slab is None:
+            ok = self._lib.ffb200_create(C.byref(self._h), self.I, self.J, self.K, self.dx, int(device))
+        else:
+            k0, k1, halo = slab
+            ok = self._lib.ffb200_create_slab(C.byref(self._h), self.I, self.J, self.K, self.dx, int(device), int(k0),
+                                              int(k1), int(halo))
+        _check(ok, "ffb200_create")
+        self.n = 0
+        self.near_dims = (-(-self.K // 3), -(-self.J // 3), -(-self.I // 3))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ffb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _call(self, name, *args):
+        _check(getattr(self._lib, name)(self._h, *args), name)
+
+    # ---- resident state ------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._call("ffb200_set_stream", C.c_void_p(int(cuda_stream) if cuda_stream else 0))
+
+    def synchronize(self):
+        self._call("ffb200_synchronize")
+
+    def timing(self):
+        t = Timing()
+        self._call("ffb200_get_timing", C.byref(t))
+        return {k: getattr(t, k) for k, _ in Timing._fields_}
+
+    def set_valid_guard(self, abs_tol, per_contrib_tol):
+        self._call("ffb200_set_valid_guard", C.c_float(abs_tol), C.c_float(per_contrib_tol))
+
+    def set_particles(self, pos, vel, affx=None, affy=None, affz=None):
+        pos = _f32(pos)
+        n = pos.shape[0]
+        vel, affx, affy, affz = (_f32(a, (n, 3)) for a in (vel, affx, affy, affz))
+        self._keep = (pos, vel, affx, affy, affz)             # host buffers stay alive until the copy is done
+        self._call("ffb200_set_particles", n, _ptr(pos), _ptr(vel), _ptr(affx), _ptr(affy), _ptr(affz))
+        self.synchronize()
+        self.n = n
+
+    def get_particles(self, pos=True, vel=True, affine=False):
+        n = self.n
+        mk = lambda want: np.empty((n, 3), np.float32) if want else None
+        p, v, ax, ay, az = mk(pos), mk(vel), mk(affine), mk(affine), mk(affine)
+        self._call("ffb200_get_particles", _ptr(p), _ptr(v), _ptr(ax), _ptr(ay), _ptr(az))
+        return p, v, ax, ay, az
+
+    def sort_particles(self):
+        self._call("ffb200_sort_particles")
+
+    def get_binning(self):
+        n = self.n
+        cell, hkey, perm = np.empty(n, np.int32), np.empty(n, np.uint32), np.empty(n, np.uint32)
+        self._call("ffb200_get_binning", _ptr(cell, _i32p), _ptr(hkey, _u32p), _ptr(perm, _u32p))
+        return cell, hkey, perm
+
+    def set_velocity_field(self, u, v, w, saved=False):
+        su, sv, sw = mac_shapes(self.I, self.J, self.K)
+        u, v, w = _f32(u, su), _f32(v, sv), _f32(w, sw)
+        self._call("ffb200_set_saved_velocity_field" if saved else "ffb200_set_velocity_field", _ptr(u), _ptr(v), _ptr(w))
+        self.synchronize()
+
+    def get_velocity_field(self):
+        su, sv, sw = mac_shapes(self.I, self.J, self.K)
+        u, v, w = np.zeros(su, np.float32), np.zeros(sv, np.float32), np.zeros(sw, np.float32)
+        vu, vv, vw = np.zeros(su, np.uint8), np.zeros(sv, np.uint8), np.zeros(sw, np.uint8)
+        self._call("ffb200_get_velocity_field", _ptr(u), _ptr(v), _ptr(w), _ptr(vu, _u8p), _ptr(vv, _u8p), _ptr(vw, _u8p))
+        return (u, v, w), (vu, vv, vw)
+
+    def get_weight_sums(self):
+        su, sv, sw = mac_shapes(self.I, self.J, self.K)
+        u, v, w = np.zeros(su, np.float32), np.zeros(sv, np.float32), np.zeros(sw, np.float32)
+        self._call("ffb200_get_weight_sums", _ptr(u), _ptr(v), _ptr(w))
+        return u, v, w
+
+    def save_velocity_field(self):
+        self._call("ffb200_save_velocity_field")
+
+    def set_solid(self, phi, near_solid):
+        phi = _f32(phi, (self.K + 1, self.J + 1, self.I + 1))
+        near = np.ascontiguousarray(near_solid, dtype=np.uint8)
+        if near.shape != self.near_dims:
+            raise ValueError(f"near-solid mask must have shape {self.near_dims}, got {near.shape}")
+        self._call("ffb200_set_solid", _ptr(phi), _ptr(near, _u8p))
+        self.synchronize()
+
+    # ---- stages on resident data ----------------------------------------------------------------
+    def p2g(self, radius, method):
+        self._call("ffb200_p2g", C.c_double(radius), int(method))
+
+    def g2p(self, method, ratio_pic_flip=0.05):
+        self._call("ffb200_g2p", int(method), C.c_double(ratio_pic_flip))
+
+    def advect(self, dt, cfl=5.0, collide=True):
+        self._call("ffb200_advect", C.c_double(dt), C.c_double(cfl), 1 if collide else 0)
+
+    # ---- reference-named host-buffer operators --------------------------------------------------------
+    def velocity_advector_advect(self, pos, vel, affx=None, affy=None, affz=None, radius=None, method=FLIP, out=None):
+        """VelocityAdvector::advect on host arrays -> ((u,v,w), (validU,validV,validW))."""
+        pos = _f32(pos)
+        n = pos.shape[0]
+        vel, affx, affy, affz = (_f32(a, (n, 3)) for a in (vel, affx, affy, affz))
+        radius = 0.5 * self.dx * np.sqrt(3.0) if radius is None else radius
+        if out is None:
+            su, sv, sw = mac_shapes(self.I, self.J, self.K)
+            out = (np.zeros(su, np.float32), np.zeros(sv, np.float32), np.zeros(sw, np.float32),
+                   np.zeros(su, np.uint8), np.zeros(sv, np.uint8), np.zeros(sw, np.uint8))
+        u, v, w, vu, vv, vw = out
+        self._call("ffb200_velocity_advector_advect", n, _ptr(pos), _ptr(vel), _ptr(affx), _ptr(affy), _ptr(affz),
+                   C.c_double(radius), int(method), _ptr(u), _ptr(v), _ptr(w), _ptr(vu, _u8p), _ptr(vv, _u8p),
+                   _ptr(vw, _u8p))
+        self.n = n
+        return (u, v, w), (vu, vv, vw)
+
+    def update_marker_particle_velocities(self, pos, vel, mac, saved=None, method=FLIP, ratio_pic_flip=0.05):
+        """G2P on host arrays. FLIP -> new velocities; APIC -> (velocities, affx, affy, affz)."""
+        pos = _f32(pos)
+        n = pos.shape[0]
+        vel = _f32(vel, (n, 3)).copy()
+        u, v, w = (_f32(a) for a in mac)
+        su, sv, sw = (None, None, None) if saved is None else (_f32(a) for a in saved)
+        apic = method == APIC
+        ax, ay, az = (np.zeros((n, 3), np.float32) if apic else None for _ in range(3))
+        self._call("ffb200_update_marker_particle_velocities", n, _ptr(pos), _ptr(vel), _ptr(ax), _ptr(ay), _ptr(az),
+                   _ptr(u), _ptr(v), _ptr(w), _ptr(su), _ptr(sv), _ptr(sw), int(method), C.c_double(ratio_pic_flip))
+        self.n = n
+        return (vel, ax, ay, az) if apic else vel
+
+    def advance_marker_particles(self, pos, mac, phi=None, near_solid=None, dt=1.0 / 60.0, cfl=5.0):
+        """RK3 + collision on host arrays -> new positions."""
+        out = _f32(pos).copy()
+        n = out.shape[0]
+        u, v, w = (_f32(a) for a in mac)
+        phi = _f32(phi)
+        near = None if near_solid is None else np.ascontiguousarray(near_solid, dtype=np.uint8)
+        self._call("ffb200_advance_marker_particles", n, _ptr(out), _ptr(u), _ptr(v), _ptr(w), _ptr(phi),
+                   _ptr(near, _u8p), C.c_double(dt), C.c_double(cfl))
+        self.n = n
+        return out

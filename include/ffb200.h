@@ -1,0 +1,154 @@
+/* ffb200.h -- C ABI of libffb200.so, the B200 (sm_100a) particle<->grid substep of the FLIP
+ * Fluids engine (rlguy/Blender-FLIP-Fluids src/engine v1.8.5).
+ *
+ * The reference has no C-ABI seam for this path: its ctypes surface stops at
+ * FluidSimulation_update (c_bindings/fluidsimulation_c.cpp:115) and the three hot stages are
+ * C++ members reached from FluidSimulation::_stepFluid (fluidsimulation.cpp:10078-10121).
+ * This header is the seam a maintainer binds instead (INTEGRATION.md shows the C++ interposer
+ * for libffengine and the ctypes stub): one entry point per reference call site, plain
+ * pointers and sizes, host buffers in the reference's own layouts.
+ *
+ *   reference call site                                         replaced by
+ *   ---------------------------------------------------------   -------------------------------
+ *   VelocityAdvector::advect(params)   velocityadvector.cpp:38  ffb200_velocity_advector_advect
+ *     (called from fluidsimulation.cpp:5652 and :6971)
+ *   FluidSimulation::_saveVelocityField       fs.cpp:5671-5679  ffb200_save_velocity_field
+ *   FluidSimulation::_updateMarkerParticleVelocitiesThread
+ *                                             fs.cpp:6845-6863  ffb200_update_marker_particle_velocities
+ *   FluidSimulation::_advanceMarkerParticles  fs.cpp:7853-7890  ffb200_advance_marker_particles
+ *     (the RK3 + _resolveCollision fan-out; _removeMarkerParticles stays on the CPU)
+ *
+ * Layouts (all little-endian, tightly packed):
+ *   particle attributes  float[3] per particle, POSITION / VELOCITY / AFFINEX / AFFINEY / AFFINEZ
+ *                        (std::vector<vmath::vec3>, particlesystem.h:303-325, vmath.h:37-61)
+ *   MAC faces            x-fastest Array3d<float>, flat = i + w*(j + h*k)  (array3d.h:774-777):
+ *                        u (I+1)*J*K, v I*(J+1)*K, w I*J*(K+1)       (macvelocityfield.cpp:46-54)
+ *   valid masks          one byte per face, same dims (ValidVelocityComponentGrid, mac.h:35-50)
+ *   solid SDF            node-centred float (I+1)*(J+1)*(K+1)          (meshlevelset.cpp:35-42)
+ *   near-solid mask      one byte per 3dx cell, dims ceil(I/3) x ceil(J/3) x ceil(K/3)
+ *                        (fluidsimulation.cpp:5448-5451)
+ *
+ * Error convention, mirroring c_bindings/cbindings.cpp:35-47: every call returns
+ * FFB200_SUCCESS (1) or FFB200_FAIL (0) -- the same values the reference writes through its
+ * trailing `int *err` -- and the message of the last failure is kept in one global buffer
+ * read by ffb200_get_error_message() (cf. CBindings_get_error_message, cbindings.cpp:100-103).
+ * There is no CPU fallback: without a CUDA device ffb200_create fails.
+ */
+#ifndef FFB200_H
+#define FFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB200_SUCCESS 1
+#define FFB200_FAIL 0
+
+/* VelocityAdvectorTransferMethod (velocityadvector.h:63-66) */
+#define FFB200_TRANSFER_FLIP 0
+#define FFB200_TRANSFER_APIC 1
+
+typedef struct ffb200_context ffb200_context;
+
+/* Device milliseconds (CUDA events on the context's stream) of the most recent call of each
+ * stage, and how many kernels of this library that call launched. */
+typedef struct ffb200_timing {
+    float sort_ms;        /* cell keys + radix sort + bin table + SoA reorder */
+    float p2g_ms;         /* the three transfer kernels (U, V, W) */
+    float g2p_ms;
+    float advect_ms;
+    float h2d_ms, d2h_ms; /* host<->device copies inside the last host-buffer call */
+    int sort_launches, p2g_launches, g2p_launches, advect_launches;
+} ffb200_timing;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* Grid of isize x jsize x ksize cells of size dx on CUDA device `device`
+ * (cf. FluidSimulation_new_from_dimensions, fluidsimulation_c.cpp:56). */
+int ffb200_create(ffb200_context **ctx, int isize, int jsize, int ksize, double dx, int device);
+
+/* z-slab flavour for one rank of a multi-GPU run: the context stores cell planes
+ * [k_begin - halo, k_end + halo) clipped to [0, ksize) and owns [k_begin, k_end). */
+int ffb200_create_slab(ffb200_context **ctx, int isize, int jsize, int ksize, double dx, int device,
+                       int k_begin, int k_end, int halo);
+
+void ffb200_destroy(ffb200_context *ctx);
+const char *ffb200_get_error_message(void);
+int ffb200_get_version(int *major, int *minor, int *revision);
+
+/* Run the context's work on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
+ * torch.cuda.current_stream().cuda_stream; NULL restores the context's own stream. */
+int ffb200_set_stream(ffb200_context *ctx, void *cuda_stream);
+int ffb200_synchronize(ffb200_context *ctx);
+int ffb200_get_timing(ffb200_context *ctx, ffb200_timing *out);
+
+/* Guard band of the valid-face test (DESIGN.md "valid masks"): faces whose fast weight sum
+ * lies within abs_tol + per_contrib_tol * contributions of the 1e-6 threshold are re-summed
+ * in the reference's exact order. Negative values restore the defaults; abs_tol = +inf
+ * sends every face through the exact path (bit-exact P2G, slow; used by the tests). */
+int ffb200_set_valid_guard(ffb200_context *ctx, float abs_tol, float per_contrib_tol);
+
+/* ---- resident particle state ------------------------------------------------------------------ */
+
+/* Upload n particles (host AoS, reference order). affx/affy/affz may be NULL (FLIP). */
+int ffb200_set_particles(ffb200_context *ctx, int n, const float *pos, const float *vel,
+                         const float *affx, const float *affy, const float *affz);
+/* Download in the ORIGINAL particle order; any pointer may be NULL. */
+int ffb200_get_particles(ffb200_context *ctx, float *pos, float *vel, float *affx, float *affy, float *affz);
+int ffb200_get_num_particles(ffb200_context *ctx, int *n);
+
+/* Cell binning + stable sort (runs implicitly before P2G when positions changed). */
+int ffb200_sort_particles(ffb200_context *ctx);
+/* Per particle in ORIGINAL order: cell = flat reference cell index or -1 (grid3d.h:55-60,
+ * 504-512), hkey = half-cell bin key; perm[j] = original index of the j-th sorted particle. */
+int ffb200_get_binning(ffb200_context *ctx, int32_t *cell, uint32_t *hkey, uint32_t *perm);
+
+/* ---- resident grids ----------------------------------------------------------------------------- */
+
+int ffb200_set_velocity_field(ffb200_context *ctx, const float *u, const float *v, const float *w);
+int ffb200_set_saved_velocity_field(ffb200_context *ctx, const float *u, const float *v, const float *w);
+int ffb200_get_velocity_field(ffb200_context *ctx, float *u, float *v, float *w,
+                              uint8_t *validu, uint8_t *validv, uint8_t *validw);
+/* Raw weight sums of the last P2G (diagnostics / tests); any pointer may be NULL. */
+int ffb200_get_weight_sums(ffb200_context *ctx, float *wu, float *wv, float *ww);
+/* _saveVelocityField: device-side deep copy current -> saved. */
+int ffb200_save_velocity_field(ffb200_context *ctx);
+int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid);
+
+/* ---- stages on resident data ---------------------------------------------------------------------- */
+
+int ffb200_p2g(ffb200_context *ctx, double particle_radius, int transfer_method);
+int ffb200_g2p(ffb200_context *ctx, int transfer_method, double ratio_pic_flip);
+int ffb200_advect(ffb200_context *ctx, double dt, double cfl_condition_number, int resolve_collisions);
+
+/* ---- one-call host-buffer entry points (what the libffengine interposer calls) ---------------------- */
+
+/* VelocityAdvector::advect: upload particles, sort, transfer, download faces + valid masks. */
+int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos, const float *vel,
+                                    const float *affx, const float *affy, const float *affz,
+                                    double particle_radius, int transfer_method,
+                                    float *u, float *v, float *w,
+                                    uint8_t *validu, uint8_t *validv, uint8_t *validw);
+
+/* _updateMarkerParticleVelocitiesThread: upload particles and both fields, gather, download.
+ * vel is updated in place; affx/affy/affz are outputs for APIC (ignored for FLIP);
+ * su/sv/sw (the saved field) may be NULL for APIC. */
+int ffb200_update_marker_particle_velocities(ffb200_context *ctx, int n, const float *pos, float *vel,
+                                             float *affx, float *affy, float *affz,
+                                             const float *u, const float *v, const float *w,
+                                             const float *su, const float *sv, const float *sw,
+                                             int transfer_method, double ratio_pic_flip);
+
+/* _advanceMarkerParticles (RK3 + _resolveCollision): pos is updated in place. phi/near_solid
+ * may be NULL to reuse the arrays of the previous call (static solids). */
+int ffb200_advance_marker_particles(ffb200_context *ctx, int n, float *pos,
+                                    const float *u, const float *v, const float *w,
+                                    const float *phi, const uint8_t *near_solid,
+                                    double dt, double cfl_condition_number);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB200_H */

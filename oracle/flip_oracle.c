@@ -48,18 +48,21 @@ static int cmp_keyidx(const void *a, const void *b) {
 
 void flip_oracle_bin_sort(int I, int J, int K, double dx, int n, const float *pos,
                           int32_t *cell, uint32_t *hkey, uint32_t *perm) {
+    const int A = 4;                                          /* half-cell apron (2 cells per side) */
     double inv2 = 2.0 * (1.0 / dx);
-    uint32_t sentinel = 8u * (uint32_t)I * (uint32_t)J * (uint32_t)K;
+    uint32_t HX = 2u * (uint32_t)I + 2u * A, HY = 2u * (uint32_t)J + 2u * A, HZ = 2u * (uint32_t)K + 2u * A;
+    uint32_t sentinel = HX * HY * HZ;
     keyidx *ki = (keyidx *)malloc(sizeof(keyidx) * (size_t)(n > 0 ? n : 1));
     for (int p = 0; p < n; p++) {
         int ci = pos2idx(pos[3 * p + 0], dx), cj = pos2idx(pos[3 * p + 1], dx), ck = pos2idx(pos[3 * p + 2], dx);
         int ok = in_range(ci, cj, ck, I, J, K);
         if (cell) cell[p] = ok ? (int32_t)(ci + I * (cj + J * ck)) : -1;
-        int hi = (int)floor((double)pos[3 * p + 0] * inv2);
-        int hj = (int)floor((double)pos[3 * p + 1] * inv2);
-        int hk = (int)floor((double)pos[3 * p + 2] * inv2);
+        int hi = (int)floor((double)pos[3 * p + 0] * inv2) + A;
+        int hj = (int)floor((double)pos[3 * p + 1] * inv2) + A;
+        int hk = (int)floor((double)pos[3 * p + 2] * inv2) + A;
         uint32_t key = sentinel;
-        if (ok) key = (uint32_t)hi + 2u * (uint32_t)I * ((uint32_t)hj + 2u * (uint32_t)J * (uint32_t)hk);
+        if (in_range(hi, hj, hk, (int)HX, (int)HY, (int)HZ))
+            key = (uint32_t)hi + HX * ((uint32_t)hj + HY * (uint32_t)hk);
         if (hkey) hkey[p] = key;
         ki[p].key = key;
         ki[p].idx = (uint32_t)p;

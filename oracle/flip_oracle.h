@@ -29,8 +29,9 @@ extern "C" {
 
 /* Cell binning: Grid3d::positionToGridIndex (grid3d.h:55-60) + getFlatIndex (grid3d.h:504-512).
  * cell[n] = i + I*(j + J*k), or -1 if the index is outside [0,I)x[0,J)x[0,K).
- * hkey[n] = half-cell key hi + 2I*(hj + 2J*hk) with h = floor(p * (2*(1.0/dx))) (so that
- * h>>1 is exactly the reference cell index), or 8*I*J*K for out-of-grid particles.
+ * hkey[n] = half-cell bin key (hi+A) + HX*((hj+A) + HY*(hk+A)) with h = floor(p * (2*(1.0/dx)))
+ * (so that h>>1 is exactly the reference cell index), A = 4 apron half-cells per side,
+ * HX = 2I+2A etc.; HX*HY*HZ for particles outside the apron.
  * perm = stable ascending sort of hkey (ties keep ascending particle index, which is the
  * order the reference accumulates a block's particles in, velocityadvector.cpp:383-413). */
 void flip_oracle_bin_sort(int I, int J, int K, double dx, int n, const float *pos,

@@ -1,0 +1,193 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (libffb200.so via
+blender_flip_fluids_b200.engine), against the C oracle on the same seeded inputs and against
+the reference-generated golden fixtures in tests/golden/.
+
+Bars (BASELINE.json north_star):
+  * cell binning, sort order, valid-face masks: bit-exact;
+  * grid velocities, particle velocities, APIC matrices, advected positions: <= 1e-5 relative.
+    "Relative" is |a-b| <= RTOL * max(|b|, scale) with scale = the largest magnitude in the
+    reference array (velocities near zero from cancellation are compared against the field's
+    scale). G2P and advection repeat the reference's arithmetic exactly, so they are in fact
+    asserted bit-exact below; the P2G sums differ only by summation order.
+"""
+import numpy as np
+import pytest
+
+from conftest import bits_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(a, b, rtol=RTOL):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    scale = float(np.max(np.abs(b))) if b.size else 0.0
+    return bool(np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), scale)))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from blender_flip_fluids_b200 import engine
+    engine.load_library()
+    return engine
+
+
+def _method(meta):
+    return 1 if meta["method"] == "apic" else 0
+
+
+P2G_FIXTURES = ["p2g_flip_23x21x25_seams", "p2g_apic_23x21x25_seams", "p2g_apic_20x20x20_dyadic",
+                "p2g_flip_21x20x22_radius2"]
+SCENES = ["scene_flip_24x20x22_nondyadic", "scene_apic_22x24x20_dyadic"]
+
+
+@pytest.mark.parametrize("name", P2G_FIXTURES)
+def test_p2g_golden(eng, name):
+    meta, g = load_golden(name)
+    aff = [g.get("in_aff" + c) for c in "xyz"]
+    with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        (u, v, w), (vu, vv, vw) = ctx.velocity_advector_advect(g["in_pos"], g["in_vel"], *aff, radius=meta["radius"],
+                                                               method=_method(meta))
+    assert np.array_equal(vu, g["out_validu"]) and np.array_equal(vv, g["out_validv"]) and np.array_equal(vw, g["out_validw"])
+    assert close(u, g["out_u"]) and close(v, g["out_v"]) and close(w, g["out_w"])
+
+
+@pytest.mark.parametrize("name", P2G_FIXTURES)
+def test_p2g_exact_path_is_bit_exact(eng, name):
+    """Guard band forced open: every face is re-summed in the reference's order."""
+    meta, g = load_golden(name)
+    aff = [g.get("in_aff" + c) for c in "xyz"]
+    with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        ctx.set_valid_guard(float("inf"), 0.0)
+        (u, v, w), (vu, vv, vw) = ctx.velocity_advector_advect(g["in_pos"], g["in_vel"], *aff, radius=meta["radius"],
+                                                               method=_method(meta))
+    assert bits_equal(u, g["out_u"]) and bits_equal(v, g["out_v"]) and bits_equal(w, g["out_w"])
+    assert np.array_equal(vu, g["out_validu"]) and np.array_equal(vv, g["out_validv"]) and np.array_equal(vw, g["out_validw"])
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_scene_chain_golden(eng, name):
+    meta, g = load_golden(name)
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    apic = meta["method"] == "apic"
+    aff = [g.get("s0_aff" + c) for c in "xyz"]
+    mac = (g["s2_u"], g["s2_v"], g["s2_w"])
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        (u, v, w), (vu, vv, vw) = ctx.velocity_advector_advect(g["s0_pos"], g["s0_vel"], *aff, radius=meta["radius"],
+                                                               method=_method(meta))
+        assert np.array_equal(vu, g["s1_validu"]) and np.array_equal(vv, g["s1_validv"]) and np.array_equal(vw, g["s1_validw"])
+        assert close(u, g["s1_u"]) and close(v, g["s1_v"]) and close(w, g["s1_w"])
+        if apic:
+            vel, ax, ay, az = ctx.update_marker_particle_velocities(g["s0_pos"], g["s0_vel"], mac, method=eng.APIC)
+            assert bits_equal(ax, g["s3_affx"]) and bits_equal(ay, g["s3_affy"]) and bits_equal(az, g["s3_affz"])
+        else:
+            vel = ctx.update_marker_particle_velocities(g["s0_pos"], g["s0_vel"], mac,
+                                                        saved=(g["s2_su"], g["s2_sv"], g["s2_sw"]), method=eng.FLIP,
+                                                        ratio_pic_flip=meta["ratio"])
+        assert bits_equal(vel, g["s3_vel"])
+        out = ctx.advance_marker_particles(g["s0_pos"], mac, g["s2_phi"], g["s2_near"], dt=meta["dt"], cfl=meta["cfl"])
+        assert bits_equal(out, g["s4_pos"])
+
+
+def test_advect_collision_golden(eng):
+    meta, g = load_golden("advect_collide_24x20x22")
+    with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        out = ctx.advance_marker_particles(g["in_pos"], (g["in_u"], g["in_v"], g["in_w"]), g["in_phi"], g["in_near"],
+                                           dt=meta["dt"], cfl=meta["cfl"])
+    assert bits_equal(out, g["out_pos"])
+
+
+def test_binning_and_sort_order(eng, oracle):
+    meta, g = load_golden("p2g_flip_23x21x25_seams")
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    pos = g["in_pos"].copy()
+    pos[:5] = [[-1e-3, 0.01, 0.01], [0.01, (J + 1) * dx, 0.01], [0.01, 0.01, K * dx + 1], [(I + 0.5) * dx, 0.0, 0.0], [0, 0, 0]]
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        ctx.set_particles(pos, g["in_vel"])
+        cell, hkey, perm = ctx.get_binning()
+        # round trip: particles come back in the original order, bit-identical
+        p2, v2, *_ = ctx.get_particles()
+    ocell, ohkey, operm = oracle.bin_sort(I, J, K, dx, pos)
+    assert np.array_equal(cell, ocell)
+    assert np.array_equal(hkey, ohkey)
+    assert np.array_equal(perm, operm)
+    assert bits_equal(p2, pos) and bits_equal(v2, g["in_vel"])
+
+
+@pytest.mark.parametrize("method", ["flip", "apic"])
+@pytest.mark.parametrize("n,dx", [(32, 1.0 / 32), (30, 0.004 * 250 / 30)])
+def test_substep_vs_oracle(eng, oracle, method, n, dx):
+    """Dam break, all three stages against the oracle on identical inputs (dyadic and not)."""
+    from blender_flip_fluids_b200 import scenes
+    apic = method == "apic"
+    sc = scenes.dam_break(n, apic=apic, dx=dx, vel="random", v0=0.5, seed=5)
+    I = J = K = n
+    m = eng.APIC if apic else eng.FLIP
+    aff = (sc.affx, sc.affy, sc.affz)
+    (ou, ov, ow), (ovu, ovv, ovw) = oracle.p2g(I, J, K, dx, sc.radius, m, sc.pos, sc.vel, *aff)
+    phi, near = scenes.analytic_solid_sdf(I, J, K, dx, sphere=(0.3 * n * dx, 0.3 * n * dx, 0.5 * n * dx, 0.12 * n * dx))
+    dt = 2.5 * dx / 0.5
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        ctx.set_particles(sc.pos, sc.vel, *aff)
+        ctx.p2g(sc.radius, m)
+        (u, v, w), (vu, vv, vw) = ctx.get_velocity_field()
+        assert np.array_equal(vu, ovu) and np.array_equal(vv, ovv) and np.array_equal(vw, ovw)
+        assert close(u, ou) and close(v, ov) and close(w, ow)
+        # feed the ORACLE's grid to both sides so G2P/advect are compared on identical inputs
+        ctx.set_velocity_field(ou, ov, ow)
+        ctx.set_velocity_field(ou * 0.9, ov * 0.9, ow * 0.9, saved=True)
+        ctx.set_solid(phi, near)
+        ctx.g2p(m, 0.05)
+        _, vel, ax, ay, az = ctx.get_particles(pos=False, vel=True, affine=apic)
+        ctx.advect(dt, 5.0, True)
+        pos1, *_ = ctx.get_particles(pos=True, vel=False)
+    if apic:
+        ovel, oax, oay, oaz = oracle.g2p_apic(I, J, K, dx, sc.pos, (ou, ov, ow))
+        assert bits_equal(ax, oax) and bits_equal(ay, oay) and bits_equal(az, oaz)
+    else:
+        ovel = oracle.g2p_flip(I, J, K, dx, sc.pos, sc.vel, (ou, ov, ow), (ou * 0.9, ov * 0.9, ow * 0.9), 0.05)
+    assert bits_equal(vel, ovel)
+    opos = oracle.advect(I, J, K, dx, sc.pos, (ou, ov, ow), phi, near, dt, 5.0, True)
+    assert bits_equal(pos1, opos)
+    free = oracle.advect(I, J, K, dx, sc.pos, (ou, ov, ow), phi, near, dt, 5.0, False)
+    assert (free != opos).any()
+
+
+def test_empty_and_tiny_inputs(eng):
+    with eng.FlipContext(12, 11, 13, 0.1) as ctx:
+        z = np.zeros((0, 3), np.float32)
+        (u, v, w), (vu, vv, vw) = ctx.velocity_advector_advect(z, z)
+        assert not u.any() and not v.any() and not w.any() and not vu.any() and not vv.any() and not vw.any()
+        p = np.array([[0.55, 0.52, 0.57]], np.float32)
+        vel = np.array([[1.0, 2.0, 3.0]], np.float32)
+        (u, v, w), (vu, vv, vw) = ctx.velocity_advector_advect(p, vel)
+        assert vu.sum() > 0 and vv.sum() > 0 and vw.sum() > 0
+        assert np.allclose(u[vu == 1], 1.0) and np.allclose(v[vv == 1], 2.0) and np.allclose(w[vw == 1], 3.0)
+
+
+def test_apic_seam_drop_probe(eng):
+    """SURVEY appendix A probe: N=32, dx=0.1, particle at (9.05dx, 6dx, 6dx): validU(9,5,5) is
+    set, validU(10,5,5) is NOT (its 10^3 block never sees the 'simple' particle)."""
+    dx = 0.1
+    with eng.FlipContext(32, 32, 32, dx) as ctx:
+        z = np.zeros((1, 3), np.float32)
+        vel = np.array([[1.0, 2.0, 3.0]], np.float32)
+        p = np.array([[9.05 * dx, 6 * dx, 6 * dx]], np.float32)
+        (_, _, _), (vu, _, _) = ctx.velocity_advector_advect(p, vel, z, z, z, method=eng.APIC)
+        assert vu[5, 5, 9] == 1 and vu[5, 5, 10] == 0
+        p = np.array([[8.95 * dx, 6 * dx, 6 * dx]], np.float32)
+        (_, _, _), (vu, _, _) = ctx.velocity_advector_advect(p, vel, z, z, z, method=eng.APIC)
+        assert vu[5, 5, 8] == 1 and vu[5, 5, 9] == 1
+
+
+def test_determinism(eng):
+    from blender_flip_fluids_b200 import scenes
+    sc = scenes.dam_break(24, apic=True, seed=9)
+    outs = []
+    for _ in range(2):
+        with eng.FlipContext(24, 24, 24, sc.dx) as ctx:
+            (u, v, w), _ = ctx.velocity_advector_advect(sc.pos, sc.vel, sc.affx, sc.affy, sc.affz, method=eng.APIC)
+            outs.append((u, v, w))
+    assert all(bits_equal(a, b) for a, b in zip(*outs))

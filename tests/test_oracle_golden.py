@@ -75,11 +75,13 @@ def test_bin_sort_properties(oracle):
     want = np.where(ok, ci[:, 0] + I * (ci[:, 1] + J * ci[:, 2]), -1)
     assert np.array_equal(cell, want)
     assert list(ok[:5]) == [False, False, False, False, True]
-    # half-cell keys refine the cell index exactly
+    # half-cell keys refine the cell index exactly (apron of 4 half-cells per side)
+    A, HX, HY, HZ = 4, 2 * I + 8, 2 * J + 8, 2 * K + 8
     hk = hkey[ok].astype(np.int64)
-    hi, hj, hk2 = hk % (2 * I), (hk // (2 * I)) % (2 * J), hk // (4 * I * J)
+    hi, hj, hk2 = hk % HX - A, (hk // HX) % HY - A, hk // (HX * HY) - A
     assert np.array_equal((hi >> 1) + I * ((hj >> 1) + J * (hk2 >> 1)), cell[ok])
-    assert (hkey[~ok] == 8 * I * J * K).all()
+    assert hkey[2] == HX * HY * HZ                      # far outside: sentinel bin
+    assert hkey[0] < HX * HY * HZ                       # just outside: still binned in the apron
     # stable order: keys ascending, ties by ascending particle index
     ks = hkey[perm]
     assert (np.diff(ks.astype(np.int64)) >= 0).all()
