@@ -42,7 +42,6 @@ struct P2GParams {
     float off[3];                // _getDirectionOffset, velocityadvector.cpp:177-188
     float r, sr, rsq, c1, c2, c3;
     float inv_s;                 // (float)(1.0 / (float)dx): vec3 / _dx of :574
-    float inv_dxf;               // fast-path 1/dx
     double chunk;                // _chunkWidth * _dx
     int wm;                      // half-cell window half width
     float guard_abs, guard_per;
@@ -134,6 +133,7 @@ struct FaceFrame {
     int lo[3];        // local node index inside the block
     float bpos[3];    // block origin, GridIndexToPosition(blockIndex, _chunkWidth*_dx)
     float gpos[3];    // local node position, GridIndexToPosition(i, j, k, _dx)
+    float gposm[3];   // position of the previous local node (lo - 1)
     int h0[3], h1[3]; // inclusive half-cell window (bin-grid coordinates, apron included)
 };
 
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(256) k_p2g(P2GParams P) {
         f.lo[a] = n[a] - f.nb[a] * kChunk;
         f.bpos[a] = idx2posf(f.nb[a], P.chunk);
         f.gpos[a] = idx2posf(f.lo[a], P.g.dx);
+        f.gposm[a] = idx2posf(f.lo[a] - 1, P.g.dx);
         const int c = 2 * n[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
         int h0 = c - P.wm, h1 = c + P.wm - 1;
         f.h0[a] = h0 < 0 ? 0 : h0;
@@ -270,12 +271,34 @@ __global__ void __launch_bounds__(256) k_p2g(P2GParams P) {
                         cnt++;
                     }
                 } else {
-                    // trilinear tent; equals the reference's (1-ipos)/ipos factors to ~1e-7
-                    const float tx = 1.0f - fabsf(vx) * P.inv_dxf;
-                    const float ty = 1.0f - fabsf(vy) * P.inv_dxf;
-                    const float tz = 1.0f - fabsf(vz) * P.inv_dxf;
-                    if (tx > 0.0f && ty > 0.0f && tz > 0.0f) {
-                        const float w = tx * ty * tz;
+                    // Trilinear factors exactly as the reference forms them (:567-592): a particle
+                    // at or above the node is in the node's cell (factor 1 - ipos), one below it
+                    // is in the previous cell (factor ipos measured from the previous node). The
+                    // float comparison stands in for the reference's double floor; the two can
+                    // only disagree within ~6e-7 cells of a node plane, and those pairs take the
+                    // reference's exact arithmetic below, so every weight is bit-identical.
+                    const bool upx = vx <= 0.0f, upy = vy <= 0.0f, upz = vz <= 0.0f;
+                    const float t0 = (xl0 - (upx ? f.gpos[0] : f.gposm[0])) * P.inv_s;
+                    const float t1 = (xl1 - (upy ? f.gpos[1] : f.gposm[1])) * P.inv_s;
+                    const float t2 = (xl2 - (upz ? f.gpos[2] : f.gposm[2])) * P.inv_s;
+                    // within a few ulps of a node plane: let the reference's own arithmetic decide
+                    const float band = 4e-6f;
+                    const bool edge = fabsf(t0) < band || fabsf(t0 - 1.0f) < band || fabsf(t1) < band ||
+                                      fabsf(t1 - 1.0f) < band || fabsf(t2) < band || fabsf(t2 - 1.0f) < band;
+                    if (edge) {
+                        float w, wv;
+                        if (exact_contribution<DIR, METHOD>(P, f, q, w, wv)) {
+                            swv += wv;
+                            sw += w;
+                            cnt++;
+                        }
+                        continue;
+                    }
+                    const float fx = upx ? 1.0f - t0 : t0;
+                    const float fy = upy ? 1.0f - t1 : t1;
+                    const float fz = upz ? 1.0f - t2 : t2;
+                    if (fx > 0.0f && fy > 0.0f && fz > 0.0f && t0 >= 0.0f && t1 >= 0.0f && t2 >= 0.0f) {
+                        const float w = fx * fy * fz;
                         const float apic = __ldg(P.ax + q) * vx + __ldg(P.ay + q) * vy + __ldg(P.az + q) * vz;
                         swv += w * (__ldg(P.vel + q) + apic);
                         sw += w;
@@ -370,7 +393,6 @@ int launch_p2g(Context &c, double radius, int method) {
         P.c2 = (17.0f / 9.0f) * (1.0f / (P.r * P.r * P.r * P.r));
         P.c3 = (22.0f / 9.0f) * (1.0f / (P.r * P.r));
         P.inv_s = (float)(1.0 / (double)(float)g.dx);
-        P.inv_dxf = (float)(1.0 / g.dx);
         P.chunk = kChunk * g.dx;
         // half-cell window: bins within sr of the face along each axis
         // FLIP: |x_p - x_face| < r  <=>  bins [c - wm, c + wm - 1], wm = ceil(2r/dx);
@@ -379,7 +401,7 @@ int launch_p2g(Context &c, double radius, int method) {
         P.wm = apic ? 2 : (int)std::floor(2.0 * (double)sr / g.dx + 1e-3) + 1;
         if (P.wm > kApron) throw CudaError("ffb200_p2g: particle radius above 2*dx is not supported");
         P.guard_abs = c.guard_abs >= 0.f ? c.guard_abs : 1e-9f;
-        P.guard_per = c.guard_per >= 0.f ? c.guard_per : (apic ? 1e-6f : 1e-12f);
+        P.guard_per = c.guard_per >= 0.f ? c.guard_per : 1e-12f;
         if (d == 0) launch_dir<0>(c, P, method);
         if (d == 1) launch_dir<1>(c, P, method);
         if (d == 2) launch_dir<2>(c, P, method);

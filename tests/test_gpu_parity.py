@@ -24,7 +24,14 @@ def close(a, b, rtol=RTOL):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     scale = float(np.max(np.abs(b))) if b.size else 0.0
-    return bool(np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), scale)))
+    err = np.abs(a - b)
+    tol = rtol * np.maximum(np.abs(b), scale)
+    ok = bool(np.all(err <= tol))
+    if not ok:
+        worst = np.unravel_index(np.argmax(err - tol), err.shape)
+        print(f"close(): {int((err > tol).sum())} of {err.size} out of tolerance; worst at {worst}: got {a[worst]!r} "
+              f"want {b[worst]!r} err {err[worst]:.3e} tol {tol[worst]:.3e} scale {scale:.3e}")
+    return ok
 
 
 @pytest.fixture(scope="module")
