@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- FLIP substep particle-updates/s (P2G + G2P + advect) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is one pass of the hot path over the scene's particles: cell binning + sort, P2G
+(U, V, W), velocity-field save, G2P, RK3 advection with collision. The workload at N=1 is
+BASELINE.json configs[1]: dam break 128^3, APIC, RK3 (4.64 M particles, synthetic, seeded).
+At N>1 the domain is 128 x 128 x (128*N), z-slab sharded, one rank per GPU (weak scaling).
+
+`value`   device-resident throughput: particle arrays and grids live in HBM, K steps timed
+          with CUDA events between barriers, max over ranks.
+`e2e`     the same metric through the reference-facing host-buffer entry points of the C ABI
+          (ffb200_velocity_advector_advect / _update_marker_particle_velocities /
+          _advance_marker_particles) with PINNED HOST buffers, H2D/D2H inside the timed region.
+`roofline` the dominant kernel (k_p2g): algorithmic bytes per launch / its live CUDA-event
+          duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` the unmodified reference engine (oracle/_ref, built from /root/reference) timed
+          on this box's host cores for the same three stages on a bounded sample.
+
+`--impl reference` times only that CPU reference arm and prints its own JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FLIP substep particle-updates/sec (P2G+G2P+advect)"
+UNIT = "particle-updates/s"
+GRID_N = 128
+METHOD = "apic"
+PPC = 8
+V0 = 0.5                      # |v| component bound of the synthetic velocities
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+
+
+# --------------------------------------------------------------------------------------------------
+def algorithmic_bytes(method: str, ppc: float):
+    """compulsory bytes per particle-update, per stage."""
+    if method == "apic":
+        return {"p2g": 60 + 15 / ppc, "g2p": 60 + 12 / ppc, "advect": 24 + 16 / ppc}
+    return {"p2g": 24 + 15 / ppc, "g2p": 36 + 24 / ppc, "advect": 24 + 16 / ppc}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+def build_scene(world: int, rank: int):
+    """Rank's share of the dam break 128 x 128 x (128*world): particles of its z-slab."""
+    from blender_flip_fluids_b200 import scenes
+    K = GRID_N * world
+    sc = scenes.dam_break(GRID_N, ppc=PPC, apic=(METHOD == "apic"), vel="random", v0=V0, dims=(GRID_N, GRID_N, K),
+                          seed=1234)
+    return sc, K
+
+
+def reference_arm(steps: int, warmup: int, sample_planes: int = 32, threads: int = 0):
+    """Time the UNMODIFIED reference (oracle/_ref/ref_harness) on host cores: P2G, G2P, advect on
+    a z-slice sample of the bench scene. Returns (value, info)."""
+    if not os.path.exists(HARNESS):
+        raise RuntimeError("oracle/_ref/ref_harness missing: run __graft_entry__.build() where /root/reference exists")
+    from blender_flip_fluids_b200 import scenes
+    sc = scenes.dam_break(GRID_N, ppc=PPC, apic=(METHOD == "apic"), vel="random", v0=V0, seed=1234)
+    n_grid, dx = GRID_N, sc.dx
+    keep = sc.pos[:, 2] < (3 + sample_planes) * dx                     # z-planes 3 .. 3+sample_planes
+    pos, vel = sc.pos[keep], sc.vel[keep]
+    aff = [a[keep] for a in (sc.affx, sc.affy, sc.affz)]
+    rng = np.random.default_rng(99)
+    shp = [(n_grid, n_grid, n_grid + 1), (n_grid, n_grid + 1, n_grid), (n_grid + 1, n_grid, n_grid)]
+    mac = [(rng.uniform(-V0, V0, size=s)).astype(np.float32) for s in shp]
+    phi, near = scenes.analytic_solid_sdf(n_grid, n_grid, n_grid, dx)
+    d = tempfile.mkdtemp(prefix="ffb200_ref_")
+    try:
+        for k, a in dict(pos=pos, vel=vel, affx=aff[0], affy=aff[1], affz=aff[2], u=mac[0], v=mac[1], w=mac[2],
+                         phi=phi, near=near).items():
+            np.save(os.path.join(d, f"in_{k}.npy"), a)
+        reps = steps + warmup
+        common = [f"I={n_grid}", f"J={n_grid}", f"K={n_grid}", f"dx={dx!r}", f"method={METHOD}", f"reps={reps}",
+                  f"threads={threads}"]
+        dt = 1.0 * dx / V0
+
+        def run(mode, *extra):
+            r = subprocess.run([HARNESS, mode, d] + common + list(extra), capture_output=True, text=True, check=True)
+            return json.loads(r.stdout.strip().splitlines()[-1])
+
+        a = run("p2g")
+        b = run("g2p", "ratio=0.05")
+        c = run("advect", f"dt={dt!r}", "cfl=5")
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    per_step = [x + y + z for x, y, z in zip(a["times"], b["times"], c["times"])][warmup:]
+    total = sum(per_step)
+    n = int(pos.shape[0])
+    info = {"particles": n, "threads": a["threads"], "t_p2g": statistics.mean(a["times"][warmup:]),
+            "t_g2p": statistics.mean(b["times"][warmup:]), "t_advect": statistics.mean(c["times"][warmup:]),
+            "ms_per_step": 1e3 * total / len(per_step),
+            "sample": f"dam break {n_grid}^3 {METHOD.upper()} ppc{PPC}, z-planes 3..{3 + sample_planes} "
+                      f"({n} particles), stage-level VelocityAdvector::advect + _updateMarkerParticleVelocitiesThread "
+                      f"+ _advanceMarkerParticlesThread (no extrapolation/removal) via oracle/_ref/ref_harness"}
+    return n * len(per_step) / total, info
+
+
+def host_cpu():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return model, os.cpu_count()
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        model, cores = host_cpu()
+        value, info = reference_arm(steps, warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (fp64 gathers)", "data": "synthetic",
+                "config": {"workload": f"dam break {GRID_N}^3, {METHOD.upper()} transfer, RK3 advection, ppc {PPC}",
+                           "cpu_model": model},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "reference",
+                                 "sample": info["sample"], "stage_s": {k: info[k] for k in ("t_p2g", "t_g2p", "t_advect")}},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from blender_flip_fluids_b200 import engine, scenes
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    apic = METHOD == "apic"
+    m = engine.APIC if apic else engine.FLIP
+    if world > 1:
+        from blender_flip_fluids_b200 import slab
+        sim = slab.SlabSimulation(GRID_N, GRID_N, GRID_N * world, 1.0 / GRID_N, rank, world, local_rank, method=m)
+        sc = sim.make_dam_break(PPC, V0, seed=1234)
+        n_local = sim.num_particles()
+    else:
+        sc, K = build_scene(1, 0)
+        sim = None
+        n_local = sc.n
+    dx = 1.0 / GRID_N
+    radius = 0.5 * dx * math.sqrt(3.0)
+    dt = 1.0 * dx / V0            # ~1 cell per substep at the velocity bound (CFL limit is 5)
+    ratio = 0.05
+
+    stream = torch.cuda.current_stream()
+    if sim is None:
+        phi, near = scenes.analytic_solid_sdf(GRID_N, GRID_N, GRID_N, dx)
+        ctx = engine.FlipContext(GRID_N, GRID_N, GRID_N, dx, device=local_rank)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_solid(phi, near)
+        ctx.set_particles(sc.pos, sc.vel, sc.affx, sc.affy, sc.affz)
+
+        def step():
+            ctx.p2g(radius, m)            # bins + sort + seam words + U, V, W transfers
+            ctx.save_velocity_field()     # _saveVelocityField; the CPU pressure solve would sit here
+            ctx.g2p(m, ratio)
+            ctx.advect(dt, 5.0, True)
+    else:
+        ctx = sim.ctx
+        ctx.set_stream(stream.cuda_stream)
+
+        def step():
+            sim.step(radius, ratio, dt)
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {"sort_ms": 0.0, "p2g_prep_ms": 0.0, "p2g_ms": 0.0, "g2p_ms": 0.0, "advect_ms": 0.0}
+    launches = 0
+    barrier()
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    sampler.stop_flag = True
+    sampler.join()
+    # per-stage durations (the library records CUDA events around every stage): one more step
+    for _ in range(3):
+        step()
+        t = ctx.timing()
+        for k in stage:
+            stage[k] += t[k] / 3.0
+        launches = t["sort_launches"] + t["p2g_prep_launches"] + t["p2g_launches"] + t["g2p_launches"] + t["advect_launches"]
+    if world > 1:
+        tt = torch.tensor([ms_total, float(n_local)], device="cuda", dtype=torch.float64)
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, n_total = float(mx[0]), int(round(float(sm[1])))
+    else:
+        n_total = n_local
+    ms_per_step = ms_total / steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_p2g, 3 launches per step) -------------------------------
+    peak, peak_src = measured_peaks()
+    balg = algorithmic_bytes(METHOD, PPC)
+    p2g_launch_ms = stage["p2g_ms"] / 3.0
+    p2g_bytes_per_launch = balg["p2g"] / 3.0 * n_local
+    achieved = p2g_bytes_per_launch / (p2g_launch_ms * 1e-3) / 1e9 if p2g_launch_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "p2g_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"kernel": "k_p2g<dir, APIC> (one launch per MAC direction)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": p2g_bytes_per_launch, "launch_ms": p2g_launch_ms,
+                "whole_step": {"algorithmic_bytes_per_particle": sum(balg.values()),
+                               "achieved_gbs": sum(balg.values()) * n_local / (ms_per_step * 1e-3) / 1e9,
+                               "frac": sum(balg.values()) * n_local / (ms_per_step * 1e-3) / 1e9 / peak},
+                "stage_ms": stage}
+
+    # ---- e2e: host buffers through the reference-facing entry points -----------------------------------
+    e2e = None
+    if not args.no_e2e and sim is None:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_pos, h_vel = pin(sc.pos), pin(sc.vel)
+        h_aff = [pin(a) for a in (sc.affx, sc.affy, sc.affz)]
+        su, sv, sw = engine.mac_shapes(GRID_N, GRID_N, GRID_N)
+        h_mac = [torch.zeros(s, dtype=torch.float32).pin_memory() for s in (su, sv, sw)]
+        h_valid = [torch.zeros(s, dtype=torch.uint8).pin_memory() for s in (su, sv, sw)]
+        h_phi, h_near = pin(phi), pin(near)
+        out = tuple(t.numpy() for t in h_mac) + tuple(t.numpy() for t in h_valid)
+        n = sc.n
+        ngrid = sum(int(np.prod(s)) for s in (su, sv, sw))
+
+        aff_np = [t.numpy() for t in h_aff]
+
+        def e2e_step():
+            # the three interposed call sites of FluidSimulation::_stepFluid, host arrays in and out
+            pos, vel = h_pos.numpy(), h_vel.numpy()
+            (u, v, w), _ = ctx.velocity_advector_advect(pos, vel, *aff_np, radius=radius, method=m, out=out)
+            ctx.update_marker_particle_velocities(pos, vel, (u, v, w), method=m, ratio_pic_flip=ratio, inplace=True,
+                                                  aff_out=aff_np)
+            ctx.advance_marker_particles(pos, (u, v, w), h_phi.numpy(), h_near.numpy(), dt=dt, cfl=5.0, inplace=True)
+
+        h2d = n * 60 + (n * 24 + ngrid * 4) + (n * 12 + ngrid * 4 + phi.nbytes + near.nbytes)
+        d2h = ngrid * 5 + n * 48 + n * 12
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        k_e2e = max(3, min(steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / k_e2e
+        e2e = {"value": n / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": t_e2e * 1e3, "steps": k_e2e,
+               "path": "ffb200_velocity_advector_advect + ffb200_update_marker_particle_velocities + "
+                       "ffb200_advance_marker_particles, pinned host buffers"}
+    elif sim is not None:
+        e2e = sim.e2e(radius, ratio, dt, steps=max(3, min(steps, 5)))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            v, info = reference_arm(3, 1)
+            cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "reference", "sample": info["sample"],
+                   "cpu_model": host_cpu()[0], "stage_s": {k: info[k] for k in ("t_p2g", "t_g2p", "t_advect")}}
+        except Exception as e:                                   # the checker is optional for the headline
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (fp64 index/gather arithmetic)", "data": "synthetic",
+                "config": {"workload": f"dam break {GRID_N}x{GRID_N}x{GRID_N * world}, {METHOD.upper()} transfer, RK3 "
+                                       f"advection + collision, ppc {PPC}, {n_total} particles",
+                           "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo + migration over NCCL",
+                           "l2": "inputs larger than L2 (particle streams + grids > 126 MB per step)",
+                           "dt": dt, "pic_flip_ratio": ratio},
+                "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches * steps, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

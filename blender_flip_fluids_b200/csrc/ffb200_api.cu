@@ -45,7 +45,7 @@ void dev_free(T *&p) {
     p = nullptr;
 }
 
-enum Stage { kSort = 0, kP2G, kG2P, kAdvect, kH2D, kD2H, kNumStages };
+enum Stage { kSort = 0, kP2GPrep, kP2G, kG2P, kAdvect, kH2D, kD2H, kNumStages };
 
 struct StageEvents {
     cudaEvent_t start[kNumStages] = {}, stop[kNumStages] = {};
@@ -284,6 +284,9 @@ void p2g_impl(ContextImpl &c, double radius, int method) {
     if (!(radius > 0.0)) throw std::domain_error("particle radius must be positive");
     if (method == FFB200_TRANSFER_APIC && !c.has_affine) throw std::logic_error("APIC transfer needs affine particle data");
     sort_impl(c);
+    StageTimer tp(c, kP2GPrep);
+    int lp = launch_p2g_prepare(c, radius);
+    tp.done(lp);
     StageTimer t(c, kP2G);
     int l = launch_p2g(c, radius, method);
     t.done(l);
@@ -365,9 +368,11 @@ int ffb200_get_timing(ffb200_context *ctx, ffb200_timing *out) {
         float ms[kNumStages] = {};
         for (int s = 0; s < kNumStages; s++)
             if (c.evs.used[s]) FFB_CUDA(cudaEventElapsedTime(&ms[s], c.evs.start[s], c.evs.stop[s]));
-        out->sort_ms = ms[kSort]; out->p2g_ms = ms[kP2G]; out->g2p_ms = ms[kG2P]; out->advect_ms = ms[kAdvect];
+        out->sort_ms = ms[kSort]; out->p2g_prep_ms = ms[kP2GPrep]; out->p2g_ms = ms[kP2G]; out->g2p_ms = ms[kG2P];
+        out->advect_ms = ms[kAdvect];
         out->h2d_ms = ms[kH2D]; out->d2h_ms = ms[kD2H];
-        out->sort_launches = c.launches[kSort]; out->p2g_launches = c.launches[kP2G];
+        out->sort_launches = c.launches[kSort]; out->p2g_prep_launches = c.launches[kP2GPrep];
+        out->p2g_launches = c.launches[kP2G];
         out->g2p_launches = c.launches[kG2P]; out->advect_launches = c.launches[kAdvect];
     });
 }

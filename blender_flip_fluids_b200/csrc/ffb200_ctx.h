@@ -93,7 +93,8 @@ int launch_sort(Context &c);             // keys -> radix sort -> bin table -> r
 int launch_binning_dump(Context &c, int32_t *cell, uint32_t *hkey, uint32_t *perm);   // device outputs
 
 // ffb200_p2g.cu
-int launch_p2g(Context &c, double radius, int method);
+int launch_p2g_prepare(Context &c, double radius);      // block masks + membership words
+int launch_p2g(Context &c, double radius, int method);  // the three transfer kernels
 
 // ffb200_g2p.cu
 int launch_g2p(Context &c, int method, double ratio);

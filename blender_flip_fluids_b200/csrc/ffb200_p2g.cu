@@ -329,7 +329,7 @@ void launch_dir(Context &c, P2GParams &P, int method) {
 
 }  // namespace
 
-int launch_p2g(Context &c, double radius, int method) {
+int launch_p2g_prepare(Context &c, double radius) {
     int launches = 0;
     const GridDesc &g = c.g;
     ParticleSoA &s = c.soa[c.cur];
@@ -367,7 +367,16 @@ int launch_p2g(Context &c, double radius, int method) {
         k_dilate26<<<(nb + 127) / 128, 128, 0, c.stream>>>(f.home, f.active, f.bi, f.bj, f.bk);
         launches++;
     }
+    FFB_CUDA(cudaGetLastError());
+    return launches;
+}
 
+int launch_p2g(Context &c, double radius, int method) {
+    int launches = 0;
+    const GridDesc &g = c.g;
+    ParticleSoA &s = c.soa[c.cur];
+    const float eps = 1e-6f;
+    const float sr = (float)(radius + (double)eps);            // float sr = _particleRadius + eps;
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];
         P2GParams P;

@@ -33,9 +33,10 @@ _i32p = C.POINTER(C.c_int32)
 
 
 class Timing(C.Structure):
-    _fields_ = [("sort_ms", C.c_float), ("p2g_ms", C.c_float), ("g2p_ms", C.c_float), ("advect_ms", C.c_float),
-                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("sort_launches", C.c_int), ("p2g_launches", C.c_int),
-                ("g2p_launches", C.c_int), ("advect_launches", C.c_int)]
+    _fields_ = [("sort_ms", C.c_float), ("p2g_prep_ms", C.c_float), ("p2g_ms", C.c_float), ("g2p_ms", C.c_float),
+                ("advect_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("sort_launches", C.c_int),
+                ("p2g_prep_launches", C.c_int), ("p2g_launches", C.c_int), ("g2p_launches", C.c_int),
+                ("advect_launches", C.c_int)]
 
 
 # name -> argtypes; every entry point of include/ffb200.h (tests/test_abi.py checks the list
@@ -245,23 +246,32 @@ class FlipContext:
         self.n = n
         return (u, v, w), (vu, vv, vw)
 
-    def update_marker_particle_velocities(self, pos, vel, mac, saved=None, method=FLIP, ratio_pic_flip=0.05):
-        """G2P on host arrays. FLIP -> new velocities; APIC -> (velocities, affx, affy, affz)."""
+    def update_marker_particle_velocities(self, pos, vel, mac, saved=None, method=FLIP, ratio_pic_flip=0.05,
+                                          inplace=False, aff_out=None):
+        """G2P on host arrays. FLIP -> new velocities; APIC -> (velocities, affx, affy, affz).
+
+        inplace=True updates ``vel`` itself, as the reference does (fluidsimulation.cpp:6782);
+        aff_out=(ax, ay, az) supplies the APIC output buffers (e.g. pinned memory)."""
         pos = _f32(pos)
         n = pos.shape[0]
-        vel = _f32(vel, (n, 3)).copy()
+        vel = _f32(vel, (n, 3))
+        if not inplace:
+            vel = vel.copy()
         u, v, w = (_f32(a) for a in mac)
         su, sv, sw = (None, None, None) if saved is None else (_f32(a) for a in saved)
         apic = method == APIC
-        ax, ay, az = (np.zeros((n, 3), np.float32) if apic else None for _ in range(3))
+        if apic and aff_out is not None:
+            ax, ay, az = (_f32(a, (n, 3)) for a in aff_out)
+        else:
+            ax, ay, az = (np.zeros((n, 3), np.float32) if apic else None for _ in range(3))
         self._call("ffb200_update_marker_particle_velocities", n, _ptr(pos), _ptr(vel), _ptr(ax), _ptr(ay), _ptr(az),
                    _ptr(u), _ptr(v), _ptr(w), _ptr(su), _ptr(sv), _ptr(sw), int(method), C.c_double(ratio_pic_flip))
         self.n = n
         return (vel, ax, ay, az) if apic else vel
 
-    def advance_marker_particles(self, pos, mac, phi=None, near_solid=None, dt=1.0 / 60.0, cfl=5.0):
-        """RK3 + collision on host arrays -> new positions."""
-        out = _f32(pos).copy()
+    def advance_marker_particles(self, pos, mac, phi=None, near_solid=None, dt=1.0 / 60.0, cfl=5.0, inplace=False):
+        """RK3 + collision on host arrays -> new positions (inplace=True overwrites ``pos``)."""
+        out = _f32(pos) if inplace else _f32(pos).copy()
         n = out.shape[0]
         u, v, w = (_f32(a) for a in mac)
         phi = _f32(phi)

@@ -56,11 +56,12 @@ typedef struct ffb200_context ffb200_context;
  * stage, and how many kernels of this library that call launched. */
 typedef struct ffb200_timing {
     float sort_ms;        /* cell keys + radix sort + bin table + SoA reorder */
+    float p2g_prep_ms;    /* block masks + 10^3-block membership words */
     float p2g_ms;         /* the three transfer kernels (U, V, W) */
     float g2p_ms;
     float advect_ms;
     float h2d_ms, d2h_ms; /* host<->device copies inside the last host-buffer call */
-    int sort_launches, p2g_launches, g2p_launches, advect_launches;
+    int sort_launches, p2g_prep_launches, p2g_launches, g2p_launches, advect_launches;
 } ffb200_timing;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */

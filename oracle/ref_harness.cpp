@@ -212,21 +212,25 @@ static int mode_p2g() {
     prm.velocityTransferMethod = apic ? VelocityAdvectorTransferMethod::APIC : VelocityAdvectorTransferMethod::FLIP;
 
     double best = 1e30;
+    std::string times = "[";
     for (int r = 0; r < reps; r++) {
         valid.reset();                                            // fluidsimulation.cpp:5630-5631
         mac.clear();
         double t0 = now();
         va.advect(prm);
-        best = std::min(best, now() - t0);
+        double t = now() - t0;
+        best = std::min(best, t);
+        times += (r ? ", " : "") + std::to_string(t);
     }
+    times += "]";
     save_grid("out_u", *mac.getArray3dU());
     save_grid("out_v", *mac.getArray3dV());
     save_grid("out_w", *mac.getArray3dW());
     save_mask("out_validu", valid.validU);
     save_mask("out_validv", valid.validV);
     save_mask("out_validw", valid.validW);
-    printf("{\"mode\": \"p2g\", \"particles\": %zu, \"threads\": %d, \"t_p2g\": %.6f}\n", ps.size(),
-           ThreadUtils::getMaxThreadCount(), best);
+    printf("{\"mode\": \"p2g\", \"particles\": %zu, \"threads\": %d, \"t_p2g\": %.6f, \"times\": %s}\n", ps.size(),
+           ThreadUtils::getMaxThreadCount(), best, times.c_str());
     return 0;
 }
 
@@ -257,12 +261,19 @@ static int mode_g2p() {
         load_grid("in_sv", *sim._savedVelocityField.getArray3dV());
         load_grid("in_sw", *sim._savedVelocityField.getArray3dW());
     }
-    double t0 = now();
-    sim._updateMarkerParticleVelocitiesThread();
-    double t = now() - t0;
-    dump_particles(sim._markerParticles, apic, "out_");
-    printf("{\"mode\": \"g2p\", \"particles\": %zu, \"threads\": %d, \"t_g2p\": %.6f}\n", sim._markerParticles.size(),
-           ThreadUtils::getMaxThreadCount(), t);
+    int reps = kvi("reps", "1");
+    std::string times = "[";
+    double t = 0;
+    for (int r = 0; r < reps; r++) {               // reps > 1 is for timing only (FLIP updates in place)
+        double t0 = now();
+        sim._updateMarkerParticleVelocitiesThread();
+        t = now() - t0;
+        if (r == 0) dump_particles(sim._markerParticles, apic, "out_");
+        times += (r ? ", " : "") + std::to_string(t);
+    }
+    times += "]";
+    printf("{\"mode\": \"g2p\", \"particles\": %zu, \"threads\": %d, \"t_g2p\": %.6f, \"times\": %s}\n",
+           sim._markerParticles.size(), ThreadUtils::getMaxThreadCount(), t, times.c_str());
     return 0;
 }
 
@@ -302,10 +313,17 @@ static int mode_advect() {
     sim._nearSolidGrid = Array3d<bool>(gi, gj, gk, false);
     load_mask("in_near", sim._nearSolidGrid);
     std::vector<vmath::vec3> out;
-    double t = run_advect(sim, dt, out);
+    int reps = kvi("reps", "1");
+    std::string times = "[";
+    double t = 0;
+    for (int r = 0; r < reps; r++) {
+        t = run_advect(sim, dt, out);
+        times += (r ? ", " : "") + std::to_string(t);
+    }
+    times += "]";
     save_vec3("out_pos", out);
-    printf("{\"mode\": \"advect\", \"particles\": %zu, \"threads\": %d, \"t_advect\": %.6f}\n", out.size(),
-           ThreadUtils::getMaxThreadCount(), t);
+    printf("{\"mode\": \"advect\", \"particles\": %zu, \"threads\": %d, \"t_advect\": %.6f, \"times\": %s}\n",
+           out.size(), ThreadUtils::getMaxThreadCount(), t, times.c_str());
     return 0;
 }
 

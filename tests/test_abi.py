@@ -1,0 +1,79 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/ffb200.h declares, the
+ctypes table covers the header, the product never touches oracle/, and without a GPU the
+library fails loudly instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ffb200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ffb200_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from blender_flip_fluids_b200 import build
+    return build.build()                    # nvcc cross-compiles without a GPU
+
+
+def test_header_symbols_exported(lib_path):
+    names = declared_symbols()
+    assert len(names) >= 25
+    lib = C.CDLL(lib_path)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ffb200.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (ffb200_[a-z0-9_]+)", out))
+    assert exported == set(names), f"header/library mismatch: {exported ^ set(names)}"
+
+
+def test_ctypes_table_matches_header():
+    from blender_flip_fluids_b200 import engine
+    assert sorted(engine.SIGNATURES) == declared_symbols()
+
+
+def test_no_gpu_fails_loudly(lib_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from blender_flip_fluids_b200 import engine
+    with pytest.raises(RuntimeError) as e:
+        engine.FlipContext(8, 8, 8, 0.1)
+    assert "no CUDA device" in str(e.value) and "no CPU fallback" in str(e.value)
+    lib = engine.load_library()
+    h = C.c_void_p()
+    assert lib.ffb200_create(C.byref(h), -1, 8, 8, 0.1, 0) == 0        # FFB200_FAIL, message set
+    assert lib.ffb200_get_error_message()
+    assert lib.ffb200_p2g(None, 0.1, 0) == 0
+    assert b"null context" in lib.ffb200_get_error_message()
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use oracle/."""
+    pkg = os.path.join(ROOT, "blender_flip_fluids_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "flip_oracle" not in text, f"{f} references the oracle"
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports oracle"
+
+
+def test_scene_generators():
+    from blender_flip_fluids_b200 import scenes
+    sc = scenes.dam_break(16, apic=True)
+    assert sc.pos.shape == sc.vel.shape == sc.affx.shape and sc.pos.dtype.name == "float32"
+    assert sc.n == 8 * (6 - 3) * (12 - 3) * (16 - 6)
+    lo, hi = sc.pos.min(axis=0), sc.pos.max(axis=0)
+    assert (lo >= 3 * sc.dx - 1e-6).all() and hi[0] < 0.4 + 1e-6 and hi[1] < 0.8 + 1e-6
+    phi, near = scenes.analytic_solid_sdf(12, 9, 15, 0.1, sphere=(0.6, 0.4, 0.7, 0.2))
+    assert phi.shape == (16, 10, 13) and near.shape == (5, 3, 4) and near.max() == 1
+    assert phi[8, 4, 6] < 0                                  # inside the sphere obstacle
