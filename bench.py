@@ -241,6 +241,7 @@ def main():
         ctx.set_stream(stream.cuda_stream)
         ctx.set_solid(phi, near)
         ctx.set_particles(sc.pos, sc.vel, sc.affx, sc.affy, sc.affz)
+        ctx.set_fixed_batch(True)     # every step re-bins, re-sorts and processes the same resident batch
 
         def step():
             ctx.p2g(radius, m)            # bins + sort + seam words + U, V, W transfers
@@ -369,6 +370,8 @@ def main():
                                        f"advection + collision, ppc {PPC}, {n_total} particles",
                            "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo + migration over NCCL",
                            "l2": "inputs larger than L2 (particle streams + grids > 126 MB per step)",
+                           "batch": "fixed resident batch: each step re-bins, re-sorts and transfers the same particles; "
+                                    "G2P/advect results go to the spare SoA buffer",
                            "dt": dt, "pic_flip_ratio": ratio},
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches * steps, "roofline": roofline,
                 "cpu_baseline": cpu}

@@ -30,7 +30,8 @@ struct AdvectParams {
     int ni, nj, nk;
     double inv_near;        // 1.0 / (3*dx)
     Box box;
-    float *px, *py, *pz;
+    const float *px, *py, *pz;   // position in
+    float *opx, *opy, *opz;      // position out
     float c2, c3, c9;       // (float)(0.5dt), (float)(0.75dt), (float)(dt/9.0f)
     float step;             // _markerParticleStepDistanceFactor * (float)_dx
     float maxdist;          // (float)(_CFLConditionNumber * _dx)
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(256) k_advect(AdvectParams P) {
     float y1 = y0 + ((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * P.c9;
     float z1 = z0 + ((k1z * 2.0f + k2z * 3.0f) + k3z * 4.0f) * P.c9;
     if (P.collide) resolve_collision(P, x0, y0, z0, x1, y1, z1);
-    P.px[j] = x1; P.py[j] = y1; P.pz[j] = z1;
+    P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
 }
 
 void box_expand(Box &b, double v) {                     // aabb.cpp:122-128
@@ -218,7 +219,9 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.box.w = g.I * g.dx; P.box.h = g.J * g.dx; P.box.d = g.K * g.dx;
     box_expand(P.box, -3 * g.dx - 1e-4);
     box_expand(P.box, -0.2f * g.dx);                    // boundary.expand(-_solidBufferWidth * _dx)
+    ParticleSoA &o = c.nondestructive ? c.soa[c.cur ^ 1] : s;
     P.px = s.p[0]; P.py = s.p[1]; P.pz = s.p[2];
+    P.opx = o.p[0]; P.opy = o.p[1]; P.opz = o.p[2];
     P.c2 = (float)(0.5 * dt);
     P.c3 = (float)(0.75 * dt);
     P.c9 = (float)(dt / 9.0f);
@@ -229,7 +232,7 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.n = c.n;
     k_advect<<<(c.n + 255) / 256, 256, 0, c.stream>>>(P);
     FFB_CUDA(cudaGetLastError());
-    c.sorted = false;                                   // positions moved: bins are stale
+    if (!c.nondestructive) c.sorted = false;            // positions moved: bins are stale
     return 1;
 }
 

@@ -283,6 +283,7 @@ void p2g_impl(ContextImpl &c, double radius, int method) {
     if (method != FFB200_TRANSFER_FLIP && method != FFB200_TRANSFER_APIC) throw std::domain_error("unknown transfer method");
     if (!(radius > 0.0)) throw std::domain_error("particle radius must be positive");
     if (method == FFB200_TRANSFER_APIC && !c.has_affine) throw std::logic_error("APIC transfer needs affine particle data");
+    if (c.nondestructive) c.sorted = false;                  // fixed-batch mode: always re-bin and re-sort
     sort_impl(c);
     StageTimer tp(c, kP2GPrep);
     int lp = launch_p2g_prepare(c, radius);
@@ -352,8 +353,19 @@ int ffb200_get_version(int *major, int *minor, int *revision) {
 int ffb200_set_stream(ffb200_context *ctx, void *cuda_stream) {
     return guarded("ffb200_set_stream", ctx, [&](Context &c) {
         FFB_CUDA(cudaStreamSynchronize(c.stream));
-        c.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c.own_stream;
+        c.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
     });
+}
+
+int ffb200_reset_stream(ffb200_context *ctx) {
+    return guarded("ffb200_reset_stream", ctx, [&](Context &c) {
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+        c.stream = c.own_stream;
+    });
+}
+
+int ffb200_set_fixed_batch(ffb200_context *ctx, int on) {
+    return guarded("ffb200_set_fixed_batch", ctx, [&](Context &c) { c.nondestructive = on != 0; });
 }
 
 int ffb200_synchronize(ffb200_context *ctx) {

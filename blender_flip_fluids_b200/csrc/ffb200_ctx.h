@@ -80,6 +80,7 @@ struct Context {
     bool has_solid = false;
 
     float guard_abs = -1.f, guard_per = -1.f;
+    bool nondestructive = false;         // G2P/advect write to the spare SoA buffer (fixed-batch benchmarking)
     ffb200_timing timing = {};
 };
 

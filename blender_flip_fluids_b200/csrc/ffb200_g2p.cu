@@ -18,7 +18,8 @@ struct G2PParams {
     GridDesc g;
     MacView cur, saved;
     const float *px, *py, *pz;
-    float *vx, *vy, *vz;
+    const float *vx, *vy, *vz;   // velocity in
+    float *ovx, *ovy, *ovz;      // velocity out (same arrays unless the context is non-destructive)
     float *a[9];
     float rp, rf;       // (float)_ratioPICFLIP, (float)(1 - _ratioPICFLIP)
     float h;            // 0.5f * _dx
@@ -37,9 +38,9 @@ __global__ void __launch_bounds__(256) k_g2p_flip(G2PParams P) {
     const float v0 = P.vx[j], v1 = P.vy[j], v2 = P.vz[j];
     // vFLIP = vel + vPIC - saved(p); v = r*vPIC + (1-r)*vFLIP   (:6779-6781)
     const float f0 = (v0 + pic[0]) - old[0], f1 = (v1 + pic[1]) - old[1], f2 = (v2 + pic[2]) - old[2];
-    P.vx[j] = pic[0] * P.rp + f0 * P.rf;
-    P.vy[j] = pic[1] * P.rp + f1 * P.rf;
-    P.vz[j] = pic[2] * P.rp + f2 * P.rf;
+    P.ovx[j] = pic[0] * P.rp + f0 * P.rf;
+    P.ovy[j] = pic[1] * P.rp + f1 * P.rf;
+    P.ovz[j] = pic[2] * P.rp + f2 * P.rf;
 }
 
 // affineDir = sum over the 8 faces around the (staggered) particle of gradWeight * Face(g).
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(256) k_g2p_apic(G2PParams P) {
     P.a[6][j] = ax; P.a[7][j] = ay; P.a[8][j] = az;
     float v0, v1, v2;
     mac_eval(P.g, P.cur, x, y, z, v0, v1, v2);
-    P.vx[j] = v0; P.vy[j] = v1; P.vz[j] = v2;
+    P.ovx[j] = v0; P.ovy[j] = v1; P.ovz[j] = v2;
 }
 
 }  // namespace
@@ -106,8 +107,10 @@ int launch_g2p(Context &c, int method, double ratio) {
     P.cur = MacView{c.face[0].vel, c.face[1].vel, c.face[2].vel};
     P.saved = MacView{c.face[0].saved, c.face[1].saved, c.face[2].saved};
     P.px = s.p[0]; P.py = s.p[1]; P.pz = s.p[2];
+    ParticleSoA &o = c.nondestructive ? c.soa[c.cur ^ 1] : s;   // spare SoA buffer keeps the inputs pristine
     P.vx = s.v[0]; P.vy = s.v[1]; P.vz = s.v[2];
-    for (int q = 0; q < 9; q++) P.a[q] = s.a[q];
+    P.ovx = o.v[0]; P.ovy = o.v[1]; P.ovz = o.v[2];
+    for (int q = 0; q < 9; q++) P.a[q] = o.a[q];
     P.rp = (float)ratio;
     P.rf = (float)(1 - ratio);
     P.h = (float)(0.5f * c.g.dx);

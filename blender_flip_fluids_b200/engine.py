@@ -48,6 +48,8 @@ SIGNATURES = {
     "ffb200_get_error_message": [],
     "ffb200_get_version": [C.POINTER(C.c_int)] * 3,
     "ffb200_set_stream": [C.c_void_p, C.c_void_p],
+    "ffb200_reset_stream": [C.c_void_p],
+    "ffb200_set_fixed_batch": [C.c_void_p, C.c_int],
     "ffb200_synchronize": [C.c_void_p],
     "ffb200_get_timing": [C.c_void_p, C.POINTER(Timing)],
     "ffb200_set_valid_guard": [C.c_void_p, C.c_float, C.c_float],
@@ -150,7 +152,14 @@ class FlipContext:
 
     # ---- resident state ------------------------------------------------------------------------
     def set_stream(self, cuda_stream):
-        self._call("ffb200_set_stream", C.c_void_p(int(cuda_stream) if cuda_stream else 0))
+        """Use an existing cudaStream_t handle (int); 0 is the legacy default stream."""
+        self._call("ffb200_set_stream", C.c_void_p(int(cuda_stream)))
+
+    def reset_stream(self):
+        self._call("ffb200_reset_stream")
+
+    def set_fixed_batch(self, on=True):
+        self._call("ffb200_set_fixed_batch", 1 if on else 0)
 
     def synchronize(self):
         self._call("ffb200_synchronize")

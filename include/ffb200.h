@@ -80,8 +80,14 @@ const char *ffb200_get_error_message(void);
 int ffb200_get_version(int *major, int *minor, int *revision);
 
 /* Run the context's work on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
- * torch.cuda.current_stream().cuda_stream; NULL restores the context's own stream. */
+ * torch.cuda.current_stream().cuda_stream; the value is taken literally, so 0 is the legacy
+ * default stream. ffb200_reset_stream goes back to the context's own non-blocking stream. */
 int ffb200_set_stream(ffb200_context *ctx, void *cuda_stream);
+int ffb200_reset_stream(ffb200_context *ctx);
+/* Fixed-batch mode (benchmarking): every ffb200_p2g re-bins and re-sorts the resident batch,
+ * and G2P / advection write their results into the spare SoA buffer instead of in place, so
+ * each step sees identical inputs. Off by default (reference semantics: in-place update). */
+int ffb200_set_fixed_batch(ffb200_context *ctx, int on);
 int ffb200_synchronize(ffb200_context *ctx);
 int ffb200_get_timing(ffb200_context *ctx, ffb200_timing *out);
 
