@@ -1,0 +1,134 @@
+// ffengine_b200.cpp -- drop-in libffengine for the FLIP Fluids addon with the particle<->grid
+// substep on B200.
+//
+// The reference calls its three hot stages through the PLT (it is built -fPIC without
+// -Bsymbolic), so a library that DEFINES those three C++ member symbols
+// and DT_NEEDEDs the unmodified engine takes the calls over without touching reference code:
+//
+//   VelocityAdvector::advect(VelocityAdvectorParameters)              velocityadvector.cpp:38
+//   FluidSimulation::_updateMarkerParticleVelocitiesThread()          fluidsimulation.cpp:6845
+//   FluidSimulation::_advanceMarkerParticles(double)                  fluidsimulation.cpp:7853
+//
+// Each definition marshals the reference's own host containers (std::vector<vmath::vec3>,
+// Array3d<float>, Array3d<bool>) into the C ABI of libffb200.so (include/ffb200.h) and throws
+// std::runtime_error on failure on the calling thread, so the reference's C bindings turn it
+// into err = 0 + CBindings_get_error_message (cbindings.h:48-154). Every other stage (pressure,
+// level sets, meshing, I/O, particle removal ...) stays on the reference CPU code.
+// Compiled against the UNMODIFIED reference headers with -fno-access-control.
+// There is no fallback to the CPU originals: if the GPU call fails, the substep fails.
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "fluidsimulation.h"
+#include "stopwatch.h"
+#include "velocityadvector.h"
+
+#include "ffb200.h"
+
+namespace {
+
+static_assert(sizeof(vmath::vec3) == 12, "vmath::vec3 must be three packed floats");
+static_assert(sizeof(bool) == 1, "Array3d<bool> must be one byte per element");
+
+std::mutex g_mutex;
+std::map<std::tuple<int, int, int, double>, ffb200_context *> g_contexts;
+
+// One device context per grid shape, created on first use. FFB200_DEVICE selects the GPU,
+// FFB200_EXACT_P2G=1 sends every face through the reference-order summation (bit-exact P2G).
+ffb200_context *context_for(int I, int J, int K, double dx) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto key = std::make_tuple(I, J, K, dx);
+    auto it = g_contexts.find(key);
+    if (it != g_contexts.end()) return it->second;
+    const char *dev = std::getenv("FFB200_DEVICE");
+    ffb200_context *ctx = nullptr;
+    if (ffb200_create(&ctx, I, J, K, dx, dev ? std::atoi(dev) : 0) != FFB200_SUCCESS)
+        throw std::runtime_error(ffb200_get_error_message());
+    const char *exact = std::getenv("FFB200_EXACT_P2G");
+    if (exact && std::atoi(exact) != 0) ffb200_set_valid_guard(ctx, 1e30f, 0.0f);
+    g_contexts[key] = ctx;
+    return ctx;
+}
+
+void check(int ok) {
+    if (ok != FFB200_SUCCESS) throw std::runtime_error(ffb200_get_error_message());
+}
+
+float *raw(std::vector<vmath::vec3> *v) { return v->empty() ? nullptr : &((*v)[0].x); }
+
+}  // namespace
+
+// ---- P2G ------------------------------------------------------------------------------------------
+void VelocityAdvector::advect(VelocityAdvectorParameters params) {
+    int I, J, K;
+    params.vfield->getGridDimensions(&I, &J, &K);
+    ffb200_context *ctx = context_for(I, J, K, params.vfield->getGridCellSize());
+
+    std::vector<vmath::vec3> *pos, *vel, *ax = nullptr, *ay = nullptr, *az = nullptr;
+    params.particles->getAttributeValues("POSITION", pos);
+    params.particles->getAttributeValues("VELOCITY", vel);
+    const bool apic = params.velocityTransferMethod == VelocityAdvectorTransferMethod::APIC;
+    if (apic) {
+        params.particles->getAttributeValues("AFFINEX", ax);
+        params.particles->getAttributeValues("AFFINEY", ay);
+        params.particles->getAttributeValues("AFFINEZ", az);
+    }
+    ValidVelocityComponentGrid *valid = params.validVelocities;
+    check(ffb200_velocity_advector_advect(
+        ctx, (int)pos->size(), raw(pos), raw(vel), apic ? raw(ax) : nullptr, apic ? raw(ay) : nullptr,
+        apic ? raw(az) : nullptr, params.particleRadius, apic ? FFB200_TRANSFER_APIC : FFB200_TRANSFER_FLIP,
+        params.vfield->getArray3dU()->getRawArray(), params.vfield->getArray3dV()->getRawArray(),
+        params.vfield->getArray3dW()->getRawArray(), reinterpret_cast<uint8_t *>(valid->validU.getRawArray()),
+        reinterpret_cast<uint8_t *>(valid->validV.getRawArray()), reinterpret_cast<uint8_t *>(valid->validW.getRawArray())));
+}
+
+// ---- G2P ------------------------------------------------------------------------------------------
+void FluidSimulation::_updateMarkerParticleVelocitiesThread() {
+    if (_markerParticles.empty()) return;
+    ffb200_context *ctx = context_for(_isize, _jsize, _ksize, _dx);
+    std::vector<vmath::vec3> *pos, *vel, *ax = nullptr, *ay = nullptr, *az = nullptr;
+    _markerParticles.getAttributeValues("POSITION", pos);
+    _markerParticles.getAttributeValues("VELOCITY", vel);
+    const bool apic = _velocityTransferMethod == VelocityTransferMethod::APIC;
+    if (apic) {
+        _markerParticles.getAttributeValues("AFFINEX", ax);
+        _markerParticles.getAttributeValues("AFFINEY", ay);
+        _markerParticles.getAttributeValues("AFFINEZ", az);
+    }
+    check(ffb200_update_marker_particle_velocities(
+        ctx, (int)pos->size(), raw(pos), raw(vel), apic ? raw(ax) : nullptr, apic ? raw(ay) : nullptr,
+        apic ? raw(az) : nullptr, _MACVelocity.getArray3dU()->getRawArray(), _MACVelocity.getArray3dV()->getRawArray(),
+        _MACVelocity.getArray3dW()->getRawArray(), apic ? nullptr : _savedVelocityField.getArray3dU()->getRawArray(),
+        apic ? nullptr : _savedVelocityField.getArray3dV()->getRawArray(),
+        apic ? nullptr : _savedVelocityField.getArray3dW()->getRawArray(),
+        apic ? FFB200_TRANSFER_APIC : FFB200_TRANSFER_FLIP, _ratioPICFLIP));
+}
+
+// ---- advect ---------------------------------------------------------------------------------------
+// Same bracket as the reference stage (log lines, the advanceMarkerParticles timer the addon's
+// stats read, fluidsimulation.cpp:7896-7897) and the same tail call: particle removal stays on
+// the CPU and still runs inside this stage.
+void FluidSimulation::_advanceMarkerParticles(double dt) {
+    _logfile.logString(_logfile.getTime() + " BEGIN       Advect Marker Particles");
+    StopWatch timer;
+    timer.start();
+    if (_isFluidInSimulation()) {
+        ffb200_context *ctx = context_for(_isize, _jsize, _ksize, _dx);
+        std::vector<vmath::vec3> *pos;
+        _markerParticles.getAttributeValues("POSITION", pos);
+        check(ffb200_advance_marker_particles(
+            ctx, (int)pos->size(), raw(pos), _MACVelocity.getArray3dU()->getRawArray(),
+            _MACVelocity.getArray3dV()->getRawArray(), _MACVelocity.getArray3dW()->getRawArray(),
+            _solidSDF._phi.getRawArray(), reinterpret_cast<uint8_t *>(_nearSolidGrid.getRawArray()), dt,
+            _CFLConditionNumber));
+        _removeMarkerParticles(_currentFrameDeltaTime);
+    }
+    timer.stop();
+    _timingData.advanceMarkerParticles += timer.getTime();
+    _logfile.logString(_logfile.getTime() + " COMPLETE    Advect Marker Particles");
+}

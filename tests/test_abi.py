@@ -77,3 +77,25 @@ def test_scene_generators():
     phi, near = scenes.analytic_solid_sdf(12, 9, 15, 0.1, sphere=(0.6, 0.4, 0.7, 0.2))
     assert phi.shape == (16, 10, 13) and near.shape == (5, 3, 4) and near.max() == 1
     assert phi[8, 4, 6] < 0                                  # inside the sphere obstacle
+
+
+def test_dropin_reexports_reference_abi():
+    """libffengine_b200.so defines exactly the three interposed C++ members and resolves the
+    reference's whole extern "C" surface through its DT_NEEDED reference library."""
+    dropin = os.path.join(ROOT, "blender_flip_fluids_b200", "lib", "libffengine_b200.so")
+    ref = os.path.join(ROOT, "oracle", "_ref", "libffengine_ref.so")
+    if not (os.path.exists(dropin) and os.path.exists(ref)):
+        pytest.skip("drop-in not built (needs /root/reference)")
+    out = subprocess.run(["nm", "-D", "--defined-only", dropin], capture_output=True, text=True, check=True).stdout
+    defined = set(re.findall(r" T (\S+)", out))
+    assert defined == {"_ZN16VelocityAdvector6advectE26VelocityAdvectorParameters",
+                       "_ZN15FluidSimulation37_updateMarkerParticleVelocitiesThreadEv",
+                       "_ZN15FluidSimulation23_advanceMarkerParticlesEd"}
+    needed = subprocess.run(["readelf", "-d", dropin], capture_output=True, text=True, check=True).stdout
+    assert "libffb200.so" in needed and "libffengine_cpu.so" in needed
+    refsyms = subprocess.run(["nm", "-D", "--defined-only", ref], capture_output=True, text=True, check=True).stdout
+    c_abi = set(re.findall(r" T ((?:FluidSimulation|MeshObject|MeshFluidSource|ForceField\w*|Mixbox|CBindings)_\w+)", refsyms))
+    assert len(c_abi) >= 700                              # SURVEY 8b: 728 extern "C" exports
+    lib = C.CDLL(dropin)
+    missing = [s for s in sorted(c_abi) if not hasattr(lib, s)]
+    assert not missing, missing[:5]
