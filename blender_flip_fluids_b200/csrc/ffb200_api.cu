@@ -93,10 +93,19 @@ void ensure_affine(ContextImpl &c) {
         }
 }
 
-void ensure_capacity(ContextImpl &c, int n, bool affine) {
+// Grow-only. With `preserve` the first c.n entries of the current SoA buffer (and their ids)
+// survive the reallocation (device-side migration appends to live data).
+void ensure_capacity(ContextImpl &c, int n, bool affine, bool preserve = false) {
     if (n > c.cap) {
         const bool had_affine = c.soa[0].a[0] != nullptr;
         FFB_CUDA(cudaStreamSynchronize(c.stream));
+        ParticleSoA old = c.soa[c.cur];
+        const int keep = preserve ? c.n : 0;
+        if (keep > 0) {                                      // detach the live buffer from free_particles
+            for (int q = 0; q < 3; q++) { c.soa[c.cur].p[q] = nullptr; c.soa[c.cur].v[q] = nullptr; }
+            for (int q = 0; q < 9; q++) c.soa[c.cur].a[q] = nullptr;
+            c.soa[c.cur].orig = nullptr;
+        }
         free_particles(c);
         c.cap = n + n / 8 + 1024;
         for (int b = 0; b < 2; b++) {
@@ -107,7 +116,23 @@ void ensure_capacity(ContextImpl &c, int n, bool affine) {
         }
         dev_alloc(c.sort.seam, (size_t)c.cap * 3);
         dev_alloc(c.aos_stage, (size_t)c.cap * 3);
-        if (had_affine) ensure_affine(c);
+        if (had_affine || affine) ensure_affine(c);
+        if (keep > 0) {
+            ParticleSoA &dst = c.soa[c.cur];
+            const size_t bytes = (size_t)keep * sizeof(float);
+            for (int q = 0; q < 3; q++) {
+                FFB_CUDA(cudaMemcpyAsync(dst.p[q], old.p[q], bytes, cudaMemcpyDeviceToDevice, c.stream));
+                FFB_CUDA(cudaMemcpyAsync(dst.v[q], old.v[q], bytes, cudaMemcpyDeviceToDevice, c.stream));
+            }
+            if (old.a[0])
+                for (int q = 0; q < 9; q++)
+                    FFB_CUDA(cudaMemcpyAsync(dst.a[q], old.a[q], bytes, cudaMemcpyDeviceToDevice, c.stream));
+            FFB_CUDA(cudaMemcpyAsync(dst.orig, old.orig, bytes, cudaMemcpyDeviceToDevice, c.stream));
+            FFB_CUDA(cudaStreamSynchronize(c.stream));
+            for (int q = 0; q < 3; q++) { dev_free(old.p[q]); dev_free(old.v[q]); }
+            for (int q = 0; q < 9; q++) dev_free(old.a[q]);
+            dev_free(old.orig);
+        }
     }
     if (affine) ensure_affine(c);
 }
@@ -409,6 +434,48 @@ int ffb200_get_num_particles(ffb200_context *ctx, int *n) {
     return guarded("ffb200_get_num_particles", ctx, [&](Context &c) {
         if (!n) throw std::invalid_argument("null output pointer");
         *n = c.n;
+    });
+}
+
+int ffb200_get_device_buffers(ffb200_context *ctx, ffb200_device_buffers *out) {
+    return guarded("ffb200_get_device_buffers", ctx, [&](Context &c) {
+        if (!out) throw std::invalid_argument("null output pointer");
+        ParticleSoA &s = c.soa[c.cur];
+        for (int q = 0; q < 3; q++) { out->pos[q] = s.p[q]; out->vel[q] = s.v[q]; }
+        for (int q = 0; q < 9; q++) out->aff[q] = s.a[q];
+        out->ids = s.orig;
+        out->n = c.n;
+        out->capacity = c.cap;
+        for (int d = 0; d < 3; d++) {
+            out->field[d] = c.face[d].vel;
+            out->saved[d] = c.face[d].saved;
+            out->valid[d] = c.face[d].valid;
+            out->face_count[d] = (long long)c.face[d].count;
+            out->face_plane[d] = c.face[d].gi * c.face[d].gj;
+        }
+        out->kbase = c.g.kbase;
+        out->kloc = c.g.kloc;
+        out->k_own_begin = c.k_own_begin;
+        out->k_own_end = c.k_own_end;
+        out->phi = c.phi;
+    });
+}
+
+int ffb200_reserve_particles(ffb200_context *ctx, int capacity, int with_affine) {
+    return guarded("ffb200_reserve_particles", ctx, [&](Context &c) {
+        if (capacity < 0) throw std::domain_error("negative capacity");
+        ensure_capacity(impl(c), capacity, with_affine != 0, true);
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+int ffb200_set_num_particles(ffb200_context *ctx, int n, int has_affine) {
+    return guarded("ffb200_set_num_particles", ctx, [&](Context &c) {
+        if (n < 0 || n > c.cap) throw std::domain_error("particle count exceeds the reserved capacity");
+        if (has_affine && !c.soa[c.cur].a[0]) throw std::logic_error("affine streams were not reserved");
+        c.n = n;
+        c.has_affine = has_affine != 0;
+        c.sorted = false;
     });
 }
 

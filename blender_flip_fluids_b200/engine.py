@@ -39,6 +39,15 @@ class Timing(C.Structure):
                 ("advect_launches", C.c_int)]
 
 
+class DeviceBuffers(C.Structure):
+    """ffb200_device_buffers: raw device pointers of the resident arrays (include/ffb200.h)."""
+    _fields_ = [("pos", C.c_void_p * 3), ("vel", C.c_void_p * 3), ("aff", C.c_void_p * 9), ("ids", C.c_void_p),
+                ("n", C.c_int), ("capacity", C.c_int), ("field", C.c_void_p * 3), ("saved", C.c_void_p * 3),
+                ("valid", C.c_void_p * 3), ("face_count", C.c_longlong * 3), ("face_plane", C.c_int * 3),
+                ("kbase", C.c_int), ("kloc", C.c_int), ("k_own_begin", C.c_int), ("k_own_end", C.c_int),
+                ("phi", C.c_void_p)]
+
+
 # name -> argtypes; every entry point of include/ffb200.h (tests/test_abi.py checks the list
 # against the header and the built library).
 SIGNATURES = {
@@ -56,6 +65,9 @@ SIGNATURES = {
     "ffb200_set_particles": [C.c_void_p, C.c_int] + [_f32p] * 5,
     "ffb200_get_particles": [C.c_void_p] + [_f32p] * 5,
     "ffb200_get_num_particles": [C.c_void_p, C.POINTER(C.c_int)],
+    "ffb200_get_device_buffers": [C.c_void_p, C.POINTER(DeviceBuffers)],
+    "ffb200_reserve_particles": [C.c_void_p, C.c_int, C.c_int],
+    "ffb200_set_num_particles": [C.c_void_p, C.c_int, C.c_int],
     "ffb200_sort_particles": [C.c_void_p],
     "ffb200_get_binning": [C.c_void_p, _i32p, _u32p, _u32p],
     "ffb200_set_velocity_field": [C.c_void_p] + [_f32p] * 3,
@@ -187,6 +199,18 @@ class FlipContext:
         p, v, ax, ay, az = mk(pos), mk(vel), mk(affine), mk(affine), mk(affine)
         self._call("ffb200_get_particles", _ptr(p), _ptr(v), _ptr(ax), _ptr(ay), _ptr(az))
         return p, v, ax, ay, az
+
+    def device_buffers(self):
+        b = DeviceBuffers()
+        self._call("ffb200_get_device_buffers", C.byref(b))
+        return b
+
+    def reserve_particles(self, capacity, with_affine=False):
+        self._call("ffb200_reserve_particles", int(capacity), 1 if with_affine else 0)
+
+    def set_num_particles(self, n, has_affine=False):
+        self._call("ffb200_set_num_particles", int(n), 1 if has_affine else 0)
+        self.n = int(n)
 
     def sort_particles(self):
         self._call("ffb200_sort_particles")

@@ -1,0 +1,306 @@
+"""z-slab multi-GPU decomposition of the substep.
+
+One process per GPU (``torch.distributed``; NCCL on GPUs, gloo in the CPU tests). Rank g owns
+the cell planes [g*K/n, (g+1)*K/n) of an I x J x K domain and stores ``halo`` more on each side.
+Only nearest-neighbour exchanges are on the path, no all-reduce:
+
+  1. ghost particles   particles within ``ghost`` cells of a slab face are copied to the
+                       z-neighbour before P2G, so every owned face is summed wholly on its owner,
+                       in the same (bin, global id) order as a single-GPU run;
+  2. face halo         after P2G (where the reference's CPU projection would sit) the ``halo``
+                       boundary planes of u, v, w are exchanged, then the field is saved;
+  3. migration         after advection, particles whose cell left the slab move to the neighbour.
+
+The driver is backend-agnostic: ``GpuBackend`` runs the stages in libffb200 on zero-copy tensor
+views of the library's device buffers; the CPU tests plug in an oracle-backed backend to check
+the exchange logic bit-for-bit against an undecomposed run.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+NSTREAM_FLIP = 6            # px py pz vx vy vz
+NSTREAM_APIC = 15           # + 9 affine components
+
+
+def slab_range(K: int, world: int, rank: int):
+    """Owned cell planes of `rank`: contiguous, as equal as possible."""
+    return (K * rank) // world, (K * (rank + 1)) // world
+
+
+class _DevArray:
+    """Adapter exposing a raw device pointer through __cuda_array_interface__."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _view(ptr, count, typestr, device):
+    if not ptr or count == 0:
+        return torch.empty(0, device=device, dtype={"<f4": torch.float32, "<u4": torch.int32, "|u1": torch.uint8}[typestr])
+    if typestr == "<u4":                         # torch has no uint32 arithmetic: ids travel as int32 bit patterns
+        typestr = "<i4"
+    return torch.as_tensor(_DevArray(ptr, count, typestr), device=device)
+
+
+class GpuBackend:
+    """The stages on one GPU through the C ABI, with zero-copy views for the exchanges."""
+
+    def __init__(self, I, J, K, dx, k_begin, k_end, halo, device_index, apic):
+        from . import engine
+        self.engine = engine
+        self.device = torch.device("cuda", device_index)
+        self.ctx = engine.FlipContext(I, J, K, dx, device=device_index, slab=(k_begin, k_end, halo))
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self.apic = apic
+        self.method = engine.APIC if apic else engine.FLIP
+        self.I, self.J, self.K, self.dx = I, J, K, dx
+
+    @property
+    def nstream(self):
+        return NSTREAM_APIC if self.apic else NSTREAM_FLIP
+
+    def reserve(self, capacity):
+        self.ctx.reserve_particles(capacity, self.apic)
+
+    def particle_views(self, n=None):
+        """(streams [nstream x n] as a list of 1-D views, ids int32 view) of the current buffer."""
+        b = self.ctx.device_buffers()
+        n = b.n if n is None else n
+        ptrs = list(b.pos) + list(b.vel) + (list(b.aff) if self.apic else [])
+        return [_view(p, n, "<f4", self.device) for p in ptrs], _view(b.ids, n, "<u4", self.device)
+
+    def load_particles(self, streams, ids):
+        n = int(ids.shape[0])
+        b = self.ctx.device_buffers()
+        if n > b.capacity:
+            self.reserve(int(n * 1.25) + 1024)
+        dst, dst_ids = self.particle_views(n)
+        for d, s in zip(dst, streams):
+            d.copy_(s)
+        dst_ids.copy_(ids)
+        self.ctx.set_num_particles(n, self.apic)
+
+    def set_count(self, n):
+        self.ctx.set_num_particles(n, self.apic)
+
+    def field_planes(self, d, saved=False):
+        b = self.ctx.device_buffers()
+        ptr = (b.saved if saved else b.field)[d]
+        plane = b.face_plane[d]
+        return _view(ptr, b.face_count[d], "<f4", self.device).view(-1, plane), b.kbase
+
+    def set_solid(self, phi, near):
+        self.ctx.set_solid(phi, near)
+
+    def p2g(self, radius):
+        self.ctx.p2g(radius, self.method)
+
+    def save_field(self):
+        self.ctx.save_velocity_field()
+
+    def g2p(self, ratio):
+        self.ctx.g2p(self.method, ratio)
+
+    def advect(self, dt, cfl=5.0, collide=True):
+        self.ctx.advect(dt, cfl, collide)
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+
+class SlabSimulation:
+    def __init__(self, I, J, K, dx, rank, world, backend, halo=7, ghost=2):
+        self.I, self.J, self.K, self.dx = I, J, K, float(dx)
+        self.rank, self.world = rank, world
+        self.kb, self.ke = slab_range(K, world, rank)
+        self.halo, self.ghost = halo, ghost
+        self.backend = backend
+        self.device = backend.device
+        self.inv_dx = 1.0 / self.dx
+        self.up = rank + 1 if rank + 1 < world else None
+        self.down = rank - 1 if rank > 0 else None
+        self.streams = None          # authoritative particle streams between substeps (list of 1-D tensors)
+        self.ids = None
+        self.exchanged_bytes = 0
+
+    # ---- particles ----------------------------------------------------------------------------------
+    def cell_k(self, pz):
+        """floor(z * (1/dx)) in double: Grid3d::positionToGridIndex (grid3d.h:55-60)."""
+        return torch.floor(pz.double() * self.inv_dx).to(torch.int64)
+
+    def set_particles(self, streams, ids):
+        self.streams = [s.contiguous() for s in streams]
+        self.ids = ids.contiguous()
+
+    def num_particles(self):
+        return int(self.ids.shape[0])
+
+    def _pack(self, mask):
+        idx = torch.nonzero(mask, as_tuple=False).squeeze(1)
+        rows = [s.index_select(0, idx) for s in self.streams]
+        rows.append(self.ids.index_select(0, idx).view(torch.float32))
+        return torch.stack(rows, 0) if idx.numel() else torch.empty((len(rows), 0), device=self.device)
+
+    def _exchange(self, to_up, to_down):
+        """Send one [rows, m] float32 block to each z-neighbour, receive theirs. Counts first."""
+        rows = to_up.shape[0]
+        dev = self.device
+        cnt_out = {self.up: to_up, self.down: to_down}
+        ops, cnt_in = [], {}
+        for peer, blk in cnt_out.items():
+            if peer is None:
+                continue
+            cnt_in[peer] = torch.zeros(1, dtype=torch.int64, device=dev)
+            ops.append(dist.P2POp(dist.isend, torch.tensor([blk.shape[1]], dtype=torch.int64, device=dev), peer))
+            ops.append(dist.P2POp(dist.irecv, cnt_in[peer], peer))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        ops, recv = [], {}
+        for peer, blk in cnt_out.items():
+            if peer is None:
+                continue
+            m = int(cnt_in[peer].item())
+            recv[peer] = torch.empty((rows, m), dtype=torch.float32, device=dev)
+            if blk.shape[1]:
+                ops.append(dist.P2POp(dist.isend, blk.contiguous(), peer))
+                self.exchanged_bytes += blk.numel() * 4
+            if m:
+                ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        empty = torch.empty((rows, 0), dtype=torch.float32, device=dev)
+        return recv.get(self.down, empty), recv.get(self.up, empty)
+
+    def _append(self, blocks):
+        ns = len(self.streams)
+        for blk in blocks:
+            if blk.shape[1] == 0:
+                continue
+            self.streams = [torch.cat([s, blk[i]]) for i, s in enumerate(self.streams)]
+            self.ids = torch.cat([self.ids, blk[ns].view(torch.int32)])
+
+    # ---- grids --------------------------------------------------------------------------------------
+    def _halo_exchange(self):
+        """Owned boundary planes of u, v, w -> the neighbours' halo planes (in place, zero copy)."""
+        H = self.halo
+        ops, keep = [], []
+        for d in range(3):
+            f, kbase = self.backend.field_planes(d)
+            extra = 1 if d == 2 else 0                       # w has one more plane; plane ke belongs to the upper slab
+            o0, o1 = self.kb - kbase, self.ke - kbase
+            if self.up is not None:
+                send = f[o1 - H:o1].contiguous()
+                recv = f[o1:o1 + H + extra]
+                buf = torch.empty_like(recv)
+                keep.append((recv, buf))
+                ops += [dist.P2POp(dist.isend, send, self.up), dist.P2POp(dist.irecv, buf, self.up)]
+                self.exchanged_bytes += send.numel() * 4
+            if self.down is not None:
+                send = f[o0:o0 + H + extra].contiguous()
+                recv = f[o0 - H:o0]
+                buf = torch.empty_like(recv)
+                keep.append((recv, buf))
+                ops += [dist.P2POp(dist.isend, send, self.down), dist.P2POp(dist.irecv, buf, self.down)]
+                self.exchanged_bytes += send.numel() * 4
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        for recv, buf in keep:
+            recv.copy_(buf)
+
+    # ---- one substep ----------------------------------------------------------------------------------
+    def step(self, radius, ratio, dt, cfl=5.0, collide=True):
+        kz = self.cell_k(self.streams[2])
+        # 1. ghost particles for P2G
+        g = self.ghost
+        up_mask = (kz >= self.ke - g) if self.up is not None else torch.zeros_like(kz, dtype=torch.bool)
+        dn_mask = (kz < self.kb + g) if self.down is not None else torch.zeros_like(kz, dtype=torch.bool)
+        from_down, from_up = self._exchange(self._pack(up_mask), self._pack(dn_mask))
+        ns = len(self.streams)
+        streams = [torch.cat([s, from_down[i], from_up[i]]) for i, s in enumerate(self.streams)]
+        ids = torch.cat([self.ids, from_down[ns].view(torch.int32), from_up[ns].view(torch.int32)])
+        self.backend.load_particles(streams, ids)
+        # 2. P2G on owned + ghost particles (sorts; owned faces are complete)
+        self.backend.p2g(radius)
+        sorted_streams, sorted_ids = self.backend.particle_views()
+        ghost_mask = ~self._owned(self.cell_k(sorted_streams[2]))
+        # 3. halo planes, then the saved copy (the CPU projection would run between the two)
+        self._halo_exchange()
+        self.backend.save_field()
+        # 4. G2P + advection (in place on the sorted streams; ghosts ride along and are dropped below)
+        self.backend.g2p(ratio)
+        self.backend.advect(dt, cfl, collide)
+        sorted_streams, sorted_ids = self.backend.particle_views()
+        # 5. migration
+        knew = self.cell_k(sorted_streams[2])
+        alive = ~ghost_mask
+        stay = alive & self._owned(knew)
+        go_up = alive & (knew >= self.ke) if self.up is not None else torch.zeros_like(stay)
+        go_dn = alive & (knew < self.kb) if self.down is not None else torch.zeros_like(stay)
+        if self.up is None:
+            stay = stay | (alive & (knew >= self.ke))           # top rank keeps what left the domain upwards
+        if self.down is None:
+            stay = stay | (alive & (knew < self.kb))
+        self.streams, self.ids = sorted_streams, sorted_ids
+        up_blk, dn_blk = self._pack(go_up), self._pack(go_dn)
+        idx = torch.nonzero(stay, as_tuple=False).squeeze(1)
+        self.streams = [s.index_select(0, idx) for s in sorted_streams]
+        self.ids = sorted_ids.index_select(0, idx)
+        from_down, from_up = self._exchange(up_blk, dn_blk)
+        self._append([from_down, from_up])
+
+    def _owned(self, kz):
+        return (kz >= self.kb) & (kz < self.ke)
+
+    # ---- helpers for tests / bench ----------------------------------------------------------------------
+    def gather_particles(self):
+        """All particles on every rank, ordered by global id (tests)."""
+        ns = len(self.streams)
+        blk = torch.stack(self.streams + [self.ids.view(torch.float32)], 0).contiguous()
+        counts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+        dist.all_gather(counts, torch.tensor([blk.shape[1]], dtype=torch.int64, device=self.device))
+        parts = [torch.empty((ns + 1, int(c.item())), dtype=torch.float32, device=self.device) for c in counts]
+        mx = max(int(c.item()) for c in counts)
+        padded = torch.zeros((ns + 1, mx), dtype=torch.float32, device=self.device)
+        padded[:, :blk.shape[1]] = blk
+        bufs = [torch.zeros_like(padded) for _ in range(self.world)]
+        dist.all_gather(bufs, padded)
+        for r in range(self.world):
+            parts[r] = bufs[r][:, :int(counts[r].item())]
+        allp = torch.cat(parts, 1)
+        ids = allp[ns].contiguous().view(torch.int32).to(torch.int64) & 0xffffffff
+        order = torch.argsort(ids)
+        return allp[:ns, order], ids[order]
+
+
+def make_slab_dam_break(I, J, K, dx, rank, world, ppc, v0, apic, seed, device):
+    """This rank's particles of the dam break I x J x K (full-z columns), generated
+    independently per rank (seed + rank); global ids are offset by the lower ranks' counts."""
+    from . import scenes
+    kb, ke = slab_range(K, world, rank)
+    rng = np.random.default_rng(seed + 7919 * rank)
+    k0, k1 = max(3, kb), min(K - 3, ke)
+    pos = scenes._seed_cells(3, max(4, int(0.4 * I)), 3, max(4, int(0.8 * J)), k0, k1, dx, ppc, rng)
+    n = pos.shape[0]
+    vel = (rng.uniform(-1.0, 1.0, size=(n, 3)) * v0).astype(np.float32)
+    cols = [pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2]]
+    if apic:
+        aff = (rng.uniform(-1.0, 1.0, size=(n, 9)) * (0.1 / dx)).astype(np.float32)
+        cols += [aff[:, q] for q in range(9)]
+    streams = [torch.from_numpy(np.ascontiguousarray(c)).to(device) for c in cols]
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=device))
+    else:
+        counts[0][0] = n
+    base = int(sum(int(c.item()) for c in counts[:rank]))
+    ids = (torch.arange(n, dtype=torch.int64, device=device) + base).to(torch.int32)
+    return streams, ids, int(sum(int(c.item()) for c in counts))

@@ -106,6 +106,30 @@ int ffb200_set_particles(ffb200_context *ctx, int n, const float *pos, const flo
 int ffb200_get_particles(ffb200_context *ctx, float *pos, float *vel, float *affx, float *affy, float *affz);
 int ffb200_get_num_particles(ffb200_context *ctx, int *n);
 
+/* ---- device-resident access (multi-GPU plumbing: halo exchange and particle migration) ---------- */
+
+/* Raw DEVICE pointers of the context's resident arrays, valid until the next call that sorts,
+ * reallocates or destroys (a sort flips the particle double buffer). The slab driver wraps them
+ * as zero-copy tensors so NCCL can send/receive grid planes and particle streams in place. */
+typedef struct ffb200_device_buffers {
+    float *pos[3], *vel[3], *aff[9];   /* particle SoA streams, `capacity` floats each (aff may be NULL) */
+    uint32_t *ids;                     /* original / global particle id per slot */
+    int n, capacity;
+    float *field[3], *saved[3];        /* u, v, w components: face_count[d] floats, stored planes only */
+    uint8_t *valid[3];
+    long long face_count[3];
+    int face_plane[3];                 /* faces per z-plane (gi*gj) */
+    int kbase, kloc;                   /* first stored cell plane, number of stored cell planes */
+    int k_own_begin, k_own_end;
+    float *phi;
+} ffb200_device_buffers;
+int ffb200_get_device_buffers(ffb200_context *ctx, ffb200_device_buffers *out);
+/* Make room for `capacity` particles (contents are preserved), with affine streams if asked. */
+int ffb200_reserve_particles(ffb200_context *ctx, int capacity, int with_affine);
+/* Declare that the streams now hold n particles written through the device pointers (ids
+ * included); the next P2G re-bins and re-sorts them. */
+int ffb200_set_num_particles(ffb200_context *ctx, int n, int has_affine);
+
 /* Cell binning + stable sort (runs implicitly before P2G when positions changed). */
 int ffb200_sort_particles(ffb200_context *ctx);
 /* Per particle in ORIGINAL order: cell = flat reference cell index or -1 (grid3d.h:55-60,

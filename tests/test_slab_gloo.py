@@ -1,0 +1,92 @@
+"""CPU suite, world_size 2 over gloo: the z-slab driver (ghost particles, face halos, migration)
+against an undecomposed oracle run, bit-for-bit, for two substeps with particles crossing the
+slab boundary. Spawns two processes on 127.0.0.1."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _scene(apic):
+    from blender_flip_fluids_b200 import scenes
+    I, J, K, dx = 12, 10, 28, 0.05
+    sc = scenes.dam_break(12, apic=apic, dx=dx, dims=(I, J, K), vel="random", v0=0.6, seed=21)
+    sc.vel[:, 2] += np.where(sc.pos[:, 2] < 0.5 * K * dx, 0.9, -0.9).astype(np.float32)   # drive particles across k = 14
+    phi, near = scenes.analytic_solid_sdf(I, J, K, dx)
+    return I, J, K, dx, sc, phi, near
+
+
+def _streams(sc, apic, sel):
+    cols = [sc.pos[sel, 0], sc.pos[sel, 1], sc.pos[sel, 2], sc.vel[sel, 0], sc.vel[sel, 1], sc.vel[sel, 2]]
+    if apic:
+        for a in (sc.affx, sc.affy, sc.affz):
+            cols += [a[sel, 0], a[sel, 1], a[sel, 2]]
+    return [torch.from_numpy(np.ascontiguousarray(c)) for c in cols]
+
+
+def _worker(rank, world, port, apic, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from blender_flip_fluids_b200 import slab
+        from cpu_slab_backend import CpuOracleBackend
+        I, J, K, dx, sc, phi, near = _scene(apic)
+        kb, ke = slab.slab_range(K, world, rank)
+        be = CpuOracleBackend(I, J, K, dx, kb, ke, 7, apic)
+        be.set_solid(phi, near)
+        sim = slab.SlabSimulation(I, J, K, dx, rank, world, be, halo=7, ghost=2)
+        kz = np.floor(sc.pos[:, 2].astype(np.float64) * (1.0 / dx)).astype(np.int64)
+        sel = np.nonzero((kz >= kb) & (kz < ke))[0]
+        sim.set_particles(_streams(sc, apic, sel), torch.from_numpy(sel.astype(np.int32)))
+        dt = 1.5 * dx / 1.5
+        moved = 0
+        for _ in range(2):
+            before = set(sim.ids.tolist())
+            sim.step(sc.radius, 0.05, dt)
+            moved += len(set(sim.ids.tolist()) - before)
+        allp, ids = sim.gather_particles()
+        if rank == 0:
+            np.savez(out, streams=allp.numpy(), ids=ids.numpy(), moved=moved, exchanged=sim.exchanged_bytes)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("apic", [False, True])
+def test_slab_two_ranks_match_single_domain(tmp_path, apic, oracle):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "slab.npz")
+    mp.spawn(_worker, args=(2, port, apic, out), nprocs=2, join=True)
+    got = np.load(out)
+    I, J, K, dx, sc, phi, near = _scene(apic)
+    pos, vel = sc.pos.copy(), sc.vel.copy()
+    aff = [sc.affx, sc.affy, sc.affz] if apic else [None] * 3
+    dt = 1.5 * dx / 1.5
+    for _ in range(2):                                      # undecomposed: P2G -> save -> G2P -> advect
+        (u, v, w), _ = oracle.p2g(I, J, K, dx, sc.radius, oracle.APIC if apic else oracle.FLIP, pos, vel, *aff)
+        if apic:
+            vel, ax, ay, az = oracle.g2p_apic(I, J, K, dx, pos, (u, v, w))
+            aff = [ax, ay, az]
+        else:
+            vel = oracle.g2p_flip(I, J, K, dx, pos, vel, (u, v, w), (u, v, w), 0.05)
+        pos = oracle.advect(I, J, K, dx, pos, (u, v, w), phi, near, dt, 5.0, True)
+    want = [pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2]]
+    if apic:
+        for a in aff:
+            want += [a[:, 0], a[:, 1], a[:, 2]]
+    assert np.array_equal(got["ids"], np.arange(sc.n))
+    assert int(got["moved"]) > 0, "the scene must exercise migration"
+    for q, wq in enumerate(want):
+        assert got["streams"][q].tobytes() == np.ascontiguousarray(wq).tobytes(), f"stream {q} differs"
