@@ -20,6 +20,7 @@
 #include "ffb200_ctx.h"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace ffb200 {
 
@@ -62,6 +63,8 @@ struct SeamParams {
     int n;
 };
 
+constexpr uint32_t kEdgeBit = 1u << 30;
+
 // Per particle and direction: (a) mark the home block exactly as _initializeActiveBlocksThread
 // does (double _chunkdx, :240-251); (b) the inclusive block range the particle is sorted into,
 // exactly as _computeGridCountDataThread does (float blockdx, float sr, :306-352).
@@ -102,6 +105,13 @@ __global__ void k_seam_home(SeamParams s) {
             // out-of-range block indices can never match a face's block: park them at 255
             if (lo1 < 0 || lo1 > 254) { lo1 = 255; span = 0; }
             word |= ((uint32_t)lo1 | ((uint32_t)span << 8)) << (10 * a);
+            // "edge" particle: within a few float ulps of a cell plane in this direction's frame.
+            // There a float compare of block-local coordinates may disagree with the reference's
+            // double floor, so the transfer kernels give such particles the exact arithmetic.
+            const double t = (double)x[a] * s.g.inv_dx;
+            const double fr = t - floor(t);
+            const double band = 4e-6 + fabs(t) * 2.5e-7;
+            if (fr < band || fr > 1.0 - band) word |= kEdgeBit;
         }
         s.seam[(size_t)dir * s.cap + j] = word;
     }
@@ -317,8 +327,563 @@ __global__ void __launch_bounds__(256) k_p2g(P2GParams P) {
     P.valid[fidx] = sw > eps ? 1 : 0;
 }
 
+// ---- shared-memory brick kernel -------------------------------------------------------------------
+//
+// One CTA owns a brick of 10 x 5 x 5 faces, a quarter of ONE reference 10^3 block, so the block
+// frame (blockOrigin) and the block membership test are CTA-uniform. The particles of the
+// brick's bin region (22 x 12 x 12 half cells for the default radius) are staged into shared
+// memory once, already transformed: (p - offset) - blockOrigin as the reference forms it,
+// non-members parked at +inf so they fail every support test, near-plane ("edge") particles
+// diverted to a short list that takes the exact arithmetic. The face loop then costs one
+// LDS.128 (two for APIC) and ~15-35 ALU instructions per candidate instead of 5-8 global loads
+// and a membership decode. Summation order per face is unchanged (bin order), so results are
+// bit-identical to k_p2g except where edge particles are involved (they are added last).
+constexpr int kBrickX = 10, kBrickY = 5, kBrickZ = 5;
+constexpr int kBrickThreads = 256;
+constexpr int kMaxRows = 256;        // (2*5 - 2 + 2*wm)^2 with wm <= 4
+constexpr int kMaxRX = 26;           // 2*10 - 2 + 2*wm
+constexpr int kMaxFlagged = 96;
+
+template <int METHOD>
+struct BrickCap {
+    static constexpr int value = METHOD == FFB200_TRANSFER_APIC ? 1536 : 2048;
+};
+
+struct BrickShared {
+    uint32_t row_gstart[kMaxRows];
+    uint32_t row_off[kMaxRows + 1];
+    uint16_t binoff[kMaxRows][kMaxRX + 2];
+    int chunk_row[66];
+    int nchunks;
+    int nflag;
+    int oversize;
+    uint32_t flagged[kMaxFlagged];
+    uint32_t scan[33];
+};
+
+template <int DIR, int METHOD>
+__device__ __forceinline__ void accumulate_global(const P2GParams &P, const FaceFrame &f, float &sw, float &swv, int &cnt);
+
+template <int DIR, int METHOD>
+__global__ void __launch_bounds__(kBrickThreads) k_p2g_brick(P2GParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CAP = BrickCap<METHOD>::value;
+    float4 *rec = reinterpret_cast<float4 *>(smem_raw);
+    float4 *rec2 = rec + (METHOD == FFB200_TRANSFER_APIC ? CAP : 0);
+    BrickShared &S = *reinterpret_cast<BrickShared *>(smem_raw + sizeof(float4) * CAP * (METHOD == FFB200_TRANSFER_APIC ? 2 : 1));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // brick -> block and face origin
+    const int nbx = (int)blockIdx.x, nby = (int)(blockIdx.y >> 1), nbz = (int)(blockIdx.z >> 1) + P.g.kbase / kChunk;
+    const int o[3] = {nbx * kChunk, nby * kChunk + (int)(blockIdx.y & 1) * kBrickY,
+                      nbz * kChunk + (int)(blockIdx.z & 1) * kBrickZ};
+    const int nbv[3] = {nbx, nby, nbz};
+    const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
+    const int dims[3] = {P.gi, P.gj, P.gk};
+    const int bsz[3] = {kBrickX, kBrickY, kBrickZ};
+
+    // this thread's face
+    const int fxl = tid % kBrickX, fyl = (tid / kBrickX) % kBrickY, fzl = tid / (kBrickX * kBrickY);
+    const int n[3] = {o[0] + fxl, o[1] + fyl, o[2] + fzl};
+    const int ks = n[2] - P.g.kbase;
+    const bool live = tid < kBrickX * kBrickY * kBrickZ && n[0] < P.gi && n[1] < P.gj && n[2] < P.gk && ks >= 0 &&
+                      ks < P.kstore;
+    const size_t fidx = live ? (size_t)n[0] + (size_t)P.gi * ((size_t)n[1] + (size_t)P.gj * ks) : 0;
+
+    if (nbx >= P.bi || nby >= P.bj || nbz >= P.bk) return;
+    if (!P.active[nbx + P.bi * (nby + P.bj * nbz)]) {
+        if (live) { P.out[fidx] = 0.0f; P.wsum[fidx] = 0.0f; P.valid[fidx] = 0; }
+        return;
+    }
+
+    // region of bins the brick's faces can see, per axis (bin-grid coordinates)
+    int r0[3], rn[3];
+    float bpos[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const int last = min(o[a] + bsz[a] - 1, dims[a] - 1);
+        const int c0 = 2 * o[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+        const int c1 = 2 * last + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+        const int lo = max(c0 - P.wm, 0), hi = min(c1 + P.wm - 1, H[a] - 1);
+        r0[a] = lo;
+        rn[a] = max(hi - lo + 1, 0);
+        bpos[a] = idx2posf(nbv[a], P.chunk);
+    }
+    const int nrows = rn[1] * rn[2];
+
+    FaceFrame f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        f.nb[a] = nbv[a];
+        f.lo[a] = n[a] - nbv[a] * kChunk;
+        f.bpos[a] = bpos[a];
+        f.gpos[a] = idx2posf(f.lo[a], P.g.dx);
+        f.gposm[a] = idx2posf(f.lo[a] - 1, P.g.dx);
+        const int c = 2 * n[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+        f.h0[a] = max(c - P.wm, 0);
+        f.h1[a] = min(c + P.wm - 1, H[a] - 1);
+    }
+
+    // ---- row table: global start and length of every (hy, hz) row of the region --------------------
+    if (tid == 0) { S.nflag = 0; S.oversize = 0; }
+    uint32_t mylen = 0;
+    if (tid < nrows) {
+        const int ry = tid % rn[1], rz = tid / rn[1];
+        const size_t row = ((size_t)(r0[2] + rz) * P.g.HY + (r0[1] + ry)) * P.g.HX + r0[0];
+        const uint32_t s = __ldg(P.bin_start + row), e = __ldg(P.bin_start + row + rn[0]);
+        S.row_gstart[tid] = s;
+        mylen = e - s;
+    }
+    {   // exclusive scan of the row lengths (nrows <= 256 = blockDim)
+        uint32_t inc = mylen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) S.scan[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = lane < kBrickThreads / 32 ? S.scan[lane] : 0u, winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += t;
+            }
+            S.scan[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t ex = S.scan[warp] + inc - mylen;
+        if (tid < nrows) {
+            S.row_off[tid] = ex;
+            if (mylen > (uint32_t)CAP || mylen > 65535u) S.oversize = 1;
+        }
+        if (tid == nrows - 1 || (nrows == 0 && tid == 0)) S.row_off[nrows] = nrows ? ex + mylen : 0u;
+    }
+    // per-bin offsets inside each row
+    for (int t = tid; t < nrows * (rn[0] + 1); t += kBrickThreads) {
+        const int r = t / (rn[0] + 1), b = t - r * (rn[0] + 1);
+        const int ry = r % rn[1], rz = r / rn[1];
+        const size_t row = ((size_t)(r0[2] + rz) * P.g.HY + (r0[1] + ry)) * P.g.HX + r0[0];
+        S.binoff[r][b] = (uint16_t)(__ldg(P.bin_start + row + b) - __ldg(P.bin_start + row));
+    }
+    __syncthreads();
+    const uint32_t total = S.row_off[nrows];
+
+    float sw = 0.0f, swv = 0.0f;
+    int cnt = 0;
+    if (tid == 0 && !S.oversize) {   // greedy row chunks of at most CAP particles
+        int nc = 0, start = 0;
+        S.chunk_row[0] = 0;
+        for (int r = 0; r < nrows; r++) {
+            if (S.row_off[r + 1] - S.row_off[start] > (uint32_t)CAP) {
+                if (nc >= 63) { S.oversize = 1; break; }
+                S.chunk_row[++nc] = r;
+                start = r;
+            }
+        }
+        S.chunk_row[++nc] = nrows;
+        S.nchunks = nc;
+    }
+    __syncthreads();
+    if (S.oversize) {
+        // the region does not fit the staging scheme (hundreds of particles per half cell):
+        // this brick reads its candidates from global memory instead
+        if (live) accumulate_global<DIR, METHOD>(P, f, sw, swv, cnt);
+    } else if (total > 0) {
+        const int nchunks = S.nchunks;
+        for (int ch = 0; ch < nchunks; ch++) {
+            const int rc0 = S.chunk_row[ch], rc1 = S.chunk_row[ch + 1];
+            const uint32_t base = S.row_off[rc0];
+            // ---- stage: one warp per row, coalesced reads of the sorted streams -----------------------
+            for (int r = rc0 + warp; r < rc1; r += kBrickThreads / 32) {
+                const uint32_t g0 = S.row_gstart[r], len = S.row_off[r + 1] - S.row_off[r];
+                const uint32_t dst0 = S.row_off[r] - base;
+                for (uint32_t i = lane; i < len; i += 32) {
+                    const uint32_t q = g0 + i;
+                    const uint32_t word = __ldg(P.seam + q);
+                    const bool member = seam_member(word, nbv[0], nbv[1], nbv[2]);
+                    const bool edge = METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit) != 0;
+                    float4 v4;
+                    v4.x = (__ldg(P.px + q) - P.off[0]) - bpos[0];
+                    v4.y = (__ldg(P.py + q) - P.off[1]) - bpos[1];
+                    v4.z = (__ldg(P.pz + q) - P.off[2]) - bpos[2];
+                    v4.w = __ldg(P.vel + q);
+                    if (!member || edge) v4.x = __int_as_float(0x7f800000);     // +inf: fails every support test
+                    rec[dst0 + i] = v4;
+                    if (METHOD == FFB200_TRANSFER_APIC)
+                        rec2[dst0 + i] = make_float4(__ldg(P.ax + q), __ldg(P.ay + q), __ldg(P.az + q), 0.0f);
+                    if (member && edge) {
+                        const int slot = atomicAdd(&S.nflag, 1);
+                        if (slot < kMaxFlagged) S.flagged[slot] = q;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- face loop over the staged rows --------------------------------------------------------
+            if (live) {
+                const int xb0 = f.h0[0] - r0[0], xb1 = f.h1[0] + 1 - r0[0];
+                for (int hz = f.h0[2]; hz <= f.h1[2]; hz++) {
+                    const int rz = hz - r0[2];
+                    for (int hy = f.h0[1]; hy <= f.h1[1]; hy++) {
+                        const int r = rz * rn[1] + (hy - r0[1]);
+                        if (r < rc0 || r >= rc1) continue;
+                        const uint32_t rb = S.row_off[r] - base;
+                        const uint32_t s = rb + S.binoff[r][xb0], e = rb + S.binoff[r][xb1];
+                        for (uint32_t q = s; q < e; q++) {
+                            const float4 pr = rec[q];
+                            const float vx = f.gpos[0] - pr.x, vy = f.gpos[1] - pr.y, vz = f.gpos[2] - pr.z;
+                            if (METHOD == FFB200_TRANSFER_FLIP) {
+                                const float d2 = vx * vx + vy * vy + vz * vz;
+                                if (d2 < P.rsq) {
+                                    const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
+                                    swv += w * pr.w;
+                                    sw += w;
+                                    cnt++;
+                                }
+                            } else {
+                                const bool upx = vx <= 0.0f, upy = vy <= 0.0f, upz = vz <= 0.0f;
+                                const float t0 = (pr.x - (upx ? f.gpos[0] : f.gposm[0])) * P.inv_s;
+                                const float t1 = (pr.y - (upy ? f.gpos[1] : f.gposm[1])) * P.inv_s;
+                                const float t2 = (pr.z - (upz ? f.gpos[2] : f.gposm[2])) * P.inv_s;
+                                const float fx = upx ? 1.0f - t0 : t0;
+                                const float fy = upy ? 1.0f - t1 : t1;
+                                const float fz = upz ? 1.0f - t2 : t2;
+                                if (fx > 0.0f && fy > 0.0f && fz > 0.0f) {
+                                    const float4 af = rec2[q];
+                                    const float w = fx * fy * fz;
+                                    const float apic = af.x * vx + af.y * vy + af.z * vz;
+                                    swv += w * (pr.w + apic);
+                                    sw += w;
+                                    cnt++;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- edge particles: the reference's exact arithmetic, in a fixed (sorted) order ----------------
+        const int nflag = S.nflag;
+        if (nflag > kMaxFlagged) {
+            // pathological: redo this brick from global memory with the per-pair exact test
+            sw = 0.0f; swv = 0.0f; cnt = 0;
+            if (live) accumulate_global<DIR, METHOD>(P, f, sw, swv, cnt);
+        } else if (nflag > 0) {
+            if (tid == 0) {   // slots were claimed in arbitrary order: sort the few entries
+                for (int i = 1; i < nflag; i++) {
+                    const uint32_t key = S.flagged[i];
+                    int j = i - 1;
+                    while (j >= 0 && S.flagged[j] > key) { S.flagged[j + 1] = S.flagged[j]; j--; }
+                    S.flagged[j + 1] = key;
+                }
+            }
+            __syncthreads();
+            if (live) {
+                for (int i = 0; i < nflag; i++) {
+                    float w, wv;
+                    if (exact_contribution<DIR, METHOD>(P, f, S.flagged[i], w, wv)) {
+                        swv += wv;
+                        sw += w;
+                        cnt++;
+                    }
+                }
+            }
+        }
+    }
+
+    if (!live) return;
+    const float eps = 1e-6f;
+    if (fabsf(sw - eps) <= P.guard_abs + P.guard_per * (float)cnt) exact_face<DIR, METHOD>(P, f, sw, swv);
+    float s = swv;
+    if (sw > eps) s /= sw;                                     // :527-531
+    P.out[fidx] = s;                                           // write-out :155-162
+    P.wsum[fidx] = sw;
+    P.valid[fidx] = sw > eps ? 1 : 0;
+}
+
+// The candidate walk of k_p2g as a device function (fallback of the brick kernel).
+template <int DIR, int METHOD>
+__device__ __forceinline__ void accumulate_global(const P2GParams &P, const FaceFrame &f, float &sw, float &swv, int &cnt) {
+    for (int hz = f.h0[2]; hz <= f.h1[2]; hz++)
+        for (int hy = f.h0[1]; hy <= f.h1[1]; hy++) {
+            const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
+            const uint32_t s = __ldg(P.bin_start + row + f.h0[0]), e = __ldg(P.bin_start + row + f.h1[0] + 1);
+            for (uint32_t q = s; q < e; q++) {
+                float w, wv;
+                if (exact_contribution<DIR, METHOD>(P, f, q, w, wv)) {
+                    swv += wv;
+                    sw += w;
+                    cnt++;
+                }
+            }
+        }
+}
+
+// ---- coloured splat kernel ------------------------------------------------------------------------
+//
+// One CTA owns ONE reference 10^3-node block and keeps its 1000 (sum w, sum w*v) pairs in shared
+// memory. This is the reference's own per-block algorithm (each particle of the block is splat
+// onto its 2x2x2 nodes in the block-local frame, velocityadvector.cpp:467-623), parallelised
+// without atomics: the block's particles are grouped by "shifted cell" (the cell of the staggered
+// frame whose corner nodes are base + {0,1}^3); two shifted cells of the same parity class touch
+// disjoint node sets, so the 8 parity classes ("colours") are processed one after the other,
+// one thread per shifted cell, with a barrier in between. Every node receives exactly one cell
+// per colour, so the accumulation order is fixed: colour order, then the sorted particle order
+// inside the cell. Per particle the separable per-axis factors are computed once (6 instead of
+// 24 evaluations) and combined in the reference's operand order, so every weight is
+// bit-identical; only the summation order differs from the reference (guard band + exact_face).
+//
+// Particles on the 11^3 shifted cells around the block are read straight from the sorted
+// streams (each once per CTA, 1.33x redundancy between neighbouring blocks). APIC "edge"
+// particles (within a few ulps of a cell plane, flagged by k_seam_home) are left out of the fast
+// path, collected from the 13^3 cells around the block, sorted, and given exact_contribution().
+constexpr int kSplatThreads = 256;
+constexpr int kSplatFlagCap = 192;
+
+struct SplatShared {
+    float sw[kChunk * kChunk * kChunk];
+    float swv[kChunk * kChunk * kChunk];
+    uint32_t flagged[kSplatFlagCap];
+    int nflag;
+};
+
+template <int DIR, int METHOD>
+__global__ void __launch_bounds__(kSplatThreads) k_p2g_splat(P2GParams P) {
+    __shared__ SplatShared S;
+    const int tid = threadIdx.x;
+    const int nbv[3] = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + P.g.kbase / kChunk};
+    const int n0[3] = {nbv[0] * kChunk, nbv[1] * kChunk, nbv[2] * kChunk};
+    const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
+    const int dims[3] = {P.gi, P.gj, P.gk};
+    const bool active = P.active[nbv[0] + P.bi * (nbv[1] + P.bj * nbv[2])] != 0;
+
+    for (int t = tid; t < kChunk * kChunk * kChunk; t += kSplatThreads) { S.sw[t] = 0.0f; S.swv[t] = 0.0f; }
+    if (tid == 0) S.nflag = 0;
+    __syncthreads();
+
+    float bpos[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) bpos[a] = idx2posf(nbv[a], P.chunk);
+
+    if (active) {
+        for (int colour = 0; colour < 8; colour++) {
+            const int par[3] = {colour & 1, (colour >> 1) & 1, colour >> 2};
+            const int ci[3] = {tid % 6, (tid / 6) % 6, tid / 36};
+            int brel[3];
+            bool mine = tid < 216;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                brel[a] = par[a] + 2 * ci[a];            // 0..10: shifted cell relative to (block origin - 1)
+                mine = mine && brel[a] <= kChunk;
+            }
+            float aw[8], awv[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) { aw[c] = 0.0f; awv[c] = 0.0f; }
+            if (mine) {
+                int hb[3];
+                float gpos0[3], gpos1[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const int lo0 = brel[a] - 1;          // local index of the cell's lower node, -1..9
+                    gpos0[a] = idx2posf(lo0, P.g.dx);
+                    gpos1[a] = idx2posf(lo0 + 1, P.g.dx);
+                    hb[a] = 2 * (n0[a] + lo0) + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+                }
+                const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
+                if (hx0 <= hx1) {
+                    for (int dz = 0; dz < 2; dz++) {
+                        const int hz = hb[2] + dz;
+                        if (hz < 0 || hz >= H[2]) continue;
+                        for (int dy = 0; dy < 2; dy++) {
+                            const int hy = hb[1] + dy;
+                            if (hy < 0 || hy >= H[1]) continue;
+                            const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
+                            const uint32_t s = __ldg(P.bin_start + row + hx0), e = __ldg(P.bin_start + row + hx1 + 1);
+                            for (uint32_t q = s; q < e; q++) {
+                                const uint32_t word = __ldg(P.seam + q);
+                                if (!seam_member(word, nbv[0], nbv[1], nbv[2])) continue;
+                                if (METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit)) continue;   // exact path below
+                                const float xl0 = (__ldg(P.px + q) - P.off[0]) - bpos[0];
+                                const float xl1 = (__ldg(P.py + q) - P.off[1]) - bpos[1];
+                                const float xl2 = (__ldg(P.pz + q) - P.off[2]) - bpos[2];
+                                const float vel = __ldg(P.vel + q);
+                                // node - particle, per axis and per node (0: lower, 1: upper)
+                                const float vx[2] = {gpos0[0] - xl0, gpos1[0] - xl0};
+                                const float vy[2] = {gpos0[1] - xl1, gpos1[1] - xl1};
+                                const float vz[2] = {gpos0[2] - xl2, gpos1[2] - xl2};
+                                if (METHOD == FFB200_TRANSFER_FLIP) {
+                                    const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
+                                    const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
+                                    const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) {
+                                        const float d2 = xx[c & 1] + yy[(c >> 1) & 1] + zz[c >> 2];
+                                        if (d2 < P.rsq) {
+                                            const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
+                                            awv[c] += w * vel;
+                                            aw[c] += w;
+                                        }
+                                    }
+                                } else {
+                                    // ipos = (p - gpos) / dx and the (1 - ipos, ipos) factors of :574-592
+                                    const float t0 = (xl0 - gpos0[0]) * P.inv_s, t1 = (xl1 - gpos0[1]) * P.inv_s,
+                                                t2 = (xl2 - gpos0[2]) * P.inv_s;
+                                    const float fx[2] = {1.0f - t0, t0}, fy[2] = {1.0f - t1, t1}, fz[2] = {1.0f - t2, t2};
+                                    const float a0 = __ldg(P.ax + q), a1 = __ldg(P.ay + q), a2 = __ldg(P.az + q);
+                                    const float ax[2] = {a0 * vx[0], a0 * vx[1]};
+                                    const float ay[2] = {a1 * vy[0], a1 * vy[1]};
+                                    const float az[2] = {a2 * vz[0], a2 * vz[1]};
+#pragma unroll
+                                    for (int c = 0; c < 8; c++) {
+                                        const float w = fx[c & 1] * fy[(c >> 1) & 1] * fz[c >> 2];
+                                        const float apic = ax[c & 1] + ay[(c >> 1) & 1] + az[c >> 2];
+                                        awv[c] += w * (vel + apic);
+                                        aw[c] += w;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int lx = brel[0] - 1 + (c & 1), ly = brel[1] - 1 + ((c >> 1) & 1), lz = brel[2] - 1 + (c >> 2);
+                    if ((unsigned)lx < (unsigned)kChunk && (unsigned)ly < (unsigned)kChunk && (unsigned)lz < (unsigned)kChunk) {
+                        const int idx = lx + kChunk * (ly + kChunk * lz);
+                        S.sw[idx] += aw[c];               // one shifted cell per colour touches a node: no race
+                        S.swv[idx] += awv[c];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (METHOD == FFB200_TRANSFER_APIC) {
+            // edge particles of the 13^3 shifted cells around the block
+            for (int t = tid; t < 13 * 13 * 13; t += kSplatThreads) {
+                const int cr[3] = {t % 13, (t / 13) % 13, t / 169};
+                int hb[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++)
+                    hb[a] = 2 * (n0[a] - 2 + cr[a]) + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+                const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
+                if (hx0 > hx1) continue;
+                for (int dz = 0; dz < 2; dz++) {
+                    const int hz = hb[2] + dz;
+                    if (hz < 0 || hz >= H[2]) continue;
+                    for (int dy = 0; dy < 2; dy++) {
+                        const int hy = hb[1] + dy;
+                        if (hy < 0 || hy >= H[1]) continue;
+                        const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
+                        const uint32_t s = __ldg(P.bin_start + row + hx0), e = __ldg(P.bin_start + row + hx1 + 1);
+                        for (uint32_t q = s; q < e; q++) {
+                            const uint32_t word = __ldg(P.seam + q);
+                            if ((word & kEdgeBit) && seam_member(word, nbv[0], nbv[1], nbv[2])) {
+                                const int slot = atomicAdd(&S.nflag, 1);
+                                if (slot < kSplatFlagCap) S.flagged[slot] = q;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {   // slots were claimed in arbitrary order: put the few entries in sorted order
+                const int m = min(S.nflag, kSplatFlagCap);
+                for (int i = 1; i < m; i++) {
+                    const uint32_t key = S.flagged[i];
+                    int j = i - 1;
+                    while (j >= 0 && S.flagged[j] > key) { S.flagged[j + 1] = S.flagged[j]; j--; }
+                    S.flagged[j + 1] = key;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue: one pass over the block's nodes -------------------------------------------------
+    const int nflag = S.nflag;
+    for (int t = tid; t < kChunk * kChunk * kChunk; t += kSplatThreads) {
+        const int l[3] = {t % kChunk, (t / kChunk) % kChunk, t / (kChunk * kChunk)};
+        const int n[3] = {n0[0] + l[0], n0[1] + l[1], n0[2] + l[2]};
+        const int ks = n[2] - P.g.kbase;
+        if (n[0] >= P.gi || n[1] >= P.gj || n[2] >= P.gk || ks < 0 || ks >= P.kstore) continue;
+        const size_t fidx = (size_t)n[0] + (size_t)P.gi * ((size_t)n[1] + (size_t)P.gj * ks);
+        float sw = S.sw[t], swv = S.swv[t];
+        if (active) {
+            FaceFrame f;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                f.nb[a] = nbv[a];
+                f.lo[a] = l[a];
+                f.bpos[a] = bpos[a];
+                f.gpos[a] = idx2posf(l[a], P.g.dx);
+                f.gposm[a] = idx2posf(l[a] - 1, P.g.dx);
+                const int c = 2 * n[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+                f.h0[a] = max(c - P.wm, 0);
+                f.h1[a] = min(c + P.wm - 1, H[a] - 1);
+            }
+            bool redo = nflag > kSplatFlagCap;            // pathological: more edge particles than the list holds
+            if (!redo) {
+                for (int i = 0; i < nflag; i++) {
+                    float w, wv;
+                    if (exact_contribution<DIR, METHOD>(P, f, S.flagged[i], w, wv)) {
+                        swv += wv;
+                        sw += w;
+                    }
+                }
+            }
+            const float eps = 1e-6f;
+            if (redo || fabsf(sw - eps) <= P.guard_abs + P.guard_per * 512.0f) exact_face<DIR, METHOD>(P, f, sw, swv);
+        }
+        const float eps = 1e-6f;
+        float s = swv;
+        if (sw > eps) s /= sw;                                 // :527-531
+        P.out[fidx] = s;                                       // write-out :155-162
+        P.wsum[fidx] = sw;
+        P.valid[fidx] = sw > eps ? 1 : 0;
+    }
+}
+
+template <int DIR, int METHOD>
+void launch_splat(Context &c, P2GParams &P) {
+    const int zb0 = P.g.kbase / kChunk, zb1 = (P.g.kbase + P.kstore - 1) / kChunk;
+    dim3 grid(P.bi, P.bj, zb1 - zb0 + 1);
+    k_p2g_splat<DIR, METHOD><<<grid, kSplatThreads, 0, c.stream>>>(P);
+}
+
+template <int DIR, int METHOD>
+void launch_brick(Context &c, P2GParams &P) {
+    constexpr int CAP = BrickCap<METHOD>::value;
+    const size_t smem = sizeof(float4) * CAP * (METHOD == FFB200_TRANSFER_APIC ? 2 : 1) + sizeof(BrickShared);
+    static bool configured = false;
+    if (!configured) {
+        FFB_CUDA(cudaFuncSetAttribute(k_p2g_brick<DIR, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int zb0 = P.g.kbase / kChunk, zb1 = (P.g.kbase + P.kstore - 1) / kChunk;
+    dim3 grid(P.bi, P.bj * 2, (zb1 - zb0 + 1) * 2);
+    k_p2g_brick<DIR, METHOD><<<grid, kBrickThreads, smem, c.stream>>>(P);
+}
+
 template <int DIR>
-void launch_dir(Context &c, P2GParams &P, int method) {
+void launch_dir(Context &c, P2GParams &P, int method, int variant) {
+    // variant 0: coloured splat (support of one cell: default radius and APIC); 1: brick gather
+    // (any radius up to 2 dx); 2: first-generation global gather. FFB200_P2G_VARIANT overrides.
+    if (variant == 0 && P.wm == 2) {
+        if (method == FFB200_TRANSFER_APIC)
+            launch_splat<DIR, FFB200_TRANSFER_APIC>(c, P);
+        else
+            launch_splat<DIR, FFB200_TRANSFER_FLIP>(c, P);
+        return;
+    }
+    if (variant <= 1) {
+        if (method == FFB200_TRANSFER_APIC)
+            launch_brick<DIR, FFB200_TRANSFER_APIC>(c, P);
+        else
+            launch_brick<DIR, FFB200_TRANSFER_FLIP>(c, P);
+        return;
+    }
     dim3 block(32, 4, 2);
     dim3 grid((P.gi + block.x - 1) / block.x, (P.gj + block.y - 1) / block.y, (P.kstore + block.z - 1) / block.z);
     if (method == FFB200_TRANSFER_APIC)
@@ -377,6 +942,8 @@ int launch_p2g(Context &c, double radius, int method) {
     ParticleSoA &s = c.soa[c.cur];
     const float eps = 1e-6f;
     const float sr = (float)(radius + (double)eps);            // float sr = _particleRadius + eps;
+    // FFB200_P2G_VARIANT: 0 coloured splat (default), 1 brick gather, 2 first-generation global gather
+    static const int variant = [] { const char *e = std::getenv("FFB200_P2G_VARIANT"); return e ? std::atoi(e) : 0; }();
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];
         P2GParams P;
@@ -411,9 +978,9 @@ int launch_p2g(Context &c, double radius, int method) {
         if (P.wm > kApron) throw CudaError("ffb200_p2g: particle radius above 2*dx is not supported");
         P.guard_abs = c.guard_abs >= 0.f ? c.guard_abs : 1e-9f;
         P.guard_per = c.guard_per >= 0.f ? c.guard_per : 1e-12f;
-        if (d == 0) launch_dir<0>(c, P, method);
-        if (d == 1) launch_dir<1>(c, P, method);
-        if (d == 2) launch_dir<2>(c, P, method);
+        if (d == 0) launch_dir<0>(c, P, method, variant);
+        if (d == 1) launch_dir<1>(c, P, method, variant);
+        if (d == 2) launch_dir<2>(c, P, method, variant);
         launches++;
     }
     FFB_CUDA(cudaGetLastError());
