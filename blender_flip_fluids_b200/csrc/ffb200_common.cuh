@@ -74,40 +74,61 @@ __device__ __forceinline__ bool pos_in_grid(double x, double y, double z, const 
     return x >= 0 && y >= 0 && z >= 0 && x < g.dx * g.I && y < g.dx * g.J && z < g.dx * g.K;
 }
 
-// MACVelocityField::_interpolateLinear{U,V,W} (macvelocityfield.cpp:519-613). COMP selects the
-// component; the caller has already done the isPositionInGrid test on the unshifted position.
-// Out-of-range corners read as 0 (_outOfRangeVector default, macvelocityfield.cpp:537-546).
+// One axis of the reference's index/fraction maths (macvelocityfield.cpp:527-535):
+// i = floor(x * (1/dx)), ix = (x - i*dx) * (1/dx), all in double.
+struct AxisCoord {
+    int i;
+    double f;
+};
+__device__ __forceinline__ AxisCoord axis_coord(double x, const GridDesc &g) {
+    AxisCoord c;
+    c.i = pos2idx(x, g.inv_dx);
+    c.f = (x - (double)c.i * g.dx) * g.inv_dx;
+    return c;
+}
+
+// MACVelocityField::_interpolateLinear{U,V,W} (macvelocityfield.cpp:519-613) for one component,
+// given the per-axis index/fraction of that component's staggered frame. Out-of-range corners
+// read as 0 (_outOfRangeVector default, macvelocityfield.cpp:537-546); the common interior case
+// skips the eight range tests. The blend is trilerp8: the reference's corner and term order.
 template <int COMP>
-__device__ __forceinline__ double mac_lerp(const GridDesc &g, const float *__restrict__ f, double x, double y, double z) {
+__device__ __forceinline__ double mac_lerp(const GridDesc &g, const float *__restrict__ f, const AxisCoord &cx,
+                                           const AxisCoord &cy, const AxisCoord &cz) {
     const int gw = g.I + (COMP == 0), gh = g.J + (COMP == 1), gd = g.K + (COMP == 2);
-    const double hdx = 0.5 * g.dx;
-    if (COMP != 0) x -= hdx;
-    if (COMP != 1) y -= hdx;
-    if (COMP != 2) z -= hdx;
-    const int i = pos2idx(x, g.inv_dx), j = pos2idx(y, g.inv_dx), k = pos2idx(z, g.inv_dx);
-    const double ix = (x - (double)i * g.dx) * g.inv_dx;
-    const double iy = (y - (double)j * g.dx) * g.inv_dx;
-    const double iz = (z - (double)k * g.dx) * g.inv_dx;
-    const bool i0 = (unsigned)i < (unsigned)gw, i1 = (unsigned)(i + 1) < (unsigned)gw;
-    const bool j0 = (unsigned)j < (unsigned)gh, j1 = (unsigned)(j + 1) < (unsigned)gh;
-    const bool k0 = (unsigned)k < (unsigned)gd, k1 = (unsigned)(k + 1) < (unsigned)gd;
+    const int i = cx.i, j = cy.i, k = cz.i;
     // stored planes start at kbase; callers guarantee the halo covers every sampled plane
     const long long sj = gw, sk = (long long)gw * gh;
-    const long long base = (long long)i + sj * j + sk * (long long)(k - g.kbase);
+    const float *b = f + ((long long)i + sj * j + sk * (long long)(k - g.kbase));
     double p[8];
-    p[0] = (i0 && j0 && k0) ? (double)__ldg(f + base) : 0.0;
-    p[1] = (i1 && j0 && k0) ? (double)__ldg(f + base + 1) : 0.0;
-    p[2] = (i0 && j1 && k0) ? (double)__ldg(f + base + sj) : 0.0;
-    p[3] = (i0 && j0 && k1) ? (double)__ldg(f + base + sk) : 0.0;
-    p[4] = (i1 && j0 && k1) ? (double)__ldg(f + base + sk + 1) : 0.0;
-    p[5] = (i0 && j1 && k1) ? (double)__ldg(f + base + sk + sj) : 0.0;
-    p[6] = (i1 && j1 && k0) ? (double)__ldg(f + base + sj + 1) : 0.0;
-    p[7] = (i1 && j1 && k1) ? (double)__ldg(f + base + sk + sj + 1) : 0.0;
-    return trilerp8(p, ix, iy, iz);
+    if ((unsigned)i < (unsigned)(gw - 1) && (unsigned)j < (unsigned)(gh - 1) && (unsigned)k < (unsigned)(gd - 1)) {
+        p[0] = (double)__ldg(b);
+        p[1] = (double)__ldg(b + 1);
+        p[2] = (double)__ldg(b + sj);
+        p[3] = (double)__ldg(b + sk);
+        p[4] = (double)__ldg(b + sk + 1);
+        p[5] = (double)__ldg(b + sk + sj);
+        p[6] = (double)__ldg(b + sj + 1);
+        p[7] = (double)__ldg(b + sk + sj + 1);
+    } else {
+        const bool i0 = (unsigned)i < (unsigned)gw, i1 = (unsigned)(i + 1) < (unsigned)gw;
+        const bool j0 = (unsigned)j < (unsigned)gh, j1 = (unsigned)(j + 1) < (unsigned)gh;
+        const bool k0 = (unsigned)k < (unsigned)gd, k1 = (unsigned)(k + 1) < (unsigned)gd;
+        p[0] = (i0 && j0 && k0) ? (double)__ldg(b) : 0.0;
+        p[1] = (i1 && j0 && k0) ? (double)__ldg(b + 1) : 0.0;
+        p[2] = (i0 && j1 && k0) ? (double)__ldg(b + sj) : 0.0;
+        p[3] = (i0 && j0 && k1) ? (double)__ldg(b + sk) : 0.0;
+        p[4] = (i1 && j0 && k1) ? (double)__ldg(b + sk + 1) : 0.0;
+        p[5] = (i0 && j1 && k1) ? (double)__ldg(b + sk + sj) : 0.0;
+        p[6] = (i1 && j1 && k0) ? (double)__ldg(b + sj + 1) : 0.0;
+        p[7] = (i1 && j1 && k1) ? (double)__ldg(b + sk + sj + 1) : 0.0;
+    }
+    return trilerp8(p, cx.f, cy.f, cz.f);
 }
 
 // MACVelocityField::evaluateVelocityAtPositionLinear(vec3) (macvelocityfield.cpp:631-645):
 // float position widened to double, zero outside the grid, components narrowed to float.
+// Each axis needs its index/fraction twice only: in the unshifted frame (the component
+// normal to it) and shifted by half a cell (the two other components).
 __device__ __forceinline__ void mac_eval(const GridDesc &g, const MacView &m, float px, float py, float pz,
                                          float &ox, float &oy, float &oz) {
     const double x = px, y = py, z = pz;
@@ -115,9 +136,12 @@ __device__ __forceinline__ void mac_eval(const GridDesc &g, const MacView &m, fl
         ox = oy = oz = 0.0f;
         return;
     }
-    ox = (float)mac_lerp<0>(g, m.u, x, y, z);
-    oy = (float)mac_lerp<1>(g, m.v, x, y, z);
-    oz = (float)mac_lerp<2>(g, m.w, x, y, z);
+    const double hdx = 0.5 * g.dx;
+    const AxisCoord xu = axis_coord(x, g), yu = axis_coord(y, g), zu = axis_coord(z, g);
+    const AxisCoord xs = axis_coord(x - hdx, g), ys = axis_coord(y - hdx, g), zs = axis_coord(z - hdx, g);
+    ox = (float)mac_lerp<0>(g, m.u, xu, ys, zs);
+    oy = (float)mac_lerp<1>(g, m.v, xs, yu, zs);
+    oz = (float)mac_lerp<2>(g, m.w, xs, ys, zu);
 }
 
 // ---- error handling -------------------------------------------------------------------------

@@ -10,6 +10,10 @@
 //          block's particles (velocityadvector.cpp:383-413).
 #include "ffb200_ctx.h"
 
+#include <cstdlib>
+#include <string>
+#include <utility>
+
 namespace ffb200 {
 
 namespace {
@@ -72,6 +76,29 @@ __global__ void k_keys(GridDesc g, const float *__restrict__ px, const float *__
     key[j] = k;
     val[j] = (uint32_t)j;
     atomicAdd(bin_count + k, 1u);
+}
+
+// Counting-sort flavour: besides the key, keep the particle's arrival rank in its bin.
+__global__ void k_keys_rank(GridDesc g, const float *__restrict__ px, const float *__restrict__ py,
+                            const float *__restrict__ pz, uint32_t *__restrict__ key, uint32_t *__restrict__ rank,
+                            uint32_t *__restrict__ bin_count, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t k = half_cell_key(g, px[j], py[j], pz[j]);
+    key[j] = k;
+    rank[j] = atomicAdd(bin_count + k, 1u);
+}
+
+// slot = bin_start[key] + rank; sorted position -> (key, source slot).
+__global__ void k_place(const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
+                        const uint32_t *__restrict__ bin_start, uint32_t *__restrict__ key_out,
+                        uint32_t *__restrict__ val_out, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t k = key[j];
+    const uint32_t dst = bin_start[k] + rank[j];
+    key_out[dst] = k;
+    val_out[dst] = (uint32_t)j;
 }
 
 // ---- exclusive scan (reduce / scan partials / apply) ---------------------------------------------------
@@ -341,10 +368,17 @@ int launch_sort(Context &c) {
     ParticleSoA &src = c.soa[c.cur], &dst = c.soa[c.cur ^ 1];
     SortScratch &s = c.sort;
 
+    // FFB200_SORT=radix selects the multi-pass LSD radix sort; the default is the single-pass
+    // counting sort (radix = the whole key), possible because the dense bin table is needed anyway.
+    static const bool use_radix = [] { const char *e = std::getenv("FFB200_SORT"); return e && std::string(e) == "radix"; }();
+
     // bin histogram + keys
     FFB_CUDA(cudaMemsetAsync(s.bin_start, 0, ((size_t)g.nbins + 2) * sizeof(uint32_t), c.stream));
     if (n > 0) {
-        k_keys<<<blocks_for(n, 256), 256, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
+        if (use_radix)
+            k_keys<<<blocks_for(n, 256), 256, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
+        else
+            k_keys_rank<<<blocks_for(n, 256), 256, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
         launches++;
     }
     launches += exclusive_scan_inplace(c, s.bin_start, (size_t)g.nbins + 2);
@@ -353,6 +387,15 @@ int launch_sort(Context &c) {
         return launches;
     }
 
+    if (!use_radix) {
+        // slot = bin_start[key] + arrival rank. The arrival order inside a bin is arbitrary (integer
+        // atomics); k_reorder re-ranks the members of every multi-particle bin by original index,
+        // so the final order is the deterministic (key, original index) order all the same.
+        k_place<<<blocks_for(n, 256), 256, 0, c.stream>>>(s.key[0], s.val[0], s.bin_start, s.key[1], s.val[1], n);
+        launches++;
+        std::swap(s.key[0], s.key[1]);
+        std::swap(s.val[0], s.val[1]);
+    } else {
     // radix passes over the bits of [0, nbins]
     int bits = 1;
     while (bits < 32 && (g.nbins >> bits) != 0u) bits++;
@@ -385,6 +428,7 @@ int launch_sort(Context &c) {
     if (in != 0) {       // keep the sorted keys/vals in buffer 0 for later readers
         std::swap(s.key[0], s.key[1]);
         std::swap(s.val[0], s.val[1]);
+    }
     }
 
     ReorderArgs a;
