@@ -264,7 +264,8 @@ def main():
             # fixed batch: every step starts from the same resident particle streams (the tensors are
             # not modified by step(), which builds new ones) and does the full exchange + stage work
             sim.set_particles(*pristine)
-            sim.step(radius, ratio, dt)
+            sim.load_resident()           # D2D restore of the pristine batch (inside the timed region)
+            sim.step_fast(radius, ratio, dt)
 
     # ---- device-resident timing ----------------------------------------------------------------
     for _ in range(warmup):
@@ -370,9 +371,12 @@ def main():
         def e2e_step():
             dev = [t.to(backend.device, non_blocking=True) for t in host_in]
             sim.set_particles(dev[:-1], dev[-1])
-            sim.step(radius, ratio, dt)
+            sim.load_resident()
+            sim.step_fast(radius, ratio, dt)
+            views, _ = backend.particle_views()
             for q in range(6):
-                host_out[q][:sim.streams[q].shape[0]].copy_(sim.streams[q][:host_out[q].shape[0]], non_blocking=True)
+                m = min(views[q].shape[0], host_out[q].shape[0])
+                host_out[q][:m].copy_(views[q][:m], non_blocking=True)
 
         for _ in range(2):
             e2e_step()

@@ -151,6 +151,7 @@ void destroy_impl(ContextImpl *c) {
     }
     dev_free(c->phi);
     dev_free(c->near_solid);
+    dev_free(c->slab_counters);
     for (int s = 0; s < kNumStages; s++) {
         if (c->evs.start[s]) cudaEventDestroy(c->evs.start[s]);
         if (c->evs.stop[s]) cudaEventDestroy(c->evs.stop[s]);
@@ -212,6 +213,7 @@ int create_impl(ffb200_context **out, int I, int J, int K, double dx, int device
         c->ni = (int)std::ceil(I * dx / cell); c->nj = (int)std::ceil(J * dx / cell); c->nk = (int)std::ceil(K * dx / cell);
         dev_alloc(c->phi, (size_t)(I + 1) * (J + 1) * (g.kloc + 1));
         dev_alloc(c->near_solid, (size_t)c->ni * c->nj * c->nk);
+        dev_alloc(c->slab_counters, 4);
         FFB_CUDA(cudaStreamSynchronize(c->stream));
         *out = reinterpret_cast<ffb200_context *>(static_cast<Context *>(c));
         return FFB200_SUCCESS;
@@ -476,6 +478,39 @@ int ffb200_set_num_particles(ffb200_context *ctx, int n, int has_affine) {
         c.n = n;
         c.has_affine = has_affine != 0;
         c.sorted = false;
+    });
+}
+
+int ffb200_slab_record_floats(ffb200_context *ctx, int *floats_per_particle) {
+    return guarded("ffb200_slab_record_floats", ctx, [&](Context &c) {
+        if (!floats_per_particle) throw std::invalid_argument("null output pointer");
+        *floats_per_particle = slab_rows(c);
+    });
+}
+
+int ffb200_slab_pack_layers(ffb200_context *ctx, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b, float *block_b,
+                            int block_capacity) {
+    return guarded("ffb200_slab_pack_layers", ctx, [&](Context &c) {
+        if (block_capacity <= 0) throw std::domain_error("block capacity must be positive");
+        launch_pack_layers(c, lo_a, hi_a, block_a, lo_b, hi_b, block_b, block_capacity);
+    });
+}
+
+int ffb200_slab_route(ffb200_context *ctx, int k_begin, int k_end, float *block_up, float *block_down, int block_capacity,
+                      int *counts) {
+    return guarded("ffb200_slab_route", ctx, [&](Context &c) {
+        if (!counts) throw std::invalid_argument("null counts pointer");
+        if ((block_up || block_down) && block_capacity <= 0) throw std::domain_error("block capacity must be positive");
+        launch_route(c, k_begin, k_end, block_up, block_down, block_capacity, counts);
+    });
+}
+
+int ffb200_slab_append(ffb200_context *ctx, const float *block, int count) {
+    return guarded("ffb200_slab_append", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (count < 0 || (count > 0 && !block)) throw std::invalid_argument("bad packed block");
+        if (c.n + count > c.cap) ensure_capacity(c, c.n + count + (c.n + count) / 8, c.has_affine, true);
+        launch_append(c, block, count);
     });
 }
 

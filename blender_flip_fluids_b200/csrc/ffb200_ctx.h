@@ -80,6 +80,7 @@ struct Context {
     bool has_solid = false;
 
     float guard_abs = -1.f, guard_per = -1.f;
+    int *slab_counters = nullptr;        // 4 device ints for the slab pack/route kernels
     bool nondestructive = false;         // G2P/advect write to the spare SoA buffer (fixed-batch benchmarking)
     ffb200_timing timing = {};
 };
@@ -102,5 +103,11 @@ int launch_g2p(Context &c, int method, double ratio);
 
 // ffb200_advect.cu
 int launch_advect(Context &c, double dt, double cfl, int collide);
+
+// ffb200_slab.cu
+int slab_rows(Context &c);
+int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b, float *block_b, int cap);
+int launch_route(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int counts_host[3]);
+int launch_append(Context &c, const float *block, int count);
 
 }  // namespace ffb200

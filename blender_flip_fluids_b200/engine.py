@@ -68,6 +68,10 @@ SIGNATURES = {
     "ffb200_get_device_buffers": [C.c_void_p, C.POINTER(DeviceBuffers)],
     "ffb200_reserve_particles": [C.c_void_p, C.c_int, C.c_int],
     "ffb200_set_num_particles": [C.c_void_p, C.c_int, C.c_int],
+    "ffb200_slab_record_floats": [C.c_void_p, C.POINTER(C.c_int)],
+    "ffb200_slab_pack_layers": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int],
+    "ffb200_slab_route": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
+    "ffb200_slab_append": [C.c_void_p, C.c_void_p, C.c_int],
     "ffb200_sort_particles": [C.c_void_p],
     "ffb200_get_binning": [C.c_void_p, _i32p, _u32p, _u32p],
     "ffb200_set_velocity_field": [C.c_void_p] + [_f32p] * 3,
@@ -211,6 +215,26 @@ class FlipContext:
     def set_num_particles(self, n, has_affine=False):
         self._call("ffb200_set_num_particles", int(n), 1 if has_affine else 0)
         self.n = int(n)
+
+    def slab_record_floats(self):
+        r = C.c_int()
+        self._call("ffb200_slab_record_floats", C.byref(r))
+        return r.value
+
+    def slab_pack_layers(self, lo_a, hi_a, ptr_a, lo_b, hi_b, ptr_b, capacity):
+        self._call("ffb200_slab_pack_layers", int(lo_a), int(hi_a), C.c_void_p(ptr_a or 0), int(lo_b), int(hi_b),
+                   C.c_void_p(ptr_b or 0), int(capacity))
+
+    def slab_route(self, k_begin, k_end, ptr_up, ptr_down, capacity):
+        counts = (C.c_int * 3)()
+        self._call("ffb200_slab_route", int(k_begin), int(k_end), C.c_void_p(ptr_up or 0), C.c_void_p(ptr_down or 0),
+                   int(capacity), counts)
+        self.n = counts[0]
+        return counts[0], counts[1], counts[2]
+
+    def slab_append(self, ptr, count):
+        self._call("ffb200_slab_append", C.c_void_p(ptr), int(count))
+        self.n += int(count)
 
     def sort_particles(self):
         self._call("ffb200_sort_particles")

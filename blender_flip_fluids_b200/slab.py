@@ -113,6 +113,28 @@ class GpuBackend:
     def synchronize(self):
         torch.cuda.synchronize(self.device)
 
+    # ---- device-side plumbing (ffb200_slab.cu) ---------------------------------------------------
+    fast = True
+
+    def record_floats(self):
+        return self.ctx.slab_record_floats()
+
+    def new_block(self, capacity):
+        """Packed-record buffer: capacity records + a 4-int header {count, overflowed, 0, 0}."""
+        return torch.zeros(capacity * self.record_floats() + 4, dtype=torch.float32, device=self.device)
+
+    def pack_layers(self, lo_a, hi_a, block_a, lo_b, hi_b, block_b, capacity):
+        self.ctx.slab_pack_layers(lo_a, hi_a, block_a.data_ptr() if block_a is not None else 0, lo_b, hi_b,
+                                  block_b.data_ptr() if block_b is not None else 0, capacity)
+
+    def route(self, k_begin, k_end, block_up, block_down, capacity):
+        return self.ctx.slab_route(k_begin, k_end, block_up.data_ptr() if block_up is not None else 0,
+                                   block_down.data_ptr() if block_down is not None else 0, capacity)
+
+    def append(self, block, count):
+        if count:
+            self.ctx.slab_append(block.data_ptr(), count)
+
 
 class SlabSimulation:
     def __init__(self, I, J, K, dx, rank, world, backend, halo=7, ghost=2):
@@ -216,7 +238,86 @@ class SlabSimulation:
         for recv, buf in keep:
             recv.copy_(buf)
 
-    # ---- one substep ----------------------------------------------------------------------------------
+    # ---- one substep, device-side plumbing (GpuBackend) ----------------------------------------------
+    INT_MIN, INT_MAX = -(2 ** 31), 2 ** 31 - 1
+
+    def load_resident(self):
+        """Make the backend's resident streams the authoritative particle state (fast path)."""
+        self.backend.load_particles(self.streams, self.ids)
+        self._resident = True
+
+    def _blocks(self, need):
+        cap = getattr(self, "_block_cap", 0)
+        if cap < need:
+            cap = max(8192, int(need))
+            self._block_cap = cap
+            self._blk = {k: self.backend.new_block(cap) for k in ("up_send", "up_recv", "dn_send", "dn_recv")}
+        return self._block_cap, self._blk
+
+    def _swap_blocks(self, cap, b):
+        """Exchange the fixed-size packed buffers with both neighbours; returns the received counts."""
+        rows = self.backend.record_floats()
+        ops = []
+        if self.up is not None:
+            ops += [dist.P2POp(dist.isend, b["up_send"], self.up), dist.P2POp(dist.irecv, b["up_recv"], self.up)]
+        if self.down is not None:
+            ops += [dist.P2POp(dist.isend, b["dn_send"], self.down), dist.P2POp(dist.irecv, b["dn_recv"], self.down)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        hdr = torch.stack([b[k][cap * rows:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()
+        self.exchanged_bytes += (int(hdr[0, 0]) + int(hdr[1, 0])) * rows * 4
+        if int(hdr[:, 1].max()) != 0 and (self.up is not None or self.down is not None):
+            return None                                     # some buffer overflowed: caller retries with a larger one
+        n_up = int(hdr[2, 0]) if self.up is not None else 0
+        n_dn = int(hdr[3, 0]) if self.down is not None else 0
+        return n_dn, n_up
+
+    def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True):
+        be = self.backend
+        n0 = be.ctx.n
+        g = self.ghost
+        cap, b = self._blocks(max(8192, int(0.03 * n0)))
+        # 1. ghost layers -> neighbours (copies), appended behind the owned particles
+        while True:
+            be.pack_layers(self.ke - g, self.ke, b["up_send"] if self.up is not None else None,
+                           self.kb, self.kb + g, b["dn_send"] if self.down is not None else None, cap)
+            got = self._swap_blocks(cap, b)
+            if got is not None:
+                break
+            cap, b = self._blocks(cap * 2)
+        be.append(b["dn_recv"], got[0])
+        be.append(b["up_recv"], got[1])
+        # 2. P2G on owned + ghost particles
+        be.p2g(radius)
+        # 3. drop the ghosts again (the end ranks keep whatever strayed past the domain)
+        kb = self.kb if self.down is not None else self.INT_MIN
+        ke = self.ke if self.up is not None else self.INT_MAX
+        be.route(kb, ke, None, None, cap)
+        # 4. face halos, saved copy
+        self._halo_exchange()
+        be.save_field()
+        # 5. G2P + advection on the owned particles
+        be.g2p(ratio)
+        be.advect(dt, cfl, collide)
+        # 6. migration
+        while True:
+            stay, nu, nd = be.route(kb, ke, b["up_send"] if self.up is not None else None,
+                                    b["dn_send"] if self.down is not None else None, cap)
+            got = self._swap_blocks(cap, b)
+            if got is not None:
+                break
+            raise RuntimeError("migration buffer overflow: more than %d particles left the slab in one substep" % cap)
+        be.append(b["dn_recv"], got[0])
+        be.append(b["up_recv"], got[1])
+
+    def sync_from_backend(self):
+        """Pull the resident streams back into self.streams / self.ids (tests, gather)."""
+        s, ids = self.backend.particle_views()
+        self.streams = [t.clone() for t in s]
+        self.ids = ids.clone()
+
+    # ---- one substep, generic plumbing (any backend; used by the CPU tests) ------------------------------
     def step(self, radius, ratio, dt, cfl=5.0, collide=True):
         kz = self.cell_k(self.streams[2])
         # 1. ghost particles for P2G

@@ -130,6 +130,23 @@ int ffb200_reserve_particles(ffb200_context *ctx, int capacity, int with_affine)
  * included); the next P2G re-bins and re-sorts them. */
 int ffb200_set_num_particles(ffb200_context *ctx, int n, int has_affine);
 
+/* Particles travel between slabs as packed records of `floats_per_particle` floats (6 or 15
+ * attribute components + the global id bit pattern), `count` records back to back in a DEVICE
+ * buffer of block_capacity records followed by a 4-int header {count, overflowed, 0, 0} that the
+ * kernels fill in, so a fixed-size buffer can be sent without a host round trip for its size. */
+int ffb200_slab_record_floats(ffb200_context *ctx, int *floats_per_particle);
+/* Copy the particles whose cell plane k = floor(z/dx) lies in [lo_a, hi_a) into block_a and
+ * those in [lo_b, hi_b) into block_b (ghost layers for the neighbours' P2G). Asynchronous. */
+int ffb200_slab_pack_layers(ffb200_context *ctx, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b,
+                            float *block_b, int block_capacity);
+/* Split the resident particles by cell plane: k in [k_begin, k_end) stay (compacted), k >= k_end
+ * are moved to block_up, k < k_begin to block_down; a NULL block drops those particles (ghost
+ * removal). counts = {stay, up, down}; synchronises the stream. */
+int ffb200_slab_route(ffb200_context *ctx, int k_begin, int k_end, float *block_up, float *block_down,
+                      int block_capacity, int *counts);
+/* Append `count` packed records (device buffer) to the resident particles. */
+int ffb200_slab_append(ffb200_context *ctx, const float *block, int count);
+
 /* Cell binning + stable sort (runs implicitly before P2G when positions changed). */
 int ffb200_sort_particles(ffb200_context *ctx);
 /* Per particle in ORIGINAL order: cell = flat reference cell index or -1 (grid3d.h:55-60,

@@ -38,8 +38,14 @@ if apic:
 dev = torch.device("cuda", lr)
 sim.set_particles([torch.from_numpy(np.ascontiguousarray(c)).to(dev) for c in cols], torch.from_numpy(sel.astype(np.int32)).to(dev))
 dt = 1.5 * dx / 0.9
-for _ in range(2):
-    sim.step(sc.radius, 0.05, dt)
+if sys.argv[4] == "fast":
+    sim.load_resident()
+    for _ in range(2):
+        sim.step_fast(sc.radius, 0.05, dt)
+    sim.sync_from_backend()
+else:
+    for _ in range(2):
+        sim.step(sc.radius, 0.05, dt)
 allp, ids = sim.gather_particles()
 if rank == 0:
     # single-GPU run of the same two substeps on this rank's device
@@ -59,8 +65,9 @@ dist.destroy_process_group()
 '''
 
 
+@pytest.mark.parametrize("plumbing", ["fast", "generic"])
 @pytest.mark.parametrize("method", ["flip", "apic"])
-def test_two_gpu_slab_matches_single_gpu(tmp_path, method):
+def test_two_gpu_slab_matches_single_gpu(tmp_path, method, plumbing):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -72,7 +79,7 @@ def test_two_gpu_slab_matches_single_gpu(tmp_path, method):
     script.write_text(WORKER)
     out = str(tmp_path / "res.npz")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT, out, method],
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT, out, method, plumbing],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     z = np.load(out)
