@@ -505,12 +505,12 @@ int ffb200_slab_route(ffb200_context *ctx, int k_begin, int k_end, float *block_
     });
 }
 
-int ffb200_slab_append(ffb200_context *ctx, const float *block, int count) {
+int ffb200_slab_append(ffb200_context *ctx, const float *block, int count, int as_ghost) {
     return guarded("ffb200_slab_append", ctx, [&](Context &cc) {
         ContextImpl &c = impl(cc);
         if (count < 0 || (count > 0 && !block)) throw std::invalid_argument("bad packed block");
         if (c.n + count > c.cap) ensure_capacity(c, c.n + count + (c.n + count) / 8, c.has_affine, true);
-        launch_append(c, block, count);
+        launch_append(c, block, count, as_ghost != 0);
     });
 }
 

@@ -56,14 +56,24 @@ __global__ void k_pack_layers(Streams src, int n, double inv_dx, int lo_a, int h
 
 // Route every particle by its cell plane: [k_begin, k_end) stays (compacted into dst), above goes
 // to block_up, below to block_down; a null block drops those particles.
+//
+// Particles whose id carries kGhostBit (set by k_append for ghost copies) are dropped here
+// whatever their position. A bin never mixes ghosts and owned particles (the slab boundary is a
+// cell plane), so the mark does not disturb the (bin, id) order of the sort.
+constexpr uint32_t kGhostBit = 0x80000000u;
+
 __global__ void k_route(Streams src, Streams dst, int n, double inv_dx, int k_begin, int k_end, float *block_up,
                         float *block_down, int cap, int *counters) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     int k = 0;
-    if (j < n) k = __double2int_rd((double)src.s[2][j] * inv_dx);
-    const bool stay = j < n && k >= k_begin && k < k_end;
-    const bool up = j < n && k >= k_end && block_up;
-    const bool down = j < n && k < k_begin && block_down;
+    bool alive = false;
+    if (j < n) {
+        k = __double2int_rd((double)src.s[2][j] * inv_dx);
+        alive = (src.ids[j] & kGhostBit) == 0u;
+    }
+    const bool stay = alive && k >= k_begin && k < k_end;
+    const bool up = alive && k >= k_end && block_up;
+    const bool down = alive && k < k_begin && block_down;
     const int ss = warp_slot(stay, counters + 0);
     const int su = warp_slot(up, counters + 1);
     const int sd = warp_slot(down, counters + 2);
@@ -86,14 +96,14 @@ __global__ void k_write_header(const int *counters, int which, int cap, int rows
     h[3] = 0;
 }
 
-__global__ void k_append(Streams dst, int offset, const float *__restrict__ block, int count) {
+__global__ void k_append(Streams dst, int offset, const float *__restrict__ block, int count, uint32_t id_or) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
     const float *r = block + (size_t)j * (dst.ns + 1);
 #pragma unroll
     for (int t = 0; t < 15; t++)
         if (t < dst.ns) dst.s[t][offset + j] = r[t];
-    dst.ids[offset + j] = __float_as_uint(r[dst.ns]);
+    dst.ids[offset + j] = __float_as_uint(r[dst.ns]) | id_or;
 }
 
 Streams streams_of(Context &c, int buf) {
@@ -145,9 +155,9 @@ int launch_route(Context &c, int k_begin, int k_end, float *block_up, float *blo
     return launches;
 }
 
-int launch_append(Context &c, const float *block, int count) {
+int launch_append(Context &c, const float *block, int count, bool as_ghost) {
     if (count <= 0) return 0;
-    k_append<<<(count + 255) / 256, 256, 0, c.stream>>>(streams_of(c, c.cur), c.n, block, count);
+    k_append<<<(count + 255) / 256, 256, 0, c.stream>>>(streams_of(c, c.cur), c.n, block, count, as_ghost ? kGhostBit : 0u);
     FFB_CUDA(cudaGetLastError());
     c.n += count;
     c.sorted = false;

@@ -71,7 +71,7 @@ SIGNATURES = {
     "ffb200_slab_record_floats": [C.c_void_p, C.POINTER(C.c_int)],
     "ffb200_slab_pack_layers": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int],
     "ffb200_slab_route": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
-    "ffb200_slab_append": [C.c_void_p, C.c_void_p, C.c_int],
+    "ffb200_slab_append": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
     "ffb200_sort_particles": [C.c_void_p],
     "ffb200_get_binning": [C.c_void_p, _i32p, _u32p, _u32p],
     "ffb200_set_velocity_field": [C.c_void_p] + [_f32p] * 3,
@@ -232,8 +232,8 @@ class FlipContext:
         self.n = counts[0]
         return counts[0], counts[1], counts[2]
 
-    def slab_append(self, ptr, count):
-        self._call("ffb200_slab_append", C.c_void_p(ptr), int(count))
+    def slab_append(self, ptr, count, as_ghost=False):
+        self._call("ffb200_slab_append", C.c_void_p(ptr), int(count), 1 if as_ghost else 0)
         self.n += int(count)
 
     def sort_particles(self):

@@ -131,9 +131,22 @@ class GpuBackend:
         return self.ctx.slab_route(k_begin, k_end, block_up.data_ptr() if block_up is not None else 0,
                                    block_down.data_ptr() if block_down is not None else 0, capacity)
 
-    def append(self, block, count):
+    def append(self, block, count, as_ghost=False):
         if count:
-            self.ctx.slab_append(block.data_ptr(), count)
+            self.ctx.slab_append(block.data_ptr(), count, as_ghost)
+
+    def halo_plan(self, kb, ke, halo, has_up, has_down):
+        """Cached (send, recv) plane views of u, v, w for the face-halo exchange (pointers of the
+        face arrays never change). w stores one more plane; plane ke belongs to the upper slab."""
+        plan = []
+        for d in range(3):
+            f, kbase = self.field_planes(d)
+            extra = 1 if d == 2 else 0
+            o0, o1 = kb - kbase, ke - kbase
+            up = (f[o1 - halo:o1], f[o1:o1 + halo + extra]) if has_up else None
+            down = (f[o0:o0 + halo + extra], f[o0 - halo:o0]) if has_down else None
+            plan.append((up, down))
+        return plan
 
 
 class SlabSimulation:
@@ -286,21 +299,19 @@ class SlabSimulation:
             if got is not None:
                 break
             cap, b = self._blocks(cap * 2)
-        be.append(b["dn_recv"], got[0])
-        be.append(b["up_recv"], got[1])
+        be.append(b["dn_recv"], got[0], as_ghost=True)
+        be.append(b["up_recv"], got[1], as_ghost=True)
         # 2. P2G on owned + ghost particles
         be.p2g(radius)
-        # 3. drop the ghosts again (the end ranks keep whatever strayed past the domain)
-        kb = self.kb if self.down is not None else self.INT_MIN
-        ke = self.ke if self.up is not None else self.INT_MAX
-        be.route(kb, ke, None, None, cap)
-        # 4. face halos, saved copy
-        self._halo_exchange()
+        # 3. face halos (zero copy, straight into the halo planes), saved copy
+        self._halo_exchange_fast()
         be.save_field()
-        # 5. G2P + advection on the owned particles
+        # 4. G2P + advection; the marked ghost copies ride along (a few %) and are dropped below
         be.g2p(ratio)
         be.advect(dt, cfl, collide)
-        # 6. migration
+        # 5. migration + ghost removal (the end ranks keep whatever strayed past the domain)
+        kb = self.kb if self.down is not None else self.INT_MIN
+        ke = self.ke if self.up is not None else self.INT_MAX
         while True:
             stay, nu, nd = be.route(kb, ke, b["up_send"] if self.up is not None else None,
                                     b["dn_send"] if self.down is not None else None, cap)
@@ -310,6 +321,23 @@ class SlabSimulation:
             raise RuntimeError("migration buffer overflow: more than %d particles left the slab in one substep" % cap)
         be.append(b["dn_recv"], got[0])
         be.append(b["up_recv"], got[1])
+
+    def _halo_exchange_fast(self):
+        plan = getattr(self, "_halo_plan", None)
+        if plan is None:
+            plan = self._halo_plan = self.backend.halo_plan(self.kb, self.ke, self.halo, self.up is not None,
+                                                            self.down is not None)
+        ops = []
+        for up, down in plan:
+            if up is not None:
+                ops += [dist.P2POp(dist.isend, up[0], self.up), dist.P2POp(dist.irecv, up[1], self.up)]
+                self.exchanged_bytes += up[0].numel() * 4
+            if down is not None:
+                ops += [dist.P2POp(dist.isend, down[0], self.down), dist.P2POp(dist.irecv, down[1], self.down)]
+                self.exchanged_bytes += down[0].numel() * 4
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
 
     def sync_from_backend(self):
         """Pull the resident streams back into self.streams / self.ids (tests, gather)."""

@@ -140,12 +140,14 @@ int ffb200_slab_record_floats(ffb200_context *ctx, int *floats_per_particle);
 int ffb200_slab_pack_layers(ffb200_context *ctx, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b,
                             float *block_b, int block_capacity);
 /* Split the resident particles by cell plane: k in [k_begin, k_end) stay (compacted), k >= k_end
- * are moved to block_up, k < k_begin to block_down; a NULL block drops those particles (ghost
- * removal). counts = {stay, up, down}; synchronises the stream. */
+ * are moved to block_up, k < k_begin to block_down; a NULL block drops those particles. Ghost
+ * copies are always dropped. counts = {stay, up, down}; synchronises the stream. */
 int ffb200_slab_route(ffb200_context *ctx, int k_begin, int k_end, float *block_up, float *block_down,
                       int block_capacity, int *counts);
-/* Append `count` packed records (device buffer) to the resident particles. */
-int ffb200_slab_append(ffb200_context *ctx, const float *block, int count);
+/* Append `count` packed records (device buffer) to the resident particles. as_ghost marks them
+ * (top id bit) as ghost copies: they take part in P2G and are dropped by the next
+ * ffb200_slab_route wherever they have moved. */
+int ffb200_slab_append(ffb200_context *ctx, const float *block, int count, int as_ghost);
 
 /* Cell binning + stable sort (runs implicitly before P2G when positions changed). */
 int ffb200_sort_particles(ffb200_context *ctx);
