@@ -404,6 +404,10 @@ def main():
         except Exception as e:                                   # the checker is optional for the headline
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
+    if sim is not None and getattr(sim, "_profile", False) and rank == 0:
+        tot = sum(sim._phase.values())
+        sys.stderr.write("slab phases (ms/step, synchronised): " + ", ".join(
+            f"{k} {1e3 * v / max(1, steps + warmup + 3):.3f}" for k, v in sim._phase.items()) + "\n")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

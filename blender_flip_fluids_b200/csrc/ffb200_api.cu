@@ -80,6 +80,7 @@ void free_particles(ContextImpl &c) {
         dev_free(c.sort.val[b]);
     }
     dev_free(c.sort.seam);
+    dev_free(c.sort.edge_list);
     dev_free(c.aos_stage);
     c.cap = 0;
 }
@@ -115,6 +116,8 @@ void ensure_capacity(ContextImpl &c, int n, bool affine, bool preserve = false) 
             dev_alloc(c.sort.val[b], (size_t)c.cap);
         }
         dev_alloc(c.sort.seam, (size_t)c.cap * 3);
+        c.sort.edge_cap = (uint32_t)(c.cap / 64 + 4096);
+        dev_alloc(c.sort.edge_list, (size_t)c.sort.edge_cap * 3);
         dev_alloc(c.aos_stage, (size_t)c.cap * 3);
         if (had_affine || affine) ensure_affine(c);
         if (keep > 0) {
@@ -152,6 +155,7 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->phi);
     dev_free(c->near_solid);
     dev_free(c->slab_counters);
+    dev_free(c->sort.edge_count);
     for (int s = 0; s < kNumStages; s++) {
         if (c->evs.start[s]) cudaEventDestroy(c->evs.start[s]);
         if (c->evs.stop[s]) cudaEventDestroy(c->evs.stop[s]);
@@ -214,6 +218,7 @@ int create_impl(ffb200_context **out, int I, int J, int K, double dx, int device
         dev_alloc(c->phi, (size_t)(I + 1) * (J + 1) * (g.kloc + 1));
         dev_alloc(c->near_solid, (size_t)c->ni * c->nj * c->nk);
         dev_alloc(c->slab_counters, 4);
+        dev_alloc(c->sort.edge_count, 4);
         FFB_CUDA(cudaStreamSynchronize(c->stream));
         *out = reinterpret_cast<ffb200_context *>(static_cast<Context *>(c));
         return FFB200_SUCCESS;

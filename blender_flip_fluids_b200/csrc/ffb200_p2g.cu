@@ -19,6 +19,7 @@
 //    reference's exact arithmetic, so the valid mask is bit-exact.
 #include "ffb200_ctx.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -30,6 +31,7 @@ struct P2GParams {
     GridDesc g;
     int gi, gj, gk;              // global face dims of this direction
     int kstore;                  // stored face planes, first one is g.kbase
+    int kw0, kw1;                // global face planes [kw0, kw1) this rank must produce (owned + 1)
     int bi, bj, bk;              // block dims
     const uint8_t *active;
     const uint32_t *bin_start;
@@ -37,6 +39,9 @@ struct P2GParams {
     const float *vel;            // sorted velocity component of this direction
     const float *ax, *ay, *az;   // sorted affine row of this direction (APIC)
     const uint32_t *seam;        // membership word of this direction per sorted slot
+    const uint32_t *edge_list;   // sorted slots of this direction's "edge" particles (unordered)
+    const uint32_t *edge_count;  // how many k_seam_home found (may exceed edge_cap: list overflowed)
+    uint32_t edge_cap;
     const uint32_t *orig;
     float *out, *wsum;
     uint8_t *valid;
@@ -53,6 +58,9 @@ struct SeamParams {
     int bdim[3][3];              // block dims per direction
     uint8_t *home[3];
     uint32_t *seam;              // [dir*cap + slot]
+    uint32_t *edge_list;         // [dir*edge_cap + i]
+    uint32_t *edge_count;        // [dir]
+    uint32_t edge_cap;
     int cap;
     const float *px, *py, *pz;
     float h;                     // (float)(0.5*dx)
@@ -114,6 +122,10 @@ __global__ void k_seam_home(SeamParams s) {
             if (fr < band || fr > 1.0 - band) word |= kEdgeBit;
         }
         s.seam[(size_t)dir * s.cap + j] = word;
+        if (word & kEdgeBit) {
+            const uint32_t slot = atomicAdd(s.edge_count + dir, 1u);
+            if (slot < s.edge_cap) s.edge_list[(size_t)dir * s.edge_cap + slot] = (uint32_t)j;
+        }
     }
 }
 
@@ -653,7 +665,7 @@ template <int DIR, int METHOD>
 __global__ void __launch_bounds__(kSplatThreads) k_p2g_splat(P2GParams P) {
     __shared__ SplatShared S;
     const int tid = threadIdx.x;
-    const int nbv[3] = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + P.g.kbase / kChunk};
+    const int nbv[3] = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + P.kw0 / kChunk};
     const int n0[3] = {nbv[0] * kChunk, nbv[1] * kChunk, nbv[2] * kChunk};
     const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
     const int dims[3] = {P.gi, P.gj, P.gk};
@@ -691,61 +703,85 @@ __global__ void __launch_bounds__(kSplatThreads) k_p2g_splat(P2GParams P) {
                     gpos1[a] = idx2posf(lo0 + 1, P.g.dx);
                     hb[a] = 2 * (n0[a] + lo0) + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
                 }
+                // the cell's particles: 2 bins x (2 x 2) rows = four runs of the sorted streams. All
+                // eight bounds are fetched up front, then the runs are walked as one list with the
+                // next particle's loads in flight while the current one is splat.
                 const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
-                if (hx0 <= hx1) {
-                    for (int dz = 0; dz < 2; dz++) {
-                        const int hz = hb[2] + dz;
-                        if (hz < 0 || hz >= H[2]) continue;
-                        for (int dy = 0; dy < 2; dy++) {
-                            const int hy = hb[1] + dy;
-                            if (hy < 0 || hy >= H[1]) continue;
-                            const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
-                            const uint32_t s = __ldg(P.bin_start + row + hx0), e = __ldg(P.bin_start + row + hx1 + 1);
-                            for (uint32_t q = s; q < e; q++) {
-                                const uint32_t word = __ldg(P.seam + q);
-                                if (!seam_member(word, nbv[0], nbv[1], nbv[2])) continue;
-                                if (METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit)) continue;   // exact path below
-                                const float xl0 = (__ldg(P.px + q) - P.off[0]) - bpos[0];
-                                const float xl1 = (__ldg(P.py + q) - P.off[1]) - bpos[1];
-                                const float xl2 = (__ldg(P.pz + q) - P.off[2]) - bpos[2];
-                                const float vel = __ldg(P.vel + q);
-                                // node - particle, per axis and per node (0: lower, 1: upper)
-                                const float vx[2] = {gpos0[0] - xl0, gpos1[0] - xl0};
-                                const float vy[2] = {gpos0[1] - xl1, gpos1[1] - xl1};
-                                const float vz[2] = {gpos0[2] - xl2, gpos1[2] - xl2};
-                                if (METHOD == FFB200_TRANSFER_FLIP) {
-                                    const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
-                                    const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
-                                    const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
+                uint32_t rs[4], re[4];
 #pragma unroll
-                                    for (int c = 0; c < 8; c++) {
-                                        const float d2 = xx[c & 1] + yy[(c >> 1) & 1] + zz[c >> 2];
-                                        if (d2 < P.rsq) {
-                                            const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
-                                            awv[c] += w * vel;
-                                            aw[c] += w;
-                                        }
-                                    }
-                                } else {
-                                    // ipos = (p - gpos) / dx and the (1 - ipos, ipos) factors of :574-592
-                                    const float t0 = (xl0 - gpos0[0]) * P.inv_s, t1 = (xl1 - gpos0[1]) * P.inv_s,
-                                                t2 = (xl2 - gpos0[2]) * P.inv_s;
-                                    const float fx[2] = {1.0f - t0, t0}, fy[2] = {1.0f - t1, t1}, fz[2] = {1.0f - t2, t2};
-                                    const float a0 = __ldg(P.ax + q), a1 = __ldg(P.ay + q), a2 = __ldg(P.az + q);
-                                    const float ax[2] = {a0 * vx[0], a0 * vx[1]};
-                                    const float ay[2] = {a1 * vy[0], a1 * vy[1]};
-                                    const float az[2] = {a2 * vz[0], a2 * vz[1]};
+                for (int rr = 0; rr < 4; rr++) {
+                    const int hz = hb[2] + (rr >> 1), hy = hb[1] + (rr & 1);
+                    rs[rr] = 0; re[rr] = 0;
+                    if (hx0 <= hx1 && hz >= 0 && hz < H[2] && hy >= 0 && hy < H[1]) {
+                        const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
+                        rs[rr] = __ldg(P.bin_start + row + hx0);
+                        re[rr] = __ldg(P.bin_start + row + hx1 + 1);
+                    }
+                }
+                int run = 0;
+                uint32_t q = rs[0];
+                while (run < 4 && q >= re[run]) { run++; if (run < 4) q = rs[run]; }
+                uint32_t word = 0;
+                float px = 0.f, py = 0.f, pz = 0.f, vel = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+                if (run < 4) {
+                    word = __ldg(P.seam + q);
+                    px = __ldg(P.px + q); py = __ldg(P.py + q); pz = __ldg(P.pz + q); vel = __ldg(P.vel + q);
+                    if (METHOD == FFB200_TRANSFER_APIC) { a0 = __ldg(P.ax + q); a1 = __ldg(P.ay + q); a2 = __ldg(P.az + q); }
+                }
+                while (run < 4) {
+                    // advance to the next particle and start its loads
+                    int nrun = run;
+                    uint32_t nq = q + 1;
+                    while (nrun < 4 && nq >= re[nrun]) { nrun++; if (nrun < 4) nq = rs[nrun]; }
+                    uint32_t nword = 0;
+                    float npx = 0.f, npy = 0.f, npz = 0.f, nvel = 0.f, na0 = 0.f, na1 = 0.f, na2 = 0.f;
+                    if (nrun < 4) {
+                        nword = __ldg(P.seam + nq);
+                        npx = __ldg(P.px + nq); npy = __ldg(P.py + nq); npz = __ldg(P.pz + nq); nvel = __ldg(P.vel + nq);
+                        if (METHOD == FFB200_TRANSFER_APIC) { na0 = __ldg(P.ax + nq); na1 = __ldg(P.ay + nq); na2 = __ldg(P.az + nq); }
+                    }
+                    const bool use = seam_member(word, nbv[0], nbv[1], nbv[2]) &&
+                                     !(METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit));   // edge: exact path below
+                    if (use) {
+                        const float xl0 = (px - P.off[0]) - bpos[0];
+                        const float xl1 = (py - P.off[1]) - bpos[1];
+                        const float xl2 = (pz - P.off[2]) - bpos[2];
+                        // node - particle, per axis and per node (0: lower, 1: upper)
+                        const float vx[2] = {gpos0[0] - xl0, gpos1[0] - xl0};
+                        const float vy[2] = {gpos0[1] - xl1, gpos1[1] - xl1};
+                        const float vz[2] = {gpos0[2] - xl2, gpos1[2] - xl2};
+                        if (METHOD == FFB200_TRANSFER_FLIP) {
+                            const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
+                            const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
+                            const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
 #pragma unroll
-                                    for (int c = 0; c < 8; c++) {
-                                        const float w = fx[c & 1] * fy[(c >> 1) & 1] * fz[c >> 2];
-                                        const float apic = ax[c & 1] + ay[(c >> 1) & 1] + az[c >> 2];
-                                        awv[c] += w * (vel + apic);
-                                        aw[c] += w;
-                                    }
+                            for (int c = 0; c < 8; c++) {
+                                const float d2 = xx[c & 1] + yy[(c >> 1) & 1] + zz[c >> 2];
+                                if (d2 < P.rsq) {
+                                    const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
+                                    awv[c] += w * vel;
+                                    aw[c] += w;
                                 }
+                            }
+                        } else {
+                            // ipos = (p - gpos) / dx and the (1 - ipos, ipos) factors of :574-592
+                            const float t0 = (xl0 - gpos0[0]) * P.inv_s, t1 = (xl1 - gpos0[1]) * P.inv_s,
+                                        t2 = (xl2 - gpos0[2]) * P.inv_s;
+                            const float fx[2] = {1.0f - t0, t0}, fy[2] = {1.0f - t1, t1}, fz[2] = {1.0f - t2, t2};
+                            const float ax[2] = {a0 * vx[0], a0 * vx[1]};
+                            const float ay[2] = {a1 * vy[0], a1 * vy[1]};
+                            const float az[2] = {a2 * vz[0], a2 * vz[1]};
+#pragma unroll
+                            for (int c = 0; c < 8; c++) {
+                                const float w = fx[c & 1] * fy[(c >> 1) & 1] * fz[c >> 2];
+                                const float apic = ax[c & 1] + ay[(c >> 1) & 1] + az[c >> 2];
+                                awv[c] += w * (vel + apic);
+                                aw[c] += w;
                             }
                         }
                     }
+                    run = nrun; q = nq; word = nword;
+                    px = npx; py = npy; pz = npz; vel = nvel; a0 = na0; a1 = na1; a2 = na2;
                 }
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
@@ -760,28 +796,41 @@ __global__ void __launch_bounds__(kSplatThreads) k_p2g_splat(P2GParams P) {
             __syncthreads();
         }
         if (METHOD == FFB200_TRANSFER_APIC) {
-            // edge particles of the 13^3 shifted cells around the block
-            for (int t = tid; t < 13 * 13 * 13; t += kSplatThreads) {
-                const int cr[3] = {t % 13, (t / 13) % 13, t / 169};
-                int hb[3];
+            // edge particles that are members of this block: from the global list k_seam_home built
+            // (a few hundred entries per direction); if that list overflowed, from the 13^3 shifted
+            // cells around the block instead
+            const uint32_t nedge = __ldg(P.edge_count);
+            if (nedge <= P.edge_cap) {
+                for (uint32_t t = tid; t < nedge; t += kSplatThreads) {
+                    const uint32_t q = __ldg(P.edge_list + t);
+                    if (seam_member(__ldg(P.seam + q), nbv[0], nbv[1], nbv[2])) {
+                        const int slot = atomicAdd(&S.nflag, 1);
+                        if (slot < kSplatFlagCap) S.flagged[slot] = q;
+                    }
+                }
+            } else {
+                for (int t = tid; t < 13 * 13 * 13; t += kSplatThreads) {
+                    const int cr[3] = {t % 13, (t / 13) % 13, t / 169};
+                    int hb[3];
 #pragma unroll
-                for (int a = 0; a < 3; a++)
-                    hb[a] = 2 * (n0[a] - 2 + cr[a]) + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
-                const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
-                if (hx0 > hx1) continue;
-                for (int dz = 0; dz < 2; dz++) {
-                    const int hz = hb[2] + dz;
-                    if (hz < 0 || hz >= H[2]) continue;
-                    for (int dy = 0; dy < 2; dy++) {
-                        const int hy = hb[1] + dy;
-                        if (hy < 0 || hy >= H[1]) continue;
-                        const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
-                        const uint32_t s = __ldg(P.bin_start + row + hx0), e = __ldg(P.bin_start + row + hx1 + 1);
-                        for (uint32_t q = s; q < e; q++) {
-                            const uint32_t word = __ldg(P.seam + q);
-                            if ((word & kEdgeBit) && seam_member(word, nbv[0], nbv[1], nbv[2])) {
-                                const int slot = atomicAdd(&S.nflag, 1);
-                                if (slot < kSplatFlagCap) S.flagged[slot] = q;
+                    for (int a = 0; a < 3; a++)
+                        hb[a] = 2 * (n0[a] - 2 + cr[a]) + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+                    const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
+                    if (hx0 > hx1) continue;
+                    for (int dz = 0; dz < 2; dz++) {
+                        const int hz = hb[2] + dz;
+                        if (hz < 0 || hz >= H[2]) continue;
+                        for (int dy = 0; dy < 2; dy++) {
+                            const int hy = hb[1] + dy;
+                            if (hy < 0 || hy >= H[1]) continue;
+                            const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
+                            const uint32_t s = __ldg(P.bin_start + row + hx0), e = __ldg(P.bin_start + row + hx1 + 1);
+                            for (uint32_t q = s; q < e; q++) {
+                                const uint32_t word = __ldg(P.seam + q);
+                                if ((word & kEdgeBit) && seam_member(word, nbv[0], nbv[1], nbv[2])) {
+                                    const int slot = atomicAdd(&S.nflag, 1);
+                                    if (slot < kSplatFlagCap) S.flagged[slot] = q;
+                                }
                             }
                         }
                     }
@@ -807,7 +856,7 @@ __global__ void __launch_bounds__(kSplatThreads) k_p2g_splat(P2GParams P) {
         const int l[3] = {t % kChunk, (t / kChunk) % kChunk, t / (kChunk * kChunk)};
         const int n[3] = {n0[0] + l[0], n0[1] + l[1], n0[2] + l[2]};
         const int ks = n[2] - P.g.kbase;
-        if (n[0] >= P.gi || n[1] >= P.gj || n[2] >= P.gk || ks < 0 || ks >= P.kstore) continue;
+        if (n[0] >= P.gi || n[1] >= P.gj || n[2] >= P.gk || n[2] < P.kw0 || n[2] >= P.kw1) continue;
         const size_t fidx = (size_t)n[0] + (size_t)P.gi * ((size_t)n[1] + (size_t)P.gj * ks);
         float sw = S.sw[t], swv = S.swv[t];
         if (active) {
@@ -847,7 +896,7 @@ __global__ void __launch_bounds__(kSplatThreads) k_p2g_splat(P2GParams P) {
 
 template <int DIR, int METHOD>
 void launch_splat(Context &c, P2GParams &P) {
-    const int zb0 = P.g.kbase / kChunk, zb1 = (P.g.kbase + P.kstore - 1) / kChunk;
+    const int zb0 = P.kw0 / kChunk, zb1 = (P.kw1 - 1) / kChunk;
     dim3 grid(P.bi, P.bj, zb1 - zb0 + 1);
     k_p2g_splat<DIR, METHOD><<<grid, kSplatThreads, 0, c.stream>>>(P);
 }
@@ -903,6 +952,7 @@ int launch_p2g_prepare(Context &c, double radius) {
     const float sr = (float)(radius + (double)eps);            // float sr = _particleRadius + eps;
 
     // block masks + membership words
+    FFB_CUDA(cudaMemsetAsync(c.sort.edge_count, 0, 4 * sizeof(uint32_t), c.stream));
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];
         FFB_CUDA(cudaMemsetAsync(f.home, 0, (size_t)f.bi * f.bj * f.bk, c.stream));
@@ -915,6 +965,9 @@ int launch_p2g_prepare(Context &c, double radius) {
             sp.home[d] = c.face[d].home;
         }
         sp.seam = c.sort.seam;
+        sp.edge_list = c.sort.edge_list;
+        sp.edge_count = c.sort.edge_count;
+        sp.edge_cap = c.sort.edge_cap;
         sp.cap = c.cap;
         sp.px = s.p[0]; sp.py = s.p[1]; sp.pz = s.p[2];
         sp.h = (float)(0.5 * g.dx);
@@ -950,6 +1003,10 @@ int launch_p2g(Context &c, double radius, int method) {
         P.g = g;
         P.gi = f.gi; P.gj = f.gj; P.gk = f.gk;
         P.kstore = f.kstore;
+        // a slab rank only produces its owned planes (+1: the shared w plane); the halo planes
+        // are filled by the face-halo exchange
+        P.kw0 = std::max(g.kbase, c.k_own_begin);
+        P.kw1 = std::min(g.kbase + f.kstore, c.k_own_end + 1);
         P.bi = f.bi; P.bj = f.bj; P.bk = f.bk;
         P.active = f.active;
         P.bin_start = c.sort.bin_start;
@@ -957,6 +1014,9 @@ int launch_p2g(Context &c, double radius, int method) {
         P.vel = s.v[d];
         P.ax = s.a[3 * d + 0]; P.ay = s.a[3 * d + 1]; P.az = s.a[3 * d + 2];
         P.seam = c.sort.seam + (size_t)d * c.cap;
+        P.edge_list = c.sort.edge_list + (size_t)d * c.sort.edge_cap;
+        P.edge_count = c.sort.edge_count + d;
+        P.edge_cap = c.sort.edge_cap;
         P.orig = s.orig;
         P.out = f.vel; P.wsum = f.wsum; P.valid = f.valid;
         const float h = (float)(0.5 * g.dx);

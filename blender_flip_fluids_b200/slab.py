@@ -286,7 +286,24 @@ class SlabSimulation:
         n_dn = int(hdr[3, 0]) if self.down is not None else 0
         return n_dn, n_up
 
+    def _tick(self, name):
+        """FFB200_SLAB_PROFILE=1: wall-clock phase breakdown (synchronising; not for benchmarking)."""
+        if not self._profile:
+            return
+        import time
+        torch.cuda.synchronize(self.device)
+        now = time.perf_counter()
+        self._phase[name] = self._phase.get(name, 0.0) + now - self._t_last
+        self._t_last = now
+
     def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True):
+        import os, time
+        if not hasattr(self, "_profile"):
+            self._profile = os.environ.get("FFB200_SLAB_PROFILE") == "1"
+            self._phase = {}
+        if self._profile:
+            torch.cuda.synchronize(self.device)
+            self._t_last = time.perf_counter()
         be = self.backend
         n0 = be.ctx.n
         g = self.ghost
@@ -301,14 +318,18 @@ class SlabSimulation:
             cap, b = self._blocks(cap * 2)
         be.append(b["dn_recv"], got[0], as_ghost=True)
         be.append(b["up_recv"], got[1], as_ghost=True)
+        self._tick("ghosts")
         # 2. P2G on owned + ghost particles
         be.p2g(radius)
+        self._tick("p2g")
         # 3. face halos (zero copy, straight into the halo planes), saved copy
         self._halo_exchange_fast()
         be.save_field()
+        self._tick("halo+save")
         # 4. G2P + advection; the marked ghost copies ride along (a few %) and are dropped below
         be.g2p(ratio)
         be.advect(dt, cfl, collide)
+        self._tick("g2p+advect")
         # 5. migration + ghost removal (the end ranks keep whatever strayed past the domain)
         kb = self.kb if self.down is not None else self.INT_MIN
         ke = self.ke if self.up is not None else self.INT_MAX
@@ -321,6 +342,7 @@ class SlabSimulation:
             raise RuntimeError("migration buffer overflow: more than %d particles left the slab in one substep" % cap)
         be.append(b["dn_recv"], got[0])
         be.append(b["up_recv"], got[1])
+        self._tick("migrate")
 
     def _halo_exchange_fast(self):
         plan = getattr(self, "_halo_plan", None)
