@@ -652,6 +652,9 @@ __device__ __forceinline__ void accumulate_global(const P2GParams &P, const Face
 // particles (within a few ulps of a cell plane, flagged by k_seam_home) are left out of the fast
 // path, collected from the 13^3 cells around the block, sorted, and given exact_contribution().
 constexpr int kSplatThreads = 256;
+#ifndef FFB_SPLAT_MINB
+#define FFB_SPLAT_MINB 4
+#endif
 constexpr int kSplatFlagCap = 192;
 
 struct SplatShared {
@@ -662,7 +665,7 @@ struct SplatShared {
 };
 
 template <int DIR, int METHOD>
-__global__ void __launch_bounds__(kSplatThreads) k_p2g_splat(P2GParams P) {
+__global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(P2GParams P) {
     __shared__ SplatShared S;
     const int tid = threadIdx.x;
     const int nbv[3] = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + P.kw0 / kChunk};
