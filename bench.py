@@ -177,7 +177,7 @@ def host_cpu():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -315,7 +315,7 @@ def main():
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"kernel": "k_p2g<dir, APIC> (one launch per MAC direction)", "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "k_p2g_splat<dir, APIC> (one launch per MAC direction)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": p2g_bytes_per_launch, "launch_ms": p2g_launch_ms,
                 "whole_step": {"algorithmic_bytes_per_particle": sum(balg.values()),
