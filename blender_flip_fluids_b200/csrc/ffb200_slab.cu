@@ -54,37 +54,77 @@ __global__ void k_pack_layers(Streams src, int n, double inv_dx, int lo_a, int h
     if (in_b) write_record(src, j, block_b, cap, sb);
 }
 
-// Route every particle by its cell plane: [k_begin, k_end) stays (compacted into dst), above goes
-// to block_up, below to block_down; a null block drops those particles.
+// Route every particle by its cell plane: [k_begin, k_end) stays, above goes to block_up, below
+// to block_down (a null block keeps those particles). Particles whose id carries kGhostBit (set
+// by k_append for ghost copies) always leave. A bin never mixes ghosts and owned particles (the
+// slab boundary is a cell plane), so the mark does not disturb the (bin, id) order of the sort.
 //
-// Particles whose id carries kGhostBit (set by k_append for ghost copies) are dropped here
-// whatever their position. A bin never mixes ghosts and owned particles (the slab boundary is a
-// cell plane), so the mark does not disturb the (bin, id) order of the sort.
+// Leavers are removed by HOLE FILLING instead of compacting every stream: pass 1 packs the
+// migrants and lists the holes; pass 2 pairs the holes in the surviving prefix [0, n - L) with
+// the stayers of the tail [n - L, n); pass 3 moves just those. Traffic is proportional to the
+// few percent that leave, not to n.
+//
+// `dec`/`dat` may differ from `cur` in fixed-batch mode, where advection and G2P wrote to the
+// spare buffer: the decision and the packed payload come from there, the resident batch is
+// left as it is (migrants are packed and sent, but not removed).
 constexpr uint32_t kGhostBit = 0x80000000u;
 
-__global__ void k_route(Streams src, Streams dst, int n, double inv_dx, int k_begin, int k_end, float *block_up,
-                        float *block_down, int cap, int *counters) {
+__global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int k_begin, int k_end, float *block_up,
+                             float *block_down, int cap, int remove_migrants, int *counters, uint32_t *holes) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int k = 0;
-    bool alive = false;
+    bool ghost = false, up = false, down = false;
     if (j < n) {
-        k = __double2int_rd((double)src.s[2][j] * inv_dx);
-        alive = (src.ids[j] & kGhostBit) == 0u;
+        const int k = __double2int_rd((double)dat.s[2][j] * inv_dx);
+        ghost = (cur.ids[j] & kGhostBit) != 0u;
+        up = !ghost && k >= k_end && block_up;
+        down = !ghost && k < k_begin && block_down;
     }
-    const bool stay = alive && k >= k_begin && k < k_end;
-    const bool up = alive && k >= k_end && block_up;
-    const bool down = alive && k < k_begin && block_down;
-    const int ss = warp_slot(stay, counters + 0);
+    const bool leave = ghost || (remove_migrants && (up || down));
     const int su = warp_slot(up, counters + 1);
     const int sd = warp_slot(down, counters + 2);
-    if (stay) {
-#pragma unroll
-        for (int t = 0; t < 15; t++)
-            if (t < src.ns) dst.s[t][ss] = src.s[t][j];
-        dst.ids[ss] = src.ids[j];
+    const int sh = warp_slot(leave, counters + 3);
+    if (up || down) {
+        Streams rec = dat;
+        rec.ids = cur.ids;
+        write_record(rec, j, up ? block_up : block_down, cap, up ? su : sd);
     }
-    if (up) write_record(src, j, block_up, cap, su);
-    if (down) write_record(src, j, block_down, cap, sd);
+    if (leave) holes[sh] = (uint32_t)j;
+}
+
+// holes below the new count, and survivors at or above it
+__global__ void k_fill_collect(Streams cur, Streams dat, int n, int n_new, int nholes, double inv_dx, int k_begin, int k_end,
+                               int has_up, int has_down, int remove_migrants, const uint32_t *holes, int *counters,
+                               uint32_t *front_hole, uint32_t *tail_stay) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool is_front = false;
+    uint32_t h = 0;
+    if (t < nholes) {
+        h = holes[t];
+        is_front = h < (uint32_t)n_new;
+    }
+    bool is_tail_stay = false;
+    const int j = n_new + t;
+    if (t < nholes && j < n) {
+        const int k = __double2int_rd((double)dat.s[2][j] * inv_dx);
+        const bool ghost = (cur.ids[j] & kGhostBit) != 0u;
+        const bool up = !ghost && k >= k_end && has_up;
+        const bool down = !ghost && k < k_begin && has_down;
+        is_tail_stay = !(ghost || (remove_migrants && (up || down)));
+    }
+    const int sa = warp_slot(is_front, counters + 0);
+    const int sb = warp_slot(is_tail_stay, counters + 1);
+    if (is_front) front_hole[sa] = h;
+    if (is_tail_stay) tail_stay[sb] = (uint32_t)j;
+}
+
+__global__ void k_fill_move(Streams cur, const int *counters, const uint32_t *front_hole, const uint32_t *tail_stay) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= counters[0]) return;                             // == counters[1]
+    const uint32_t dst = front_hole[t], src = tail_stay[t];
+#pragma unroll
+    for (int q = 0; q < 15; q++)
+        if (q < cur.ns) cur.s[q][dst] = cur.s[q][src];
+    cur.ids[dst] = cur.ids[src];
 }
 
 __global__ void k_write_header(const int *counters, int which, int cap, int rows, float *block) {
@@ -135,23 +175,43 @@ int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b,
     return launches;
 }
 
-// Returns the launch count; counts_host[3] = {stay, up, down} after a stream synchronisation.
+// Returns the launch count; counts_host[3] = {stay, up, down}. Synchronises the stream (the host
+// needs the counts to size the following launches).
 int launch_route(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int counts_host[3]) {
     int launches = 0;
+    const int n = c.n;
+    const int rows = slab_rows(c);
+    const bool fixed = c.nondestructive;
+    Streams cur = streams_of(c, c.cur);
+    Streams dat = fixed ? streams_of(c, c.cur ^ 1) : cur;      // fixed batch: advect / G2P wrote to the spare buffer
+    uint32_t *holes = c.sort.key[1], *front_hole = c.sort.val[1], *tail_stay = c.sort.key[0];   // free after P2G
     FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 4 * sizeof(int), c.stream));
-    if (c.n > 0) {
-        k_route<<<(c.n + 255) / 256, 256, 0, c.stream>>>(streams_of(c, c.cur), streams_of(c, c.cur ^ 1), c.n, c.g.inv_dx,
-                                                         k_begin, k_end, block_up, block_down, cap, c.slab_counters);
+    if (n > 0) {
+        k_route_mark<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, block_up, block_down, cap,
+                                                            fixed ? 0 : 1, c.slab_counters, holes);
         launches++;
     }
-    const int rows = slab_rows(c);
     if (block_up) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, cap, rows, block_up); launches++; }
     if (block_down) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, cap, rows, block_down); launches++; }
-    FFB_CUDA(cudaMemcpyAsync(counts_host, c.slab_counters, 3 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    int h[4] = {0, 0, 0, 0};
+    FFB_CUDA(cudaMemcpyAsync(h, c.slab_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     FFB_CUDA(cudaStreamSynchronize(c.stream));
-    c.cur ^= 1;
-    c.n = counts_host[0];
+    const int nholes = h[3], n_new = n - nholes;
+    if (nholes > 0 && n_new > 0) {
+        FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 2 * sizeof(int), c.stream));
+        k_fill_collect<<<(nholes + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, n_new, nholes, c.g.inv_dx, k_begin, k_end,
+                                                                   block_up != nullptr, block_down != nullptr, fixed ? 0 : 1,
+                                                                   holes, c.slab_counters, front_hole, tail_stay);
+        // the two lists have the same length by construction (holes in the prefix == survivors in the tail)
+        k_fill_move<<<(nholes + 255) / 256, 256, 0, c.stream>>>(cur, c.slab_counters, front_hole, tail_stay);
+        launches += 2;
+    }
+    counts_host[0] = n_new;
+    counts_host[1] = h[1];
+    counts_host[2] = h[2];
+    c.n = n_new;
     c.sorted = false;
+    FFB_CUDA(cudaGetLastError());
     return launches;
 }
 

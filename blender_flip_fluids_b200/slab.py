@@ -296,7 +296,11 @@ class SlabSimulation:
         self._phase[name] = self._phase.get(name, 0.0) + now - self._t_last
         self._t_last = now
 
-    def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True):
+    def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True, apply_migration=True):
+        """One substep with device-side plumbing. apply_migration=False is the fixed-batch
+        benchmark mode (context in ffb200_set_fixed_batch): ghosts are added and removed and
+        migrants are selected, packed and exchanged as usual, but the resident batch itself is
+        left untouched so every step sees identical inputs."""
         import os, time
         if not hasattr(self, "_profile"):
             self._profile = os.environ.get("FFB200_SLAB_PROFILE") == "1"
@@ -340,8 +344,9 @@ class SlabSimulation:
             if got is not None:
                 break
             raise RuntimeError("migration buffer overflow: more than %d particles left the slab in one substep" % cap)
-        be.append(b["dn_recv"], got[0])
-        be.append(b["up_recv"], got[1])
+        if apply_migration:
+            be.append(b["dn_recv"], got[0])
+            be.append(b["up_recv"], got[1])
         self._tick("migrate")
 
     def _halo_exchange_fast(self):
