@@ -508,7 +508,23 @@ int ffb200_slab_route(ffb200_context *ctx, int k_begin, int k_end, float *block_
     return guarded("ffb200_slab_route", ctx, [&](Context &c) {
         if (!counts) throw std::invalid_argument("null counts pointer");
         if ((block_up || block_down) && block_capacity <= 0) throw std::domain_error("block capacity must be positive");
-        launch_route(c, k_begin, k_end, block_up, block_down, block_capacity, counts);
+        launch_route_begin(c, k_begin, k_end, block_up, block_down, block_capacity);
+        launch_route_end(c, counts);
+    });
+}
+
+int ffb200_slab_route_begin(ffb200_context *ctx, int k_begin, int k_end, float *block_up, float *block_down,
+                            int block_capacity) {
+    return guarded("ffb200_slab_route_begin", ctx, [&](Context &c) {
+        if ((block_up || block_down) && block_capacity <= 0) throw std::domain_error("block capacity must be positive");
+        launch_route_begin(c, k_begin, k_end, block_up, block_down, block_capacity);
+    });
+}
+
+int ffb200_slab_route_end(ffb200_context *ctx, int *counts) {
+    return guarded("ffb200_slab_route_end", ctx, [&](Context &c) {
+        if (!counts) throw std::invalid_argument("null counts pointer");
+        launch_route_end(c, counts);
     });
 }
 

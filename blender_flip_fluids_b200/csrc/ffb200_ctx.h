@@ -111,7 +111,8 @@ int launch_advect(Context &c, double dt, double cfl, int collide);
 // ffb200_slab.cu
 int slab_rows(Context &c);
 int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b, float *block_b, int cap);
-int launch_route(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int counts_host[3]);
+int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap);
+int launch_route_end(Context &c, int counts_host[3]);
 int launch_append(Context &c, const float *block, int count, bool as_ghost);
 
 }  // namespace ffb200

@@ -175,16 +175,22 @@ int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b,
     return launches;
 }
 
-// Returns the launch count; counts_host[3] = {stay, up, down}. Synchronises the stream (the host
-// needs the counts to size the following launches).
-int launch_route(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int counts_host[3]) {
+// Routing is split in two so the host can overlap the neighbour exchange with it:
+// launch_route_begin packs the migrants and lists the holes (asynchronous); launch_route_end
+// reads the counts (synchronises the stream), fills the holes and sets the new particle count.
+struct RouteState {
+    int k_begin, k_end, has_up, has_down, n;
+};
+static RouteState g_route;      // one routing in flight per process (one context per rank)
+
+int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap) {
     int launches = 0;
     const int n = c.n;
     const int rows = slab_rows(c);
     const bool fixed = c.nondestructive;
     Streams cur = streams_of(c, c.cur);
     Streams dat = fixed ? streams_of(c, c.cur ^ 1) : cur;      // fixed batch: advect / G2P wrote to the spare buffer
-    uint32_t *holes = c.sort.key[1], *front_hole = c.sort.val[1], *tail_stay = c.sort.key[0];   // free after P2G
+    uint32_t *holes = c.sort.key[1];                           // key/val scratch is free after P2G
     FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 4 * sizeof(int), c.stream));
     if (n > 0) {
         k_route_mark<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, block_up, block_down, cap,
@@ -193,6 +199,18 @@ int launch_route(Context &c, int k_begin, int k_end, float *block_up, float *blo
     }
     if (block_up) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, cap, rows, block_up); launches++; }
     if (block_down) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, cap, rows, block_down); launches++; }
+    g_route = RouteState{k_begin, k_end, block_up != nullptr, block_down != nullptr, n};
+    FFB_CUDA(cudaGetLastError());
+    return launches;
+}
+
+int launch_route_end(Context &c, int counts_host[3]) {
+    int launches = 0;
+    const int n = g_route.n, k_begin = g_route.k_begin, k_end = g_route.k_end;
+    const bool fixed = c.nondestructive;
+    Streams cur = streams_of(c, c.cur);
+    Streams dat = fixed ? streams_of(c, c.cur ^ 1) : cur;
+    uint32_t *holes = c.sort.key[1], *front_hole = c.sort.val[1], *tail_stay = c.sort.key[0];
     int h[4] = {0, 0, 0, 0};
     FFB_CUDA(cudaMemcpyAsync(h, c.slab_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     FFB_CUDA(cudaStreamSynchronize(c.stream));
@@ -200,7 +218,7 @@ int launch_route(Context &c, int k_begin, int k_end, float *block_up, float *blo
     if (nholes > 0 && n_new > 0) {
         FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 2 * sizeof(int), c.stream));
         k_fill_collect<<<(nholes + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, n_new, nholes, c.g.inv_dx, k_begin, k_end,
-                                                                   block_up != nullptr, block_down != nullptr, fixed ? 0 : 1,
+                                                                   g_route.has_up, g_route.has_down, fixed ? 0 : 1,
                                                                    holes, c.slab_counters, front_hole, tail_stay);
         // the two lists have the same length by construction (holes in the prefix == survivors in the tail)
         k_fill_move<<<(nholes + 255) / 256, 256, 0, c.stream>>>(cur, c.slab_counters, front_hole, tail_stay);

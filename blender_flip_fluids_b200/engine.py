@@ -71,6 +71,8 @@ SIGNATURES = {
     "ffb200_slab_record_floats": [C.c_void_p, C.POINTER(C.c_int)],
     "ffb200_slab_pack_layers": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int],
     "ffb200_slab_route": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
+    "ffb200_slab_route_begin": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int],
+    "ffb200_slab_route_end": [C.c_void_p, C.POINTER(C.c_int)],
     "ffb200_slab_append": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
     "ffb200_sort_particles": [C.c_void_p],
     "ffb200_get_binning": [C.c_void_p, _i32p, _u32p, _u32p],
@@ -229,6 +231,16 @@ class FlipContext:
         counts = (C.c_int * 3)()
         self._call("ffb200_slab_route", int(k_begin), int(k_end), C.c_void_p(ptr_up or 0), C.c_void_p(ptr_down or 0),
                    int(capacity), counts)
+        self.n = counts[0]
+        return counts[0], counts[1], counts[2]
+
+    def slab_route_begin(self, k_begin, k_end, ptr_up, ptr_down, capacity):
+        self._call("ffb200_slab_route_begin", int(k_begin), int(k_end), C.c_void_p(ptr_up or 0), C.c_void_p(ptr_down or 0),
+                   int(capacity))
+
+    def slab_route_end(self):
+        counts = (C.c_int * 3)()
+        self._call("ffb200_slab_route_end", counts)
         self.n = counts[0]
         return counts[0], counts[1], counts[2]
 

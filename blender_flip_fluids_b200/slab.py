@@ -131,6 +131,13 @@ class GpuBackend:
         return self.ctx.slab_route(k_begin, k_end, block_up.data_ptr() if block_up is not None else 0,
                                    block_down.data_ptr() if block_down is not None else 0, capacity)
 
+    def route_begin(self, k_begin, k_end, block_up, block_down, capacity):
+        self.ctx.slab_route_begin(k_begin, k_end, block_up.data_ptr() if block_up is not None else 0,
+                                  block_down.data_ptr() if block_down is not None else 0, capacity)
+
+    def route_end(self):
+        return self.ctx.slab_route_end()
+
     def append(self, block, count, as_ghost=False):
         if count:
             self.ctx.slab_append(block.data_ptr(), count, as_ghost)
@@ -337,12 +344,11 @@ class SlabSimulation:
         # 5. migration + ghost removal (the end ranks keep whatever strayed past the domain)
         kb = self.kb if self.down is not None else self.INT_MIN
         ke = self.ke if self.up is not None else self.INT_MAX
-        while True:
-            stay, nu, nd = be.route(kb, ke, b["up_send"] if self.up is not None else None,
-                                    b["dn_send"] if self.down is not None else None, cap)
-            got = self._swap_blocks(cap, b)
-            if got is not None:
-                break
+        be.route_begin(kb, ke, b["up_send"] if self.up is not None else None,
+                       b["dn_send"] if self.down is not None else None, cap)
+        got = self._swap_blocks(cap, b)           # one synchronisation serves the exchange and the routing
+        be.route_end()
+        if got is None:
             raise RuntimeError("migration buffer overflow: more than %d particles left the slab in one substep" % cap)
         if apply_migration:
             be.append(b["dn_recv"], got[0])

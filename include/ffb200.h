@@ -144,6 +144,12 @@ int ffb200_slab_pack_layers(ffb200_context *ctx, int lo_a, int hi_a, float *bloc
  * copies are always dropped. counts = {stay, up, down}; synchronises the stream. */
 int ffb200_slab_route(ffb200_context *ctx, int k_begin, int k_end, float *block_up, float *block_down,
                       int block_capacity, int *counts);
+/* The same in two halves, so the neighbour exchange of the packed buffers can be issued while
+ * the routing kernel runs: _begin is asynchronous, _end synchronises, fills the holes the
+ * leavers left and returns counts = {stay, up, down}. */
+int ffb200_slab_route_begin(ffb200_context *ctx, int k_begin, int k_end, float *block_up, float *block_down,
+                            int block_capacity);
+int ffb200_slab_route_end(ffb200_context *ctx, int *counts);
 /* Append `count` packed records (device buffer) to the resident particles. as_ghost marks them
  * (top id bit) as ghost copies: they take part in P2G and are dropped by the next
  * ffb200_slab_route wherever they have moved. */
