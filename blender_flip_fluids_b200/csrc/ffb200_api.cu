@@ -81,7 +81,6 @@ void free_particles(ContextImpl &c) {
     }
     dev_free(c.sort.seam);
     dev_free(c.sort.edge_list);
-    dev_free(c.sort.rec);
     dev_free(c.aos_stage);
     c.cap = 0;
 }
@@ -119,7 +118,6 @@ void ensure_capacity(ContextImpl &c, int n, bool affine, bool preserve = false) 
         dev_alloc(c.sort.seam, (size_t)c.cap * 3);
         c.sort.edge_cap = (uint32_t)(c.cap / 64 + 4096);
         dev_alloc(c.sort.edge_list, (size_t)c.sort.edge_cap * 3);
-        dev_alloc(c.sort.rec, (size_t)c.cap * 6);
         dev_alloc(c.aos_stage, (size_t)c.cap * 3);
         if (had_affine || affine) ensure_affine(c);
         if (keep > 0) {

@@ -54,7 +54,6 @@ struct SortScratch {
     uint32_t *scan_partials = nullptr;   // block sums for the scans
     size_t scan_partials_cap = 0;
     uint32_t *seam = nullptr;            // 3 words per slot [dir*cap + slot]: 10^3-block membership
-    float4 *rec = nullptr;               // packed per-direction P2G records [3][2][cap] (k_seam_home -> splat)
     uint32_t *edge_list = nullptr;       // 3 x edge_cap sorted slots of near-plane ("edge") particles
     uint32_t *edge_count = nullptr;      // 4 counters (one per direction)
     uint32_t edge_cap = 0;

@@ -39,8 +39,6 @@ struct P2GParams {
     const float *vel;            // sorted velocity component of this direction
     const float *ax, *ay, *az;   // sorted affine row of this direction (APIC)
     const uint32_t *seam;        // membership word of this direction per sorted slot
-    const float4 *rec0;          // packed per-direction records: {p - offset (xyz), velocity component}
-    const float4 *rec1;          //                               {affine row (xyz), membership word bits}
     const uint32_t *edge_list;   // sorted slots of this direction's "edge" particles (unordered)
     const uint32_t *edge_count;  // how many k_seam_home found (may exceed edge_cap: list overflowed)
     uint32_t edge_cap;
@@ -60,9 +58,6 @@ struct SeamParams {
     int bdim[3][3];              // block dims per direction
     uint8_t *home[3];
     uint32_t *seam;              // [dir*cap + slot]
-    float4 *rec;                 // packed records [dir][part 0/1][cap] read by the splat kernel
-    const float *vel[3];         // sorted velocity streams
-    const float *aff[9];         // sorted affine streams (null for FLIP)
     uint32_t *edge_list;         // [dir*edge_cap + i]
     uint32_t *edge_count;        // [dir]
     uint32_t edge_cap;
@@ -127,12 +122,6 @@ __global__ void k_seam_home(SeamParams s) {
             if (fr < band || fr > 1.0 - band) word |= kEdgeBit;
         }
         s.seam[(size_t)dir * s.cap + j] = word;
-        // one 16-byte record (+ one more for APIC) per particle and direction: the splat kernel
-        // then needs a single fully used sector per particle instead of 5-8 scattered 4-byte loads
-        float4 *r0 = s.rec + ((size_t)dir * 2 + 0) * s.cap, *r1 = s.rec + ((size_t)dir * 2 + 1) * s.cap;
-        r0[j] = make_float4(x[0], x[1], x[2], s.vel[dir][j]);
-        if (s.aff[0])
-            r1[j] = make_float4(s.aff[3 * dir + 0][j], s.aff[3 * dir + 1][j], s.aff[3 * dir + 2][j], __uint_as_float(word));
         if (word & kEdgeBit) {
             const uint32_t slot = atomicAdd(s.edge_count + dir, 1u);
             if (slot < s.edge_cap) s.edge_list[(size_t)dir * s.edge_cap + slot] = (uint32_t)j;
@@ -736,11 +725,11 @@ __global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(P2G
                 uint32_t q = rs[0];
                 while (run < 4 && q >= re[run]) { run++; if (run < 4) q = rs[run]; }
                 uint32_t word = 0;
-                float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float px = 0.f, py = 0.f, pz = 0.f, vel = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
                 if (run < 4) {
-                    r0 = __ldg(P.rec0 + q);
-                    if (METHOD == FFB200_TRANSFER_APIC) { r1 = __ldg(P.rec1 + q); word = __float_as_uint(r1.w); }
-                    else word = __ldg(P.seam + q);
+                    word = __ldg(P.seam + q);
+                    px = __ldg(P.px + q); py = __ldg(P.py + q); pz = __ldg(P.pz + q); vel = __ldg(P.vel + q);
+                    if (METHOD == FFB200_TRANSFER_APIC) { a0 = __ldg(P.ax + q); a1 = __ldg(P.ay + q); a2 = __ldg(P.az + q); }
                 }
                 while (run < 4) {
                     // advance to the next particle and start its loads
@@ -748,17 +737,18 @@ __global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(P2G
                     uint32_t nq = q + 1;
                     while (nrun < 4 && nq >= re[nrun]) { nrun++; if (nrun < 4) nq = rs[nrun]; }
                     uint32_t nword = 0;
-                    float4 n0r = make_float4(0.f, 0.f, 0.f, 0.f), n1r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float npx = 0.f, npy = 0.f, npz = 0.f, nvel = 0.f, na0 = 0.f, na1 = 0.f, na2 = 0.f;
                     if (nrun < 4) {
-                        n0r = __ldg(P.rec0 + nq);
-                        if (METHOD == FFB200_TRANSFER_APIC) { n1r = __ldg(P.rec1 + nq); nword = __float_as_uint(n1r.w); }
-                        else nword = __ldg(P.seam + nq);
+                        nword = __ldg(P.seam + nq);
+                        npx = __ldg(P.px + nq); npy = __ldg(P.py + nq); npz = __ldg(P.pz + nq); nvel = __ldg(P.vel + nq);
+                        if (METHOD == FFB200_TRANSFER_APIC) { na0 = __ldg(P.ax + nq); na1 = __ldg(P.ay + nq); na2 = __ldg(P.az + nq); }
                     }
                     const bool use = seam_member(word, nbv[0], nbv[1], nbv[2]) &&
                                      !(METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit));   // edge: exact path below
                     if (use) {
-                        const float xl0 = r0.x - bpos[0], xl1 = r0.y - bpos[1], xl2 = r0.z - bpos[2];   // (p - offset) - blockOrigin
-                        const float vel = r0.w, a0 = r1.x, a1 = r1.y, a2 = r1.z;
+                        const float xl0 = (px - P.off[0]) - bpos[0];
+                        const float xl1 = (py - P.off[1]) - bpos[1];
+                        const float xl2 = (pz - P.off[2]) - bpos[2];
                         // node - particle, per axis and per node (0: lower, 1: upper)
                         const float vx[2] = {gpos0[0] - xl0, gpos1[0] - xl0};
                         const float vy[2] = {gpos0[1] - xl1, gpos1[1] - xl1};
@@ -794,7 +784,7 @@ __global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(P2G
                         }
                     }
                     run = nrun; q = nq; word = nword;
-                    r0 = n0r; r1 = n1r;
+                    px = npx; py = npy; pz = npz; vel = nvel; a0 = na0; a1 = na1; a2 = na2;
                 }
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
@@ -978,9 +968,6 @@ int launch_p2g_prepare(Context &c, double radius) {
             sp.home[d] = c.face[d].home;
         }
         sp.seam = c.sort.seam;
-        sp.rec = c.sort.rec;
-        for (int q = 0; q < 3; q++) sp.vel[q] = s.v[q];
-        for (int q = 0; q < 9; q++) sp.aff[q] = c.has_affine ? s.a[q] : nullptr;
         sp.edge_list = c.sort.edge_list;
         sp.edge_count = c.sort.edge_count;
         sp.edge_cap = c.sort.edge_cap;
@@ -1030,8 +1017,6 @@ int launch_p2g(Context &c, double radius, int method) {
         P.vel = s.v[d];
         P.ax = s.a[3 * d + 0]; P.ay = s.a[3 * d + 1]; P.az = s.a[3 * d + 2];
         P.seam = c.sort.seam + (size_t)d * c.cap;
-        P.rec0 = c.sort.rec + ((size_t)d * 2 + 0) * c.cap;
-        P.rec1 = c.sort.rec + ((size_t)d * 2 + 1) * c.cap;
         P.edge_list = c.sort.edge_list + (size_t)d * c.sort.edge_cap;
         P.edge_count = c.sort.edge_count + d;
         P.edge_cap = c.sort.edge_cap;
