@@ -179,7 +179,7 @@ __device__ __noinline__ void resolve_collision(const AdvectParams &P, float ox, 
     nx = rx; ny = ry; nz = rz;
 }
 
-__global__ void __launch_bounds__(256) k_advect(AdvectParams P) {
+__global__ void __launch_bounds__(256) k_advect(const __grid_constant__ AdvectParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];

@@ -156,6 +156,10 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->near_solid);
     dev_free(c->slab_counters);
     dev_free(c->sort.edge_count);
+    if (c->sort.partial) cudaFree(c->sort.partial);
+    dev_free(c->sort.cell_flag);
+    if (c->sort.ovf) cudaFree(c->sort.ovf);
+    dev_free(c->sort.ovf_count);
     for (int s = 0; s < kNumStages; s++) {
         if (c->evs.start[s]) cudaEventDestroy(c->evs.start[s]);
         if (c->evs.stop[s]) cudaEventDestroy(c->evs.stop[s]);

@@ -54,6 +54,11 @@ struct SortScratch {
     uint32_t *scan_partials = nullptr;   // block sums for the scans
     size_t scan_partials_cap = 0;
     uint32_t *seam = nullptr;            // 3 words per slot [dir*cap + slot]: 10^3-block membership
+    void *partial = nullptr;             // cell-partial splat scratch: 8 float2 per shifted cell
+    uint8_t *cell_flag = nullptr;
+    size_t partial_cells = 0;
+    void *ovf = nullptr;                 // edge-particle overflow list + its counter
+    int *ovf_count = nullptr;
     uint32_t *edge_list = nullptr;       // 3 x edge_cap sorted slots of near-plane ("edge") particles
     uint32_t *edge_count = nullptr;      // 4 counters (one per direction)
     uint32_t edge_cap = 0;

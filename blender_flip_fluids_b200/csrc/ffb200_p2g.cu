@@ -27,6 +27,8 @@ namespace ffb200 {
 
 namespace {
 
+struct OverflowEntry;
+
 struct P2GParams {
     GridDesc g;
     int gi, gj, gk;              // global face dims of this direction
@@ -43,6 +45,11 @@ struct P2GParams {
     const uint32_t *edge_count;  // how many k_seam_home found (may exceed edge_cap: list overflowed)
     uint32_t edge_cap;
     const uint32_t *orig;
+    float2 *partial;             // cell-partial splat: 8 (sum w, sum w*v) pairs per shifted cell
+    uint8_t *cell_flag;          // 1 if the cell holds particles (its partial slot is valid)
+    int ccx, ccy, ccz, ck0;      // shifted-cell grid: cells b = (ix-1, iy-1, iz+ck0)
+    OverflowEntry *ovf;          // contributions of edge particles outside their bin cell
+    int *ovf_count;
     float *out, *wsum;
     uint8_t *valid;
     float off[3];                // _getDirectionOffset, velocityadvector.cpp:177-188
@@ -241,7 +248,7 @@ __device__ __noinline__ void exact_face(const P2GParams &P, const FaceFrame &f, 
 }
 
 template <int DIR, int METHOD>
-__global__ void __launch_bounds__(256) k_p2g(P2GParams P) {
+__global__ void __launch_bounds__(256) k_p2g(const __grid_constant__ P2GParams P) {
     const int ni = blockIdx.x * blockDim.x + threadIdx.x;
     const int nj = blockIdx.y * blockDim.y + threadIdx.y;
     const int ks = blockIdx.z * blockDim.z + threadIdx.z;     // stored plane
@@ -377,7 +384,7 @@ template <int DIR, int METHOD>
 __device__ __forceinline__ void accumulate_global(const P2GParams &P, const FaceFrame &f, float &sw, float &swv, int &cnt);
 
 template <int DIR, int METHOD>
-__global__ void __launch_bounds__(kBrickThreads) k_p2g_brick(P2GParams P) {
+__global__ void __launch_bounds__(kBrickThreads) k_p2g_brick(const __grid_constant__ P2GParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CAP = BrickCap<METHOD>::value;
     float4 *rec = reinterpret_cast<float4 *>(smem_raw);
@@ -665,7 +672,7 @@ struct SplatShared {
 };
 
 template <int DIR, int METHOD>
-__global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(P2GParams P) {
+__global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(const __grid_constant__ P2GParams P) {
     __shared__ SplatShared S;
     const int tid = threadIdx.x;
     const int nbv[3] = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + P.kw0 / kChunk};
@@ -897,6 +904,333 @@ __global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(P2G
     }
 }
 
+// ---- cell-partial splat (default) -------------------------------------------------------------------
+//
+// The splat again, but with no CTA structure at all, so every particle is visited exactly once
+// per direction and all lanes stay busy:
+//
+//   k_p2g_cells   one thread per SHIFTED CELL (the staggered-frame cell whose corner nodes are
+//                 base + {0,1}^3; its particles are four runs of the sorted streams). The thread
+//                 splats its particles onto its own 8 corner nodes -- each in the frame of THAT
+//                 node's 10^3 block, with that block's membership test, exactly as the reference
+//                 would when it processes the block -- and stores the 8 (sum w, sum w*v) pairs in
+//                 its private slot of `partial`. No two threads share a slot: no atomics, no
+//                 colouring, no barriers.
+//   k_p2g_nodes   one thread per face: adds the 8 partial sums of the cells around it in a fixed
+//                 order, then the guard-band / exact_face / normalise / valid-byte epilogue.
+//
+// Summation order per face: cell order (fixed), sorted particle order inside a cell: bitwise
+// deterministic. APIC "edge" particles take exact_contribution() inside their cell; the rare
+// case that the reference's double floor puts such a particle in a neighbouring cell, so that it
+// also reaches nodes outside its bin cell, is collected by k_p2g_edge_overflow into a short list
+// that k_p2g_nodes adds in sorted order.
+struct OverflowEntry {
+    uint32_t node;      // flat stored face index
+    uint32_t q;         // sorted particle slot
+    float w, wv;
+};
+constexpr int kOverflowCap = 4096;
+
+struct AxisNodes {
+    int nb[2];          // block of node 0 / node 1 (-1: node outside the face grid)
+    float bpos[2];      // blockOrigin of that block
+    float gpos[2];      // local node position in that block's frame
+    float gposm1;       // position of local node (lo1 - 1) in node 1's frame
+    int lo[2];
+};
+
+__device__ __forceinline__ AxisNodes axis_nodes(int b, int dim, double chunk, double dx) {
+    AxisNodes a;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int n = b + j;
+        const bool ok = n >= 0 && n < dim;
+        const int nb = ok ? n / kChunk : 0;
+        a.nb[j] = ok ? nb : -1;
+        a.lo[j] = n - nb * kChunk;
+        a.bpos[j] = idx2posf(nb, chunk);
+        a.gpos[j] = idx2posf(a.lo[j], dx);
+    }
+    a.gposm1 = idx2posf(a.lo[1] - 1, dx);
+    return a;
+}
+
+template <int DIR, int METHOD>
+__global__ void __launch_bounds__(128) k_p2g_cells(const __grid_constant__ P2GParams P) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)P.ccx * P.ccy * P.ccz) return;
+    const int ix = (int)(t % P.ccx), iy = (int)((t / P.ccx) % P.ccy), iz = (int)(t / ((long long)P.ccx * P.ccy));
+    const int b[3] = {ix - 1, iy - 1, iz + P.ck0};
+    const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
+    int hb[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) hb[a] = 2 * b[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+
+    // the cell's four runs
+    const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
+    uint32_t rs[4], re[4];
+    uint32_t total = 0;
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int hz = hb[2] + (rr >> 1), hy = hb[1] + (rr & 1);
+        rs[rr] = 0; re[rr] = 0;
+        if (hx0 <= hx1 && hz >= 0 && hz < H[2] && hy >= 0 && hy < H[1]) {
+            const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
+            rs[rr] = __ldg(P.bin_start + row + hx0);
+            re[rr] = __ldg(P.bin_start + row + hx1 + 1);
+        }
+        total += re[rr] - rs[rr];
+    }
+    if (total == 0) {
+        P.cell_flag[t] = 0;
+        return;
+    }
+
+    const AxisNodes X = axis_nodes(b[0], P.gi, P.chunk, P.g.dx), Y = axis_nodes(b[1], P.gj, P.chunk, P.g.dx),
+                    Z = axis_nodes(b[2], P.gk, P.chunk, P.g.dx);
+    float aw[8], awv[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) { aw[c] = 0.0f; awv[c] = 0.0f; }
+
+    int run = 0;
+    uint32_t q = rs[0];
+    while (run < 4 && q >= re[run]) { run++; if (run < 4) q = rs[run]; }
+    uint32_t word = 0;
+    float px = 0.f, py = 0.f, pz = 0.f, vel = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (run < 4) {
+        word = __ldg(P.seam + q);
+        px = __ldg(P.px + q); py = __ldg(P.py + q); pz = __ldg(P.pz + q); vel = __ldg(P.vel + q);
+        if (METHOD == FFB200_TRANSFER_APIC) { a0 = __ldg(P.ax + q); a1 = __ldg(P.ay + q); a2 = __ldg(P.az + q); }
+    }
+    while (run < 4) {
+        int nrun = run;
+        uint32_t nq = q + 1;
+        while (nrun < 4 && nq >= re[nrun]) { nrun++; if (nrun < 4) nq = rs[nrun]; }
+        uint32_t nword = 0;
+        float npx = 0.f, npy = 0.f, npz = 0.f, nvel = 0.f, na0 = 0.f, na1 = 0.f, na2 = 0.f;
+        if (nrun < 4) {
+            nword = __ldg(P.seam + nq);
+            npx = __ldg(P.px + nq); npy = __ldg(P.py + nq); npz = __ldg(P.pz + nq); nvel = __ldg(P.vel + nq);
+            if (METHOD == FFB200_TRANSFER_APIC) { na0 = __ldg(P.ax + nq); na1 = __ldg(P.ay + nq); na2 = __ldg(P.az + nq); }
+        }
+        // membership of the particle in the block of node 0 / node 1, per axis
+        const int lx = (int)(word & 255u) - 1, sx = (int)((word >> 8) & 3u);
+        const int ly = (int)((word >> 10) & 255u) - 1, sy = (int)((word >> 18) & 3u);
+        const int lz = (int)((word >> 20) & 255u) - 1, sz = (int)((word >> 28) & 3u);
+        const bool mx[2] = {X.nb[0] >= 0 && (unsigned)(X.nb[0] - lx) <= (unsigned)sx,
+                            X.nb[1] >= 0 && (unsigned)(X.nb[1] - lx) <= (unsigned)sx};
+        const bool my[2] = {Y.nb[0] >= 0 && (unsigned)(Y.nb[0] - ly) <= (unsigned)sy,
+                            Y.nb[1] >= 0 && (unsigned)(Y.nb[1] - ly) <= (unsigned)sy};
+        const bool mz[2] = {Z.nb[0] >= 0 && (unsigned)(Z.nb[0] - lz) <= (unsigned)sz,
+                            Z.nb[1] >= 0 && (unsigned)(Z.nb[1] - lz) <= (unsigned)sz};
+        if (METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit)) {
+            // near a cell plane: the reference's own arithmetic, node by node
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+                if (!(mx[cx] && my[cy] && mz[cz])) continue;
+                FaceFrame f;
+                f.nb[0] = X.nb[cx]; f.nb[1] = Y.nb[cy]; f.nb[2] = Z.nb[cz];
+                f.lo[0] = X.lo[cx]; f.lo[1] = Y.lo[cy]; f.lo[2] = Z.lo[cz];
+                f.bpos[0] = X.bpos[cx]; f.bpos[1] = Y.bpos[cy]; f.bpos[2] = Z.bpos[cz];
+                f.gpos[0] = X.gpos[cx]; f.gpos[1] = Y.gpos[cy]; f.gpos[2] = Z.gpos[cz];
+                float w, wv;
+                if (exact_contribution<DIR, METHOD>(P, f, q, w, wv)) {
+                    awv[c] += wv;
+                    aw[c] += w;
+                }
+            }
+        } else {
+            const float xs = px - P.off[0], ys = py - P.off[1], zs = pz - P.off[2];
+            // block-local coordinates in the frame of node 0's and node 1's block (equal unless the
+            // cell straddles a block seam)
+            const float xl[2] = {xs - X.bpos[0], xs - X.bpos[1]};
+            const float yl[2] = {ys - Y.bpos[0], ys - Y.bpos[1]};
+            const float zl[2] = {zs - Z.bpos[0], zs - Z.bpos[1]};
+            const float vx[2] = {X.gpos[0] - xl[0], X.gpos[1] - xl[1]};
+            const float vy[2] = {Y.gpos[0] - yl[0], Y.gpos[1] - yl[1]};
+            const float vz[2] = {Z.gpos[0] - zl[0], Z.gpos[1] - zl[1]};
+            if (METHOD == FFB200_TRANSFER_FLIP) {
+                const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
+                const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
+                const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+                    const float d2 = xx[cx] + yy[cy] + zz[cz];
+                    if (mx[cx] && my[cy] && mz[cz] && d2 < P.rsq) {
+                        const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
+                        awv[c] += w * vel;
+                        aw[c] += w;
+                    }
+                }
+            } else {
+                // node 0: the particle is in node 0's cell, factor 1 - ipos; node 1: it is in the cell
+                // below node 1, factor ipos measured from the node before node 1 (:567-592)
+                const float fx[2] = {1.0f - (xl[0] - X.gpos[0]) * P.inv_s, (xl[1] - X.gposm1) * P.inv_s};
+                const float fy[2] = {1.0f - (yl[0] - Y.gpos[0]) * P.inv_s, (yl[1] - Y.gposm1) * P.inv_s};
+                const float fz[2] = {1.0f - (zl[0] - Z.gpos[0]) * P.inv_s, (zl[1] - Z.gposm1) * P.inv_s};
+                const float ax[2] = {a0 * vx[0], a0 * vx[1]};
+                const float ay[2] = {a1 * vy[0], a1 * vy[1]};
+                const float az[2] = {a2 * vz[0], a2 * vz[1]};
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+                    if (mx[cx] && my[cy] && mz[cz]) {
+                        const float w = fx[cx] * fy[cy] * fz[cz];
+                        const float apic = ax[cx] + ay[cy] + az[cz];
+                        awv[c] += w * (vel + apic);
+                        aw[c] += w;
+                    }
+                }
+            }
+        }
+        run = nrun; q = nq; word = nword;
+        px = npx; py = npy; pz = npz; vel = nvel; a0 = na0; a1 = na1; a2 = na2;
+    }
+    P.cell_flag[t] = 1;
+    // corner-major layout: the faces of one x-row read consecutive cells of one corner plane
+    const size_t plane = (size_t)P.ccx * P.ccy * P.ccz;
+#pragma unroll
+    for (int c = 0; c < 8; c++) P.partial[(size_t)c * plane + t] = make_float2(aw[c], awv[c]);
+}
+
+// Edge particles whose exact cell (the reference's double floor in some block frame) differs from
+// their bin cell also reach nodes outside the 8 corners their cell thread handles: list those
+// contributions (almost always none).
+template <int DIR, int METHOD>
+__global__ void k_p2g_edge_overflow(const __grid_constant__ P2GParams P) {
+    const uint32_t nedge = min(__ldg(P.edge_count), P.edge_cap);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nedge) return;
+    const uint32_t q = __ldg(P.edge_list + t);
+    const float p[3] = {__ldg(P.px + q), __ldg(P.py + q), __ldg(P.pz + q)};
+    const int dims[3] = {P.gi, P.gj, P.gk};
+    const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
+    int b[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const int h = __double2int_rd((double)p[a] * P.g.inv_2dx);
+        b[a] = (h - (a == DIR ? 0 : 1)) >> 1;                 // the shifted cell whose thread owns this particle
+    }
+    for (int dz = -1; dz <= 2; dz++)
+        for (int dy = -1; dy <= 2; dy++)
+            for (int dx = -1; dx <= 2; dx++) {
+                if ((unsigned)dx <= 1u && (unsigned)dy <= 1u && (unsigned)dz <= 1u) continue;   // the cell's own corners
+                const int n[3] = {b[0] + dx, b[1] + dy, b[2] + dz};
+                if (n[0] < 0 || n[1] < 0 || n[2] < 0 || n[0] >= dims[0] || n[1] >= dims[1] || n[2] >= dims[2]) continue;
+                if (n[2] < P.kw0 || n[2] >= P.kw1) continue;
+                FaceFrame f;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    f.nb[a] = n[a] / kChunk;
+                    f.lo[a] = n[a] - f.nb[a] * kChunk;
+                    f.bpos[a] = idx2posf(f.nb[a], P.chunk);
+                    f.gpos[a] = idx2posf(f.lo[a], P.g.dx);
+                    f.gposm[a] = idx2posf(f.lo[a] - 1, P.g.dx);
+                    f.h0[a] = 0; f.h1[a] = H[a] - 1;
+                }
+                float w, wv;
+                if (exact_contribution<DIR, METHOD>(P, f, q, w, wv)) {
+                    const int slot = atomicAdd(P.ovf_count, 1);
+                    if (slot < kOverflowCap) {
+                        OverflowEntry e;
+                        e.node = (uint32_t)((size_t)n[0] + (size_t)P.gi * ((size_t)n[1] + (size_t)P.gj * (n[2] - P.g.kbase)));
+                        e.q = q; e.w = w; e.wv = wv;
+                        P.ovf[slot] = e;
+                    }
+                }
+            }
+}
+
+template <int DIR, int METHOD>
+__global__ void __launch_bounds__(128) k_p2g_nodes(const __grid_constant__ P2GParams P) {
+    const int ni = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nj = blockIdx.y * blockDim.y + threadIdx.y;
+    const int nk = blockIdx.z * blockDim.z + threadIdx.z + P.kw0;
+    if (ni >= P.gi || nj >= P.gj || nk >= P.kw1) return;
+    const size_t fidx = (size_t)ni + (size_t)P.gi * ((size_t)nj + (size_t)P.gj * (nk - P.g.kbase));
+    const int n[3] = {ni, nj, nk};
+    const int nbv[3] = {ni / kChunk, nj / kChunk, nk / kChunk};
+    if (!P.active[nbv[0] + P.bi * (nbv[1] + P.bj * nbv[2])]) {
+        P.out[fidx] = 0.0f;
+        P.wsum[fidx] = 0.0f;
+        P.valid[fidx] = 0;
+        return;
+    }
+    float sw = 0.0f, swv = 0.0f;
+    const size_t plane = (size_t)P.ccx * P.ccy * P.ccz;
+    // node n is corner c = (cx, cy, cz) of the shifted cell n - (cx, cy, cz)
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+        const int ix = ni - cx + 1, iy = nj - cy + 1, iz = nk - cz - P.ck0;
+        if (iz < 0 || iz >= P.ccz) continue;                  // cells outside this rank's range hold nothing for it
+        const size_t cell = (size_t)ix + (size_t)P.ccx * ((size_t)iy + (size_t)P.ccy * iz);
+        if (!__ldg(P.cell_flag + cell)) continue;
+        const float2 pr = __ldg(P.partial + (size_t)c * plane + cell);
+        sw += pr.x;
+        swv += pr.y;
+    }
+    const int novf = *P.ovf_count;
+    bool redo = novf > kOverflowCap || __ldg(P.edge_count) > P.edge_cap;
+    if (!redo && novf > 0) {                                   // rare: add the matching entries in ascending slot order
+        long long last = -1;
+        for (;;) {
+            long long best = 0x7fffffffffffffffLL;
+            int bi = -1;
+            for (int i = 0; i < novf; i++) {
+                const OverflowEntry e = P.ovf[i];
+                if (e.node == (uint32_t)fidx && (long long)e.q > last && (long long)e.q < best) { best = e.q; bi = i; }
+            }
+            if (bi < 0) break;
+            last = best;
+            sw += P.ovf[bi].w;
+            swv += P.ovf[bi].wv;
+        }
+    }
+    const float eps = 1e-6f;
+    if (redo || fabsf(sw - eps) <= P.guard_abs + P.guard_per * 512.0f) {
+        FaceFrame f;
+        const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            f.nb[a] = nbv[a];
+            f.lo[a] = n[a] - nbv[a] * kChunk;
+            f.bpos[a] = idx2posf(nbv[a], P.chunk);
+            f.gpos[a] = idx2posf(f.lo[a], P.g.dx);
+            f.gposm[a] = idx2posf(f.lo[a] - 1, P.g.dx);
+            const int c = 2 * n[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
+            f.h0[a] = max(c - P.wm, 0);
+            f.h1[a] = min(c + P.wm - 1, H[a] - 1);
+        }
+        exact_face<DIR, METHOD>(P, f, sw, swv);
+    }
+    float s = swv;
+    if (sw > eps) s /= sw;                                     // :527-531
+    P.out[fidx] = s;                                           // write-out :155-162
+    P.wsum[fidx] = sw;
+    P.valid[fidx] = sw > eps ? 1 : 0;
+}
+
+template <int DIR, int METHOD>
+int launch_cells(Context &c, P2GParams &P) {
+    int launches = 0;
+    FFB_CUDA(cudaMemsetAsync(P.ovf_count, 0, sizeof(int), c.stream));
+    const long long ncell = (long long)P.ccx * P.ccy * P.ccz;
+    k_p2g_cells<DIR, METHOD><<<(unsigned)((ncell + 127) / 128), 128, 0, c.stream>>>(P);
+    launches++;
+    if (METHOD == FFB200_TRANSFER_APIC) {
+        k_p2g_edge_overflow<DIR, METHOD><<<(P.edge_cap + 127) / 128, 128, 0, c.stream>>>(P);
+        launches++;
+    }
+    dim3 block(32, 4, 1);
+    dim3 grid((P.gi + 31) / 32, (P.gj + 3) / 4, P.kw1 - P.kw0);
+    k_p2g_nodes<DIR, METHOD><<<grid, block, 0, c.stream>>>(P);
+    launches++;
+    return launches;
+}
+
 template <int DIR, int METHOD>
 void launch_splat(Context &c, P2GParams &P) {
     const int zb0 = P.kw0 / kChunk, zb1 = (P.kw1 - 1) / kChunk;
@@ -919,22 +1253,27 @@ void launch_brick(Context &c, P2GParams &P) {
 }
 
 template <int DIR>
-void launch_dir(Context &c, P2GParams &P, int method, int variant) {
-    // variant 0: coloured splat (support of one cell: default radius and APIC); 1: brick gather
-    // (any radius up to 2 dx); 2: first-generation global gather. FFB200_P2G_VARIANT overrides.
+int launch_dir(Context &c, P2GParams &P, int method, int variant) {
+    // variant 0: cell-partial splat (support of one cell: default radius and APIC); 3: coloured block
+    // splat (same support); 1: brick gather (any radius up to 2 dx); 2: first-generation global
+    // gather. FFB200_P2G_VARIANT overrides; radii above dx always take the brick gather.
     if (variant == 0 && P.wm == 2) {
+        if (method == FFB200_TRANSFER_APIC) return launch_cells<DIR, FFB200_TRANSFER_APIC>(c, P);
+        return launch_cells<DIR, FFB200_TRANSFER_FLIP>(c, P);
+    }
+    if (variant == 3 && P.wm == 2) {
         if (method == FFB200_TRANSFER_APIC)
             launch_splat<DIR, FFB200_TRANSFER_APIC>(c, P);
         else
             launch_splat<DIR, FFB200_TRANSFER_FLIP>(c, P);
-        return;
+        return 1;
     }
     if (variant <= 1) {
         if (method == FFB200_TRANSFER_APIC)
             launch_brick<DIR, FFB200_TRANSFER_APIC>(c, P);
         else
             launch_brick<DIR, FFB200_TRANSFER_FLIP>(c, P);
-        return;
+        return 1;
     }
     dim3 block(32, 4, 2);
     dim3 grid((P.gi + block.x - 1) / block.x, (P.gj + block.y - 1) / block.y, (P.kstore + block.z - 1) / block.z);
@@ -942,6 +1281,7 @@ void launch_dir(Context &c, P2GParams &P, int method, int variant) {
         k_p2g<DIR, FFB200_TRANSFER_APIC><<<grid, block, 0, c.stream>>>(P);
     else
         k_p2g<DIR, FFB200_TRANSFER_FLIP><<<grid, block, 0, c.stream>>>(P);
+    return 1;
 }
 
 }  // namespace
@@ -998,7 +1338,7 @@ int launch_p2g(Context &c, double radius, int method) {
     ParticleSoA &s = c.soa[c.cur];
     const float eps = 1e-6f;
     const float sr = (float)(radius + (double)eps);            // float sr = _particleRadius + eps;
-    // FFB200_P2G_VARIANT: 0 coloured splat (default), 1 brick gather, 2 first-generation global gather
+    // FFB200_P2G_VARIANT: 0 cell-partial splat (default), 3 coloured block splat, 1 brick gather, 2 global gather
     static const int variant = [] { const char *e = std::getenv("FFB200_P2G_VARIANT"); return e ? std::atoi(e) : 0; }();
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];
@@ -1041,10 +1381,30 @@ int launch_p2g(Context &c, double radius, int method) {
         if (P.wm > kApron) throw CudaError("ffb200_p2g: particle radius above 2*dx is not supported");
         P.guard_abs = c.guard_abs >= 0.f ? c.guard_abs : 1e-9f;
         P.guard_per = c.guard_per >= 0.f ? c.guard_per : 1e-12f;
-        if (d == 0) launch_dir<0>(c, P, method, variant);
-        if (d == 1) launch_dir<1>(c, P, method, variant);
-        if (d == 2) launch_dir<2>(c, P, method, variant);
-        launches++;
+        P.ccx = f.gi + 1; P.ccy = f.gj + 1; P.ccz = P.kw1 - P.kw0 + 1; P.ck0 = P.kw0 - 1;
+        P.partial = nullptr; P.cell_flag = nullptr; P.ovf = nullptr; P.ovf_count = nullptr;
+        if (variant == 0 && P.wm == 2) {
+            const size_t cells = (size_t)P.ccx * P.ccy * P.ccz;
+            if (cells > c.sort.partial_cells) {                // grow-only scratch shared by the three directions
+                FFB_CUDA(cudaStreamSynchronize(c.stream));
+                if (c.sort.partial) FFB_CUDA(cudaFree(c.sort.partial));
+                if (c.sort.cell_flag) FFB_CUDA(cudaFree(c.sort.cell_flag));
+                c.sort.partial_cells = cells + cells / 16;
+                FFB_CUDA(cudaMalloc(&c.sort.partial, c.sort.partial_cells * 8 * sizeof(float2)));
+                FFB_CUDA(cudaMalloc(&c.sort.cell_flag, c.sort.partial_cells));
+            }
+            if (!c.sort.ovf) {
+                FFB_CUDA(cudaMalloc(&c.sort.ovf, (size_t)kOverflowCap * sizeof(OverflowEntry)));
+                FFB_CUDA(cudaMalloc(&c.sort.ovf_count, sizeof(int)));
+            }
+            P.partial = reinterpret_cast<float2 *>(c.sort.partial);
+            P.cell_flag = c.sort.cell_flag;
+            P.ovf = reinterpret_cast<OverflowEntry *>(c.sort.ovf);
+            P.ovf_count = c.sort.ovf_count;
+        }
+        if (d == 0) launches += launch_dir<0>(c, P, method, variant);
+        if (d == 1) launches += launch_dir<1>(c, P, method, variant);
+        if (d == 2) launches += launch_dir<2>(c, P, method, variant);
     }
     FFB_CUDA(cudaGetLastError());
     return launches;
