@@ -955,8 +955,11 @@ __device__ __forceinline__ AxisNodes axis_nodes(int b, int dim, double chunk, do
     return a;
 }
 
+#ifndef FFB_CELLS_MINB
+#define FFB_CELLS_MINB 8
+#endif
 template <int DIR, int METHOD>
-__global__ void __launch_bounds__(128) k_p2g_cells(const __grid_constant__ P2GParams P) {
+__global__ void __launch_bounds__(128, FFB_CELLS_MINB) k_p2g_cells(const __grid_constant__ P2GParams P) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)P.ccx * P.ccy * P.ccz) return;
     const int ix = (int)(t % P.ccx), iy = (int)((t / P.ccx) % P.ccy), iz = (int)(t / ((long long)P.ccx * P.ccy));

@@ -34,10 +34,15 @@ __device__ __forceinline__ int warp_slot(bool pred, int *counter) {
 __device__ __forceinline__ void write_record(const Streams &src, int j, float *block, int cap, int slot) {
     if (slot >= cap) return;                                  // overflow is reported through the header
     float *r = block + (size_t)slot * (src.ns + 1);
+    float v[15];
 #pragma unroll
     for (int t = 0; t < 15; t++)
-        if (t < src.ns) r[t] = src.s[t][j];
-    r[src.ns] = __uint_as_float(src.ids[j]);
+        if (t < src.ns) v[t] = src.s[t][j];
+    const uint32_t id = src.ids[j];
+#pragma unroll
+    for (int t = 0; t < 15; t++)
+        if (t < src.ns) r[t] = v[t];
+    r[src.ns] = __uint_as_float(id);
 }
 
 // Copy (not move) the particles of two cell-plane ranges into two packed buffers.

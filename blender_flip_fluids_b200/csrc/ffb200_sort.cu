@@ -321,9 +321,16 @@ __global__ void k_reorder(ReorderArgs a, const uint32_t *__restrict__ key, const
         dst = s + rank;
     }
     orig_new[dst] = my;
+    // all gathers first (independent, through the read-only path), then all stores: the stream
+    // pointers may alias as far as the compiler knows, so a load/store-per-stream loop would
+    // serialise on the memory latency
+    float v[15];
 #pragma unroll
     for (int t = 0; t < 15; t++)
-        if (t < a.nstreams) a.dst[t][dst] = a.src[t][slot];
+        if (t < a.nstreams) v[t] = __ldg(a.src[t] + slot);
+#pragma unroll
+    for (int t = 0; t < 15; t++)
+        if (t < a.nstreams) a.dst[t][dst] = v[t];
 }
 
 __global__ void k_binning_dump(GridDesc g, const float *__restrict__ px, const float *__restrict__ py,
