@@ -33,12 +33,15 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Build the library. `extra_flags`/`out` build a tuning variant (e.g. -DFFB_CELLS_MINB=4) next to
+    the default one; engine.load_library() picks it up through FFB200_LIBRARY."""
+    out = out or LIB
+    if not force and out == LIB and not is_stale():
         return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [nvcc_path()] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + list(extra_flags)
+    cmd = [nvcc_path()] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     env = dict(os.environ)
     env.pop("CXX", None), env.pop("CC", None)      # the image's CXX wrapper lacks libgomp specs; nvcc wants plain g++
     r = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], capture_output=True, text=True, env=env)
@@ -46,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libffb200.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

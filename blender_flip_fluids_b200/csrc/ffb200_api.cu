@@ -156,10 +156,17 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->near_solid);
     dev_free(c->slab_counters);
     dev_free(c->sort.edge_count);
-    if (c->sort.partial) cudaFree(c->sort.partial);
-    dev_free(c->sort.cell_flag);
-    if (c->sort.ovf) cudaFree(c->sort.ovf);
-    dev_free(c->sort.ovf_count);
+    for (auto &cs : c->sort.cell) {
+        if (cs.partial) cudaFree(cs.partial);
+        if (cs.cell_list) cudaFree(cs.cell_list);
+        if (cs.ovf) cudaFree(cs.ovf);
+        dev_free(cs.cell_flag);
+        dev_free(cs.list_count);
+        dev_free(cs.ovf_count);
+        if (cs.done) cudaEventDestroy(cs.done);
+        if (cs.stream) cudaStreamDestroy(cs.stream);
+    }
+    if (c->sort.fork) cudaEventDestroy(c->sort.fork);
     for (int s = 0; s < kNumStages; s++) {
         if (c->evs.start[s]) cudaEventDestroy(c->evs.start[s]);
         if (c->evs.stop[s]) cudaEventDestroy(c->evs.stop[s]);
@@ -184,6 +191,7 @@ int create_impl(ffb200_context **out, int I, int J, int K, double dx, int device
         FFB_CUDA(cudaSetDevice(device));
         c = new ContextImpl();
         c->device = device;
+        FFB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         c->k_own_begin = k_begin; c->k_own_end = k_end; c->halo = halo;
         GridDesc &g = c->g;
         g.I = I; g.J = J; g.K = K;

@@ -54,11 +54,20 @@ struct SortScratch {
     uint32_t *scan_partials = nullptr;   // block sums for the scans
     size_t scan_partials_cap = 0;
     uint32_t *seam = nullptr;            // 3 words per slot [dir*cap + slot]: 10^3-block membership
-    void *partial = nullptr;             // cell-partial splat scratch: 8 float2 per shifted cell
-    uint8_t *cell_flag = nullptr;
-    size_t partial_cells = 0;
-    void *ovf = nullptr;                 // edge-particle overflow list + its counter
-    int *ovf_count = nullptr;
+    // cell-partial splat scratch, one set per MAC direction so that the three transfers can run
+    // concurrently (direction 0 on the context stream, 1 and 2 on auxiliary streams)
+    struct CellScratch {
+        void *partial = nullptr;         // 8 float2 per shifted cell
+        uint8_t *cell_flag = nullptr;
+        void *cell_list = nullptr;       // occupied shifted cells (plain from the front, seam from the back)
+        uint32_t *list_count = nullptr;
+        void *ovf = nullptr;             // edge-particle overflow list + its counter
+        int *ovf_count = nullptr;
+        size_t cells = 0;
+        cudaStream_t stream = nullptr;   // auxiliary stream (directions 1, 2)
+        cudaEvent_t done = nullptr;
+    } cell[3];
+    cudaEvent_t fork = nullptr;
     uint32_t *edge_list = nullptr;       // 3 x edge_cap sorted slots of near-plane ("edge") particles
     uint32_t *edge_count = nullptr;      // 4 counters (one per direction)
     uint32_t edge_cap = 0;
@@ -67,6 +76,7 @@ struct SortScratch {
 struct Context {
     GridDesc g;
     int device = 0;
+    int sm_count = 148;                  // multiprocessors of `device` (grid sizing of the persistent kernels)
     int k_own_begin = 0, k_own_end = 0, halo = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -28,6 +28,7 @@ namespace ffb200 {
 namespace {
 
 struct OverflowEntry;
+struct CellRec;
 
 struct P2GParams {
     GridDesc g;
@@ -47,6 +48,9 @@ struct P2GParams {
     const uint32_t *orig;
     float2 *partial;             // cell-partial splat: 8 (sum w, sum w*v) pairs per shifted cell
     uint8_t *cell_flag;          // 1 if the cell holds particles (its partial slot is valid)
+    CellRec *cell_list;          // occupied shifted cells: plain ones from the front, seam ones from the back
+    uint32_t *list_count;        // [0] plain, [1] seam
+    uint32_t list_cap;
     int ccx, ccy, ccz, ck0;      // shifted-cell grid: cells b = (ix-1, iy-1, iz+ck0)
     OverflowEntry *ovf;          // contributions of edge particles outside their bin cell
     int *ovf_count;
@@ -909,21 +913,24 @@ __global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(con
 // The splat again, but with no CTA structure at all, so every particle is visited exactly once
 // per direction and all lanes stay busy:
 //
-//   k_p2g_cells   one thread per SHIFTED CELL (the staggered-frame cell whose corner nodes are
-//                 base + {0,1}^3; its particles are four runs of the sorted streams). The thread
-//                 splats its particles onto its own 8 corner nodes -- each in the frame of THAT
-//                 node's 10^3 block, with that block's membership test, exactly as the reference
-//                 would when it processes the block -- and stores the 8 (sum w, sum w*v) pairs in
-//                 its private slot of `partial`. No two threads share a slot: no atomics, no
-//                 colouring, no barriers.
+//   k_p2g_cell_list  lists the occupied SHIFTED CELLS (the staggered-frame cells whose corner nodes
+//                 are base + {0,1}^3; a cell's particles are four runs of the sorted streams) in two
+//                 classes: plain (one 10^3 block holds all 8 corners) and seam / border.
+//   k_p2g_cells   one thread per listed cell, so warps are full whatever the fill pattern. The
+//                 thread splats its particles onto its own 8 corner nodes -- each in the frame of
+//                 THAT node's 10^3 block, with that block's membership test, exactly as the
+//                 reference would when it processes the block -- and stores the 8 (sum w, sum w*v)
+//                 pairs in its private slot of `partial`. No two threads share a slot: no atomics,
+//                 no colouring, no barriers. Plain cells (73 %) share the per-axis factors between
+//                 the corners: ~80 float operations per particle and direction.
 //   k_p2g_nodes   one thread per face: adds the 8 partial sums of the cells around it in a fixed
 //                 order, then the guard-band / exact_face / normalise / valid-byte epilogue.
 //
 // Summation order per face: cell order (fixed), sorted particle order inside a cell: bitwise
-// deterministic. APIC "edge" particles take exact_contribution() inside their cell; the rare
-// case that the reference's double floor puts such a particle in a neighbouring cell, so that it
-// also reaches nodes outside its bin cell, is collected by k_p2g_edge_overflow into a short list
-// that k_p2g_nodes adds in sorted order.
+// deterministic. APIC "edge" particles are skipped by the splat and added by k_p2g_edge with
+// exact_contribution(): to their own cell's partial sums, and -- the rare case that the
+// reference's double floor puts such a particle in a neighbouring cell, so that it also reaches
+// nodes outside its bin cell -- to a short overflow list that k_p2g_nodes adds in sorted order.
 struct OverflowEntry {
     uint32_t node;      // flat stored face index
     uint32_t q;         // sorted particle slot
@@ -955,154 +962,369 @@ __device__ __forceinline__ AxisNodes axis_nodes(int b, int dim, double chunk, do
     return a;
 }
 
-#ifndef FFB_CELLS_MINB
-#define FFB_CELLS_MINB 8
-#endif
-template <int DIR, int METHOD>
-__global__ void __launch_bounds__(128, FFB_CELLS_MINB) k_p2g_cells(const __grid_constant__ P2GParams P) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)P.ccx * P.ccy * P.ccz) return;
-    const int ix = (int)(t % P.ccx), iy = (int)((t / P.ccx) % P.ccy), iz = (int)(t / ((long long)P.ccx * P.ccy));
-    const int b[3] = {ix - 1, iy - 1, iz + P.ck0};
+// One listed (occupied) shifted cell: its flat index and its four runs of sorted slots (two
+// half-cell rows in y times two in z; the two x half-cells of a row are adjacent bins).
+struct __align__(16) CellRec {
+    uint32_t t;         // flat shifted-cell index
+    uint32_t rs[4];     // first slot of each run
+    uint32_t n01, n23;  // run lengths, 16 bits each (0xffffffff in n01: lengths do not fit, re-read the bin table)
+    uint32_t pad;
+};
+
+// Loads are unconditional on clamped indices so that all eight are in flight together. The bin
+// table has fewer than 2^32 entries (32-bit keys), so 32-bit index arithmetic is exact.
+template <int DIR>
+__device__ __forceinline__ uint32_t cell_runs(const P2GParams &P, const int b[3], uint32_t rs[4], uint32_t re[4]) {
     const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
     int hb[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) hb[a] = 2 * b[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
-
-    // the cell's four runs
     const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
-    uint32_t rs[4], re[4];
-    uint32_t total = 0;
+    uint32_t i0[4], i1[4];
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) {
         const int hz = hb[2] + (rr >> 1), hy = hb[1] + (rr & 1);
-        rs[rr] = 0; re[rr] = 0;
-        if (hx0 <= hx1 && hz >= 0 && hz < H[2] && hy >= 0 && hy < H[1]) {
-            const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
-            rs[rr] = __ldg(P.bin_start + row + hx0);
-            re[rr] = __ldg(P.bin_start + row + hx1 + 1);
-        }
-        total += re[rr] - rs[rr];
+        const bool ok = hx0 <= hx1 && (unsigned)hz < (unsigned)H[2] && (unsigned)hy < (unsigned)H[1];
+        const uint32_t row = ((uint32_t)hz * (uint32_t)P.g.HY + (uint32_t)hy) * (uint32_t)P.g.HX;
+        i0[rr] = ok ? row + (uint32_t)hx0 : 0u;
+        i1[rr] = ok ? row + (uint32_t)hx1 + 1u : 0u;
     }
-    if (total == 0) {
-        P.cell_flag[t] = 0;
-        return;
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        rs[rr] = __ldg(P.bin_start + i0[rr]);
+        re[rr] = __ldg(P.bin_start + i1[rr]);
+    }
+    return (re[0] - rs[0]) + (re[1] - rs[1]) + (re[2] - rs[2]) + (re[3] - rs[3]);
+}
+
+// Pass 1: classify every shifted cell of this direction and list the occupied ones, so that the
+// splat kernel below runs on full warps. Class "plain": both corner nodes of every axis lie inside
+// the face grid and in the same 10^3 block -- one block frame, one membership test per particle.
+// Class "seam": everything else (block seams, grid border). Plain cells are listed from the front
+// of cell_list, seam cells from the back; a CTA reserves its entries with one atomic per class and
+// keeps x-neighbours together. The list order has no influence on the result (every cell owns
+// its slot of `partial`).
+constexpr int kListThreads = 256;
+template <int DIR>
+__global__ void __launch_bounds__(kListThreads) k_p2g_cell_list(const __grid_constant__ P2GParams P) {
+    __shared__ uint32_t warp_cnt[2][kListThreads / 32];
+    __shared__ uint32_t cta_base[2];
+    const uint32_t nxy = (uint32_t)P.ccx * (uint32_t)P.ccy;
+    const uint32_t xy = blockIdx.x * (uint32_t)kListThreads + threadIdx.x;
+    const int iz = (int)blockIdx.y;
+    int cls = 0;                                              // 0 empty, 1 plain, 2 seam
+    CellRec rec;
+    rec.t = 0; rec.n01 = rec.n23 = rec.pad = 0;
+    rec.rs[0] = rec.rs[1] = rec.rs[2] = rec.rs[3] = 0;
+    if (xy < nxy) {
+        const int iy = (int)(xy / (uint32_t)P.ccx), ix = (int)(xy - (uint32_t)iy * (uint32_t)P.ccx);
+        rec.t = xy + nxy * (uint32_t)iz;
+        const int b[3] = {ix - 1, iy - 1, iz + P.ck0};
+        // a cell can only hold particles if its 10^3 block is in the (dilated) particle block mask
+        const int kb = min(max(b[2], 0) / kChunk, P.bk - 1);
+        const bool maybe = P.active[max(b[0], 0) / kChunk + P.bi * (max(b[1], 0) / kChunk + P.bj * kb)] != 0;
+        uint32_t re[4] = {0u, 0u, 0u, 0u};
+        const uint32_t total = maybe ? cell_runs<DIR>(P, b, rec.rs, re) : 0u;
+        const uint32_t n0 = re[0] - rec.rs[0], n1 = re[1] - rec.rs[1], n2 = re[2] - rec.rs[2], n3 = re[3] - rec.rs[3];
+        rec.n01 = n0 | (n1 << 16);
+        rec.n23 = n2 | (n3 << 16);
+        if ((n0 | n1 | n2 | n3) > 0xffffu) rec.n01 = 0xffffffffu;
+        const int dims[3] = {P.gi, P.gj, P.gk};
+        bool plain = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) plain = plain && b[a] >= 0 && b[a] + 1 < dims[a] && (b[a] % kChunk) != kChunk - 1;
+        cls = total == 0 ? 0 : (plain ? 1 : 2);
+        P.cell_flag[rec.t] = total != 0;
+    }
+    const unsigned mp = __ballot_sync(0xffffffffu, cls == 1), ms = __ballot_sync(0xffffffffu, cls == 2);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, below = (1u << lane) - 1u;
+    if (lane == 0) { warp_cnt[0][warp] = __popc(mp); warp_cnt[1][warp] = __popc(ms); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        uint32_t sum = 0;
+        for (int w = 0; w < kListThreads / 32; w++) sum += warp_cnt[threadIdx.x][w];
+        cta_base[threadIdx.x] = sum ? atomicAdd(P.list_count + threadIdx.x, sum) : 0u;
+    }
+    __syncthreads();
+    if (cls) {
+        const int k = cls - 1;
+        uint32_t pos = cta_base[k] + __popc((k ? ms : mp) & below);
+        for (unsigned w = 0; w < warp; w++) pos += warp_cnt[k][w];
+        CellRec *dst = P.cell_list + (k ? P.list_cap - 1u - pos : pos);
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(rec.t, rec.rs[0], rec.rs[1], rec.rs[2]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(rec.rs[3], rec.n01, rec.n23, 0u);
+    }
+}
+
+// APIC "edge" particle (within a few ulps of a cell plane) of shifted cell b: the reference's own
+// arithmetic, corner by corner. Out of line: it is rare, and it would otherwise dominate the
+// register budget of the splat loop. Returns the mask of corners that received a contribution.
+template <int DIR, int METHOD>
+__device__ __noinline__ unsigned edge_cell_contrib(const P2GParams &P, uint32_t q, int bx, int by, int bz, float2 *out) {
+    const AxisNodes X = axis_nodes(bx, P.gi, P.chunk, P.g.dx), Y = axis_nodes(by, P.gj, P.chunk, P.g.dx),
+                    Z = axis_nodes(bz, P.gk, P.chunk, P.g.dx);
+    const uint32_t word = __ldg(P.seam + q);
+    const int lx = (int)(word & 255u) - 1, sx = (int)((word >> 8) & 3u);
+    const int ly = (int)((word >> 10) & 255u) - 1, sy = (int)((word >> 18) & 3u);
+    const int lz = (int)((word >> 20) & 255u) - 1, sz = (int)((word >> 28) & 3u);
+    unsigned mask = 0;
+    for (int c = 0; c < 8; c++) {
+        const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+        out[c] = make_float2(0.0f, 0.0f);
+        if (X.nb[cx] < 0 || Y.nb[cy] < 0 || Z.nb[cz] < 0) continue;
+        if ((unsigned)(X.nb[cx] - lx) > (unsigned)sx || (unsigned)(Y.nb[cy] - ly) > (unsigned)sy ||
+            (unsigned)(Z.nb[cz] - lz) > (unsigned)sz)
+            continue;
+        FaceFrame f;
+        f.nb[0] = X.nb[cx]; f.nb[1] = Y.nb[cy]; f.nb[2] = Z.nb[cz];
+        f.lo[0] = X.lo[cx]; f.lo[1] = Y.lo[cy]; f.lo[2] = Z.lo[cz];
+        f.bpos[0] = X.bpos[cx]; f.bpos[1] = Y.bpos[cy]; f.bpos[2] = Z.bpos[cz];
+        f.gpos[0] = X.gpos[cx]; f.gpos[1] = Y.gpos[cy]; f.gpos[2] = Z.gpos[cz];
+        float w, wv;
+        if (exact_contribution<DIR, METHOD>(P, f, q, w, wv)) {
+            out[c] = make_float2(w, wv);
+            mask |= 1u << c;
+        }
+    }
+    return mask;
+}
+
+// Particle staging of the splat kernel: every thread copies the records of (up to) kStage of ITS
+// cell's particles into its private shared-memory column with 4-byte cp.async, all at once, and
+// only then starts the arithmetic. A cell-per-thread walk has no other memory parallelism: with
+// plain loads a thread has one particle in flight. No barrier is needed -- a thread only reads
+// what it copied itself (cp.async.wait_group makes that visible to it).
+constexpr int kCellThreads = 128;
+#ifndef FFB_CELLS_STAGE
+#define FFB_CELLS_STAGE 4
+#endif
+constexpr int kStage = FFB_CELLS_STAGE;
+
+template <int METHOD>
+struct CellStage {
+    float4 a[kStage][kCellThreads];                                           // px, py, pz, vel
+    float4 b[METHOD == FFB200_TRANSFER_APIC ? kStage : 1][kCellThreads];      // affine row, seam word (APIC)
+    uint32_t w[METHOD == FFB200_TRANSFER_APIC ? 1 : kStage][kCellThreads];    // seam word (FLIP)
+};
+
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Pass 2, one listed cell per thread: splat the cell's particles onto its 8 corner nodes.
+template <int DIR, int METHOD, bool SEAM>
+__device__ __forceinline__ void splat_cell(const P2GParams &P, const CellRec *__restrict__ recp, CellStage<METHOD> &S) {
+    const int tid = threadIdx.x;
+    const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(recp)), r1 = __ldg(reinterpret_cast<const uint4 *>(recp) + 1);
+    const uint32_t t = r0.x;
+    const uint32_t nxy = (uint32_t)P.ccx * (uint32_t)P.ccy;
+    const int iz = (int)(t / nxy);
+    const uint32_t xy = t - (uint32_t)iz * nxy;
+    const int iy = (int)(xy / (uint32_t)P.ccx), ix = (int)(xy - (uint32_t)iy * (uint32_t)P.ccx);
+    const int b[3] = {ix - 1, iy - 1, iz + P.ck0};
+    uint32_t rs[4] = {r0.y, r0.z, r0.w, r1.x};
+    uint32_t n[4] = {r1.y & 0xffffu, r1.y >> 16, r1.z & 0xffffu, r1.z >> 16};
+    if (r1.y == 0xffffffffu) {                                 // run lengths above 65535: re-read the bin table
+        uint32_t re[4];
+        cell_runs<DIR>(P, b, rs, re);
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) n[rr] = re[rr] - rs[rr];
+    }
+    // flattened walk over the four runs: slot of the i-th particle = i + o(i)
+    const uint32_t c1 = n[0], c2 = c1 + n[1], c3 = c2 + n[2], total = c3 + n[3];
+    const uint32_t o0 = rs[0], o1 = rs[1] - c1, o2 = rs[2] - c2, o3 = rs[3] - c3;
+#define FFB_SLOT(i) ((i) + ((i) < c1 ? o0 : ((i) < c2 ? o1 : ((i) < c3 ? o2 : o3))))
+#define FFB_STAGE_FILL(i0)                                                                               \
+    {                                                                                                    \
+        _Pragma("unroll") for (int k = 0; k < kStage; k++) {                                            \
+            const uint32_t i = (i0) + k;                                                                 \
+            if (i < total) {                                                                             \
+                const uint32_t q = FFB_SLOT(i);                                                          \
+                cp_async4(&S.a[k][tid].x, P.px + q);                                                     \
+                cp_async4(&S.a[k][tid].y, P.py + q);                                                     \
+                cp_async4(&S.a[k][tid].z, P.pz + q);                                                     \
+                cp_async4(&S.a[k][tid].w, P.vel + q);                                                    \
+                if (METHOD == FFB200_TRANSFER_APIC) {                                                    \
+                    cp_async4(&S.b[k][tid].x, P.ax + q);                                                 \
+                    cp_async4(&S.b[k][tid].y, P.ay + q);                                                 \
+                    cp_async4(&S.b[k][tid].z, P.az + q);                                                 \
+                    cp_async4(&S.b[k][tid].w, P.seam + q);                                               \
+                } else {                                                                                 \
+                    cp_async4(&S.w[k][tid], P.seam + q);                                                 \
+                }                                                                                        \
+            }                                                                                            \
+        }                                                                                                \
+        cp_async_wait_all();                                                                             \
     }
 
-    const AxisNodes X = axis_nodes(b[0], P.gi, P.chunk, P.g.dx), Y = axis_nodes(b[1], P.gj, P.chunk, P.g.dx),
-                    Z = axis_nodes(b[2], P.gk, P.chunk, P.g.dx);
+    FFB_STAGE_FILL(0u);
+
     float aw[8], awv[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) { aw[c] = 0.0f; awv[c] = 0.0f; }
 
-    int run = 0;
-    uint32_t q = rs[0];
-    while (run < 4 && q >= re[run]) { run++; if (run < 4) q = rs[run]; }
-    uint32_t word = 0;
-    float px = 0.f, py = 0.f, pz = 0.f, vel = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (run < 4) {
-        word = __ldg(P.seam + q);
-        px = __ldg(P.px + q); py = __ldg(P.py + q); pz = __ldg(P.pz + q); vel = __ldg(P.vel + q);
-        if (METHOD == FFB200_TRANSFER_APIC) { a0 = __ldg(P.ax + q); a1 = __ldg(P.ay + q); a2 = __ldg(P.az + q); }
-    }
-    while (run < 4) {
-        int nrun = run;
-        uint32_t nq = q + 1;
-        while (nrun < 4 && nq >= re[nrun]) { nrun++; if (nrun < 4) nq = rs[nrun]; }
-        uint32_t nword = 0;
-        float npx = 0.f, npy = 0.f, npz = 0.f, nvel = 0.f, na0 = 0.f, na1 = 0.f, na2 = 0.f;
-        if (nrun < 4) {
-            nword = __ldg(P.seam + nq);
-            npx = __ldg(P.px + nq); npy = __ldg(P.py + nq); npz = __ldg(P.pz + nq); nvel = __ldg(P.vel + nq);
-            if (METHOD == FFB200_TRANSFER_APIC) { na0 = __ldg(P.ax + nq); na1 = __ldg(P.ay + nq); na2 = __ldg(P.az + nq); }
-        }
-        // membership of the particle in the block of node 0 / node 1, per axis
-        const int lx = (int)(word & 255u) - 1, sx = (int)((word >> 8) & 3u);
-        const int ly = (int)((word >> 10) & 255u) - 1, sy = (int)((word >> 18) & 3u);
-        const int lz = (int)((word >> 20) & 255u) - 1, sz = (int)((word >> 28) & 3u);
-        const bool mx[2] = {X.nb[0] >= 0 && (unsigned)(X.nb[0] - lx) <= (unsigned)sx,
-                            X.nb[1] >= 0 && (unsigned)(X.nb[1] - lx) <= (unsigned)sx};
-        const bool my[2] = {Y.nb[0] >= 0 && (unsigned)(Y.nb[0] - ly) <= (unsigned)sy,
-                            Y.nb[1] >= 0 && (unsigned)(Y.nb[1] - ly) <= (unsigned)sy};
-        const bool mz[2] = {Z.nb[0] >= 0 && (unsigned)(Z.nb[0] - lz) <= (unsigned)sz,
-                            Z.nb[1] >= 0 && (unsigned)(Z.nb[1] - lz) <= (unsigned)sz};
-        if (METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit)) {
-            // near a cell plane: the reference's own arithmetic, node by node
+    if (!SEAM) {
+        // ---- plain cell: one block frame ---------------------------------------------------------------
+        const int nbx = b[0] / kChunk, nby = b[1] / kChunk, nbz = b[2] / kChunk;
+        const float bpx = idx2posf(nbx, P.chunk), bpy = idx2posf(nby, P.chunk), bpz = idx2posf(nbz, P.chunk);
+        const int lox = b[0] - nbx * kChunk, loy = b[1] - nby * kChunk, loz = b[2] - nbz * kChunk;
+        const float gx[2] = {idx2posf(lox, P.g.dx), idx2posf(lox + 1, P.g.dx)};
+        const float gy[2] = {idx2posf(loy, P.g.dx), idx2posf(loy + 1, P.g.dx)};
+        const float gz[2] = {idx2posf(loz, P.g.dx), idx2posf(loz + 1, P.g.dx)};
+        for (uint32_t i0 = 0; i0 < total; i0 += kStage) {
+            if (i0) FFB_STAGE_FILL(i0);
+            const int cnt = (int)min(total - i0, (uint32_t)kStage);
+            for (int k = 0; k < cnt; k++) {
+                const float4 pa = S.a[k][tid];
+                float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t word;
+                if (METHOD == FFB200_TRANSFER_APIC) { pb = S.b[k][tid]; word = __float_as_uint(pb.w); } else word = S.w[k][tid];
+                const int lx = (int)(word & 255u) - 1, sx = (int)((word >> 8) & 3u);
+                const int ly = (int)((word >> 10) & 255u) - 1, sy = (int)((word >> 18) & 3u);
+                const int lz = (int)((word >> 20) & 255u) - 1, sz = (int)((word >> 28) & 3u);
+                const bool member = (unsigned)(nbx - lx) <= (unsigned)sx && (unsigned)(nby - ly) <= (unsigned)sy &&
+                                    (unsigned)(nbz - lz) <= (unsigned)sz;
+                // APIC edge particles (near a cell plane) are added by k_p2g_edge with the exact arithmetic
+                if (member && !(METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit))) {
+                    const float xl = (pa.x - P.off[0]) - bpx, yl = (pa.y - P.off[1]) - bpy, zl = (pa.z - P.off[2]) - bpz;
+                    const float vx[2] = {gx[0] - xl, gx[1] - xl};
+                    const float vy[2] = {gy[0] - yl, gy[1] - yl};
+                    const float vz[2] = {gz[0] - zl, gz[1] - zl};
+                    if (METHOD == FFB200_TRANSFER_FLIP) {
+                        const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
+                        const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
+                        const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
-                if (!(mx[cx] && my[cy] && mz[cz])) continue;
-                FaceFrame f;
-                f.nb[0] = X.nb[cx]; f.nb[1] = Y.nb[cy]; f.nb[2] = Z.nb[cz];
-                f.lo[0] = X.lo[cx]; f.lo[1] = Y.lo[cy]; f.lo[2] = Z.lo[cz];
-                f.bpos[0] = X.bpos[cx]; f.bpos[1] = Y.bpos[cy]; f.bpos[2] = Z.bpos[cz];
-                f.gpos[0] = X.gpos[cx]; f.gpos[1] = Y.gpos[cy]; f.gpos[2] = Z.gpos[cz];
-                float w, wv;
-                if (exact_contribution<DIR, METHOD>(P, f, q, w, wv)) {
-                    awv[c] += wv;
-                    aw[c] += w;
-                }
-            }
-        } else {
-            const float xs = px - P.off[0], ys = py - P.off[1], zs = pz - P.off[2];
-            // block-local coordinates in the frame of node 0's and node 1's block (equal unless the
-            // cell straddles a block seam)
-            const float xl[2] = {xs - X.bpos[0], xs - X.bpos[1]};
-            const float yl[2] = {ys - Y.bpos[0], ys - Y.bpos[1]};
-            const float zl[2] = {zs - Z.bpos[0], zs - Z.bpos[1]};
-            const float vx[2] = {X.gpos[0] - xl[0], X.gpos[1] - xl[1]};
-            const float vy[2] = {Y.gpos[0] - yl[0], Y.gpos[1] - yl[1]};
-            const float vz[2] = {Z.gpos[0] - zl[0], Z.gpos[1] - zl[1]};
-            if (METHOD == FFB200_TRANSFER_FLIP) {
-                const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
-                const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
-                const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
+                        for (int c = 0; c < 8; c++) {
+                            const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+                            const float d2 = xx[cx] + yy[cy] + zz[cz];
+                            if (d2 < P.rsq) {
+                                const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
+                                awv[c] += w * pa.w;
+                                aw[c] += w;
+                            }
+                        }
+                    } else {
+                        // ipos = (xl - gpos(cell)) * inv_s (:567-592); xl - g0 == -(g0 - xl) exactly
+                        const float tx = (-vx[0]) * P.inv_s, ty = (-vy[0]) * P.inv_s, tz = (-vz[0]) * P.inv_s;
+                        const float fx[2] = {1.0f - tx, tx}, fy[2] = {1.0f - ty, ty}, fz[2] = {1.0f - tz, tz};
+                        const float ax[2] = {pb.x * vx[0], pb.x * vx[1]};
+                        const float ay[2] = {pb.y * vy[0], pb.y * vy[1]};
+                        const float az[2] = {pb.z * vz[0], pb.z * vz[1]};
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
-                    const float d2 = xx[cx] + yy[cy] + zz[cz];
-                    if (mx[cx] && my[cy] && mz[cz] && d2 < P.rsq) {
-                        const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
-                        awv[c] += w * vel;
-                        aw[c] += w;
-                    }
-                }
-            } else {
-                // node 0: the particle is in node 0's cell, factor 1 - ipos; node 1: it is in the cell
-                // below node 1, factor ipos measured from the node before node 1 (:567-592)
-                const float fx[2] = {1.0f - (xl[0] - X.gpos[0]) * P.inv_s, (xl[1] - X.gposm1) * P.inv_s};
-                const float fy[2] = {1.0f - (yl[0] - Y.gpos[0]) * P.inv_s, (yl[1] - Y.gposm1) * P.inv_s};
-                const float fz[2] = {1.0f - (zl[0] - Z.gpos[0]) * P.inv_s, (zl[1] - Z.gposm1) * P.inv_s};
-                const float ax[2] = {a0 * vx[0], a0 * vx[1]};
-                const float ay[2] = {a1 * vy[0], a1 * vy[1]};
-                const float az[2] = {a2 * vz[0], a2 * vz[1]};
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
-                    if (mx[cx] && my[cy] && mz[cz]) {
-                        const float w = fx[cx] * fy[cy] * fz[cz];
-                        const float apic = ax[cx] + ay[cy] + az[cz];
-                        awv[c] += w * (vel + apic);
-                        aw[c] += w;
+                        for (int c = 0; c < 8; c++) {
+                            const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+                            const float w = fx[cx] * fy[cy] * fz[cz];
+                            const float apic = ax[cx] + ay[cy] + az[cz];
+                            awv[c] += w * (pa.w + apic);
+                            aw[c] += w;
+                        }
                     }
                 }
             }
         }
-        run = nrun; q = nq; word = nword;
-        px = npx; py = npy; pz = npz; vel = nvel; a0 = na0; a1 = na1; a2 = na2;
+    } else {
+        // ---- seam / border cell: node 0 and node 1 of an axis may sit in different blocks ---------------
+        const AxisNodes X = axis_nodes(b[0], P.gi, P.chunk, P.g.dx), Y = axis_nodes(b[1], P.gj, P.chunk, P.g.dx),
+                        Z = axis_nodes(b[2], P.gk, P.chunk, P.g.dx);
+        for (uint32_t i0 = 0; i0 < total; i0 += kStage) {
+            if (i0) FFB_STAGE_FILL(i0);
+            const int cnt = (int)min(total - i0, (uint32_t)kStage);
+            for (int k = 0; k < cnt; k++) {
+                const float4 pa = S.a[k][tid];
+                float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t word;
+                if (METHOD == FFB200_TRANSFER_APIC) { pb = S.b[k][tid]; word = __float_as_uint(pb.w); } else word = S.w[k][tid];
+                if (!(METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit))) {
+                    // membership of the particle in the block of node 0 / node 1, per axis
+                    const int lx = (int)(word & 255u) - 1, sx = (int)((word >> 8) & 3u);
+                    const int ly = (int)((word >> 10) & 255u) - 1, sy = (int)((word >> 18) & 3u);
+                    const int lz = (int)((word >> 20) & 255u) - 1, sz = (int)((word >> 28) & 3u);
+                    const bool mx[2] = {X.nb[0] >= 0 && (unsigned)(X.nb[0] - lx) <= (unsigned)sx,
+                                        X.nb[1] >= 0 && (unsigned)(X.nb[1] - lx) <= (unsigned)sx};
+                    const bool my[2] = {Y.nb[0] >= 0 && (unsigned)(Y.nb[0] - ly) <= (unsigned)sy,
+                                        Y.nb[1] >= 0 && (unsigned)(Y.nb[1] - ly) <= (unsigned)sy};
+                    const bool mz[2] = {Z.nb[0] >= 0 && (unsigned)(Z.nb[0] - lz) <= (unsigned)sz,
+                                        Z.nb[1] >= 0 && (unsigned)(Z.nb[1] - lz) <= (unsigned)sz};
+                    const float xs = pa.x - P.off[0], ys = pa.y - P.off[1], zs = pa.z - P.off[2];
+                    // block-local coordinates in the frame of node 0's and node 1's block
+                    const float xl[2] = {xs - X.bpos[0], xs - X.bpos[1]};
+                    const float yl[2] = {ys - Y.bpos[0], ys - Y.bpos[1]};
+                    const float zl[2] = {zs - Z.bpos[0], zs - Z.bpos[1]};
+                    const float vx[2] = {X.gpos[0] - xl[0], X.gpos[1] - xl[1]};
+                    const float vy[2] = {Y.gpos[0] - yl[0], Y.gpos[1] - yl[1]};
+                    const float vz[2] = {Z.gpos[0] - zl[0], Z.gpos[1] - zl[1]};
+                    if (METHOD == FFB200_TRANSFER_FLIP) {
+                        const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
+                        const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
+                        const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+                            const float d2 = xx[cx] + yy[cy] + zz[cz];
+                            if (mx[cx] && my[cy] && mz[cz] && d2 < P.rsq) {
+                                const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
+                                awv[c] += w * pa.w;
+                                aw[c] += w;
+                            }
+                        }
+                    } else {
+                        // node 0: the particle is in node 0's cell, factor 1 - ipos; node 1: it is in the cell
+                        // below node 1, factor ipos measured from the node before node 1 (:567-592)
+                        const float fx[2] = {1.0f - (xl[0] - X.gpos[0]) * P.inv_s, (xl[1] - X.gposm1) * P.inv_s};
+                        const float fy[2] = {1.0f - (yl[0] - Y.gpos[0]) * P.inv_s, (yl[1] - Y.gposm1) * P.inv_s};
+                        const float fz[2] = {1.0f - (zl[0] - Z.gpos[0]) * P.inv_s, (zl[1] - Z.gposm1) * P.inv_s};
+                        const float ax[2] = {pb.x * vx[0], pb.x * vx[1]};
+                        const float ay[2] = {pb.y * vy[0], pb.y * vy[1]};
+                        const float az[2] = {pb.z * vz[0], pb.z * vz[1]};
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
+                            if (mx[cx] && my[cy] && mz[cz]) {
+                                const float w = fx[cx] * fy[cy] * fz[cz];
+                                const float apic = ax[cx] + ay[cy] + az[cz];
+                                awv[c] += w * (pa.w + apic);
+                                aw[c] += w;
+                            }
+                        }
+                    }
+                }
+            }
+        }
     }
-    P.cell_flag[t] = 1;
+#undef FFB_STAGE_FILL
+#undef FFB_SLOT
     // corner-major layout: the faces of one x-row read consecutive cells of one corner plane
     const size_t plane = (size_t)P.ccx * P.ccy * P.ccz;
 #pragma unroll
     for (int c = 0; c < 8; c++) P.partial[(size_t)c * plane + t] = make_float2(aw[c], awv[c]);
 }
 
-// Edge particles whose exact cell (the reference's double floor in some block frame) differs from
-// their bin cell also reach nodes outside the 8 corners their cell thread handles: list those
-// contributions (almost always none).
+#ifndef FFB_CELLS_MINB
+#define FFB_CELLS_MINB 6
+#endif
+#ifndef FFB_SEAMCELLS_MINB
+#define FFB_SEAMCELLS_MINB 5
+#endif
+template <int DIR, int METHOD, bool SEAM>
+__global__ void __launch_bounds__(kCellThreads, SEAM ? FFB_SEAMCELLS_MINB : FFB_CELLS_MINB)
+    k_p2g_cells(const __grid_constant__ P2GParams P) {
+    __shared__ CellStage<METHOD> S;
+    const uint32_t stride = gridDim.x * (uint32_t)kCellThreads;
+    const uint32_t count = __ldg(P.list_count + (SEAM ? 1 : 0));
+    for (uint32_t e = blockIdx.x * (uint32_t)kCellThreads + threadIdx.x; e < count; e += stride)
+        splat_cell<DIR, METHOD, SEAM>(P, P.cell_list + (SEAM ? P.list_cap - 1u - e : e), S);
+}
+
+// APIC edge particles, one thread each. (1) An edge particle whose exact cell (the reference's
+// double floor in some block frame) differs from its bin cell also reaches nodes outside the 8
+// corners of its cell: list those contributions (almost always none). (2) Its contributions to its
+// own cell's corners, see below.
 template <int DIR, int METHOD>
-__global__ void k_p2g_edge_overflow(const __grid_constant__ P2GParams P) {
+__global__ void k_p2g_edge(const __grid_constant__ P2GParams P) {
     const uint32_t nedge = min(__ldg(P.edge_count), P.edge_cap);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nedge) return;
@@ -1144,6 +1366,31 @@ __global__ void k_p2g_edge_overflow(const __grid_constant__ P2GParams P) {
                     }
                 }
             }
+    // ---- own cell: k_p2g_cells left the edge particles out. The thread of the cell's first edge
+    // particle (in the splat's walk order) adds all of them to the cell's 8 partial sums, with the
+    // reference's arithmetic; one thread per cell, after the splat: no race, fixed order.
+    const int ix = b[0] + 1, iy = b[1] + 1, iz = b[2] - P.ck0;
+    if ((unsigned)ix >= (unsigned)P.ccx || (unsigned)iy >= (unsigned)P.ccy || (unsigned)iz >= (unsigned)P.ccz) return;
+    uint32_t rs[4], re[4];
+    cell_runs<DIR>(P, b, rs, re);
+    uint32_t firstq = 0xffffffffu;
+    for (int rr = 0; rr < 4 && firstq == 0xffffffffu; rr++)
+        for (uint32_t qq = rs[rr]; qq < re[rr]; qq++)
+            if (__ldg(P.seam + qq) & kEdgeBit) { firstq = qq; break; }
+    if (firstq != q) return;
+    const size_t cell = (size_t)ix + (size_t)P.ccx * ((size_t)iy + (size_t)P.ccy * iz);
+    const size_t plane = (size_t)P.ccx * P.ccy * P.ccz;
+    float2 acc[8];
+    for (int c = 0; c < 8; c++) acc[c] = P.partial[(size_t)c * plane + cell];
+    for (int rr = 0; rr < 4; rr++)
+        for (uint32_t qq = rs[rr]; qq < re[rr]; qq++) {
+            if (!(__ldg(P.seam + qq) & kEdgeBit)) continue;
+            float2 tmp[8];
+            const unsigned mask = edge_cell_contrib<DIR, METHOD>(P, qq, b[0], b[1], b[2], tmp);
+            for (int c = 0; c < 8; c++)
+                if (mask & (1u << c)) { acc[c].y += tmp[c].y; acc[c].x += tmp[c].x; }
+        }
+    for (int c = 0; c < 8; c++) P.partial[(size_t)c * plane + cell] = acc[c];
 }
 
 template <int DIR, int METHOD>
@@ -1163,18 +1410,31 @@ __global__ void __launch_bounds__(128) k_p2g_nodes(const __grid_constant__ P2GPa
     }
     float sw = 0.0f, swv = 0.0f;
     const size_t plane = (size_t)P.ccx * P.ccy * P.ccz;
-    // node n is corner c = (cx, cy, cz) of the shifted cell n - (cx, cy, cz)
+    // node n is corner c = (cx, cy, cz) of the shifted cell n - (cx, cy, cz). Flags, then partial
+    // sums, as two batches of independent loads; the additions keep the fixed corner order.
+    size_t cell[8];
+    bool have[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
         const int ix = ni - cx + 1, iy = nj - cy + 1, iz = nk - cz - P.ck0;
-        if (iz < 0 || iz >= P.ccz) continue;                  // cells outside this rank's range hold nothing for it
-        const size_t cell = (size_t)ix + (size_t)P.ccx * ((size_t)iy + (size_t)P.ccy * iz);
-        if (!__ldg(P.cell_flag + cell)) continue;
-        const float2 pr = __ldg(P.partial + (size_t)c * plane + cell);
-        sw += pr.x;
-        swv += pr.y;
+        have[c] = iz >= 0 && iz < P.ccz;                       // cells outside this rank's range hold nothing for it
+        cell[c] = have[c] ? (size_t)ix + (size_t)P.ccx * ((size_t)iy + (size_t)P.ccy * iz) : 0;
     }
+#pragma unroll
+    for (int c = 0; c < 8; c++) have[c] = have[c] && __ldg(P.cell_flag + cell[c]) != 0;
+    float2 pr[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        pr[c] = make_float2(0.0f, 0.0f);
+        if (have[c]) pr[c] = __ldg(P.partial + (size_t)c * plane + cell[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        if (have[c]) {
+            sw += pr[c].x;
+            swv += pr[c].y;
+        }
     const int novf = *P.ovf_count;
     bool redo = novf > kOverflowCap || __ldg(P.edge_count) > P.edge_cap;
     if (!redo && novf > 0) {                                   // rare: add the matching entries in ascending slot order
@@ -1217,19 +1477,27 @@ __global__ void __launch_bounds__(128) k_p2g_nodes(const __grid_constant__ P2GPa
 }
 
 template <int DIR, int METHOD>
-int launch_cells(Context &c, P2GParams &P) {
+int launch_cells(Context &c, P2GParams &P, cudaStream_t st) {
     int launches = 0;
-    FFB_CUDA(cudaMemsetAsync(P.ovf_count, 0, sizeof(int), c.stream));
+    FFB_CUDA(cudaMemsetAsync(P.ovf_count, 0, sizeof(int), st));
+    FFB_CUDA(cudaMemsetAsync(P.list_count, 0, 2 * sizeof(uint32_t), st));
     const long long ncell = (long long)P.ccx * P.ccy * P.ccz;
-    k_p2g_cells<DIR, METHOD><<<(unsigned)((ncell + 127) / 128), 128, 0, c.stream>>>(P);
+    const unsigned nxy = (unsigned)P.ccx * (unsigned)P.ccy;
+    k_p2g_cell_list<DIR><<<dim3((nxy + kListThreads - 1) / kListThreads, P.ccz), kListThreads, 0, st>>>(P);
     launches++;
+    // grid-stride over the device-side list: enough CTAs to cover every cell once, capped at a few waves
+    const long long want = (ncell + kCellThreads - 1) / kCellThreads;
+    const unsigned ctas = (unsigned)std::min<long long>(want, (long long)c.sm_count * FFB_CELLS_MINB * 8);
+    k_p2g_cells<DIR, METHOD, false><<<ctas, kCellThreads, 0, st>>>(P);
+    k_p2g_cells<DIR, METHOD, true><<<std::max(ctas / 2, 1u), kCellThreads, 0, st>>>(P);
+    launches += 2;
     if (METHOD == FFB200_TRANSFER_APIC) {
-        k_p2g_edge_overflow<DIR, METHOD><<<(P.edge_cap + 127) / 128, 128, 0, c.stream>>>(P);
+        k_p2g_edge<DIR, METHOD><<<(P.edge_cap + 127) / 128, 128, 0, st>>>(P);
         launches++;
     }
     dim3 block(32, 4, 1);
     dim3 grid((P.gi + 31) / 32, (P.gj + 3) / 4, P.kw1 - P.kw0);
-    k_p2g_nodes<DIR, METHOD><<<grid, block, 0, c.stream>>>(P);
+    k_p2g_nodes<DIR, METHOD><<<grid, block, 0, st>>>(P);
     launches++;
     return launches;
 }
@@ -1256,13 +1524,13 @@ void launch_brick(Context &c, P2GParams &P) {
 }
 
 template <int DIR>
-int launch_dir(Context &c, P2GParams &P, int method, int variant) {
+int launch_dir(Context &c, P2GParams &P, int method, int variant, cudaStream_t st) {
     // variant 0: cell-partial splat (support of one cell: default radius and APIC); 3: coloured block
     // splat (same support); 1: brick gather (any radius up to 2 dx); 2: first-generation global
     // gather. FFB200_P2G_VARIANT overrides; radii above dx always take the brick gather.
     if (variant == 0 && P.wm == 2) {
-        if (method == FFB200_TRANSFER_APIC) return launch_cells<DIR, FFB200_TRANSFER_APIC>(c, P);
-        return launch_cells<DIR, FFB200_TRANSFER_FLIP>(c, P);
+        if (method == FFB200_TRANSFER_APIC) return launch_cells<DIR, FFB200_TRANSFER_APIC>(c, P, st);
+        return launch_cells<DIR, FFB200_TRANSFER_FLIP>(c, P, st);
     }
     if (variant == 3 && P.wm == 2) {
         if (method == FFB200_TRANSFER_APIC)
@@ -1343,6 +1611,9 @@ int launch_p2g(Context &c, double radius, int method) {
     const float sr = (float)(radius + (double)eps);            // float sr = _particleRadius + eps;
     // FFB200_P2G_VARIANT: 0 cell-partial splat (default), 3 coloured block splat, 1 brick gather, 2 global gather
     static const int variant = [] { const char *e = std::getenv("FFB200_P2G_VARIANT"); return e ? std::atoi(e) : 0; }();
+    static const bool multi_stream = [] { const char *e = std::getenv("FFB200_P2G_STREAMS"); return e ? std::atoi(e) != 0 : true; }();
+    bool forked = false;
+    P2GParams deferred;
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];
         P2GParams P;
@@ -1386,29 +1657,58 @@ int launch_p2g(Context &c, double radius, int method) {
         P.guard_per = c.guard_per >= 0.f ? c.guard_per : 1e-12f;
         P.ccx = f.gi + 1; P.ccy = f.gj + 1; P.ccz = P.kw1 - P.kw0 + 1; P.ck0 = P.kw0 - 1;
         P.partial = nullptr; P.cell_flag = nullptr; P.ovf = nullptr; P.ovf_count = nullptr;
+        P.cell_list = nullptr; P.list_count = nullptr; P.list_cap = 0;
+        cudaStream_t st = c.stream;
         if (variant == 0 && P.wm == 2) {
+            SortScratch::CellScratch &cs = c.sort.cell[d];
             const size_t cells = (size_t)P.ccx * P.ccy * P.ccz;
-            if (cells > c.sort.partial_cells) {                // grow-only scratch shared by the three directions
-                FFB_CUDA(cudaStreamSynchronize(c.stream));
-                if (c.sort.partial) FFB_CUDA(cudaFree(c.sort.partial));
-                if (c.sort.cell_flag) FFB_CUDA(cudaFree(c.sort.cell_flag));
-                c.sort.partial_cells = cells + cells / 16;
-                FFB_CUDA(cudaMalloc(&c.sort.partial, c.sort.partial_cells * 8 * sizeof(float2)));
-                FFB_CUDA(cudaMalloc(&c.sort.cell_flag, c.sort.partial_cells));
+            if (cells > cs.cells) {                            // grow-only scratch
+                FFB_CUDA(cudaDeviceSynchronize());
+                if (cs.partial) FFB_CUDA(cudaFree(cs.partial));
+                if (cs.cell_flag) FFB_CUDA(cudaFree(cs.cell_flag));
+                if (cs.cell_list) FFB_CUDA(cudaFree(cs.cell_list));
+                cs.cells = cells + cells / 16;
+                if (cs.cells >= 0xffffffffull) throw CudaError("ffb200_p2g: more than 2^32 shifted cells per rank");
+                FFB_CUDA(cudaMalloc(&cs.partial, cs.cells * 8 * sizeof(float2)));
+                FFB_CUDA(cudaMalloc(&cs.cell_flag, cs.cells));
+                FFB_CUDA(cudaMalloc(&cs.cell_list, cs.cells * sizeof(CellRec)));
             }
-            if (!c.sort.ovf) {
-                FFB_CUDA(cudaMalloc(&c.sort.ovf, (size_t)kOverflowCap * sizeof(OverflowEntry)));
-                FFB_CUDA(cudaMalloc(&c.sort.ovf_count, sizeof(int)));
+            if (!cs.ovf) {
+                FFB_CUDA(cudaMalloc(&cs.ovf, (size_t)kOverflowCap * sizeof(OverflowEntry)));
+                FFB_CUDA(cudaMalloc(&cs.ovf_count, sizeof(int)));
+                FFB_CUDA(cudaMalloc(&cs.list_count, 2 * sizeof(uint32_t)));
             }
-            P.partial = reinterpret_cast<float2 *>(c.sort.partial);
-            P.cell_flag = c.sort.cell_flag;
-            P.ovf = reinterpret_cast<OverflowEntry *>(c.sort.ovf);
-            P.ovf_count = c.sort.ovf_count;
+            P.partial = reinterpret_cast<float2 *>(cs.partial);
+            P.cell_flag = cs.cell_flag;
+            P.ovf = reinterpret_cast<OverflowEntry *>(cs.ovf);
+            P.ovf_count = cs.ovf_count;
+            P.cell_list = reinterpret_cast<CellRec *>(cs.cell_list);
+            P.list_count = cs.list_count;
+            P.list_cap = (uint32_t)cells;
+            // the three directions are independent: 1 and 2 run on auxiliary streams, forked from and
+            // joined back into the context stream with events (FFB200_P2G_STREAMS=0: one stream)
+            if (d > 0 && multi_stream) {
+                if (!cs.stream) {
+                    FFB_CUDA(cudaStreamCreateWithFlags(&cs.stream, cudaStreamNonBlocking));
+                    FFB_CUDA(cudaEventCreateWithFlags(&cs.done, cudaEventDisableTiming));
+                }
+                if (!c.sort.fork) FFB_CUDA(cudaEventCreateWithFlags(&c.sort.fork, cudaEventDisableTiming));
+                if (!forked) {
+                    FFB_CUDA(cudaEventRecord(c.sort.fork, c.stream));
+                    forked = true;
+                }
+                FFB_CUDA(cudaStreamWaitEvent(cs.stream, c.sort.fork, 0));
+                st = cs.stream;
+            }
         }
-        if (d == 0) launches += launch_dir<0>(c, P, method, variant);
-        if (d == 1) launches += launch_dir<1>(c, P, method, variant);
-        if (d == 2) launches += launch_dir<2>(c, P, method, variant);
+        if (d == 0) deferred = P;                              // direction 0 is enqueued last, after the forks
+        if (d == 1) launches += launch_dir<1>(c, P, method, variant, st);
+        if (d == 2) launches += launch_dir<2>(c, P, method, variant, st);
+        if (st != c.stream) FFB_CUDA(cudaEventRecord(c.sort.cell[d].done, st));
     }
+    launches += launch_dir<0>(c, deferred, method, variant, c.stream);
+    if (forked)
+        for (int d = 1; d < 3; d++) FFB_CUDA(cudaStreamWaitEvent(c.stream, c.sort.cell[d].done, 0));
     FFB_CUDA(cudaGetLastError());
     return launches;
 }

@@ -96,10 +96,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not found: run `python -m blender_flip_fluids_b200.build` "
+    path = os.environ.get("FFB200_LIBRARY", LIB_PATH)      # tuning builds (build.build(out=...)); default: in-tree lib
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: run `python -m blender_flip_fluids_b200.build` "
                            "(or __graft_entry__.build()); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
