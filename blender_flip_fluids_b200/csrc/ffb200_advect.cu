@@ -13,6 +13,8 @@
 // neighbours, which keeps warps mostly convergent on the gate.
 #include "ffb200_ctx.h"
 
+#include <cstdlib>
+
 namespace ffb200 {
 
 namespace {
@@ -31,6 +33,7 @@ struct AdvectParams {
     double inv_near;        // 1.0 / (3*dx)
     Box box;
     const float *px, *py, *pz;   // position in
+    const float *k1x, *k1y, *k1z;   // RK3 stage-1 samples left by an APIC G2P on the same field (or null)
     float *opx, *opy, *opz;      // position out
     float c2, c3, c9;       // (float)(0.5dt), (float)(0.75dt), (float)(dt/9.0f)
     float step;             // _markerParticleStepDistanceFactor * (float)_dx
@@ -184,7 +187,11 @@ __global__ void __launch_bounds__(256) k_advect(const __grid_constant__ AdvectPa
     if (j >= P.n) return;
     const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
     float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
-    mac_eval(P.g, P.mac, x0, y0, z0, k1x, k1y, k1z);
+    if (P.k1x) {
+        k1x = P.k1x[j]; k1y = P.k1y[j]; k1z = P.k1z[j];
+    } else {
+        mac_eval(P.g, P.mac, x0, y0, z0, k1x, k1y, k1z);
+    }
     mac_eval(P.g, P.mac, x0 + k1x * P.c2, y0 + k1y * P.c2, z0 + k1z * P.c2, k2x, k2y, k2z);
     mac_eval(P.g, P.mac, x0 + k2x * P.c3, y0 + k2y * P.c3, z0 + k2z * P.c3, k3x, k3y, k3z);
     float x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
@@ -222,6 +229,12 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     ParticleSoA &o = c.nondestructive ? c.soa[c.cur ^ 1] : s;
     P.px = s.p[0]; P.py = s.p[1]; P.pz = s.p[2];
     P.opx = o.p[0]; P.opy = o.p[1]; P.opz = o.p[2];
+    P.k1x = P.k1y = P.k1z = nullptr;
+    static const bool reuse = [] { const char *e = std::getenv("FFB200_REUSE_G2P"); return e ? std::atoi(e) != 0 : true; }();
+    if (reuse && c.k1_epoch == c.epoch) {                  // nothing touched particles or field since the APIC G2P
+        ParticleSoA &k = c.soa[c.k1_buf];
+        P.k1x = k.v[0]; P.k1y = k.v[1]; P.k1z = k.v[2];
+    }
     P.c2 = (float)(0.5 * dt);
     P.c3 = (float)(0.75 * dt);
     P.c9 = (float)(dt / 9.0f);

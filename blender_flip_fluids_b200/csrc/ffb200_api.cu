@@ -19,11 +19,12 @@ char g_error[4096] = "";
 void set_error(const char *fn, const char *what) { snprintf(g_error, sizeof(g_error), "%s - %s", fn, what); }
 
 template <class F>
-int guarded(const char *fn, ffb200_context *ctx, F &&body) {
+int guarded(const char *fn, ffb200_context *ctx, F &&body, bool mutates = true) {
     try {
         if (!ctx) throw std::invalid_argument("null context");
         Context &c = *reinterpret_cast<Context *>(ctx);
         FFB_CUDA(cudaSetDevice(c.device));
+        if (mutates) c.epoch++;                               // anything cached about particles / field is stale
         body(c);
         return FFB200_SUCCESS;
     } catch (const std::exception &e) {
@@ -346,6 +347,12 @@ void g2p_impl(ContextImpl &c, int method, double ratio) {
     StageTimer t(c, kG2P);
     int l = launch_g2p(c, method, ratio);
     t.done(l);
+    if (method == FFB200_TRANSFER_APIC) {
+        // the APIC particle velocity IS the field sampled at the particle (fluidsimulation.cpp:6839-6841),
+        // i.e. the first RK3 stage of the advection that follows: remember where it lives
+        c.k1_epoch = c.epoch;
+        c.k1_buf = c.nondestructive ? (c.cur ^ 1) : c.cur;
+    }
 }
 
 void advect_impl(ContextImpl &c, double dt, double cfl, int collide) {
@@ -413,7 +420,7 @@ int ffb200_set_fixed_batch(ffb200_context *ctx, int on) {
 }
 
 int ffb200_synchronize(ffb200_context *ctx) {
-    return guarded("ffb200_synchronize", ctx, [&](Context &c) { FFB_CUDA(cudaStreamSynchronize(c.stream)); });
+    return guarded("ffb200_synchronize", ctx, [&](Context &c) { FFB_CUDA(cudaStreamSynchronize(c.stream)); }, false);
 }
 
 int ffb200_get_timing(ffb200_context *ctx, ffb200_timing *out) {
@@ -430,14 +437,14 @@ int ffb200_get_timing(ffb200_context *ctx, ffb200_timing *out) {
         out->sort_launches = c.launches[kSort]; out->p2g_prep_launches = c.launches[kP2GPrep];
         out->p2g_launches = c.launches[kP2G];
         out->g2p_launches = c.launches[kG2P]; out->advect_launches = c.launches[kAdvect];
-    });
+    }, false);
 }
 
 int ffb200_set_valid_guard(ffb200_context *ctx, float abs_tol, float per_contrib_tol) {
     return guarded("ffb200_set_valid_guard", ctx, [&](Context &c) {
         c.guard_abs = abs_tol;
         c.guard_per = per_contrib_tol;
-    });
+    }, false);
 }
 
 int ffb200_set_particles(ffb200_context *ctx, int n, const float *pos, const float *vel, const float *affx,
@@ -453,7 +460,7 @@ int ffb200_get_num_particles(ffb200_context *ctx, int *n) {
     return guarded("ffb200_get_num_particles", ctx, [&](Context &c) {
         if (!n) throw std::invalid_argument("null output pointer");
         *n = c.n;
-    });
+    }, false);
 }
 
 int ffb200_get_device_buffers(ffb200_context *ctx, ffb200_device_buffers *out) {
@@ -502,7 +509,7 @@ int ffb200_slab_record_floats(ffb200_context *ctx, int *floats_per_particle) {
     return guarded("ffb200_slab_record_floats", ctx, [&](Context &c) {
         if (!floats_per_particle) throw std::invalid_argument("null output pointer");
         *floats_per_particle = slab_rows(c);
-    });
+    }, false);
 }
 
 int ffb200_slab_pack_layers(ffb200_context *ctx, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b, float *block_b,
@@ -580,7 +587,7 @@ int ffb200_set_saved_velocity_field(ffb200_context *ctx, const float *u, const f
 int ffb200_get_velocity_field(ffb200_context *ctx, float *u, float *v, float *w, uint8_t *validu, uint8_t *validv,
                               uint8_t *validw) {
     return guarded("ffb200_get_velocity_field", ctx,
-                   [&](Context &c) { get_field_impl(impl(c), u, v, w, validu, validv, validw); });
+                   [&](Context &c) { get_field_impl(impl(c), u, v, w, validu, validv, validw); }, false);
 }
 
 int ffb200_get_weight_sums(ffb200_context *ctx, float *wu, float *wv, float *ww) {
@@ -592,14 +599,14 @@ int ffb200_get_weight_sums(ffb200_context *ctx, float *wu, float *wv, float *ww)
             if (h[d]) FFB_CUDA(cudaMemcpyAsync(h[d] + off, f.wsum, f.count * 4, cudaMemcpyDeviceToHost, c.stream));
         }
         FFB_CUDA(cudaStreamSynchronize(c.stream));
-    });
+    }, false);
 }
 
 int ffb200_save_velocity_field(ffb200_context *ctx) {
     return guarded("ffb200_save_velocity_field", ctx, [&](Context &c) {
         for (int d = 0; d < 3; d++)
             FFB_CUDA(cudaMemcpyAsync(c.face[d].saved, c.face[d].vel, c.face[d].count * 4, cudaMemcpyDeviceToDevice, c.stream));
-    });
+    }, false);
 }
 
 int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid) {
@@ -615,8 +622,14 @@ int ffb200_g2p(ffb200_context *ctx, int transfer_method, double ratio_pic_flip) 
 }
 
 int ffb200_advect(ffb200_context *ctx, double dt, double cfl_condition_number, int resolve_collisions) {
-    return guarded("ffb200_advect", ctx,
-                   [&](Context &c) { advect_impl(impl(c), dt, cfl_condition_number, resolve_collisions); });
+    // not counted as a mutation at entry: an advection that directly follows ffb200_g2p reuses its samples
+    return guarded(
+        "ffb200_advect", ctx,
+        [&](Context &c) {
+            advect_impl(impl(c), dt, cfl_condition_number, resolve_collisions);
+            c.epoch++;
+        },
+        false);
 }
 
 int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos, const float *vel, const float *affx,

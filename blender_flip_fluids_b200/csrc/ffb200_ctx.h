@@ -99,6 +99,10 @@ struct Context {
 
     float guard_abs = -1.f, guard_per = -1.f;
     int *slab_counters = nullptr;        // 4 device ints for the slab pack/route kernels
+    // API-call epoch: bumped by every call that may change particles or fields. An APIC ffb200_g2p
+    // records it; an ffb200_advect that finds it unchanged reuses the G2P samples as RK3 stage 1.
+    unsigned long long epoch = 0, k1_epoch = ~0ull;
+    int k1_buf = 0;
     bool nondestructive = false;         // G2P/advect write to the spare SoA buffer (fixed-batch benchmarking)
     ffb200_timing timing = {};
 };

@@ -28,7 +28,7 @@ struct G2PParams {
     int n;
 };
 
-__global__ void __launch_bounds__(256) k_g2p_flip(G2PParams P) {
+__global__ void __launch_bounds__(256) k_g2p_flip(const __grid_constant__ G2PParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float x = P.px[j], y = P.py[j], z = P.pz[j];
@@ -43,10 +43,15 @@ __global__ void __launch_bounds__(256) k_g2p_flip(G2PParams P) {
     P.ovz[j] = pic[2] * P.rp + f2 * P.rf;
 }
 
-// affineDir = sum over the 8 faces around the (staggered) particle of gradWeight * Face(g).
+// One MAC component of the APIC update: the affine row (sum over the 8 faces around the particle
+// in the component's staggered frame of gradWeight * face, :6709-6769, float arithmetic) and the
+// interpolated velocity (mac_lerp, double arithmetic). Both read the same 8 faces whenever the
+// float and the double index arithmetic agree on the cell -- always, except within an ulp of a
+// cell plane -- so they are loaded once.
 template <int DIR>
-__device__ __forceinline__ void apic_affine(const G2PParams &P, const float *__restrict__ f, float px, float py, float pz,
-                                            float &ox, float &oy, float &oz) {
+__device__ __forceinline__ void apic_component(const G2PParams &P, const float *__restrict__ f, float px, float py, float pz,
+                                               bool in_grid, const AxisCoord &cx, const AxisCoord &cy, const AxisCoord &cz,
+                                               float &vel, float &ox, float &oy, float &oz) {
     const GridDesc &g = P.g;
     const int gw = g.I + (DIR == 0), gh = g.J + (DIR == 1), gd = g.K + (DIR == 2);
     const float x = px - (DIR == 0 ? 0.0f : P.h), y = py - (DIR == 1 ? 0.0f : P.h), z = pz - (DIR == 2 ? 0.0f : P.h);
@@ -56,44 +61,75 @@ __device__ __forceinline__ void apic_affine(const G2PParams &P, const float *__r
     const float iz = (z - idx2posf(gk, g.dx)) * P.inv_s;
     const float invdx = P.invdx;
     const float mx = 1.0f - ix, my = 1.0f - iy, mz = 1.0f - iz;
-    // gradient weights in the reference's operand order (fluidsimulation.cpp:6737-6768)
-    float w[8][3];
-    w[0][0] = -invdx * my * mz;      w[0][1] = -invdx * mx * mz;      w[0][2] = -invdx * mx * my;
-    w[1][0] = invdx * my * mz;       w[1][1] = ix * (-invdx) * mz;    w[1][2] = ix * my * (-invdx);
-    w[2][0] = (-invdx) * iy * mz;    w[2][1] = mx * invdx * mz;       w[2][2] = mx * iy * (-invdx);
-    w[3][0] = invdx * iy * mz;       w[3][1] = ix * invdx * mz;       w[3][2] = ix * iy * (-invdx);
-    w[4][0] = (-invdx) * my * iz;    w[4][1] = mx * (-invdx) * iz;    w[4][2] = mx * my * invdx;
-    w[5][0] = invdx * my * iz;       w[5][1] = ix * (-invdx) * iz;    w[5][2] = ix * my * invdx;
-    w[6][0] = (-invdx) * iy * iz;    w[6][1] = mx * invdx * iz;       w[6][2] = mx * iy * invdx;
-    w[7][0] = invdx * iy * iz;       w[7][1] = ix * invdx * iz;       w[7][2] = ix * iy * invdx;
-    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+
+    // faces in the order c = di + 2 dj + 4 dk; out-of-range faces read 0 (skipping a term and adding
+    // w * 0 give the same sum)
     const long long sj = gw, sk = (long long)gw * gh;
-    const long long base = (long long)gi + sj * gj + sk * (long long)(gk - g.kbase);
+    const float *b = f + ((long long)gi + sj * gj + sk * (long long)(gk - g.kbase));
+    float v[8];
+    if ((unsigned)gi < (unsigned)(gw - 1) && (unsigned)gj < (unsigned)(gh - 1) && (unsigned)gk < (unsigned)(gd - 1)) {
+        v[0] = __ldg(b);          v[1] = __ldg(b + 1);
+        v[2] = __ldg(b + sj);     v[3] = __ldg(b + sj + 1);
+        v[4] = __ldg(b + sk);     v[5] = __ldg(b + sk + 1);
+        v[6] = __ldg(b + sk + sj); v[7] = __ldg(b + sk + sj + 1);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const int di = c & 1, dj = (c >> 1) & 1, dk = (c >> 2) & 1;
-        if (!in_range3(gi + di, gj + dj, gk + dk, gw, gh, gd)) continue;
-        const float fv = __ldg(f + base + di + sj * dj + sk * dk);
-        sx += w[c][0] * fv;
-        sy += w[c][1] * fv;
-        sz += w[c][2] * fv;
+        for (int c = 0; c < 8; c++) {
+            const int di = c & 1, dj = (c >> 1) & 1, dk = c >> 2;
+            v[c] = in_range3(gi + di, gj + dj, gk + dk, gw, gh, gd) ? __ldg(b + di + sj * dj + sk * dk) : 0.0f;
+        }
     }
+
+    // gradient weights (fluidsimulation.cpp:6737-6768). The reference's 24 three-factor products
+    // reduce to 21 multiplications: (-a)*b == -(a*b) exactly, and factors are shared where the
+    // reference associates them the same way. Signs are applied in the sums below.
+    const float C = invdx * my, D = invdx * iy;               // x row: ((+-invdx) * {my|iy}) * {mz|iz}
+    const float xw[4] = {C * mz, D * mz, C * iz, D * iz};
+    const float A = mx * invdx, B = ix * invdx;               // y row: ({mx|ix} * (+-invdx)) * {mz|iz}
+    const float yw[4] = {A * mz, B * mz, A * iz, B * iz};
+    const float z0 = A * my;                                   // z row: (-invdx*mx)*my, then ({mx|ix}*{my|iy}) * (+-invdx)
+    const float z1 = (ix * my) * invdx, z2 = (mx * iy) * invdx, z3 = (ix * iy) * invdx, z4 = (mx * my) * invdx;
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    sx -= xw[0] * v[0]; sy -= yw[0] * v[0]; sz -= z0 * v[0];
+    sx += xw[0] * v[1]; sy -= yw[1] * v[1]; sz -= z1 * v[1];
+    sx -= xw[1] * v[2]; sy += yw[0] * v[2]; sz -= z2 * v[2];
+    sx += xw[1] * v[3]; sy += yw[1] * v[3]; sz -= z3 * v[3];
+    sx -= xw[2] * v[4]; sy -= yw[2] * v[4]; sz += z4 * v[4];
+    sx += xw[2] * v[5]; sy -= yw[3] * v[5]; sz += z1 * v[5];
+    sx -= xw[3] * v[6]; sy += yw[2] * v[6]; sz += z2 * v[6];
+    sx += xw[3] * v[7]; sy += yw[3] * v[7]; sz += z3 * v[7];
     ox = sx; oy = sy; oz = sz;
+
+    // velocity component (zero outside the grid, macvelocityfield.cpp:631-645)
+    if (!in_grid) {
+        vel = 0.0f;
+    } else if (gi == cx.i && gj == cy.i && gk == cz.i) {
+        // trilerp8 corner order {000,100,010,001,101,011,110,111}
+        const double p[8] = {(double)v[0], (double)v[1], (double)v[2], (double)v[4],
+                             (double)v[5], (double)v[6], (double)v[3], (double)v[7]};
+        vel = (float)trilerp8(p, cx.f, cy.f, cz.f);
+    } else {
+        vel = (float)mac_lerp<DIR>(g, f, cx, cy, cz);
+    }
 }
 
-__global__ void __launch_bounds__(256) k_g2p_apic(G2PParams P) {
+__global__ void __launch_bounds__(256) k_g2p_apic(const __grid_constant__ G2PParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
-    const float x = P.px[j], y = P.py[j], z = P.pz[j];
-    float ax, ay, az;
-    apic_affine<0>(P, P.cur.u, x, y, z, ax, ay, az);
+    const float px = P.px[j], py = P.py[j], pz = P.pz[j];
+    const GridDesc &g = P.g;
+    const double x = px, y = py, z = pz;
+    const bool in_grid = pos_in_grid(x, y, z, g);
+    const double hdx = 0.5 * g.dx;
+    const AxisCoord xu = axis_coord(x, g), yu = axis_coord(y, g), zu = axis_coord(z, g);
+    const AxisCoord xs = axis_coord(x - hdx, g), ys = axis_coord(y - hdx, g), zs = axis_coord(z - hdx, g);
+    float v0, v1, v2, ax, ay, az;
+    apic_component<0>(P, P.cur.u, px, py, pz, in_grid, xu, ys, zs, v0, ax, ay, az);
     P.a[0][j] = ax; P.a[1][j] = ay; P.a[2][j] = az;
-    apic_affine<1>(P, P.cur.v, x, y, z, ax, ay, az);
+    apic_component<1>(P, P.cur.v, px, py, pz, in_grid, xs, yu, zs, v1, ax, ay, az);
     P.a[3][j] = ax; P.a[4][j] = ay; P.a[5][j] = az;
-    apic_affine<2>(P, P.cur.w, x, y, z, ax, ay, az);
+    apic_component<2>(P, P.cur.w, px, py, pz, in_grid, xs, ys, zu, v2, ax, ay, az);
     P.a[6][j] = ax; P.a[7][j] = ay; P.a[8][j] = az;
-    float v0, v1, v2;
-    mac_eval(P.g, P.cur, x, y, z, v0, v1, v2);
     P.ovx[j] = v0; P.ovy[j] = v1; P.ovz[j] = v2;
 }
 
