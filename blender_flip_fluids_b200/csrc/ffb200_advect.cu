@@ -231,9 +231,13 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.opx = o.p[0]; P.opy = o.p[1]; P.opz = o.p[2];
     P.k1x = P.k1y = P.k1z = nullptr;
     static const bool reuse = [] { const char *e = std::getenv("FFB200_REUSE_G2P"); return e ? std::atoi(e) != 0 : true; }();
-    if (reuse && c.k1_epoch == c.epoch) {                  // nothing touched particles or field since the APIC G2P
-        ParticleSoA &k = c.soa[c.k1_buf];
-        P.k1x = k.v[0]; P.k1y = k.v[1]; P.k1z = k.v[2];
+    if (reuse && c.k1_epoch == c.epoch) {                  // nothing touched particles or field since the G2P
+        if (c.k1_buf == 2) {
+            P.k1x = c.k1s[0]; P.k1y = c.k1s[1]; P.k1z = c.k1s[2];
+        } else {
+            ParticleSoA &k = c.soa[c.k1_buf];
+            P.k1x = k.v[0]; P.k1y = k.v[1]; P.k1z = k.v[2];
+        }
     }
     P.c2 = (float)(0.5 * dt);
     P.c3 = (float)(0.75 * dt);

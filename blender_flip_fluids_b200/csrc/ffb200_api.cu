@@ -9,6 +9,9 @@
 
 #include "ffb200_ctx.h"
 
+#include <cstdlib>
+#include "ffb200_seam.cuh"
+
 using namespace ffb200;
 
 namespace {
@@ -157,6 +160,7 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->near_solid);
     dev_free(c->slab_counters);
     dev_free(c->sort.edge_count);
+    for (int q = 0; q < 3; q++) dev_free(c->k1s[q]);
     for (auto &cs : c->sort.cell) {
         if (cs.partial) cudaFree(cs.partial);
         if (cs.cell_list) cudaFree(cs.cell_list);
@@ -329,9 +333,21 @@ void p2g_impl(ContextImpl &c, double radius, int method) {
     if (!(radius > 0.0)) throw std::domain_error("particle radius must be positive");
     if (method == FFB200_TRANSFER_APIC && !c.has_affine) throw std::logic_error("APIC transfer needs affine particle data");
     if (c.nondestructive) c.sorted = false;                  // fixed-batch mode: always re-bin and re-sort
-    sort_impl(c);
+    bool seam_done = false;
+    static const bool fuse_seam = [] { const char *e = std::getenv("FFB200_FUSE_SEAM"); return e ? std::atoi(e) != 0 : true; }();
+    if (fuse_seam && !c.sorted && c.n > 0) {
+        // the reorder pass of the sort also computes the membership words of this transfer
+        StageTimer ts(c, kSort);
+        SeamParams sp;
+        p2g_seam_begin(c, radius, sp);
+        int ls = launch_sort(c, &sp);
+        ts.done(ls);
+        seam_done = true;
+    } else {
+        sort_impl(c);
+    }
     StageTimer tp(c, kP2GPrep);
-    int lp = launch_p2g_prepare(c, radius);
+    int lp = launch_p2g_prepare(c, radius, seam_done);
     tp.done(lp);
     StageTimer t(c, kP2G);
     int l = launch_p2g(c, radius, method);
@@ -344,9 +360,21 @@ void g2p_impl(ContextImpl &c, int method, double ratio) {
         ensure_capacity(c, c.n, true);
         c.has_affine = true;
     }
+    if (method == FFB200_TRANSFER_FLIP && c.k1s_cap < c.cap) {   // vPIC streams, grow-only
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+        for (int q = 0; q < 3; q++) {
+            dev_free(c.k1s[q]);
+            dev_alloc(c.k1s[q], (size_t)c.cap);
+        }
+        c.k1s_cap = c.cap;
+    }
     StageTimer t(c, kG2P);
     int l = launch_g2p(c, method, ratio);
     t.done(l);
+    if (method == FFB200_TRANSFER_FLIP) {
+        c.k1_epoch = c.epoch;
+        c.k1_buf = 2;
+    }
     if (method == FFB200_TRANSFER_APIC) {
         // the APIC particle velocity IS the field sampled at the particle (fluidsimulation.cpp:6839-6841),
         // i.e. the first RK3 stage of the advection that follows: remember where it lives

@@ -125,6 +125,40 @@ __device__ __forceinline__ double mac_lerp(const GridDesc &g, const float *__res
     return trilerp8(p, cx.f, cy.f, cz.f);
 }
 
+// mac_lerp of two fields of the same component at the same point (FLIP: new and saved field):
+// one index / range computation, two sets of loads.
+template <int COMP>
+__device__ __forceinline__ void mac_lerp_pair(const GridDesc &g, const float *__restrict__ fa, const float *__restrict__ fb,
+                                              const AxisCoord &cx, const AxisCoord &cy, const AxisCoord &cz, double &ra,
+                                              double &rb) {
+    const int gw = g.I + (COMP == 0), gh = g.J + (COMP == 1), gd = g.K + (COMP == 2);
+    const int i = cx.i, j = cy.i, k = cz.i;
+    const long long sj = gw, sk = (long long)gw * gh;
+    const long long base = (long long)i + sj * j + sk * (long long)(k - g.kbase);
+    const long long off[8] = {0, 1, sj, sk, sk + 1, sk + sj, sj + 1, sk + sj + 1};
+    double pa[8], pb[8];
+    if ((unsigned)i < (unsigned)(gw - 1) && (unsigned)j < (unsigned)(gh - 1) && (unsigned)k < (unsigned)(gd - 1)) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            pa[q] = (double)__ldg(fa + base + off[q]);
+            pb[q] = (double)__ldg(fb + base + off[q]);
+        }
+    } else {
+        const bool i0 = (unsigned)i < (unsigned)gw, i1 = (unsigned)(i + 1) < (unsigned)gw;
+        const bool j0 = (unsigned)j < (unsigned)gh, j1 = (unsigned)(j + 1) < (unsigned)gh;
+        const bool k0 = (unsigned)k < (unsigned)gd, k1 = (unsigned)(k + 1) < (unsigned)gd;
+        const bool ok[8] = {i0 && j0 && k0, i1 && j0 && k0, i0 && j1 && k0, i0 && j0 && k1,
+                            i1 && j0 && k1, i0 && j1 && k1, i1 && j1 && k0, i1 && j1 && k1};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            pa[q] = ok[q] ? (double)__ldg(fa + base + off[q]) : 0.0;
+            pb[q] = ok[q] ? (double)__ldg(fb + base + off[q]) : 0.0;
+        }
+    }
+    ra = trilerp8(pa, cx.f, cy.f, cz.f);
+    rb = trilerp8(pb, cx.f, cy.f, cz.f);
+}
+
 // MACVelocityField::evaluateVelocityAtPositionLinear(vec3) (macvelocityfield.cpp:631-645):
 // float position widened to double, zero outside the grid, components narrowed to float.
 // Each axis needs its index/fraction twice only: in the unshifted frame (the component

@@ -102,7 +102,9 @@ struct Context {
     // API-call epoch: bumped by every call that may change particles or fields. An APIC ffb200_g2p
     // records it; an ffb200_advect that finds it unchanged reuses the G2P samples as RK3 stage 1.
     unsigned long long epoch = 0, k1_epoch = ~0ull;
-    int k1_buf = 0;
+    int k1_buf = 0;                      // 0/1: soa[k1_buf].v (APIC), 2: k1s (FLIP vPIC)
+    float *k1s[3] = {nullptr, nullptr, nullptr};
+    int k1s_cap = 0;
     bool nondestructive = false;         // G2P/advect write to the spare SoA buffer (fixed-batch benchmarking)
     ffb200_timing timing = {};
 };
@@ -113,11 +115,15 @@ struct Context {
 int launch_unpack_aos(Context &c, const float *aos, float *const dst[3], int n);
 int launch_pack_aos(Context &c, const float *const src[3], const uint32_t *orig, float *aos, int n);
 int launch_iota(Context &c, uint32_t *dst, int n);
-int launch_sort(Context &c);             // keys -> radix sort -> bin table -> reorder; flips c.cur
+struct SeamParams;                        // ffb200_seam.cuh
+// keys -> counting sort -> bin table -> reorder (flips c.cur). With `seam`, the reorder also writes the
+// P2G membership words / home marks / edge list of every particle (what k_seam_home would do next).
+int launch_sort(Context &c, const SeamParams *seam = nullptr);
 int launch_binning_dump(Context &c, int32_t *cell, uint32_t *hkey, uint32_t *perm);   // device outputs
 
 // ffb200_p2g.cu
-int launch_p2g_prepare(Context &c, double radius);      // block masks + membership words
+void p2g_seam_begin(Context &c, double radius, SeamParams &sp);   // clears marks / counters, fills sp
+int launch_p2g_prepare(Context &c, double radius, bool seam_done);   // [membership words +] block masks
 int launch_p2g(Context &c, double radius, int method);  // the three transfer kernels
 
 // ffb200_g2p.cu

@@ -21,6 +21,7 @@ struct G2PParams {
     const float *vx, *vy, *vz;   // velocity in
     float *ovx, *ovy, *ovz;      // velocity out (same arrays unless the context is non-destructive)
     float *a[9];
+    float *k1[3];       // FLIP: vPIC per particle, kept for the advection
     float rp, rf;       // (float)_ratioPICFLIP, (float)(1 - _ratioPICFLIP)
     float h;            // 0.5f * _dx
     float inv_s;        // (float)(1.0 / (float)_dx)   (vec3 / _dx)
@@ -31,16 +32,30 @@ struct G2PParams {
 __global__ void __launch_bounds__(256) k_g2p_flip(const __grid_constant__ G2PParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
-    const float x = P.px[j], y = P.py[j], z = P.pz[j];
-    float pic[3], old[3];
-    mac_eval(P.g, P.cur, x, y, z, pic[0], pic[1], pic[2]);
-    mac_eval(P.g, P.saved, x, y, z, old[0], old[1], old[2]);
+    const float px = P.px[j], py = P.py[j], pz = P.pz[j];
+    const GridDesc &g = P.g;
+    const double x = px, y = py, z = pz;
+    float pic[3] = {0.0f, 0.0f, 0.0f}, old[3] = {0.0f, 0.0f, 0.0f};
+    if (pos_in_grid(x, y, z, g)) {                             // both fields sampled with one index computation
+        const double hdx = 0.5 * g.dx;
+        const AxisCoord xu = axis_coord(x, g), yu = axis_coord(y, g), zu = axis_coord(z, g);
+        const AxisCoord xs = axis_coord(x - hdx, g), ys = axis_coord(y - hdx, g), zs = axis_coord(z - hdx, g);
+        double a, b;
+        mac_lerp_pair<0>(g, P.cur.u, P.saved.u, xu, ys, zs, a, b);
+        pic[0] = (float)a; old[0] = (float)b;
+        mac_lerp_pair<1>(g, P.cur.v, P.saved.v, xs, yu, zs, a, b);
+        pic[1] = (float)a; old[1] = (float)b;
+        mac_lerp_pair<2>(g, P.cur.w, P.saved.w, xs, ys, zu, a, b);
+        pic[2] = (float)a; old[2] = (float)b;
+    }
     const float v0 = P.vx[j], v1 = P.vy[j], v2 = P.vz[j];
     // vFLIP = vel + vPIC - saved(p); v = r*vPIC + (1-r)*vFLIP   (:6779-6781)
     const float f0 = (v0 + pic[0]) - old[0], f1 = (v1 + pic[1]) - old[1], f2 = (v2 + pic[2]) - old[2];
     P.ovx[j] = pic[0] * P.rp + f0 * P.rf;
     P.ovy[j] = pic[1] * P.rp + f1 * P.rf;
     P.ovz[j] = pic[2] * P.rp + f2 * P.rf;
+    // vPIC is also the first RK3 stage of the advection that follows
+    P.k1[0][j] = pic[0]; P.k1[1][j] = pic[1]; P.k1[2][j] = pic[2];
 }
 
 // One MAC component of the APIC update: the affine row (sum over the 8 faces around the particle
@@ -147,6 +162,7 @@ int launch_g2p(Context &c, int method, double ratio) {
     P.vx = s.v[0]; P.vy = s.v[1]; P.vz = s.v[2];
     P.ovx = o.v[0]; P.ovy = o.v[1]; P.ovz = o.v[2];
     for (int q = 0; q < 9; q++) P.a[q] = o.a[q];
+    for (int q = 0; q < 3; q++) P.k1[q] = c.k1s[q];
     P.rp = (float)ratio;
     P.rf = (float)(1 - ratio);
     P.h = (float)(0.5f * c.g.dx);

@@ -18,6 +18,7 @@
 //    threshold (:160, :527) are re-summed by exact_face() in the reference's order with the
 //    reference's exact arithmetic, so the valid mask is bit-exact.
 #include "ffb200_ctx.h"
+#include "ffb200_seam.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -64,80 +65,12 @@ struct P2GParams {
     float guard_abs, guard_per;
 };
 
-struct SeamParams {
-    GridDesc g;
-    int bdim[3][3];              // block dims per direction
-    uint8_t *home[3];
-    uint32_t *seam;              // [dir*cap + slot]
-    uint32_t *edge_list;         // [dir*edge_cap + i]
-    uint32_t *edge_count;        // [dir]
-    uint32_t edge_cap;
-    int cap;
-    const float *px, *py, *pz;
-    float h;                     // (float)(0.5*dx)
-    float sr;                    // (float)(radius + 1e-6f)
-    float blockdx;               // (float)_chunkdx
-    double inv_blockdx;          // 1.0 / (double)blockdx
-    double inv_chunkdx;          // 1.0 / _chunkdx
-    int n;
-};
-
-constexpr uint32_t kEdgeBit = 1u << 30;
-
-// Per particle and direction: (a) mark the home block exactly as _initializeActiveBlocksThread
-// does (double _chunkdx, :240-251); (b) the inclusive block range the particle is sorted into,
-// exactly as _computeGridCountDataThread does (float blockdx, float sr, :306-352).
-// Word layout per axis a (10 bits at 10a): (lo+1) in 8 bits, (hi-lo) in 2 bits.
-__global__ void k_seam_home(SeamParams s) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= s.n) return;
-    const float p[3] = {s.px[j], s.py[j], s.pz[j]};
-#pragma unroll
-    for (int dir = 0; dir < 3; dir++) {
-        float x[3];
-#pragma unroll
-        for (int a = 0; a < 3; a++) x[a] = p[a] - (a == dir ? 0.0f : s.h);
-        // (a) home block
-        const int hbx = pos2idx(x[0], s.inv_chunkdx), hby = pos2idx(x[1], s.inv_chunkdx), hbz = pos2idx(x[2], s.inv_chunkdx);
-        if (in_range3(hbx, hby, hbz, s.bdim[dir][0], s.bdim[dir][1], s.bdim[dir][2]))
-            s.home[dir][hbx + s.bdim[dir][0] * (hby + s.bdim[dir][1] * hbz)] = 1;
-        // (b) membership range
-        int b[3];
-        bool simple = true;
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            b[a] = pos2idx(x[a], s.inv_blockdx);
-            const float bp = idx2posf(b[a], (double)s.blockdx);
-            simple = simple && (x[a] - s.sr > bp) && (x[a] + s.sr < bp + s.blockdx);
-        }
-        uint32_t word = 0;
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            int lo = b[a], hi = b[a];
-            if (!simple) {
-                lo = pos2idx(x[a] - s.sr, s.inv_blockdx);
-                hi = pos2idx(x[a] + s.sr, s.inv_blockdx);
-            }
-            int span = hi - lo;
-            span = span < 0 ? 0 : (span > 3 ? 3 : span);
-            int lo1 = lo + 1;
-            // out-of-range block indices can never match a face's block: park them at 255
-            if (lo1 < 0 || lo1 > 254) { lo1 = 255; span = 0; }
-            word |= ((uint32_t)lo1 | ((uint32_t)span << 8)) << (10 * a);
-            // "edge" particle: within a few float ulps of a cell plane in this direction's frame.
-            // There a float compare of block-local coordinates may disagree with the reference's
-            // double floor, so the transfer kernels give such particles the exact arithmetic.
-            const double t = (double)x[a] * s.g.inv_dx;
-            const double fr = t - floor(t);
-            const double band = 4e-6 + fabs(t) * 2.5e-7;
-            if (fr < band || fr > 1.0 - band) word |= kEdgeBit;
-        }
-        s.seam[(size_t)dir * s.cap + j] = word;
-        if (word & kEdgeBit) {
-            const uint32_t slot = atomicAdd(s.edge_count + dir, 1u);
-            if (slot < s.edge_cap) s.edge_list[(size_t)dir * s.edge_cap + slot] = (uint32_t)j;
-        }
-    }
+__global__ void __launch_bounds__(256) k_seam_home(const __grid_constant__ SeamParams s) {
+    __shared__ int sh[3 * 256];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int hidx[3] = {-1, -1, -1};
+    if (j < s.n) seam_particle(s, s.px[j], s.py[j], s.pz[j], j, hidx);
+    seam_mark_home(s, hidx, sh);
 }
 
 // featherGrid26 (gridutils.cpp:264-297) as a gather: active = OR of home over the 3x3x3 stencil.
@@ -1557,41 +1490,42 @@ int launch_dir(Context &c, P2GParams &P, int method, int variant, cudaStream_t s
 
 }  // namespace
 
-int launch_p2g_prepare(Context &c, double radius) {
-    int launches = 0;
+void p2g_seam_begin(Context &c, double radius, SeamParams &sp) {
     const GridDesc &g = c.g;
-    ParticleSoA &s = c.soa[c.cur];
     const double chunkdx = g.dx * kChunk;                     // velocityadvector.cpp:53
     const float eps = 1e-6f;
-    const float sr = (float)(radius + (double)eps);            // float sr = _particleRadius + eps;
-
-    // block masks + membership words
     FFB_CUDA(cudaMemsetAsync(c.sort.edge_count, 0, 4 * sizeof(uint32_t), c.stream));
+    sp.g = g;
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];
         FFB_CUDA(cudaMemsetAsync(f.home, 0, (size_t)f.bi * f.bj * f.bk, c.stream));
+        sp.bdim[d][0] = f.bi; sp.bdim[d][1] = f.bj; sp.bdim[d][2] = f.bk;
+        sp.home[d] = f.home;
     }
-    if (c.n > 0) {
+    sp.seam = c.sort.seam;
+    sp.edge_list = c.sort.edge_list;
+    sp.edge_count = c.sort.edge_count;
+    sp.edge_cap = c.sort.edge_cap;
+    sp.cap = c.cap;
+    ParticleSoA &s = c.soa[c.cur];
+    sp.px = s.p[0]; sp.py = s.p[1]; sp.pz = s.p[2];
+    sp.h = (float)(0.5 * g.dx);
+    sp.sr = (float)(radius + (double)eps);                     // float sr = _particleRadius + eps;
+    sp.blockdx = (float)chunkdx;
+    sp.inv_blockdx = 1.0 / (double)sp.blockdx;
+    sp.inv_chunkdx = 1.0 / chunkdx;
+    sp.n = c.n;
+}
+
+int launch_p2g_prepare(Context &c, double radius, bool seam_done) {
+    int launches = 0;
+    if (!seam_done) {                                          // particles were already sorted: stand-alone pass
         SeamParams sp;
-        sp.g = g;
-        for (int d = 0; d < 3; d++) {
-            sp.bdim[d][0] = c.face[d].bi; sp.bdim[d][1] = c.face[d].bj; sp.bdim[d][2] = c.face[d].bk;
-            sp.home[d] = c.face[d].home;
+        p2g_seam_begin(c, radius, sp);
+        if (c.n > 0) {
+            k_seam_home<<<(c.n + 255) / 256, 256, 0, c.stream>>>(sp);
+            launches++;
         }
-        sp.seam = c.sort.seam;
-        sp.edge_list = c.sort.edge_list;
-        sp.edge_count = c.sort.edge_count;
-        sp.edge_cap = c.sort.edge_cap;
-        sp.cap = c.cap;
-        sp.px = s.p[0]; sp.py = s.p[1]; sp.pz = s.p[2];
-        sp.h = (float)(0.5 * g.dx);
-        sp.sr = sr;
-        sp.blockdx = (float)chunkdx;
-        sp.inv_blockdx = 1.0 / (double)sp.blockdx;
-        sp.inv_chunkdx = 1.0 / chunkdx;
-        sp.n = c.n;
-        k_seam_home<<<(c.n + 255) / 256, 256, 0, c.stream>>>(sp);
-        launches++;
     }
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];

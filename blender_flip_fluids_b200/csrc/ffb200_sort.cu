@@ -9,6 +9,7 @@
 //   ties = ascending original particle index, the order in which the reference accumulates a
 //          block's particles (velocityadvector.cpp:383-413).
 #include "ffb200_ctx.h"
+#include "ffb200_seam.cuh"
 
 #include <cstdlib>
 #include <string>
@@ -305,32 +306,40 @@ struct ReorderArgs {
     int nstreams;
 };
 
-__global__ void k_reorder(ReorderArgs a, const uint32_t *__restrict__ key, const uint32_t *__restrict__ val,
-                          const uint32_t *__restrict__ bin_start, const uint32_t *__restrict__ orig_old,
-                          uint32_t *__restrict__ orig_new, int n) {
+template <bool SEAM>
+__global__ void __launch_bounds__(256) k_reorder(const __grid_constant__ ReorderArgs a, const __grid_constant__ SeamParams sp,
+                                                 const uint32_t *__restrict__ key, const uint32_t *__restrict__ val,
+                                                 const uint32_t *__restrict__ bin_start, const uint32_t *__restrict__ orig_old,
+                                                 uint32_t *__restrict__ orig_new, int n) {
+    __shared__ int sh[SEAM ? 3 * 256 : 1];
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint32_t slot = val[j];
-    const uint32_t kk = key[j];
-    const uint32_t s = bin_start[kk], e = bin_start[kk + 1];
-    const uint32_t my = orig_old[slot];
-    uint32_t dst = (uint32_t)j;
-    if (e - s > 1u) {
-        uint32_t rank = 0;
-        for (uint32_t q = s; q < e; q++) rank += orig_old[val[q]] < my ? 1u : 0u;
-        dst = s + rank;
+    int hidx[3] = {-1, -1, -1};
+    if (j < n) {
+        const uint32_t slot = val[j];
+        const uint32_t kk = key[j];
+        const uint32_t s = bin_start[kk], e = bin_start[kk + 1];
+        const uint32_t my = orig_old[slot];
+        uint32_t dst = (uint32_t)j;
+        if (e - s > 1u) {
+            uint32_t rank = 0;
+            for (uint32_t q = s; q < e; q++) rank += orig_old[val[q]] < my ? 1u : 0u;
+            dst = s + rank;
+        }
+        orig_new[dst] = my;
+        // all gathers first (independent, through the read-only path), then all stores: the stream
+        // pointers may alias as far as the compiler knows, so a load/store-per-stream loop would
+        // serialise on the memory latency
+        float v[15];
+#pragma unroll
+        for (int t = 0; t < 15; t++)
+            if (t < a.nstreams) v[t] = __ldg(a.src[t] + slot);
+#pragma unroll
+        for (int t = 0; t < 15; t++)
+            if (t < a.nstreams) a.dst[t][dst] = v[t];
+        // the P2G membership arithmetic of the particle rides along while the kernel waits for memory
+        if (SEAM) seam_particle(sp, v[0], v[1], v[2], (int)dst, hidx);
     }
-    orig_new[dst] = my;
-    // all gathers first (independent, through the read-only path), then all stores: the stream
-    // pointers may alias as far as the compiler knows, so a load/store-per-stream loop would
-    // serialise on the memory latency
-    float v[15];
-#pragma unroll
-    for (int t = 0; t < 15; t++)
-        if (t < a.nstreams) v[t] = __ldg(a.src[t] + slot);
-#pragma unroll
-    for (int t = 0; t < 15; t++)
-        if (t < a.nstreams) a.dst[t][dst] = v[t];
+    if (SEAM) seam_mark_home(sp, hidx, sh);
 }
 
 __global__ void k_binning_dump(GridDesc g, const float *__restrict__ px, const float *__restrict__ py,
@@ -368,7 +377,7 @@ int launch_iota(Context &c, uint32_t *dst, int n) {
     return 1;
 }
 
-int launch_sort(Context &c) {
+int launch_sort(Context &c, const SeamParams *seam) {
     const int n = c.n;
     int launches = 0;
     const GridDesc &g = c.g;
@@ -446,7 +455,10 @@ int launch_sort(Context &c) {
         for (int q = 0; q < 9; q++) { a.src[t] = src.a[q]; a.dst[t] = dst.a[q]; t++; }
     a.nstreams = t;
     for (; t < 15; t++) { a.src[t] = nullptr; a.dst[t] = nullptr; }
-    k_reorder<<<blocks_for(n, 256), 256, 0, c.stream>>>(a, s.key[0], s.val[0], s.bin_start, src.orig, dst.orig, n);
+    if (seam)
+        k_reorder<true><<<blocks_for(n, 256), 256, 0, c.stream>>>(a, *seam, s.key[0], s.val[0], s.bin_start, src.orig, dst.orig, n);
+    else
+        k_reorder<false><<<blocks_for(n, 256), 256, 0, c.stream>>>(a, SeamParams{}, s.key[0], s.val[0], s.bin_start, src.orig, dst.orig, n);
     launches++;
     c.cur ^= 1;
     c.sorted = true;
