@@ -1332,7 +1332,8 @@ __global__ void __launch_bounds__(128) k_p2g_nodes(const __grid_constant__ P2GPa
     const int nj = blockIdx.y * blockDim.y + threadIdx.y;
     const int nk = blockIdx.z * blockDim.z + threadIdx.z + P.kw0;
     if (ni >= P.gi || nj >= P.gj || nk >= P.kw1) return;
-    const size_t fidx = (size_t)ni + (size_t)P.gi * ((size_t)nj + (size_t)P.gj * (nk - P.g.kbase));
+    // face and cell counts fit 32 bits (checked by the launcher): 32-bit index arithmetic
+    const uint32_t fidx = (uint32_t)ni + (uint32_t)P.gi * ((uint32_t)nj + (uint32_t)P.gj * (uint32_t)(nk - P.g.kbase));
     const int n[3] = {ni, nj, nk};
     const int nbv[3] = {ni / kChunk, nj / kChunk, nk / kChunk};
     if (!P.active[nbv[0] + P.bi * (nbv[1] + P.bj * nbv[2])]) {
@@ -1345,14 +1346,17 @@ __global__ void __launch_bounds__(128) k_p2g_nodes(const __grid_constant__ P2GPa
     const size_t plane = (size_t)P.ccx * P.ccy * P.ccz;
     // node n is corner c = (cx, cy, cz) of the shifted cell n - (cx, cy, cz). Flags, then partial
     // sums, as two batches of independent loads; the additions keep the fixed corner order.
-    size_t cell[8];
+    const uint32_t sy = (uint32_t)P.ccx, sz = (uint32_t)P.ccx * (uint32_t)P.ccy;
+    const int iz1 = nk - P.ck0;                                // cell layer of the corners with cz = 0
+    const uint32_t base = (uint32_t)(ni + 1) + sy * (uint32_t)(nj + 1) + sz * (uint32_t)max(iz1, 0);
+    const bool zok[2] = {iz1 >= 0 && iz1 < P.ccz, iz1 - 1 >= 0 && iz1 - 1 < P.ccz};   // cells outside this rank's range hold nothing
+    uint32_t cell[8];
     bool have[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         const int cx = c & 1, cy = (c >> 1) & 1, cz = c >> 2;
-        const int ix = ni - cx + 1, iy = nj - cy + 1, iz = nk - cz - P.ck0;
-        have[c] = iz >= 0 && iz < P.ccz;                       // cells outside this rank's range hold nothing for it
-        cell[c] = have[c] ? (size_t)ix + (size_t)P.ccx * ((size_t)iy + (size_t)P.ccy * iz) : 0;
+        have[c] = zok[cz];
+        cell[c] = have[c] ? base - (uint32_t)cx - (cy ? sy : 0u) - (cz && iz1 > 0 ? sz : 0u) : 0u;
     }
 #pragma unroll
     for (int c = 0; c < 8; c++) have[c] = have[c] && __ldg(P.cell_flag + cell[c]) != 0;
@@ -1602,7 +1606,8 @@ int launch_p2g(Context &c, double radius, int method) {
                 if (cs.cell_flag) FFB_CUDA(cudaFree(cs.cell_flag));
                 if (cs.cell_list) FFB_CUDA(cudaFree(cs.cell_list));
                 cs.cells = cells + cells / 16;
-                if (cs.cells >= 0xffffffffull) throw CudaError("ffb200_p2g: more than 2^32 shifted cells per rank");
+                if (cs.cells >= 0xffffffffull || (unsigned long long)f.count >= 0xffffffffull)
+                    throw CudaError("ffb200_p2g: more than 2^32 shifted cells / faces per rank");
                 FFB_CUDA(cudaMalloc(&cs.partial, cs.cells * 8 * sizeof(float2)));
                 FFB_CUDA(cudaMalloc(&cs.cell_flag, cs.cells));
                 FFB_CUDA(cudaMalloc(&cs.cell_list, cs.cells * sizeof(CellRec)));
