@@ -188,6 +188,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
+    # stdout carries exactly one JSON line: everything libraries write to fd 1 meanwhile (NCCL prints its
+    # version banner there) is sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         if rank != 0:
             return 0
@@ -201,7 +210,7 @@ def main():
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "reference",
                                  "sample": info["sample"], "stage_s": {k: info[k] for k in ("t_p2g", "t_g2p", "t_advect")}},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -422,7 +431,7 @@ def main():
                            "dt": dt, "pic_flip_ratio": ratio},
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches * steps, "roofline": roofline,
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
