@@ -154,7 +154,7 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->sort.scan_partials);
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c->face[d];
-        dev_free(f.vel); dev_free(f.saved); dev_free(f.wsum); dev_free(f.valid); dev_free(f.home); dev_free(f.active);
+        dev_free(f.vel); dev_free(f.saved); dev_free(f.wsum); dev_free(f.valid); dev_free(f.home); dev_free(f.active); dev_free(f.status[0]); dev_free(f.status[1]);
     }
     dev_free(c->phi);
     dev_free(c->near_solid);
@@ -637,6 +637,25 @@ int ffb200_save_velocity_field(ffb200_context *ctx) {
     }, false);
 }
 
+int ffb200_set_valid_velocities(ffb200_context *ctx, const uint8_t *validu, const uint8_t *validv, const uint8_t *validw) {
+    return guarded("ffb200_set_valid_velocities", ctx, [&](Context &c) {
+        const uint8_t *h[3] = {validu, validv, validw};
+        for (int d = 0; d < 3; d++) {
+            if (!h[d]) throw std::invalid_argument("null valid-mask pointer");
+            FaceGrid &f = c.face[d];
+            const size_t off = (size_t)f.gi * f.gj * c.g.kbase;
+            FFB_CUDA(cudaMemcpyAsync(f.valid, h[d] + off, f.count, cudaMemcpyHostToDevice, c.stream));
+        }
+    });
+}
+
+int ffb200_extrapolate_velocity_field(ffb200_context *ctx, int num_layers) {
+    return guarded("ffb200_extrapolate_velocity_field", ctx, [&](Context &c) {
+        if (num_layers < 0) throw std::domain_error("negative layer count");
+        launch_extrapolate(c, num_layers);
+    });
+}
+
 int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid) {
     return guarded("ffb200_set_solid", ctx, [&](Context &c) { set_solid_impl(impl(c), phi, near_solid); });
 }
@@ -668,6 +687,29 @@ int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos
         set_particles_impl(c, n, pos, vel, affx, affy, affz);
         p2g_impl(c, particle_radius, transfer_method);
         get_field_impl(c, u, v, w, validu, validv, validw);
+    });
+}
+
+int ffb200_extrapolate_fluid_velocities(ffb200_context *ctx, float *u, float *v, float *w, const uint8_t *validu,
+                                        const uint8_t *validv, const uint8_t *validw, int num_layers,
+                                        int device_field_is_current) {
+    return guarded("ffb200_extrapolate_fluid_velocities", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (num_layers < 0) throw std::domain_error("negative layer count");
+        if (!u || !v || !w) throw std::invalid_argument("null velocity field pointer");
+        if (!device_field_is_current) {
+            if (!validu || !validv || !validw) throw std::invalid_argument("null valid-mask pointer");
+            StageTimer t(c, kH2D);
+            upload_field(c, false, u, v, w);
+            const uint8_t *h[3] = {validu, validv, validw};
+            for (int d = 0; d < 3; d++) {
+                FaceGrid &f = c.face[d];
+                FFB_CUDA(cudaMemcpyAsync(f.valid, h[d] + (size_t)f.gi * f.gj * c.g.kbase, f.count, cudaMemcpyHostToDevice, c.stream));
+            }
+            t.done(0);
+        }
+        launch_extrapolate(c, num_layers);
+        get_field_impl(c, u, v, w, nullptr, nullptr, nullptr);
     });
 }
 

@@ -43,6 +43,7 @@ struct FaceGrid {
     float *wsum = nullptr;        // weight sums of the last P2G
     uint8_t *valid = nullptr;
     uint8_t *home = nullptr, *active = nullptr;   // block masks (bi*bj*bk)
+    uint8_t *status[2] = {nullptr, nullptr};      // extrapolation status, ping-pong (lazy)
 };
 
 struct SortScratch {
@@ -120,6 +121,9 @@ struct SeamParams;                        // ffb200_seam.cuh
 // P2G membership words / home marks / edge list of every particle (what k_seam_home would do next).
 int launch_sort(Context &c, const SeamParams *seam = nullptr);
 int launch_binning_dump(Context &c, int32_t *cell, uint32_t *hkey, uint32_t *perm);   // device outputs
+
+// ffb200_extrapolate.cu
+int launch_extrapolate(Context &c, int layers);          // GridUtils::extrapolateGrid on u, v, w in place
 
 // ffb200_p2g.cu
 void p2g_seam_begin(Context &c, double radius, SeamParams &sp);   // clears marks / counters, fills sp

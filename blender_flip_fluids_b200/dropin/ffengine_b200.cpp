@@ -1,11 +1,13 @@
 // ffengine_b200.cpp -- drop-in libffengine for the FLIP Fluids addon with the particle<->grid
 // substep on B200.
 //
-// The reference calls its three hot stages through the PLT (it is built -fPIC without
-// -Bsymbolic), so a library that DEFINES those three C++ member symbols
+// The reference calls these four stages through the PLT (it is built -fPIC without
+// -Bsymbolic), so a library that DEFINES those four C++ member symbols
 // and DT_NEEDEDs the unmodified engine takes the calls over without touching reference code:
 //
 //   VelocityAdvector::advect(VelocityAdvectorParameters)              velocityadvector.cpp:38
+//   FluidSimulation::_extrapolateFluidVelocities(MACVelocityField&,   fluidsimulation.cpp:6282
+//                                   ValidVelocityComponentGrid&)
 //   FluidSimulation::_updateMarkerParticleVelocitiesThread()          fluidsimulation.cpp:6845
 //   FluidSimulation::_advanceMarkerParticles(double)                  fluidsimulation.cpp:7853
 //
@@ -16,6 +18,7 @@
 // level sets, meshing, I/O, particle removal ...) stays on the reference CPU code.
 // Compiled against the UNMODIFIED reference headers with -fno-access-control.
 // There is no fallback to the CPU originals: if the GPU call fails, the substep fails.
+#include <cmath>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -61,6 +64,11 @@ void check(int ok) {
 
 float *raw(std::vector<vmath::vec3> *v) { return v->empty() ? nullptr : &((*v)[0].x); }
 
+// The field object whose host arrays were just filled by our P2G (and are therefore identical to
+// the device-resident field): lets the extrapolation that follows it (fluidsimulation.cpp:5652-5654)
+// skip the upload. Cleared by every other interposed stage.
+MACVelocityField *g_fresh_p2g_field = nullptr;
+
 }  // namespace
 
 // ---- P2G ------------------------------------------------------------------------------------------
@@ -85,10 +93,27 @@ void VelocityAdvector::advect(VelocityAdvectorParameters params) {
         params.vfield->getArray3dU()->getRawArray(), params.vfield->getArray3dV()->getRawArray(),
         params.vfield->getArray3dW()->getRawArray(), reinterpret_cast<uint8_t *>(valid->validU.getRawArray()),
         reinterpret_cast<uint8_t *>(valid->validV.getRawArray()), reinterpret_cast<uint8_t *>(valid->validW.getRawArray())));
+    g_fresh_p2g_field = params.vfield;
+}
+
+// ---- valid-face extrapolation -----------------------------------------------------------------------
+void FluidSimulation::_extrapolateFluidVelocities(MACVelocityField &MACGrid, ValidVelocityComponentGrid &validVelocities) {
+    int I, J, K;
+    MACGrid.getGridDimensions(&I, &J, &K);
+    ffb200_context *ctx = context_for(I, J, K, MACGrid.getGridCellSize());
+    const int numLayers = (int)std::ceil(std::sqrt(3) * _CFLConditionNumber) + 3;      // fluidsimulation.cpp:6284
+    const bool fresh = g_fresh_p2g_field == &MACGrid;
+    g_fresh_p2g_field = nullptr;
+    check(ffb200_extrapolate_fluid_velocities(
+        ctx, MACGrid.getArray3dU()->getRawArray(), MACGrid.getArray3dV()->getRawArray(), MACGrid.getArray3dW()->getRawArray(),
+        reinterpret_cast<uint8_t *>(validVelocities.validU.getRawArray()),
+        reinterpret_cast<uint8_t *>(validVelocities.validV.getRawArray()),
+        reinterpret_cast<uint8_t *>(validVelocities.validW.getRawArray()), numLayers, fresh ? 1 : 0));
 }
 
 // ---- G2P ------------------------------------------------------------------------------------------
 void FluidSimulation::_updateMarkerParticleVelocitiesThread() {
+    g_fresh_p2g_field = nullptr;
     if (_markerParticles.empty()) return;
     ffb200_context *ctx = context_for(_isize, _jsize, _ksize, _dx);
     std::vector<vmath::vec3> *pos, *vel, *ax = nullptr, *ay = nullptr, *az = nullptr;
@@ -117,6 +142,7 @@ void FluidSimulation::_advanceMarkerParticles(double dt) {
     _logfile.logString(_logfile.getTime() + " BEGIN       Advect Marker Particles");
     StopWatch timer;
     timer.start();
+    g_fresh_p2g_field = nullptr;
     if (_isFluidInSimulation()) {
         ffb200_context *ctx = context_for(_isize, _jsize, _ksize, _dx);
         std::vector<vmath::vec3> *pos;

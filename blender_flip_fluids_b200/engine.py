@@ -81,11 +81,14 @@ SIGNATURES = {
     "ffb200_get_velocity_field": [C.c_void_p] + [_f32p] * 3 + [_u8p] * 3,
     "ffb200_get_weight_sums": [C.c_void_p] + [_f32p] * 3,
     "ffb200_save_velocity_field": [C.c_void_p],
+    "ffb200_set_valid_velocities": [C.c_void_p, _u8p, _u8p, _u8p],
+    "ffb200_extrapolate_velocity_field": [C.c_void_p, C.c_int],
     "ffb200_set_solid": [C.c_void_p, _f32p, _u8p],
     "ffb200_p2g": [C.c_void_p, C.c_double, C.c_int],
     "ffb200_g2p": [C.c_void_p, C.c_int, C.c_double],
     "ffb200_advect": [C.c_void_p, C.c_double, C.c_double, C.c_int],
     "ffb200_velocity_advector_advect": [C.c_void_p, C.c_int] + [_f32p] * 5 + [C.c_double, C.c_int] + [_f32p] * 3 + [_u8p] * 3,
+    "ffb200_extrapolate_fluid_velocities": [C.c_void_p, _f32p, _f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int],
     "ffb200_update_marker_particle_velocities": [C.c_void_p, C.c_int] + [_f32p] * 11 + [C.c_int, C.c_double],
     "ffb200_advance_marker_particles": [C.c_void_p, C.c_int] + [_f32p] * 5 + [_u8p, C.c_double, C.c_double],
 }
@@ -279,6 +282,21 @@ class FlipContext:
 
     def save_velocity_field(self):
         self._call("ffb200_save_velocity_field")
+
+    def set_valid_velocities(self, validu, validv, validw):
+        su, sv, sw = mac_shapes(self.I, self.J, self.K)
+        m = [np.ascontiguousarray(a, dtype=np.uint8) for a in (validu, validv, validw)]
+        for a, s in zip(m, (su, sv, sw)):
+            if tuple(a.shape) != tuple(s):
+                raise ValueError(f"expected shape {s}, got {a.shape}")
+        self._call("ffb200_set_valid_velocities", *[_ptr(a, _u8p) for a in m])
+
+    def extrapolate_velocity_field(self, num_layers=None, cfl=5.0):
+        """_extrapolateFluidVelocities: num_layers defaults to ceil(sqrt(3) * cfl) + 3 (fluidsimulation.cpp:6284)."""
+        if num_layers is None:
+            import math
+            num_layers = int(math.ceil(math.sqrt(3) * cfl)) + 3
+        self._call("ffb200_extrapolate_velocity_field", C.c_int(num_layers))
 
     def set_solid(self, phi, near_solid):
         phi = _f32(phi, (self.K + 1, self.J + 1, self.I + 1))

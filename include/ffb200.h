@@ -12,6 +12,8 @@
  *   ---------------------------------------------------------   -------------------------------
  *   VelocityAdvector::advect(params)   velocityadvector.cpp:38  ffb200_velocity_advector_advect
  *     (called from fluidsimulation.cpp:5652 and :6971)
+ *   FluidSimulation::_extrapolateFluidVelocities
+ *                                             fs.cpp:6282-6286  ffb200_extrapolate_fluid_velocities
  *   FluidSimulation::_saveVelocityField       fs.cpp:5671-5679  ffb200_save_velocity_field
  *   FluidSimulation::_updateMarkerParticleVelocitiesThread
  *                                             fs.cpp:6845-6863  ffb200_update_marker_particle_velocities
@@ -171,6 +173,15 @@ int ffb200_get_velocity_field(ffb200_context *ctx, float *u, float *v, float *w,
 int ffb200_get_weight_sums(ffb200_context *ctx, float *wu, float *wv, float *ww);
 /* _saveVelocityField: device-side deep copy current -> saved. */
 int ffb200_save_velocity_field(ffb200_context *ctx);
+/* Valid masks of the current field (ValidVelocityComponentGrid, one byte per face, the layout of
+ * ffb200_get_velocity_field). ffb200_p2g leaves them on the device; this uploads them from the host. */
+int ffb200_set_valid_velocities(ffb200_context *ctx, const uint8_t *validu, const uint8_t *validv, const uint8_t *validw);
+/* FluidSimulation::_extrapolateFluidVelocities (fluidsimulation.cpp:6282-6286) ->
+ * MACVelocityField::extrapolateVelocityField (macvelocityfield.cpp:671-677) -> GridUtils::extrapolateGrid
+ * (gridutils.h:94-163): grows the valid faces of u, v, w by num_layers 6-neighbour layers, in place, bit
+ * for bit as the reference does (the reference passes ceil(sqrt(3) * CFL) + 3 = 12). Uses the valid
+ * masks of the last ffb200_p2g / ffb200_set_valid_velocities. Whole-grid contexts only. */
+int ffb200_extrapolate_velocity_field(ffb200_context *ctx, int num_layers);
 int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid);
 
 /* ---- stages on resident data ---------------------------------------------------------------------- */
@@ -187,6 +198,15 @@ int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos
                                     double particle_radius, int transfer_method,
                                     float *u, float *v, float *w,
                                     uint8_t *validu, uint8_t *validv, uint8_t *validw);
+
+/* _extrapolateFluidVelocities (fluidsimulation.cpp:6282-6286; the reference passes
+ * num_layers = ceil(sqrt(3) * CFL) + 3): u, v, w are extrapolated in place on the host arrays.
+ * device_field_is_current != 0 states that u, v, w and the valid masks are exactly what the
+ * immediately preceding ffb200_velocity_advector_advect on this context returned (the reference's
+ * call order, fluidsimulation.cpp:5652-5654): the upload is skipped and the valid pointers may be NULL. */
+int ffb200_extrapolate_fluid_velocities(ffb200_context *ctx, float *u, float *v, float *w,
+                                        const uint8_t *validu, const uint8_t *validv, const uint8_t *validw,
+                                        int num_layers, int device_field_is_current);
 
 /* _updateMarkerParticleVelocitiesThread: upload particles and both fields, gather, download.
  * vel is updated in place; affx/affy/affz are outputs for APIC (ignored for FLIP);

@@ -616,3 +616,57 @@ void flip_oracle_advect(int I, int J, int K, double dx, int n, const float *pos_
         pos_out[3 * (size_t)p + 2] = p1[2];
     }
 }
+
+/* ---- valid-face extrapolation (next-row f1) -------------------------------------------------------
+ * GridUtils::extrapolateGrid (gridutils.h:94-163) with _initializeStatusGridThread /
+ * _findExtrapolationCells (gridutils.cpp:99-173) and _extrapolateCellsThread (gridutils.h:42-91),
+ * called per MAC component by MACVelocityField::extrapolateVelocityField (macvelocityfield.cpp:671-677)
+ * with numLayers = ceil(sqrt(3) * CFL) + 3 (fluidsimulation.cpp:6282-6286).
+ * The reference splits both passes over threads; the set of cells found per layer and every cell's
+ * neighbour sum (fixed +i,-i,+j,-j,+k,-k order, DONE neighbours only) do not depend on that split,
+ * so this sequential restatement is bit-identical to the threaded original. */
+void flip_oracle_extrapolate(int w, int h, int d, float *grid, const uint8_t *valid, int layers) {
+    enum { UNKNOWN = 0, WAITING = 1, KNOWN = 2, DONE = 3 };
+    size_t n = (size_t)w * h * d;
+    unsigned char *status = (unsigned char *)calloc(n ? n : 1, 1);
+    size_t *cells = (size_t *)malloc((n ? n : 1) * sizeof(size_t));
+    const long long off[6] = {1, -1, w, -(long long)w, (long long)w * h, -(long long)w * h};
+    for (int k = 0; k < d; k++)
+        for (int j = 0; j < h; j++)
+            for (int i = 0; i < w; i++) {
+                size_t idx = (size_t)i + (size_t)w * ((size_t)j + (size_t)h * k);
+                int border = i == 0 || j == 0 || k == 0 || i == w - 1 || j == h - 1 || k == d - 1;
+                status[idx] = border ? DONE : (valid[idx] ? KNOWN : UNKNOWN);
+            }
+    for (int layer = 0; layer < layers; layer++) {
+        size_t ncells = 0;
+        for (size_t idx = 0; idx < n; idx++) {                 /* _findExtrapolationCells */
+            if (status[idx] != KNOWN) continue;
+            for (int q = 0; q < 6; q++) {
+                size_t nb = (size_t)((long long)idx + off[q]);
+                if (status[nb] == UNKNOWN) {
+                    status[nb] = WAITING;
+                    cells[ncells++] = nb;
+                }
+            }
+            status[idx] = DONE;
+        }
+        for (size_t c = 0; c < ncells; c++) {                  /* _extrapolateCellsThread */
+            size_t idx = cells[c];
+            float sum = 0.0f;
+            int count = 0;
+            for (int q = 0; q < 6; q++) {
+                size_t nb = (size_t)((long long)idx + off[q]);
+                if (status[nb] == DONE) {
+                    sum += grid[nb];
+                    count++;
+                }
+            }
+            grid[idx] = sum / (float)count;
+        }
+        if (layer != layers - 1)
+            for (size_t c = 0; c < ncells; c++) status[cells[c]] = KNOWN;
+    }
+    free(cells);
+    free(status);
+}

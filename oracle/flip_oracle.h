@@ -80,6 +80,9 @@ void flip_oracle_advect(int I, int J, int K, double dx, int n, const float *pos_
 /* near-solid grid dimensions used by flip_oracle_advect. */
 void flip_oracle_near_dims(int I, int J, int K, double dx, int *gi, int *gj, int *gk);
 
+/* GridUtils::extrapolateGrid (gridutils.h:94-163) on one w x h x d float grid (x fastest), in place. */
+void flip_oracle_extrapolate(int w, int h, int d, float *grid, const uint8_t *valid, int layers);
+
 #ifdef __cplusplus
 }
 #endif

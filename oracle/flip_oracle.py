@@ -122,3 +122,18 @@ def advect(I, J, K, dx, pos, mac, phi, near, dt, cfl=5.0, collide=True):
                              _p(out), _p(u), _p(v), _p(w), _p(phi), _p(near, C.c_uint8), C.c_double(dt),
                              C.c_double(cfl), C.c_int(1 if collide else 0))
     return out
+
+
+def extrapolate(grid, valid, layers):
+    """GridUtils::extrapolateGrid on one (d, h, w) float grid; returns the extrapolated copy."""
+    g = np.array(grid, dtype=np.float32, order="C", copy=True)
+    v = np.ascontiguousarray(valid, dtype=np.uint8)
+    d, h, w = g.shape
+    lib().flip_oracle_extrapolate(C.c_int(w), C.c_int(h), C.c_int(d), _p(g), _p(v, C.c_uint8), C.c_int(layers))
+    return g
+
+
+def extrapolation_layers(cfl=5.0):
+    """fluidsimulation.cpp:6284."""
+    import math
+    return int(math.ceil(math.sqrt(3) * cfl)) + 3

@@ -484,9 +484,41 @@ static int mode_scene() {
     return 0;
 }
 
+// extrapolate: MACVelocityField::extrapolateVelocityField (macvelocityfield.cpp:671-677 ->
+// GridUtils::extrapolateGrid, gridutils.h:94-163) on a given field + valid masks.
+static int mode_extrapolate() {
+    int I = kvi("I"), J = kvi("J"), K = kvi("K");
+    double dx = kvd("dx");
+    int layers = kvi("layers", "12");
+    MACVelocityField f(I, J, K, dx);
+    ValidVelocityComponentGrid valid(I, J, K);
+    load_grid("in_u", *f.getArray3dU());
+    load_grid("in_v", *f.getArray3dV());
+    load_grid("in_w", *f.getArray3dW());
+    load_mask("in_validu", valid.validU);
+    load_mask("in_validv", valid.validV);
+    load_mask("in_validw", valid.validW);
+    int reps = kvi("reps", "1");
+    double t = 0;
+    for (int r = 0; r < reps; r++) {
+        MACVelocityField g = f;
+        double t0 = now();
+        g.extrapolateVelocityField(valid, layers);
+        t = now() - t0;
+        if (r == 0) {
+            save_grid("out_u", *g.getArray3dU());
+            save_grid("out_v", *g.getArray3dV());
+            save_grid("out_w", *g.getArray3dW());
+        }
+    }
+    printf("{\"mode\": \"extrapolate\", \"layers\": %d, \"threads\": %d, \"t_extrapolate\": %.6f}\n", layers,
+           ThreadUtils::getMaxThreadCount(), t);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 3) {
-        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene> <workdir> key=value ...\n");
+        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene|extrapolate> <workdir> key=value ...\n");
         return 2;
     }
     std::string mode = argv[1];
@@ -503,6 +535,7 @@ int main(int argc, char **argv) {
     if (mode == "g2p") return mode_g2p();
     if (mode == "advect") return mode_advect();
     if (mode == "scene") return mode_scene();
+    if (mode == "extrapolate") return mode_extrapolate();
     fprintf(stderr, "ref_harness: unknown mode %s\n", mode.c_str());
     return 2;
 }

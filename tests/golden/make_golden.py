@@ -150,6 +150,29 @@ def fixture_advect(name, scene_npz, seed, cells_per_step=4.0):
     print(name, m2, "moved", int((out != pos).any(axis=1).sum()))
 
 
+def fixture_extrapolate(name, scene_npz, layers, threads):
+    """Valid-face extrapolation (GridUtils::extrapolateGrid via MACVelocityField::extrapolateVelocityField)
+    of the reference's own P2G output + valid masks taken from a scene fixture. Run with several
+    reference thread counts: the outputs must agree (the threaded passes are order-independent)."""
+    z = np.load(os.path.join(OUT, scene_npz + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    outs = []
+    for t in threads:
+        d = tempfile.mkdtemp(prefix="ffgold_")
+        save_inputs(d, u=z["s1_u"], v=z["s1_v"], w=z["s1_w"], validu=z["s1_validu"], validv=z["s1_validv"],
+                    validw=z["s1_validw"])
+        run("extrapolate", d, I=I, J=J, K=K, dx=float(dx), layers=layers, threads=t)
+        outs.append(load_all(d, "out_"))
+        shutil.rmtree(d)
+    for o in outs[1:]:
+        for k in outs[0]:
+            assert o[k].tobytes() == outs[0][k].tobytes(), f"reference extrapolation depends on the thread count ({k})"
+    m2 = dict(I=I, J=J, K=K, dx=dx, layers=layers, scene=scene_npz, threads=list(threads))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), **outs[0])
+    print(name, m2)
+
+
 if __name__ == "__main__":
     if not os.path.exists(HARNESS):
         sys.exit("build oracle/_ref first: make -C oracle -j8 all")
@@ -163,3 +186,6 @@ if __name__ == "__main__":
     fixture_p2g("p2g_flip_21x20x22_radius2", 21, 20, 22, 0.01, "flip", 24, radius_scale=2.0)
     # collision-heavy advection
     fixture_advect("advect_collide_24x20x22", "scene_flip_24x20x22_nondyadic", 31)
+    # valid-face extrapolation of the reference's own P2G output (inputs: s1_* of the scene fixtures)
+    fixture_extrapolate("extrapolate_flip_24x20x22", "scene_flip_24x20x22_nondyadic", 12, (1, 3, 16))
+    fixture_extrapolate("extrapolate_apic_22x24x20", "scene_apic_22x24x20_dyadic", 12, (1, 3, 16))

@@ -80,7 +80,7 @@ def test_scene_generators():
 
 
 def test_dropin_reexports_reference_abi():
-    """libffengine_b200.so defines exactly the three interposed C++ members and resolves the
+    """libffengine_b200.so defines exactly the four interposed C++ members and resolves the
     reference's whole extern "C" surface through its DT_NEEDED reference library."""
     dropin = os.path.join(ROOT, "blender_flip_fluids_b200", "lib", "libffengine_b200.so")
     ref = os.path.join(ROOT, "oracle", "_ref", "libffengine_ref.so")
@@ -90,7 +90,8 @@ def test_dropin_reexports_reference_abi():
     defined = set(re.findall(r" T (\S+)", out))
     assert defined == {"_ZN16VelocityAdvector6advectE26VelocityAdvectorParameters",
                        "_ZN15FluidSimulation37_updateMarkerParticleVelocitiesThreadEv",
-                       "_ZN15FluidSimulation23_advanceMarkerParticlesEd"}
+                       "_ZN15FluidSimulation23_advanceMarkerParticlesEd",
+                       "_ZN15FluidSimulation27_extrapolateFluidVelocitiesER16MACVelocityFieldR26ValidVelocityComponentGrid"}
     needed = subprocess.run(["readelf", "-d", dropin], capture_output=True, text=True, check=True).stdout
     assert "libffb200.so" in needed and "libffengine_cpu.so" in needed
     refsyms = subprocess.run(["nm", "-D", "--defined-only", ref], capture_output=True, text=True, check=True).stdout

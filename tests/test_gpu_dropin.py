@@ -1,6 +1,7 @@
 """Drop-in test (-m gpu): the same small simulation driven through the reference's own
 `FluidSimulation_*` C ABI, once with the unmodified reference library and once with
-libffengine_b200.so (the three hot stages on the GPU, everything else reference CPU code).
+libffengine_b200.so (P2G, valid-face extrapolation, G2P and advection on the GPU, everything else
+reference CPU code).
 
 With FFB200_EXACT_P2G=1 the GPU P2G sums every face in the reference's order, and since G2P
 and advection are bit-exact, the WHOLE simulation must come out bit-identical. With the

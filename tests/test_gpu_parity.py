@@ -240,3 +240,54 @@ def test_alternate_kernel_paths(env, tmp_path):
     e.update(env)
     r = subprocess.run([sys.executable, "-c", VARIANT_CHECK, root], capture_output=True, text=True, env=e, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+# ---- valid-face extrapolation (GridUtils::extrapolateGrid) ----------------------------------------------------
+@pytest.mark.parametrize("name,scene", [("extrapolate_flip_24x20x22", "scene_flip_24x20x22_nondyadic"),
+                                        ("extrapolate_apic_22x24x20", "scene_apic_22x24x20_dyadic")])
+def test_extrapolate_golden(eng, name, scene):
+    """Device extrapolation against the unmodified reference's output: bit-exact."""
+    meta, e = load_golden(name)
+    _, g = load_golden(scene)
+    with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        ctx.set_velocity_field(g["s1_u"], g["s1_v"], g["s1_w"])
+        ctx.set_valid_velocities(g["s1_validu"], g["s1_validv"], g["s1_validw"])
+        ctx.extrapolate_velocity_field(meta["layers"])
+        (u, v, w), _ = ctx.get_velocity_field()
+        assert bits_equal(u, e["out_u"]) and bits_equal(v, e["out_v"]) and bits_equal(w, e["out_w"])
+        # default layer count = the reference's ceil(sqrt(3) * CFL) + 3
+        ctx.set_velocity_field(g["s1_u"], g["s1_v"], g["s1_w"])
+        ctx.extrapolate_velocity_field()
+        (u2, _, _), _ = ctx.get_velocity_field()
+        assert bits_equal(u2, e["out_u"])
+
+
+@pytest.mark.parametrize("layers", [0, 1, 5, 12])
+def test_extrapolate_vs_oracle_random_masks(eng, oracle, layers):
+    rng = np.random.default_rng(100 + layers)
+    I, J, K, dx = 19, 17, 23, 0.013
+    shapes = eng.mac_shapes(I, J, K)
+    grids = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    masks = [(rng.random(s) < p).astype(np.uint8) for s, p in zip(shapes, (0.02, 0.3, 0.0005))]
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        ctx.set_velocity_field(*grids)
+        ctx.set_valid_velocities(*masks)
+        ctx.extrapolate_velocity_field(layers)
+        got, _ = ctx.get_velocity_field()
+    for a, gr, m in zip(got, grids, masks):
+        assert bits_equal(a, oracle.extrapolate(gr, m, layers))
+
+
+def test_p2g_extrapolate_save_chain(eng, oracle):
+    """The reference's 'Advect Velocity Field' stage on the device: P2G -> extrapolate -> save
+    (fluidsimulation.cpp:5652-5654, 5671-5679), bit-exact in the exact-sum P2G mode."""
+    meta, g = load_golden("scene_apic_22x24x20_dyadic")
+    _, e = load_golden("extrapolate_apic_22x24x20")
+    with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        ctx.set_valid_guard(float("inf"), 0.0)
+        ctx.set_particles(g["s0_pos"], g["s0_vel"], g["s0_affx"], g["s0_affy"], g["s0_affz"])
+        ctx.p2g(meta["radius"], eng.APIC)
+        ctx.extrapolate_velocity_field()
+        ctx.save_velocity_field()
+        (u, v, w), _ = ctx.get_velocity_field()
+        assert bits_equal(u, e["out_u"]) and bits_equal(v, e["out_v"]) and bits_equal(w, e["out_w"])

@@ -88,3 +88,39 @@ def test_bin_sort_properties(oracle):
     same = np.diff(ks.astype(np.int64)) == 0
     assert (np.diff(perm.astype(np.int64))[same] > 0).all()
     assert np.array_equal(np.sort(perm), np.arange(len(pos)))
+
+
+EXTRAPOLATE = [("extrapolate_flip_24x20x22", "scene_flip_24x20x22_nondyadic"),
+               ("extrapolate_apic_22x24x20", "scene_apic_22x24x20_dyadic")]
+
+
+@pytest.mark.parametrize("name,scene", EXTRAPOLATE)
+def test_extrapolate_fixture(oracle, name, scene):
+    """GridUtils::extrapolateGrid: the reference's output (identical for 1, 3 and 16 reference threads,
+    checked by make_golden.py) on its own P2G output + valid masks."""
+    meta, e = load_golden(name)
+    _, g = load_golden(scene)
+    assert meta["layers"] == oracle.extrapolation_layers(5.0) == 12
+    for c in "uvw":
+        out = oracle.extrapolate(g["s1_" + c], g["s1_valid" + c], meta["layers"])
+        assert bits_equal(out, e["out_" + c]), c
+        assert (out != g["s1_" + c]).sum() > 0               # something was extrapolated
+        assert bits_equal(out[g["s1_valid" + c] == 1], g["s1_" + c][g["s1_valid" + c] == 1])   # valid faces untouched
+
+
+def test_extrapolate_edge_cases(oracle):
+    rng = np.random.default_rng(5)
+    grid = rng.standard_normal((6, 7, 8)).astype(np.float32)
+    none = np.zeros(grid.shape, np.uint8)
+    assert bits_equal(oracle.extrapolate(grid, none, 12), grid)            # nothing valid: nothing changes
+    full = np.ones(grid.shape, np.uint8)
+    assert bits_equal(oracle.extrapolate(grid, full, 12), grid)            # everything valid: nothing changes
+    one = none.copy()
+    one[3, 3, 4] = 1
+    assert bits_equal(oracle.extrapolate(grid, one, 0), grid)              # zero layers
+    out = oracle.extrapolate(grid, one, 1)
+    # first layer: the six neighbours take the mean of their DONE neighbours = the seed (border cells
+    # are DONE from the start and join the mean where they touch)
+    assert out[3, 3, 5] == grid[3, 3, 4] and out[3, 3, 3] == grid[3, 3, 4]
+    changed = np.argwhere(out != grid)
+    assert len(changed) <= 6
