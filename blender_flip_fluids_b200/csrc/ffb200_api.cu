@@ -656,6 +656,10 @@ int ffb200_extrapolate_velocity_field(ffb200_context *ctx, int num_layers) {
     });
 }
 
+int ffb200_declare_resident(ffb200_context *ctx, unsigned mask) {
+    return guarded("ffb200_declare_resident", ctx, [&](Context &c) { c.resident_next = mask; }, false);
+}
+
 int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid) {
     return guarded("ffb200_set_solid", ctx, [&](Context &c) { set_solid_impl(impl(c), phi, near_solid); });
 }
@@ -722,10 +726,16 @@ int ffb200_update_marker_particle_velocities(ffb200_context *ctx, int n, const f
         const bool apic = transfer_method == FFB200_TRANSFER_APIC;
         if (apic && (!affx || !affy || !affz)) throw std::invalid_argument("APIC needs affine output buffers");
         if (!apic && (!su || !sv || !sw)) throw std::invalid_argument("FLIP needs the saved velocity field");
-        set_particles_impl(c, n, pos, vel, nullptr, nullptr, nullptr);
-        upload_field(c, false, u, v, w);
+        const unsigned res = c.resident_next;
+        c.resident_next = 0;
+        if (res & FFB200_RESIDENT_PARTICLES) {                 // the caller vouches: same particles as the previous call
+            if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
+        } else {
+            set_particles_impl(c, n, pos, vel, nullptr, nullptr, nullptr);
+        }
+        if (!(res & FFB200_RESIDENT_FIELD)) upload_field(c, false, u, v, w);
         if (!apic) upload_field(c, true, su, sv, sw);
-        sort_impl(c);                                          // spatial order for the gathers
+        sort_impl(c);                                          // spatial order for the gathers (no-op if still sorted)
         g2p_impl(c, transfer_method, ratio_pic_flip);
         get_particles_impl(c, nullptr, vel, apic ? affx : nullptr, apic ? affy : nullptr, apic ? affz : nullptr);
     });
@@ -734,26 +744,40 @@ int ffb200_update_marker_particle_velocities(ffb200_context *ctx, int n, const f
 int ffb200_advance_marker_particles(ffb200_context *ctx, int n, float *pos, const float *u, const float *v,
                                     const float *w, const float *phi, const uint8_t *near_solid, double dt,
                                     double cfl_condition_number) {
-    return guarded("ffb200_advance_marker_particles", ctx, [&](Context &cc) {
-        ContextImpl &c = impl(cc);
-        if (n > 0 && !pos) throw std::invalid_argument("null position pointer");
-        // velocities are not needed by advection: upload positions twice is avoided by a zero-copy alias
-        ensure_capacity(c, n, false);
-        c.n = n;
-        c.has_affine = false;
-        c.sorted = false;
-        if (n > 0) {
-            StageTimer t(c, kH2D);
-            upload_attr(c, pos, c.soa[c.cur].p, n);
-            launch_iota(c, c.soa[c.cur].orig, n);
-            t.done(0);
-        }
-        upload_field(c, false, u, v, w);
-        if (phi && near_solid) set_solid_impl(c, phi, near_solid);
-        sort_impl(c);
-        advect_impl(c, dt, cfl_condition_number, 1);
-        get_particles_impl(c, pos, nullptr, nullptr, nullptr, nullptr);
-    });
+    // epoch handling by hand: with resident particles and field this advection directly follows the G2P
+    // of the same state and may reuse its samples (see ffb200_advect)
+    return guarded(
+        "ffb200_advance_marker_particles", ctx,
+        [&](Context &cc) {
+            ContextImpl &c = impl(cc);
+            if (n > 0 && !pos) throw std::invalid_argument("null position pointer");
+            const unsigned res = c.resident_next;
+            c.resident_next = 0;
+            const unsigned both = FFB200_RESIDENT_PARTICLES | FFB200_RESIDENT_FIELD;
+            if ((res & both) != both) c.epoch++;
+            if (res & FFB200_RESIDENT_PARTICLES) {
+                if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
+            } else {
+                // velocities are not needed by advection
+                ensure_capacity(c, n, false);
+                c.n = n;
+                c.has_affine = false;
+                c.sorted = false;
+                if (n > 0) {
+                    StageTimer t(c, kH2D);
+                    upload_attr(c, pos, c.soa[c.cur].p, n);
+                    launch_iota(c, c.soa[c.cur].orig, n);
+                    t.done(0);
+                }
+            }
+            if (!(res & FFB200_RESIDENT_FIELD)) upload_field(c, false, u, v, w);
+            if (phi && near_solid) set_solid_impl(c, phi, near_solid);
+            sort_impl(c);
+            advect_impl(c, dt, cfl_condition_number, 1);
+            c.epoch++;
+            get_particles_impl(c, pos, nullptr, nullptr, nullptr, nullptr);
+        },
+        false);
 }
 
 }  // extern "C"

@@ -106,6 +106,7 @@ struct Context {
     int k1_buf = 0;                      // 0/1: soa[k1_buf].v (APIC), 2: k1s (FLIP vPIC)
     float *k1s[3] = {nullptr, nullptr, nullptr};
     int k1s_cap = 0;
+    unsigned resident_next = 0;          // ffb200_declare_resident: inputs the next host-buffer call may skip uploading
     bool nondestructive = false;         // G2P/advect write to the spare SoA buffer (fixed-batch benchmarking)
     ffb200_timing timing = {};
 };

@@ -69,6 +69,14 @@ float *raw(std::vector<vmath::vec3> *v) { return v->empty() ? nullptr : &((*v)[0
 // skip the upload. Cleared by every other interposed stage.
 MACVelocityField *g_fresh_p2g_field = nullptr;
 
+// Resident-input tracking (ffb200_declare_resident): the particle system whose arrays our P2G
+// uploaded last and how many particles it held, and the field object our G2P uploaded last.
+// fluidsimulation.cpp:10078-10121: between the P2G and the G2P only sheet seeding can add or remove
+// marker particles, between the G2P and the advection nothing touches particles or _MACVelocity.
+ParticleSystem *g_resident_particles = nullptr;
+size_t g_resident_count = 0;
+MACVelocityField *g_resident_field = nullptr;
+
 }  // namespace
 
 // ---- P2G ------------------------------------------------------------------------------------------
@@ -94,6 +102,9 @@ void VelocityAdvector::advect(VelocityAdvectorParameters params) {
         params.vfield->getArray3dW()->getRawArray(), reinterpret_cast<uint8_t *>(valid->validU.getRawArray()),
         reinterpret_cast<uint8_t *>(valid->validV.getRawArray()), reinterpret_cast<uint8_t *>(valid->validW.getRawArray())));
     g_fresh_p2g_field = params.vfield;
+    g_resident_particles = params.particles;
+    g_resident_count = pos->size();
+    g_resident_field = nullptr;
 }
 
 // ---- valid-face extrapolation -----------------------------------------------------------------------
@@ -125,6 +136,11 @@ void FluidSimulation::_updateMarkerParticleVelocitiesThread() {
         _markerParticles.getAttributeValues("AFFINEY", ay);
         _markerParticles.getAttributeValues("AFFINEZ", az);
     }
+    const bool same_particles = !_isSheetSeedingEnabled && g_resident_particles == &_markerParticles &&
+                                g_resident_count == pos->size();
+    if (same_particles) check(ffb200_declare_resident(ctx, FFB200_RESIDENT_PARTICLES));
+    g_resident_particles = &_markerParticles;
+    g_resident_count = pos->size();
     check(ffb200_update_marker_particle_velocities(
         ctx, (int)pos->size(), raw(pos), raw(vel), apic ? raw(ax) : nullptr, apic ? raw(ay) : nullptr,
         apic ? raw(az) : nullptr, _MACVelocity.getArray3dU()->getRawArray(), _MACVelocity.getArray3dV()->getRawArray(),
@@ -132,6 +148,7 @@ void FluidSimulation::_updateMarkerParticleVelocitiesThread() {
         apic ? nullptr : _savedVelocityField.getArray3dV()->getRawArray(),
         apic ? nullptr : _savedVelocityField.getArray3dW()->getRawArray(),
         apic ? FFB200_TRANSFER_APIC : FFB200_TRANSFER_FLIP, _ratioPICFLIP));
+    g_resident_field = &_MACVelocity;
 }
 
 // ---- advect ---------------------------------------------------------------------------------------
@@ -147,6 +164,13 @@ void FluidSimulation::_advanceMarkerParticles(double dt) {
         ffb200_context *ctx = context_for(_isize, _jsize, _ksize, _dx);
         std::vector<vmath::vec3> *pos;
         _markerParticles.getAttributeValues("POSITION", pos);
+        // directly after our G2P of the same particle system and field: nothing to upload but the solid
+        unsigned resident = 0;
+        if (g_resident_particles == &_markerParticles && g_resident_count == pos->size() && g_resident_field == &_MACVelocity)
+            resident = FFB200_RESIDENT_PARTICLES | FFB200_RESIDENT_FIELD;
+        g_resident_particles = nullptr;
+        g_resident_field = nullptr;
+        if (resident) check(ffb200_declare_resident(ctx, resident));
         check(ffb200_advance_marker_particles(
             ctx, (int)pos->size(), raw(pos), _MACVelocity.getArray3dU()->getRawArray(),
             _MACVelocity.getArray3dV()->getRawArray(), _MACVelocity.getArray3dW()->getRawArray(),

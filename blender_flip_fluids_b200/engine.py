@@ -88,6 +88,7 @@ SIGNATURES = {
     "ffb200_g2p": [C.c_void_p, C.c_int, C.c_double],
     "ffb200_advect": [C.c_void_p, C.c_double, C.c_double, C.c_int],
     "ffb200_velocity_advector_advect": [C.c_void_p, C.c_int] + [_f32p] * 5 + [C.c_double, C.c_int] + [_f32p] * 3 + [_u8p] * 3,
+    "ffb200_declare_resident": [C.c_void_p, C.c_uint],
     "ffb200_extrapolate_fluid_velocities": [C.c_void_p, _f32p, _f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int],
     "ffb200_update_marker_particle_velocities": [C.c_void_p, C.c_int] + [_f32p] * 11 + [C.c_int, C.c_double],
     "ffb200_advance_marker_particles": [C.c_void_p, C.c_int] + [_f32p] * 5 + [_u8p, C.c_double, C.c_double],
@@ -282,6 +283,10 @@ class FlipContext:
 
     def save_velocity_field(self):
         self._call("ffb200_save_velocity_field")
+
+    def declare_resident(self, particles=False, field=False):
+        """ffb200_declare_resident: the next host-buffer call may skip uploading what the device already holds."""
+        self._call("ffb200_declare_resident", C.c_uint((1 if particles else 0) | (2 if field else 0)))
 
     def set_valid_velocities(self, validu, validv, validw):
         su, sv, sw = mac_shapes(self.I, self.J, self.K)

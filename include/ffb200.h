@@ -199,6 +199,20 @@ int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos
                                     float *u, float *v, float *w,
                                     uint8_t *validu, uint8_t *validv, uint8_t *validw);
 
+/* The reference hands the SAME particle arrays to its P2G, its G2P and its advection within one
+ * substep (fluidsimulation.cpp:10078-10121: nothing moves marker particles in between unless sheet
+ * seeding is on), and the same MAC field to the G2P and the advection. A caller that knows this may
+ * say so: the mask applies to the NEXT host-buffer entry point on this context only and lets it
+ * skip the upload of what the device already holds from the previous one (particles stay in their
+ * sorted order on the device; outputs are still written to the host arrays in the caller's order).
+ *   FFB200_RESIDENT_PARTICLES  positions, velocities (and affine rows) equal those of the previous call
+ *   FFB200_RESIDENT_FIELD      u, v, w equal those of the previous call
+ * Honoured by ffb200_update_marker_particle_velocities and ffb200_advance_marker_particles; the
+ * particle count must match or the call fails. */
+#define FFB200_RESIDENT_PARTICLES 1u
+#define FFB200_RESIDENT_FIELD 2u
+int ffb200_declare_resident(ffb200_context *ctx, unsigned mask);
+
 /* _extrapolateFluidVelocities (fluidsimulation.cpp:6282-6286; the reference passes
  * num_layers = ceil(sqrt(3) * CFL) + 3): u, v, w are extrapolated in place on the host arrays.
  * device_field_is_current != 0 states that u, v, w and the valid masks are exactly what the

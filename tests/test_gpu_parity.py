@@ -291,3 +291,39 @@ def test_p2g_extrapolate_save_chain(eng, oracle):
         ctx.save_velocity_field()
         (u, v, w), _ = ctx.get_velocity_field()
         assert bits_equal(u, e["out_u"]) and bits_equal(v, e["out_v"]) and bits_equal(w, e["out_w"])
+
+
+@pytest.mark.parametrize("method", ["flip", "apic"])
+def test_declare_resident_matches_full_uploads(eng, method):
+    """ffb200_declare_resident only skips uploads: the three host-buffer entry points give the same
+    bytes with and without it (and a wrong particle count is refused)."""
+    from blender_flip_fluids_b200 import scenes
+    apic = method == "apic"
+    m = eng.APIC if apic else eng.FLIP
+    sc = scenes.dam_break(24, apic=apic, vel="random", v0=0.4, seed=9)
+    phi, near = scenes.analytic_solid_sdf(24, 24, 24, sc.dx)
+    aff = [sc.affx, sc.affy, sc.affz] if apic else [None] * 3
+    results = []
+    for declare in (False, True):
+        with eng.FlipContext(24, 24, 24, sc.dx) as ctx:
+            pos, vel = sc.pos.copy(), sc.vel.copy()
+            (u, v, w), _ = ctx.velocity_advector_advect(pos, vel, *aff, radius=sc.radius, method=m)
+            saved = None if apic else (u * 0.5, v * 0.5, w * 0.5)
+            if declare:
+                ctx.declare_resident(particles=True)
+            g2p = ctx.update_marker_particle_velocities(pos, vel, (u, v, w), saved=saved, method=m, ratio_pic_flip=0.05)
+            if declare:
+                ctx.declare_resident(particles=True, field=True)
+            newpos = ctx.advance_marker_particles(pos, (u, v, w), phi, near, dt=0.8 * sc.dx / 0.4, cfl=5.0)
+            results.append((g2p, newpos))
+            if declare:
+                ctx.declare_resident(particles=True)
+                with pytest.raises(RuntimeError):
+                    ctx.advance_marker_particles(pos[:-1], (u, v, w), phi, near, dt=0.01, cfl=5.0)
+    (g0, p0), (g1, p1) = results
+    if apic:
+        assert all(bits_equal(a, b) for a, b in zip(g0, g1))
+    else:
+        assert bits_equal(g0, g1)
+    assert bits_equal(p0, p1)
+    assert (p0 != sc.pos).any()
