@@ -280,6 +280,8 @@ def main():
     for _ in range(warmup):
         step()
     barrier()
+    if sim is not None and getattr(sim, "_profile", False):
+        sim._phase = {}                   # FFB200_SLAB_PROFILE=1: steady-state phases only
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -424,7 +426,7 @@ def main():
     if sim is not None and getattr(sim, "_profile", False) and rank == 0:
         tot = sum(sim._phase.values())
         sys.stderr.write("slab phases (ms/step, synchronised): " + ", ".join(
-            f"{k} {1e3 * v / max(1, steps + warmup + 3):.3f}" for k, v in sim._phase.items()) + "\n")
+            f"{k} {1e3 * v / max(1, steps + 3):.3f}" for k, v in sim._phase.items()) + "\n")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

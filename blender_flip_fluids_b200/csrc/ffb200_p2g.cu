@@ -901,7 +901,7 @@ struct __align__(16) CellRec {
     uint32_t t;         // flat shifted-cell index
     uint32_t rs[4];     // first slot of each run
     uint32_t n01, n23;  // run lengths, 16 bits each (0xffffffff in n01: lengths do not fit, re-read the bin table)
-    uint32_t pad;
+    uint32_t seam;      // class: 0 plain, 1 seam / border
 };
 
 // Loads are unconditional on clamped indices so that all eight are in flight together. The bin
@@ -933,21 +933,25 @@ __device__ __forceinline__ uint32_t cell_runs(const P2GParams &P, const int b[3]
 // Pass 1: classify every shifted cell of this direction and list the occupied ones, so that the
 // splat kernel below runs on full warps. Class "plain": both corner nodes of every axis lie inside
 // the face grid and in the same 10^3 block -- one block frame, one membership test per particle.
-// Class "seam": everything else (block seams, grid border). Plain cells are listed from the front
-// of cell_list, seam cells from the back; a CTA reserves its entries with one atomic per class and
-// keeps x-neighbours together. The list order has no influence on the result (every cell owns
-// its slot of `partial`).
+// Class "seam": everything else (block seams, grid border). A CTA covers a region of 256
+// consecutive cells and appends [its plain cells][its seam cells], each group padded to a multiple
+// of 32 entries, with one atomic: every warp of the splat kernel sees one class only, and the
+// plain and seam cells of a region -- whose particles share 32-byte sectors -- are processed at
+// the same time by neighbouring warps. The list order has no influence on the result (every cell
+// owns its slot of `partial`).
 constexpr int kListThreads = 256;
+constexpr uint32_t kEmptyCell = 0xffffffffu;              // padding entry of the cell list
 template <int DIR>
 __global__ void __launch_bounds__(kListThreads) k_p2g_cell_list(const __grid_constant__ P2GParams P) {
     __shared__ uint32_t warp_cnt[2][kListThreads / 32];
-    __shared__ uint32_t cta_base[2];
+    __shared__ uint32_t cta_cnt[2];
+    __shared__ uint32_t cta_base;
     const uint32_t nxy = (uint32_t)P.ccx * (uint32_t)P.ccy;
     const uint32_t xy = blockIdx.x * (uint32_t)kListThreads + threadIdx.x;
     const int iz = (int)blockIdx.y;
     int cls = 0;                                              // 0 empty, 1 plain, 2 seam
     CellRec rec;
-    rec.t = 0; rec.n01 = rec.n23 = rec.pad = 0;
+    rec.t = 0; rec.n01 = rec.n23 = rec.seam = 0;
     rec.rs[0] = rec.rs[1] = rec.rs[2] = rec.rs[3] = 0;
     if (xy < nxy) {
         const int iy = (int)(xy / (uint32_t)P.ccx), ix = (int)(xy - (uint32_t)iy * (uint32_t)P.ccx);
@@ -973,20 +977,29 @@ __global__ void __launch_bounds__(kListThreads) k_p2g_cell_list(const __grid_con
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, below = (1u << lane) - 1u;
     if (lane == 0) { warp_cnt[0][warp] = __popc(mp); warp_cnt[1][warp] = __popc(ms); }
     __syncthreads();
-    if (threadIdx.x < 2) {
-        uint32_t sum = 0;
-        for (int w = 0; w < kListThreads / 32; w++) sum += warp_cnt[threadIdx.x][w];
-        cta_base[threadIdx.x] = sum ? atomicAdd(P.list_count + threadIdx.x, sum) : 0u;
+    if (threadIdx.x == 0) {
+        uint32_t np = 0, ns = 0;
+        for (int w = 0; w < kListThreads / 32; w++) { np += warp_cnt[0][w]; ns += warp_cnt[1][w]; }
+        cta_cnt[0] = np; cta_cnt[1] = ns;
+        const uint32_t padded = ((np + 31u) & ~31u) + ((ns + 31u) & ~31u);
+        cta_base = padded ? atomicAdd(P.list_count, padded) : 0u;
     }
     __syncthreads();
+    // region layout in the list: [plain cells, padded to a warp][seam cells, padded to a warp]
+    const uint32_t np = cta_cnt[0], ns = cta_cnt[1], np32 = (np + 31u) & ~31u, ns32 = (ns + 31u) & ~31u;
+    const uint32_t seam_base = cta_base + np32;
     if (cls) {
         const int k = cls - 1;
-        uint32_t pos = cta_base[k] + __popc((k ? ms : mp) & below);
+        uint32_t pos = (k ? seam_base : cta_base) + __popc((k ? ms : mp) & below);
         for (unsigned w = 0; w < warp; w++) pos += warp_cnt[k][w];
-        CellRec *dst = P.cell_list + (k ? P.list_cap - 1u - pos : pos);
+        CellRec *dst = P.cell_list + pos;
         reinterpret_cast<uint4 *>(dst)[0] = make_uint4(rec.t, rec.rs[0], rec.rs[1], rec.rs[2]);
-        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(rec.rs[3], rec.n01, rec.n23, 0u);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(rec.rs[3], rec.n01, rec.n23, (uint32_t)k);
     }
+    if (threadIdx.x < np32 - np)
+        reinterpret_cast<uint4 *>(P.cell_list + cta_base + np + threadIdx.x)[0] = make_uint4(kEmptyCell, 0u, 0u, 0u);
+    if (threadIdx.x < ns32 - ns)
+        reinterpret_cast<uint4 *>(P.cell_list + seam_base + ns + threadIdx.x)[0] = make_uint4(kEmptyCell, 0u, 0u, 0u);
 }
 
 // APIC "edge" particle (within a few ulps of a cell plane) of shifted cell b: the reference's own
@@ -1049,9 +1062,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // Pass 2, one listed cell per thread: splat the cell's particles onto its 8 corner nodes.
 template <int DIR, int METHOD, bool SEAM>
-__device__ __forceinline__ void splat_cell(const P2GParams &P, const CellRec *__restrict__ recp, CellStage<METHOD> &S) {
+__device__ __forceinline__ void splat_cell(const P2GParams &P, const uint4 r0, const uint4 r1, CellStage<METHOD> &S) {
     const int tid = threadIdx.x;
-    const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(recp)), r1 = __ldg(reinterpret_cast<const uint4 *>(recp) + 1);
     const uint32_t t = r0.x;
     const uint32_t nxy = (uint32_t)P.ccx * (uint32_t)P.ccy;
     const int iz = (int)(t / nxy);
@@ -1239,17 +1251,21 @@ __device__ __forceinline__ void splat_cell(const P2GParams &P, const CellRec *__
 #ifndef FFB_CELLS_MINB
 #define FFB_CELLS_MINB 6
 #endif
-#ifndef FFB_SEAMCELLS_MINB
-#define FFB_SEAMCELLS_MINB 5
-#endif
-template <int DIR, int METHOD, bool SEAM>
-__global__ void __launch_bounds__(kCellThreads, SEAM ? FFB_SEAMCELLS_MINB : FFB_CELLS_MINB)
-    k_p2g_cells(const __grid_constant__ P2GParams P) {
+template <int DIR, int METHOD>
+__global__ void __launch_bounds__(kCellThreads, FFB_CELLS_MINB) k_p2g_cells(const __grid_constant__ P2GParams P) {
     __shared__ CellStage<METHOD> S;
-    const uint32_t stride = gridDim.x * (uint32_t)kCellThreads;
-    const uint32_t count = __ldg(P.list_count + (SEAM ? 1 : 0));
-    for (uint32_t e = blockIdx.x * (uint32_t)kCellThreads + threadIdx.x; e < count; e += stride)
-        splat_cell<DIR, METHOD, SEAM>(P, P.cell_list + (SEAM ? P.list_cap - 1u - e : e), S);
+    const uint32_t stride = gridDim.x * (uint32_t)kCellThreads;       // a multiple of 32: warps stay aligned to the list
+    const uint32_t count = __ldg(P.list_count);
+    for (uint32_t e = blockIdx.x * (uint32_t)kCellThreads + threadIdx.x; e < count; e += stride) {
+        const uint4 *rec = reinterpret_cast<const uint4 *>(P.cell_list + e);
+        const uint4 r0 = __ldg(rec);
+        if (r0.x == kEmptyCell) continue;                      // padding
+        const uint4 r1 = __ldg(rec + 1);
+        if (r1.w)                                              // uniform per warp by construction of the list
+            splat_cell<DIR, METHOD, true>(P, r0, r1, S);
+        else
+            splat_cell<DIR, METHOD, false>(P, r0, r1, S);
+    }
 }
 
 // APIC edge particles, one thread each. (1) An edge particle whose exact cell (the reference's
@@ -1425,9 +1441,8 @@ int launch_cells(Context &c, P2GParams &P, cudaStream_t st) {
     // grid-stride over the device-side list: enough CTAs to cover every cell once, capped at a few waves
     const long long want = (ncell + kCellThreads - 1) / kCellThreads;
     const unsigned ctas = (unsigned)std::min<long long>(want, (long long)c.sm_count * FFB_CELLS_MINB * 8);
-    k_p2g_cells<DIR, METHOD, false><<<ctas, kCellThreads, 0, st>>>(P);
-    k_p2g_cells<DIR, METHOD, true><<<std::max(ctas / 2, 1u), kCellThreads, 0, st>>>(P);
-    launches += 2;
+    k_p2g_cells<DIR, METHOD><<<ctas, kCellThreads, 0, st>>>(P);
+    launches++;
     if (METHOD == FFB200_TRANSFER_APIC) {
         k_p2g_edge<DIR, METHOD><<<(P.edge_cap + 127) / 128, 128, 0, st>>>(P);
         launches++;
@@ -1610,7 +1625,8 @@ int launch_p2g(Context &c, double radius, int method) {
                     throw CudaError("ffb200_p2g: more than 2^32 shifted cells / faces per rank");
                 FFB_CUDA(cudaMalloc(&cs.partial, cs.cells * 8 * sizeof(float2)));
                 FFB_CUDA(cudaMalloc(&cs.cell_flag, cs.cells));
-                FFB_CUDA(cudaMalloc(&cs.cell_list, cs.cells * sizeof(CellRec)));
+                // occupied cells + the per-region padding of the two classes (at most 62 entries per 256 cells)
+                FFB_CUDA(cudaMalloc(&cs.cell_list, (cs.cells + cs.cells / 4 + 64 * (size_t)(P.ccz + 16)) * sizeof(CellRec)));
             }
             if (!cs.ovf) {
                 FFB_CUDA(cudaMalloc(&cs.ovf, (size_t)kOverflowCap * sizeof(OverflowEntry)));

@@ -41,9 +41,8 @@ struct AxisSeam {
 
 // Everything k_seam_home needs from one coordinate in one frame (unshifted or shifted by dx/2).
 // A direction combines three of these, and only six distinct ones exist per particle.
-// Conversions (float<->double, double->int) run on the quarter-rate XU pipe, which is what bounds
-// this arithmetic: every double evaluation below is screened by a float test that decides the
-// common case exactly, and the warp only falls through for lanes near a block or cell plane.
+// (Screening the block floors below with float tests that decide the common case was tried: the
+// compiler if-converts them and the kernel gets slower, so only the edge test keeps its screen.)
 __device__ __forceinline__ AxisSeam axis_seam(float x, const SeamParams &s) {
     AxisSeam r;
     r.b = pos2idx(x, s.inv_blockdx);
@@ -52,19 +51,9 @@ __device__ __forceinline__ AxisSeam axis_seam(float x, const SeamParams &s) {
     const float bp = __fmul_rn((float)r.b, s.blockdx);
     const float xm = x - s.sr, xp = x + s.sr, top = bp + s.blockdx;
     r.simple = (xm > bp) && (xp < top);
-    const float ulp8 = 8.0f * 1.1920929e-7f * fabsf(top);
-    // home block by the double _chunkdx: equals b unless x is within rounding of a block plane
-    // (blockdx is _chunkdx rounded to float: the planes differ by < 1e-7 relative)
-    r.home = r.b;
-    if (!(x - bp > ulp8 && top - x > ulp8)) r.home = pos2idx(x, s.inv_chunkdx);
-    // block range of x -+ sr: lo == b follows from xm > bp; hi == b needs xp clear of the plane by
-    // more than the rounding of bp + blockdx
-    r.lo = r.b;
-    r.hi = r.b;
-    if (!(r.simple && xp < top - ulp8)) {
-        r.lo = pos2idx(xm, s.inv_blockdx);
-        r.hi = pos2idx(xp, s.inv_blockdx);
-    }
+    r.home = pos2idx(x, s.inv_chunkdx);
+    r.lo = pos2idx(xm, s.inv_blockdx);
+    r.hi = pos2idx(xp, s.inv_blockdx);
     // "edge": within a few float ulps of a cell plane in this frame. There a float compare of
     // block-local coordinates may disagree with the reference's double floor, so the transfer
     // kernels give such particles the exact arithmetic. Float screen: distance of t = x/dx to the
