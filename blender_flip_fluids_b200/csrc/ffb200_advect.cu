@@ -29,6 +29,7 @@ struct AdvectParams {
     MacView mac;
     const float *phi;       // (I+1)(J+1)(kloc+1), first stored node plane = kbase
     const uint8_t *near_solid;
+    const uint8_t *clear;   // per stored cell: Chebyshev distance (cells, capped) to the nearest cell with a node phi <= margin
     int ni, nj, nk;
     double inv_near;        // 1.0 / (3*dx)
     Box box;
@@ -46,6 +47,13 @@ struct AdvectParams {
 __device__ __forceinline__ bool box_inside(const Box &b, float x, float y, float z) {
     return x >= b.px && y >= b.py && z >= b.pz && (double)x < (double)b.px + b.w && (double)y < (double)b.py + b.h &&
            (double)z < (double)b.pz + b.d;
+}
+
+// inside with room to spare (1e-4 of the box size): rounding of interpolated points cannot leave the box
+__device__ __forceinline__ bool box_inside_margin(const Box &b, float x, float y, float z) {
+    const double mx = 1e-4 * b.w, my = 1e-4 * b.h, mz = 1e-4 * b.d;
+    return (double)x > (double)b.px + mx && (double)y > (double)b.py + my && (double)z > (double)b.pz + mz &&
+           (double)x < (double)b.px + b.w - mx && (double)y < (double)b.py + b.h - my && (double)z < (double)b.pz + b.d - mz;
 }
 
 __device__ __forceinline__ void box_nearest_inside(const Box &b, float &x, float &y, float &z) {
@@ -127,6 +135,21 @@ __device__ __noinline__ void resolve_collision(const AdvectParams &P, float ox, 
     const int gi = pos2idx(nx, g.inv_dx), gj = pos2idx(ny, g.inv_dx), gk = pos2idx(nz, g.inv_dx);
     if (!in_range3(gi, gj, gk, g.I, g.J, g.K)) box_nearest_inside(P.box, nx, ny, nz);
     if (!near_solid(P, ox, oy, oz) && !near_solid(P, nx, ny, nz)) return;
+    // Exact shortcut of the march below. Every sample lies on the segment o -> n. If all SDF nodes of
+    // all cells within the segment's cell bounding box (+1 cell for rounding of the sample positions)
+    // are positive by a margin, every trilinear sample -- a convex combination of 8 such nodes -- is
+    // positive, and if both end points are inside the (convex) boundary box by a margin so is every
+    // sample: the march finds nothing and returns n unchanged. `clear` holds, per cell, the distance to
+    // the nearest cell with a non-positive node (k_solid_clearance).
+    {
+        const int oi = pos2idx(ox, g.inv_dx), oj = pos2idx(oy, g.inv_dx), ok = pos2idx(oz, g.inv_dx);
+        const int ni2 = pos2idx(nx, g.inv_dx), nj2 = pos2idx(ny, g.inv_dx), nk2 = pos2idx(nz, g.inv_dx);
+        if (in_range3(oi, oj, ok - g.kbase, g.I, g.J, g.kloc)) {
+            const int reach = max(max(abs(ni2 - oi), abs(nj2 - oj)), abs(nk2 - ok)) + 1;
+            const int c = P.clear[(size_t)oi + (size_t)g.I * ((size_t)oj + (size_t)g.J * (ok - g.kbase))];
+            if (c > reach && box_inside_margin(P.box, ox, oy, oz) && box_inside_margin(P.box, nx, ny, nz)) return;
+        }
+    }
 
     const float eps = 1e-6f;
     const float dxx = nx - ox, dyy = ny - oy, dzz = nz - oz;
@@ -201,6 +224,35 @@ __global__ void __launch_bounds__(256) k_advect(const __grid_constant__ AdvectPa
     P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
 }
 
+// clearance pass 1: 0 for a cell with any of its 8 SDF nodes <= margin (or outside the stored slab), else the cap
+__global__ void k_solid_unsafe(const float *__restrict__ phi, uint8_t *__restrict__ clear, int I, int J, int kloc, float margin,
+                               int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+    if (i >= I || j >= J) return;
+    const size_t sj = I + 1, sk = (size_t)(I + 1) * (J + 1);
+    const float *b = phi + i + sj * j + sk * k;
+    float m = b[0];
+    m = fminf(m, b[1]); m = fminf(m, b[sj]); m = fminf(m, b[sj + 1]);
+    m = fminf(m, b[sk]); m = fminf(m, b[sk + 1]); m = fminf(m, b[sk + sj]); m = fminf(m, b[sk + sj + 1]);
+    clear[(size_t)i + (size_t)I * ((size_t)j + (size_t)J * k)] = (m > margin) ? (uint8_t)cap : (uint8_t)0;   // NaN -> 0
+}
+
+// clearance pass 2 (repeated cap times): Chebyshev distance relaxation over the 26 neighbours; cells
+// beyond the stored range count as unsafe
+__global__ void k_solid_relax(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int I, int J, int kloc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, k = blockIdx.z;
+    if (i >= I || j >= J) return;
+    int m = in[(size_t)i + (size_t)I * ((size_t)j + (size_t)J * k)];
+    for (int c = -1; c <= 1; c++)
+        for (int b = -1; b <= 1; b++)
+            for (int a = -1; a <= 1; a++) {
+                const int v = in_range3(i + a, j + b, k + c, I, J, kloc)
+                                  ? in[(size_t)(i + a) + (size_t)I * ((size_t)(j + b) + (size_t)J * (k + c))] : 0;
+                m = min(m, v + 1);
+            }
+    out[(size_t)i + (size_t)I * ((size_t)j + (size_t)J * k)] = (uint8_t)m;
+}
+
 void box_expand(Box &b, double v) {                     // aabb.cpp:122-128
     const double hh = 0.5 * v;
     const float hf = (float)hh;
@@ -209,6 +261,23 @@ void box_expand(Box &b, double v) {                     // aabb.cpp:122-128
 }
 
 }  // namespace
+
+// Called whenever the solid SDF changes (ffb200_set_solid): per-cell clearance used by the march shortcut.
+int launch_solid_clearance(Context &c) {
+    const GridDesc &g = c.g;
+    const size_t cells = (size_t)g.I * g.J * g.kloc;
+    if (!c.solid_clear[0]) {
+        FFB_CUDA(cudaMalloc(&c.solid_clear[0], cells));
+        FFB_CUDA(cudaMalloc(&c.solid_clear[1], cells));
+    }
+    constexpr int cap = 8;                                 // displacements are bounded by CFL * dx (5 cells)
+    dim3 block(32, 4, 1), grid((g.I + 31) / 32, (g.J + 3) / 4, g.kloc);
+    k_solid_unsafe<<<grid, block, 0, c.stream>>>(c.phi, c.solid_clear[0], g.I, g.J, g.kloc, (float)(1e-3 * g.dx), cap);
+    for (int it = 0; it < cap; it++)
+        k_solid_relax<<<grid, block, 0, c.stream>>>(c.solid_clear[it & 1], c.solid_clear[(it & 1) ^ 1], g.I, g.J, g.kloc);
+    FFB_CUDA(cudaGetLastError());
+    return cap + 1;                                        // result in solid_clear[0] (cap is even)
+}
 
 int launch_advect(Context &c, double dt, double cfl, int collide) {
     if (c.n == 0) return 0;
@@ -220,6 +289,7 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.mac = MacView{c.face[0].vel, c.face[1].vel, c.face[2].vel};
     P.phi = c.phi;
     P.near_solid = c.near_solid;
+    P.clear = c.solid_clear[0];
     P.ni = c.ni; P.nj = c.nj; P.nk = c.nk;
     P.inv_near = 1.0 / (3 * g.dx);                      // _nearSolidGridCellSizeFactor * _dx
     P.box.px = P.box.py = P.box.pz = 0.0f;              // _getBoundaryAABB

@@ -158,6 +158,8 @@ void destroy_impl(ContextImpl *c) {
     }
     dev_free(c->phi);
     dev_free(c->near_solid);
+    dev_free(c->solid_clear[0]);
+    dev_free(c->solid_clear[1]);
     dev_free(c->slab_counters);
     dev_free(c->sort.edge_count);
     for (int q = 0; q < 3; q++) dev_free(c->k1s[q]);
@@ -325,6 +327,7 @@ void set_solid_impl(ContextImpl &c, const float *phi, const uint8_t *near_solid)
     const size_t plane = (size_t)(g.I + 1) * (g.J + 1);
     FFB_CUDA(cudaMemcpyAsync(c.phi, phi + plane * g.kbase, plane * (g.kloc + 1) * 4, cudaMemcpyHostToDevice, c.stream));
     FFB_CUDA(cudaMemcpyAsync(c.near_solid, near_solid, (size_t)c.ni * c.nj * c.nk, cudaMemcpyHostToDevice, c.stream));
+    launch_solid_clearance(c);
     c.has_solid = true;
 }
 

@@ -95,6 +95,7 @@ struct Context {
 
     float *phi = nullptr;                // (I+1)(J+1)(kloc+1) node-centred solid SDF
     uint8_t *near_solid = nullptr;       // ni*nj*nk
+    uint8_t *solid_clear[2] = {nullptr, nullptr};   // per stored cell: distance to the nearest cell with a non-positive SDF node
     int ni = 0, nj = 0, nk = 0;
     bool has_solid = false;
 
@@ -135,6 +136,7 @@ int launch_p2g(Context &c, double radius, int method);  // the three transfer ke
 int launch_g2p(Context &c, int method, double ratio);
 
 // ffb200_advect.cu
+int launch_solid_clearance(Context &c);                  // after every change of the solid SDF
 int launch_advect(Context &c, double dt, double cfl, int collide);
 
 // ffb200_slab.cu
