@@ -933,7 +933,7 @@ __device__ __forceinline__ uint32_t cell_runs(const P2GParams &P, const int b[3]
 // Pass 1: classify every shifted cell of this direction and list the occupied ones, so that the
 // splat kernel below runs on full warps. Class "plain": both corner nodes of every axis lie inside
 // the face grid and in the same 10^3 block -- one block frame, one membership test per particle.
-// Class "seam": everything else (block seams, grid border). A CTA covers a region of 256
+// Class "seam": everything else (block seams, grid border). A CTA covers a region of 1024
 // consecutive cells and appends [its plain cells][its seam cells], each group padded to a multiple
 // of 32 entries, with one atomic: every warp of the splat kernel sees one class only, and the
 // plain and seam cells of a region -- whose particles share 32-byte sectors -- are processed at
@@ -941,45 +941,55 @@ __device__ __forceinline__ uint32_t cell_runs(const P2GParams &P, const int b[3]
 // owns its slot of `partial`).
 constexpr int kListThreads = 256;
 constexpr uint32_t kEmptyCell = 0xffffffffu;              // padding entry of the cell list
+constexpr int kListRounds = 4;                             // cells per thread: a CTA lists a region of 1024 cells
 template <int DIR>
 __global__ void __launch_bounds__(kListThreads) k_p2g_cell_list(const __grid_constant__ P2GParams P) {
-    __shared__ uint32_t warp_cnt[2][kListThreads / 32];
+    constexpr int kWarps = kListThreads / 32;
+    __shared__ uint32_t warp_cnt[2][kListRounds][kWarps];
     __shared__ uint32_t cta_cnt[2];
     __shared__ uint32_t cta_base;
     const uint32_t nxy = (uint32_t)P.ccx * (uint32_t)P.ccy;
-    const uint32_t xy = blockIdx.x * (uint32_t)kListThreads + threadIdx.x;
     const int iz = (int)blockIdx.y;
-    int cls = 0;                                              // 0 empty, 1 plain, 2 seam
-    CellRec rec;
-    rec.t = 0; rec.n01 = rec.n23 = rec.seam = 0;
-    rec.rs[0] = rec.rs[1] = rec.rs[2] = rec.rs[3] = 0;
-    if (xy < nxy) {
-        const int iy = (int)(xy / (uint32_t)P.ccx), ix = (int)(xy - (uint32_t)iy * (uint32_t)P.ccx);
-        rec.t = xy + nxy * (uint32_t)iz;
-        const int b[3] = {ix - 1, iy - 1, iz + P.ck0};
-        // a cell can only hold particles if its 10^3 block is in the (dilated) particle block mask
-        const int kb = min(max(b[2], 0) / kChunk, P.bk - 1);
-        const bool maybe = P.active[max(b[0], 0) / kChunk + P.bi * (max(b[1], 0) / kChunk + P.bj * kb)] != 0;
-        uint32_t re[4] = {0u, 0u, 0u, 0u};
-        const uint32_t total = maybe ? cell_runs<DIR>(P, b, rec.rs, re) : 0u;
-        const uint32_t n0 = re[0] - rec.rs[0], n1 = re[1] - rec.rs[1], n2 = re[2] - rec.rs[2], n3 = re[3] - rec.rs[3];
-        rec.n01 = n0 | (n1 << 16);
-        rec.n23 = n2 | (n3 << 16);
-        if ((n0 | n1 | n2 | n3) > 0xffffu) rec.n01 = 0xffffffffu;
-        const int dims[3] = {P.gi, P.gj, P.gk};
-        bool plain = true;
-#pragma unroll
-        for (int a = 0; a < 3; a++) plain = plain && b[a] >= 0 && b[a] + 1 < dims[a] && (b[a] % kChunk) != kChunk - 1;
-        cls = total == 0 ? 0 : (plain ? 1 : 2);
-        P.cell_flag[rec.t] = total != 0;
-    }
-    const unsigned mp = __ballot_sync(0xffffffffu, cls == 1), ms = __ballot_sync(0xffffffffu, cls == 2);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, below = (1u << lane) - 1u;
-    if (lane == 0) { warp_cnt[0][warp] = __popc(mp); warp_cnt[1][warp] = __popc(ms); }
+    int cls[kListRounds];                                     // 0 empty, 1 plain, 2 seam
+    uint4 ra[kListRounds], rb[kListRounds];                   // the CellRec of this thread's cell of round r
+    uint32_t rank[kListRounds];                               // rank inside its warp's class group
+#pragma unroll
+    for (int r = 0; r < kListRounds; r++) {
+        const uint32_t xy = (blockIdx.x * (uint32_t)kListRounds + r) * (uint32_t)kListThreads + threadIdx.x;
+        cls[r] = 0;
+        ra[r] = make_uint4(0u, 0u, 0u, 0u);
+        rb[r] = make_uint4(0u, 0u, 0u, 0u);
+        if (xy < nxy) {
+            const int iy = (int)(xy / (uint32_t)P.ccx), ix = (int)(xy - (uint32_t)iy * (uint32_t)P.ccx);
+            const uint32_t t = xy + nxy * (uint32_t)iz;
+            const int b[3] = {ix - 1, iy - 1, iz + P.ck0};
+            // a cell can only hold particles if its 10^3 block is in the (dilated) particle block mask
+            const int kb = min(max(b[2], 0) / kChunk, P.bk - 1);
+            const bool maybe = P.active[max(b[0], 0) / kChunk + P.bi * (max(b[1], 0) / kChunk + P.bj * kb)] != 0;
+            uint32_t rs[4] = {0u, 0u, 0u, 0u}, re[4] = {0u, 0u, 0u, 0u};
+            const uint32_t total = maybe ? cell_runs<DIR>(P, b, rs, re) : 0u;
+            const uint32_t n0 = re[0] - rs[0], n1 = re[1] - rs[1], n2 = re[2] - rs[2], n3 = re[3] - rs[3];
+            uint32_t n01 = n0 | (n1 << 16);
+            if ((n0 | n1 | n2 | n3) > 0xffffu) n01 = 0xffffffffu;
+            const int dims[3] = {P.gi, P.gj, P.gk};
+            bool plain = true;
+#pragma unroll
+            for (int a = 0; a < 3; a++) plain = plain && b[a] >= 0 && b[a] + 1 < dims[a] && (b[a] % kChunk) != kChunk - 1;
+            cls[r] = total == 0 ? 0 : (plain ? 1 : 2);
+            P.cell_flag[t] = total != 0;
+            ra[r] = make_uint4(t, rs[0], rs[1], rs[2]);
+            rb[r] = make_uint4(rs[3], n01, n2 | (n3 << 16), plain ? 0u : 1u);
+        }
+        const unsigned mp = __ballot_sync(0xffffffffu, cls[r] == 1), ms = __ballot_sync(0xffffffffu, cls[r] == 2);
+        if (lane == 0) { warp_cnt[0][r][warp] = __popc(mp); warp_cnt[1][r][warp] = __popc(ms); }
+        rank[r] = __popc((cls[r] == 2 ? ms : mp) & below);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t np = 0, ns = 0;
-        for (int w = 0; w < kListThreads / 32; w++) { np += warp_cnt[0][w]; ns += warp_cnt[1][w]; }
+        for (int r = 0; r < kListRounds; r++)
+            for (int w = 0; w < kWarps; w++) { np += warp_cnt[0][r][w]; ns += warp_cnt[1][r][w]; }
         cta_cnt[0] = np; cta_cnt[1] = ns;
         const uint32_t padded = ((np + 31u) & ~31u) + ((ns + 31u) & ~31u);
         cta_base = padded ? atomicAdd(P.list_count, padded) : 0u;
@@ -988,13 +998,16 @@ __global__ void __launch_bounds__(kListThreads) k_p2g_cell_list(const __grid_con
     // region layout in the list: [plain cells, padded to a warp][seam cells, padded to a warp]
     const uint32_t np = cta_cnt[0], ns = cta_cnt[1], np32 = (np + 31u) & ~31u, ns32 = (ns + 31u) & ~31u;
     const uint32_t seam_base = cta_base + np32;
-    if (cls) {
-        const int k = cls - 1;
-        uint32_t pos = (k ? seam_base : cta_base) + __popc((k ? ms : mp) & below);
-        for (unsigned w = 0; w < warp; w++) pos += warp_cnt[k][w];
-        CellRec *dst = P.cell_list + pos;
-        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(rec.t, rec.rs[0], rec.rs[1], rec.rs[2]);
-        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(rec.rs[3], rec.n01, rec.n23, (uint32_t)k);
+#pragma unroll
+    for (int r = 0; r < kListRounds; r++) {
+        if (!cls[r]) continue;
+        const int k = cls[r] - 1;
+        uint32_t pos = (k ? seam_base : cta_base) + rank[r];
+        for (int rr = 0; rr <= r; rr++)
+            for (unsigned w = 0; w < (rr == r ? warp : (unsigned)kWarps); w++) pos += warp_cnt[k][rr][w];
+        uint4 *dst = reinterpret_cast<uint4 *>(P.cell_list + pos);
+        dst[0] = ra[r];
+        dst[1] = rb[r];
     }
     if (threadIdx.x < np32 - np)
         reinterpret_cast<uint4 *>(P.cell_list + cta_base + np + threadIdx.x)[0] = make_uint4(kEmptyCell, 0u, 0u, 0u);
@@ -1436,7 +1449,7 @@ int launch_cells(Context &c, P2GParams &P, cudaStream_t st) {
     FFB_CUDA(cudaMemsetAsync(P.list_count, 0, 2 * sizeof(uint32_t), st));
     const long long ncell = (long long)P.ccx * P.ccy * P.ccz;
     const unsigned nxy = (unsigned)P.ccx * (unsigned)P.ccy;
-    k_p2g_cell_list<DIR><<<dim3((nxy + kListThreads - 1) / kListThreads, P.ccz), kListThreads, 0, st>>>(P);
+    k_p2g_cell_list<DIR><<<dim3((nxy + kListThreads * kListRounds - 1) / (kListThreads * kListRounds), P.ccz), kListThreads, 0, st>>>(P);
     launches++;
     // grid-stride over the device-side list: enough CTAs to cover every cell once, capped at a few waves
     const long long want = (ncell + kCellThreads - 1) / kCellThreads;
