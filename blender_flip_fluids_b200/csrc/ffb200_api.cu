@@ -236,7 +236,7 @@ int create_impl(ffb200_context **out, int I, int J, int K, double dx, int device
         c->ni = (int)std::ceil(I * dx / cell); c->nj = (int)std::ceil(J * dx / cell); c->nk = (int)std::ceil(K * dx / cell);
         dev_alloc(c->phi, (size_t)(I + 1) * (J + 1) * (g.kloc + 1));
         dev_alloc(c->near_solid, (size_t)c->ni * c->nj * c->nk);
-        dev_alloc(c->slab_counters, 4);
+        dev_alloc(c->slab_counters, 8);
         dev_alloc(c->sort.edge_count, 4);
         FFB_CUDA(cudaStreamSynchronize(c->stream));
         *out = reinterpret_cast<ffb200_context *>(static_cast<Context *>(c));
@@ -566,6 +566,15 @@ int ffb200_slab_route_begin(ffb200_context *ctx, int k_begin, int k_end, float *
     return guarded("ffb200_slab_route_begin", ctx, [&](Context &c) {
         if ((block_up || block_down) && block_capacity <= 0) throw std::domain_error("block capacity must be positive");
         launch_route_begin(c, k_begin, k_end, block_up, block_down, block_capacity);
+    });
+}
+
+int ffb200_slab_route_ghosts_begin(ffb200_context *ctx, int k_begin, int k_end, int ghost_layers, float *block_up,
+                                   float *block_down, int block_capacity) {
+    return guarded("ffb200_slab_route_ghosts_begin", ctx, [&](Context &c) {
+        if (ghost_layers <= 0) throw std::domain_error("ghost layer count must be positive");
+        if ((block_up || block_down) && block_capacity <= 0) throw std::domain_error("block capacity must be positive");
+        launch_route_begin(c, k_begin, k_end, block_up, block_down, block_capacity, ghost_layers);
     });
 }
 

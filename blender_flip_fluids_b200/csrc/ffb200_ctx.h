@@ -100,7 +100,7 @@ struct Context {
     bool has_solid = false;
 
     float guard_abs = -1.f, guard_per = -1.f;
-    int *slab_counters = nullptr;        // 4 device ints for the slab pack/route kernels
+    int *slab_counters = nullptr;        // 8 device ints for the slab pack/route kernels
     // API-call epoch: bumped by every call that may change particles or fields. An APIC ffb200_g2p
     // records it; an ffb200_advect that finds it unchanged reuses the G2P samples as RK3 stage 1.
     unsigned long long epoch = 0, k1_epoch = ~0ull;
@@ -142,7 +142,7 @@ int launch_advect(Context &c, double dt, double cfl, int collide);
 // ffb200_slab.cu
 int slab_rows(Context &c);
 int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b, float *block_b, int cap);
-int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap);
+int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int ghost_layers = 0);
 int launch_route_end(Context &c, int counts_host[3]);
 int launch_append(Context &c, const float *block, int count, bool as_ghost);
 

@@ -75,7 +75,8 @@ __global__ void k_pack_layers(Streams src, int n, double inv_dx, int lo_a, int h
 constexpr uint32_t kGhostBit = 0x80000000u;
 
 __global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int k_begin, int k_end, float *block_up,
-                             float *block_down, int cap, int remove_migrants, int *counters, uint32_t *holes) {
+                             float *block_down, int cap, int remove_migrants, int *counters, uint32_t *holes,
+                             uint8_t *leave_flag) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     bool ghost = false, up = false, down = false;
     if (j < n) {
@@ -94,11 +95,65 @@ __global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int
         write_record(rec, j, up ? block_up : block_down, cap, up ? su : sd);
     }
     if (leave) holes[sh] = (uint32_t)j;
+    if (j < n) leave_flag[j] = leave ? 1 : 0;
+}
+
+// The same routing with the NEXT substep's ghost exchange folded in, so that one neighbour
+// exchange per substep carries both. Blocks have two sections of `cap` records: [migrants][ghost
+// copies] and an 8-int header {migrants, overflow, ghosts, overflow, 0...}.
+//  * an owned particle that stays and sits within `g` cell planes of a slab face is copied into the
+//    ghost section for that neighbour (it is what k_pack_layers would select at the start of the
+//    next substep);
+//  * a migrant that lands within `g` planes beyond the face is sent AND kept here with the ghost
+//    bit set: its new owner would send it straight back as a ghost copy otherwise;
+//  * ghost copies of the substep that just ended leave, as before.
+// Fixed-batch mode (remove_migrants = 0): nothing is removed or converted; ghost copies are taken
+// from the resident (pristine) batch, exactly what a start-of-substep exchange would send.
+__global__ void k_route_mark_ghosts(Streams cur, Streams dat, int n, double inv_dx, int k_begin, int k_end, int g,
+                                    float *block_up, float *block_down, int cap, int remove_migrants, int *counters,
+                                    uint32_t *holes, uint8_t *leave_flag) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ghost = false, up = false, down = false, gup = false, gdown = false, keep = false;
+    if (j < n) {
+        const int kd = __double2int_rd((double)dat.s[2][j] * inv_dx);      // where the particle is going
+        const int kc = __double2int_rd((double)cur.s[2][j] * inv_dx);      // where the resident copy is
+        ghost = (cur.ids[j] & kGhostBit) != 0u;
+        up = !ghost && kd >= k_end && block_up;
+        down = !ghost && kd < k_begin && block_down;
+        const bool owned_after = !ghost && !(remove_migrants && (up || down));
+        gup = owned_after && block_up && kc >= k_end - g;
+        gdown = owned_after && block_down && kc < k_begin + g;
+        keep = remove_migrants && ((up && kd < k_end + g) || (down && kd >= k_begin - g));
+    }
+    const bool leave = ghost || (remove_migrants && (up || down) && !keep);
+    const int su = warp_slot(up, counters + 1);
+    const int sd = warp_slot(down, counters + 2);
+    const int sh = warp_slot(leave, counters + 3);
+    const int sgu = warp_slot(gup, counters + 4);
+    const int sgd = warp_slot(gdown, counters + 5);
+    const size_t section = (size_t)cap * (cur.ns + 1);
+    if (up || down) {
+        Streams rec = dat;
+        rec.ids = cur.ids;
+        write_record(rec, j, up ? block_up : block_down, cap, up ? su : sd);
+    }
+    if (gup) write_record(cur, j, block_up + section, cap, sgu);
+    if (gdown) write_record(cur, j, block_down + section, cap, sgd);
+    if (keep) cur.ids[j] |= kGhostBit;                        // after its record (with the clean id) was written
+    if (leave) holes[sh] = (uint32_t)j;
+    if (j < n) leave_flag[j] = leave ? 1 : 0;
+}
+
+__global__ void k_write_header2(const int *counters, int which_m, int which_g, int cap, int rows, float *block) {
+    int *h = reinterpret_cast<int *>(block + (size_t)2 * cap * rows);
+    const int m = counters[which_m], gc = counters[which_g];
+    h[0] = m; h[1] = m > cap ? 1 : 0;
+    h[2] = gc; h[3] = gc > cap ? 1 : 0;
+    h[4] = h[5] = h[6] = h[7] = 0;
 }
 
 // holes below the new count, and survivors at or above it
-__global__ void k_fill_collect(Streams cur, Streams dat, int n, int n_new, int nholes, double inv_dx, int k_begin, int k_end,
-                               int has_up, int has_down, int remove_migrants, const uint32_t *holes, int *counters,
+__global__ void k_fill_collect(int n, int n_new, int nholes, const uint8_t *leave_flag, const uint32_t *holes, int *counters,
                                uint32_t *front_hole, uint32_t *tail_stay) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool is_front = false;
@@ -107,15 +162,8 @@ __global__ void k_fill_collect(Streams cur, Streams dat, int n, int n_new, int n
         h = holes[t];
         is_front = h < (uint32_t)n_new;
     }
-    bool is_tail_stay = false;
     const int j = n_new + t;
-    if (t < nholes && j < n) {
-        const int k = __double2int_rd((double)dat.s[2][j] * inv_dx);
-        const bool ghost = (cur.ids[j] & kGhostBit) != 0u;
-        const bool up = !ghost && k >= k_end && has_up;
-        const bool down = !ghost && k < k_begin && has_down;
-        is_tail_stay = !(ghost || (remove_migrants && (up || down)));
-    }
+    const bool is_tail_stay = t < nholes && j < n && !leave_flag[j];
     const int sa = warp_slot(is_front, counters + 0);
     const int sb = warp_slot(is_tail_stay, counters + 1);
     if (is_front) front_hole[sa] = h;
@@ -188,7 +236,7 @@ struct RouteState {
 };
 static RouteState g_route;      // one routing in flight per process (one context per rank)
 
-int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap) {
+int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int ghost_layers) {
     int launches = 0;
     const int n = c.n;
     const int rows = slab_rows(c);
@@ -196,14 +244,26 @@ int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, floa
     Streams cur = streams_of(c, c.cur);
     Streams dat = fixed ? streams_of(c, c.cur ^ 1) : cur;      // fixed batch: advect / G2P wrote to the spare buffer
     uint32_t *holes = c.sort.key[1];                           // key/val scratch is free after P2G
-    FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 4 * sizeof(int), c.stream));
-    if (n > 0) {
-        k_route_mark<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, block_up, block_down, cap,
-                                                            fixed ? 0 : 1, c.slab_counters, holes);
-        launches++;
+    uint8_t *leave_flag = reinterpret_cast<uint8_t *>(c.sort.val[0]);
+    FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 8 * sizeof(int), c.stream));
+    if (ghost_layers > 0) {
+        if (n > 0) {
+            k_route_mark_ghosts<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, ghost_layers,
+                                                                       block_up, block_down, cap, fixed ? 0 : 1,
+                                                                       c.slab_counters, holes, leave_flag);
+            launches++;
+        }
+        if (block_up) { k_write_header2<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, 4, cap, rows, block_up); launches++; }
+        if (block_down) { k_write_header2<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, 5, cap, rows, block_down); launches++; }
+    } else {
+        if (n > 0) {
+            k_route_mark<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, block_up, block_down,
+                                                                cap, fixed ? 0 : 1, c.slab_counters, holes, leave_flag);
+            launches++;
+        }
+        if (block_up) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, cap, rows, block_up); launches++; }
+        if (block_down) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, cap, rows, block_down); launches++; }
     }
-    if (block_up) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, cap, rows, block_up); launches++; }
-    if (block_down) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, cap, rows, block_down); launches++; }
     g_route = RouteState{k_begin, k_end, block_up != nullptr, block_down != nullptr, n};
     FFB_CUDA(cudaGetLastError());
     return launches;
@@ -211,20 +271,18 @@ int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, floa
 
 int launch_route_end(Context &c, int counts_host[3]) {
     int launches = 0;
-    const int n = g_route.n, k_begin = g_route.k_begin, k_end = g_route.k_end;
-    const bool fixed = c.nondestructive;
-    Streams cur = streams_of(c, c.cur);
-    Streams dat = fixed ? streams_of(c, c.cur ^ 1) : cur;
+    const int n = g_route.n;
     uint32_t *holes = c.sort.key[1], *front_hole = c.sort.val[1], *tail_stay = c.sort.key[0];
+    const uint8_t *leave_flag = reinterpret_cast<const uint8_t *>(c.sort.val[0]);
+    Streams cur = streams_of(c, c.cur);
     int h[4] = {0, 0, 0, 0};
     FFB_CUDA(cudaMemcpyAsync(h, c.slab_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     FFB_CUDA(cudaStreamSynchronize(c.stream));
     const int nholes = h[3], n_new = n - nholes;
     if (nholes > 0 && n_new > 0) {
         FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 2 * sizeof(int), c.stream));
-        k_fill_collect<<<(nholes + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, n_new, nholes, c.g.inv_dx, k_begin, k_end,
-                                                                   g_route.has_up, g_route.has_down, fixed ? 0 : 1,
-                                                                   holes, c.slab_counters, front_hole, tail_stay);
+        k_fill_collect<<<(nholes + 255) / 256, 256, 0, c.stream>>>(n, n_new, nholes, leave_flag, holes, c.slab_counters,
+                                                                   front_hole, tail_stay);
         // the two lists have the same length by construction (holes in the prefix == survivors in the tail)
         k_fill_move<<<(nholes + 255) / 256, 256, 0, c.stream>>>(cur, c.slab_counters, front_hole, tail_stay);
         launches += 2;

@@ -138,6 +138,18 @@ class GpuBackend:
     def route_end(self):
         return self.ctx.slab_route_end()
 
+    def new_block2(self, capacity):
+        """Two-section packed buffer [migrants][ghost copies] + an 8-int header (ffb200_slab_route_ghosts_begin)."""
+        return torch.zeros(2 * capacity * self.record_floats() + 8, dtype=torch.float32, device=self.device)
+
+    def route_ghosts_begin(self, k_begin, k_end, ghost_layers, block_up, block_down, capacity):
+        self.ctx.slab_route_ghosts_begin(k_begin, k_end, ghost_layers, block_up.data_ptr() if block_up is not None else 0,
+                                         block_down.data_ptr() if block_down is not None else 0, capacity)
+
+    def append_section(self, block, section, capacity, count, as_ghost=False):
+        if count:
+            self.ctx.slab_append(block.data_ptr() + 4 * section * capacity * self.record_floats(), count, as_ghost)
+
     def append(self, block, count, as_ghost=False):
         if count:
             self.ctx.slab_append(block.data_ptr(), count, as_ghost)
@@ -265,6 +277,7 @@ class SlabSimulation:
         """Make the backend's resident streams the authoritative particle state (fast path)."""
         self.backend.load_particles(self.streams, self.ids)
         self._resident = True
+        self._ghosts_ready = False          # the resident set holds no ghost copies yet
 
     def _blocks(self, need):
         cap = getattr(self, "_block_cap", 0)
@@ -316,19 +329,23 @@ class SlabSimulation:
             torch.cuda.synchronize(self.device)
             self._t_last = time.perf_counter()
         be = self.backend
-        n0 = be.ctx.n
         g = self.ghost
-        cap, b = self._blocks(max(8192, int(0.03 * n0)))
-        # 1. ghost layers -> neighbours (copies), appended behind the owned particles
-        while True:
-            be.pack_layers(self.ke - g, self.ke, b["up_send"] if self.up is not None else None,
-                           self.kb, self.kb + g, b["dn_send"] if self.down is not None else None, cap)
-            got = self._swap_blocks(cap, b)
-            if got is not None:
-                break
-            cap, b = self._blocks(cap * 2)
-        be.append(b["dn_recv"], got[0], as_ghost=True)
-        be.append(b["up_recv"], got[1], as_ghost=True)
+        # 1. the very first substep after load_resident fetches its ghost layers with an exchange of its own;
+        #    afterwards they arrive with the previous substep's migration (step 5)
+        if not getattr(self, "_ghosts_ready", False):
+            n0 = be.ctx.n
+            cap, b = self._blocks(max(8192, int(0.03 * n0)))
+            while True:
+                be.pack_layers(self.ke - g, self.ke, b["up_send"] if self.up is not None else None,
+                               self.kb, self.kb + g, b["dn_send"] if self.down is not None else None, cap)
+                got = self._swap_blocks(cap, b)
+                if got is not None:
+                    break
+                cap, b = self._blocks(cap * 2)
+            be.append(b["dn_recv"], got[0], as_ghost=True)
+            be.append(b["up_recv"], got[1], as_ghost=True)
+            self._ghosts_ready = True
+            self._n_owned = n0
         self._tick("ghosts")
         # 2. P2G on owned + ghost particles
         be.p2g(radius)
@@ -341,19 +358,55 @@ class SlabSimulation:
         be.g2p(ratio)
         be.advect(dt, cfl, collide)
         self._tick("g2p+advect")
-        # 5. migration + ghost removal (the end ranks keep whatever strayed past the domain)
+        # 5. ONE exchange: migrants + the ghost copies of the next substep. Ghosts of this substep are
+        #    dropped; the end ranks keep whatever strayed past the domain
         kb = self.kb if self.down is not None else self.INT_MIN
         ke = self.ke if self.up is not None else self.INT_MAX
-        be.route_begin(kb, ke, b["up_send"] if self.up is not None else None,
-                       b["dn_send"] if self.down is not None else None, cap)
-        got = self._swap_blocks(cap, b)           # one synchronisation serves the exchange and the routing
-        be.route_end()
+        planes = max(1, self.ke - self.kb)
+        cap2, b2 = self._blocks2(int(1.5 * self._n_owned * (g + 1) / planes) + 8192)
+        be.route_ghosts_begin(kb, ke, g, b2["up_send"] if self.up is not None else None,
+                              b2["dn_send"] if self.down is not None else None, cap2)
+        got = self._swap_blocks2(cap2, b2)        # one synchronisation serves the exchange and the routing
+        n_owned, _, _ = be.route_end()
         if got is None:
-            raise RuntimeError("migration buffer overflow: more than %d particles left the slab in one substep" % cap)
+            self._block2_cap = 0                      # next call allocates larger buffers
+            raise RuntimeError("slab exchange buffer overflow: more than %d migrants or ghost copies per face" % cap2)
+        mig_dn, mig_up, gh_dn, gh_up = got
         if apply_migration:
-            be.append(b["dn_recv"], got[0])
-            be.append(b["up_recv"], got[1])
+            be.append_section(b2["dn_recv"], 0, cap2, mig_dn)
+            be.append_section(b2["up_recv"], 0, cap2, mig_up)
+            n_owned += mig_dn + mig_up
+        self._n_owned = n_owned
+        be.append_section(b2["dn_recv"], 1, cap2, gh_dn, as_ghost=True)
+        be.append_section(b2["up_recv"], 1, cap2, gh_up, as_ghost=True)
         self._tick("migrate")
+
+    def _blocks2(self, need):
+        cap = getattr(self, "_block2_cap", 0)
+        if cap < need:
+            cap = max(8192, int(need * 1.25))
+            self._block2_cap = cap
+            self._blk2 = {k: self.backend.new_block2(cap) for k in ("up_send", "up_recv", "dn_send", "dn_recv")}
+        return self._block2_cap, self._blk2
+
+    def _swap_blocks2(self, cap, b):
+        """Exchange the two-section buffers with both neighbours; returns the received
+        (migrants from below, from above, ghosts from below, from above) or None on overflow."""
+        rows = self.backend.record_floats()
+        ops = []
+        if self.up is not None:
+            ops += [dist.P2POp(dist.isend, b["up_send"], self.up), dist.P2POp(dist.irecv, b["up_recv"], self.up)]
+        if self.down is not None:
+            ops += [dist.P2POp(dist.isend, b["dn_send"], self.down), dist.P2POp(dist.irecv, b["dn_recv"], self.down)]
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        hdr = torch.stack([b[k][2 * cap * rows:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()
+        self.exchanged_bytes += int(hdr[0, 0] + hdr[0, 2] + hdr[1, 0] + hdr[1, 2]) * rows * 4
+        if (self.up is not None or self.down is not None) and int(torch.maximum(hdr[:, 1], hdr[:, 3]).max()) != 0:
+            return None
+        up, dn = self.up is not None, self.down is not None
+        return (int(hdr[3, 0]) if dn else 0, int(hdr[2, 0]) if up else 0, int(hdr[3, 2]) if dn else 0, int(hdr[2, 2]) if up else 0)
 
     def _halo_exchange_fast(self):
         plan = getattr(self, "_halo_plan", None)
@@ -375,8 +428,9 @@ class SlabSimulation:
     def sync_from_backend(self):
         """Pull the resident streams back into self.streams / self.ids (tests, gather)."""
         s, ids = self.backend.particle_views()
-        self.streams = [t.clone() for t in s]
-        self.ids = ids.clone()
+        own = torch.nonzero(ids.view(torch.int32) >= 0, as_tuple=False).squeeze(1)    # ghost copies carry the top id bit
+        self.streams = [t.index_select(0, own) for t in s]
+        self.ids = ids.index_select(0, own)
 
     # ---- one substep, generic plumbing (any backend; used by the CPU tests) ------------------------------
     def step(self, radius, ratio, dt, cfl=5.0, collide=True):
