@@ -326,7 +326,7 @@ def main():
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"kernel": "P2G transfer of one MAC direction: k_p2g_cells + k_p2g_edge_overflow + k_p2g_nodes <dir, APIC>",
+    roofline = {"kernel": "P2G transfer of one MAC direction: k_p2g_cell_list + k_p2g_cells + k_p2g_edge + k_p2g_nodes <dir, APIC>",
                 "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": p2g_bytes_per_launch, "launch_ms": p2g_launch_ms,
