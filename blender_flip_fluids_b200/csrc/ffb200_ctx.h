@@ -43,7 +43,7 @@ struct FaceGrid {
     float *wsum = nullptr;        // weight sums of the last P2G
     uint8_t *valid = nullptr;
     uint8_t *home = nullptr, *active = nullptr;   // block masks (bi*bj*bk)
-    uint8_t *status[2] = {nullptr, nullptr};      // extrapolation status, ping-pong (lazy)
+    uint8_t *status[2] = {nullptr, nullptr};      // extrapolation: [0] layer stamp per face, [1] tile flags (lazy)
 };
 
 struct SortScratch {
