@@ -62,15 +62,23 @@ struct ContextImpl : Context {
     int launches[kNumStages] = {};
 };
 
+// Stage timing events are skipped while the stream is being captured into a CUDA graph (a caller may
+// capture whole substeps: every launch of the resident stages is capturable once the scratch buffers
+// exist, i.e. after one eager substep; event timing inside a graph is not).
 struct StageTimer {
     ContextImpl &c;
     Stage s;
-    StageTimer(ContextImpl &ctx, Stage st) : c(ctx), s(st) {
-        FFB_CUDA(cudaEventRecord(c.evs.start[s], c.stream));
+    bool live;
+    StageTimer(ContextImpl &ctx, Stage st) : c(ctx), s(st), live(true) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c.stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) live = false;
+        if (live) FFB_CUDA(cudaEventRecord(c.evs.start[s], c.stream));
     }
     void done(int launched) {
-        FFB_CUDA(cudaEventRecord(c.evs.stop[s], c.stream));
-        c.evs.used[s] = true;
+        if (live) {
+            FFB_CUDA(cudaEventRecord(c.evs.stop[s], c.stream));
+            c.evs.used[s] = true;
+        }
         c.launches[s] = launched;
     }
 };
