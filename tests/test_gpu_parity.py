@@ -381,3 +381,39 @@ def test_cuda_graph_capture_matches_eager(eng, method):
     if apic:
         assert all(bits_equal(x, y) for x, y in zip(a0, a1))
     assert (p0 != sc.pos).any()
+
+
+@pytest.mark.parametrize("method", ["flip", "apic"])
+def test_p2g_dense_and_clustered_cells_vs_oracle(eng, oracle, method):
+    """27 particles per cell (several staging chunks per shifted cell) plus 600 particles crowded into
+    one cell octant and 300 more on a block seam: the cell walk, the tie re-ranking of the sort and
+    the seam frames with long runs."""
+    from blender_flip_fluids_b200 import scenes
+    apic = method == "apic"
+    m = eng.APIC if apic else eng.FLIP
+    n, dx = 22, 0.013
+    sc = scenes.dam_break(n, ppc=27, apic=apic, dx=dx, vel="random", v0=0.7, seed=21)
+    rng = np.random.default_rng(8)
+    crowd = (np.array([7.1, 9.6, 12.3]) + rng.random((600, 3)) * 0.4) * dx          # one octant of cell (7, 9, 12)
+    seam = (np.array([9.8, 10.2, 9.9]) + rng.random((300, 3)) * np.array([0.4, 0.1, 0.3])) * dx   # across the 10-node seams
+    pos = np.concatenate([sc.pos, crowd.astype(np.float32), seam.astype(np.float32)])
+    k = pos.shape[0] - sc.n
+    vel = np.concatenate([sc.vel, rng.uniform(-1, 1, (k, 3)).astype(np.float32)])
+    aff = [None] * 3
+    if apic:
+        aff = [np.concatenate([a, (rng.uniform(-1, 1, (k, 3)) * 0.1 / dx).astype(np.float32)]) for a in (sc.affx, sc.affy, sc.affz)]
+    (ou, ov, ow), (ovu, ovv, ovw) = oracle.p2g(n, n, n, dx, sc.radius, m, pos, vel, *aff)
+    with eng.FlipContext(n, n, n, dx) as ctx:
+        ctx.set_particles(pos, vel, *aff)
+        ctx.p2g(sc.radius, m)
+        (u, v, w), (vu, vv, vw) = ctx.get_velocity_field()
+        assert np.array_equal(vu, ovu) and np.array_equal(vv, ovv) and np.array_equal(vw, ovw)
+        assert close(u, ou) and close(v, ov) and close(w, ow)
+        cell, hkey, perm = ctx.get_binning()
+        ocell, ohkey, operm = oracle.bin_sort(n, n, n, dx, pos)
+        assert np.array_equal(cell, ocell) and np.array_equal(hkey, ohkey) and np.array_equal(perm, operm)
+        ctx.set_valid_guard(float("inf"), 0.0)                 # every face through the reference-order sum
+        ctx.set_particles(pos, vel, *aff)
+        ctx.p2g(sc.radius, m)
+        (u, v, w), _ = ctx.get_velocity_field()
+        assert bits_equal(u, ou) and bits_equal(v, ov) and bits_equal(w, ow)
