@@ -680,6 +680,20 @@ int ffb200_declare_resident(ffb200_context *ctx, unsigned mask) {
     return guarded("ffb200_declare_resident", ctx, [&](Context &c) { c.resident_next = mask; }, false);
 }
 
+int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed) {
+    return guarded("ffb200_get_maximum_particle_speed", ctx, [&](Context &c) {
+        if (!speed) throw std::invalid_argument("null output pointer");
+        uint32_t *dev = reinterpret_cast<uint32_t *>(c.slab_counters) + 7;     // a spare device word
+        launch_max_speed_sq(c, dev);
+        uint32_t bits = 0;
+        FFB_CUDA(cudaMemcpyAsync(&bits, dev, sizeof(bits), cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+        float f;
+        std::memcpy(&f, &bits, sizeof(f));
+        *speed = std::sqrt((double)f);                         // sqrt(maxsq), maxsq the double of a float dot product
+    }, false);
+}
+
 int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid) {
     return guarded("ffb200_set_solid", ctx, [&](Context &c) { set_solid_impl(impl(c), phi, near_solid); });
 }

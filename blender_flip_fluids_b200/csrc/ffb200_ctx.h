@@ -138,6 +138,7 @@ int launch_g2p(Context &c, int method, double ratio);
 // ffb200_advect.cu
 int launch_solid_clearance(Context &c);                  // after every change of the solid SDF
 int launch_advect(Context &c, double dt, double cfl, int collide);
+int launch_max_speed_sq(Context &c, uint32_t *out_bits);  // bits of max float v.v over the owned particles (device word)
 
 // ffb200_slab.cu
 int slab_rows(Context &c);

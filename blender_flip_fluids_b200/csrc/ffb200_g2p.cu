@@ -148,7 +148,34 @@ __global__ void __launch_bounds__(256) k_g2p_apic(const __grid_constant__ G2PPar
     P.ovx[j] = v0; P.ovy[j] = v1; P.ovz[j] = v2;
 }
 
+// FluidSimulation::_getMaximumMarkerParticleSpeed (fluidsimulation.cpp:10188-10202): max over the particles of
+// the float dot product v.v (left to right); a max is order independent, so the reduction is bit-exact.
+// Non-negative floats order like their bit patterns: integer atomicMax.
+__global__ void k_max_speed_sq(const float *__restrict__ vx, const float *__restrict__ vy, const float *__restrict__ vz,
+                               const uint32_t *__restrict__ ids, int n, uint32_t *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    float d = 0.0f;
+    if (j < n && !(ids[j] & 0x80000000u)) {                    // ghost copies of a z-slab rank belong to the neighbour
+        const float x = vx[j], y = vy[j], z = vz[j];
+        d = x * x + y * y + z * z;
+        if (!(d >= 0.0f)) d = 0.0f;                            // NaN never wins the reference's `distsq > maxsq` either
+    }
+    uint32_t b = __float_as_uint(d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(out, b);
+}
+
 }  // namespace
+
+int launch_max_speed_sq(Context &c, uint32_t *out_bits) {
+    FFB_CUDA(cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), c.stream));
+    if (c.n == 0) return 0;
+    ParticleSoA &s = c.soa[c.cur];
+    k_max_speed_sq<<<(c.n + 255) / 256, 256, 0, c.stream>>>(s.v[0], s.v[1], s.v[2], s.orig, c.n, out_bits);
+    FFB_CUDA(cudaGetLastError());
+    return 1;
+}
 
 int launch_g2p(Context &c, int method, double ratio) {
     if (c.n == 0) return 0;

@@ -90,6 +90,7 @@ SIGNATURES = {
     "ffb200_advect": [C.c_void_p, C.c_double, C.c_double, C.c_int],
     "ffb200_velocity_advector_advect": [C.c_void_p, C.c_int] + [_f32p] * 5 + [C.c_double, C.c_int] + [_f32p] * 3 + [_u8p] * 3,
     "ffb200_declare_resident": [C.c_void_p, C.c_uint],
+    "ffb200_get_maximum_particle_speed": [C.c_void_p, C.POINTER(C.c_double)],
     "ffb200_extrapolate_fluid_velocities": [C.c_void_p, _f32p, _f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int],
     "ffb200_update_marker_particle_velocities": [C.c_void_p, C.c_int] + [_f32p] * 11 + [C.c_int, C.c_double],
     "ffb200_advance_marker_particles": [C.c_void_p, C.c_int] + [_f32p] * 5 + [_u8p, C.c_double, C.c_double],
@@ -288,6 +289,12 @@ class FlipContext:
 
     def save_velocity_field(self):
         self._call("ffb200_save_velocity_field")
+
+    def maximum_particle_speed(self):
+        """_getMaximumMarkerParticleSpeed on the resident velocities (the CFL time step's input)."""
+        out = C.c_double()
+        self._call("ffb200_get_maximum_particle_speed", C.byref(out))
+        return out.value
 
     def declare_resident(self, particles=False, field=False):
         """ffb200_declare_resident: the next host-buffer call may skip uploading what the device already holds."""

@@ -193,6 +193,11 @@ int ffb200_set_valid_velocities(ffb200_context *ctx, const uint8_t *validu, cons
  * masks of the last ffb200_p2g / ffb200_set_valid_velocities. Whole-grid contexts only. */
 int ffb200_extrapolate_velocity_field(ffb200_context *ctx, int num_layers);
 int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid);
+/* FluidSimulation::_getMaximumMarkerParticleSpeed (fluidsimulation.cpp:10188-10202), the input of the CFL
+ * time step (_calculateNextTimeStep, :10229-10262), on the resident velocities: sqrt of the largest float
+ * dot product v.v, bit-identical to the reference. Synchronises the stream. On a z-slab context the ghost
+ * copies are ignored (reduce the per-rank values with a max). */
+int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed);
 
 /* ---- stages on resident data ---------------------------------------------------------------------- */
 

@@ -670,3 +670,15 @@ void flip_oracle_extrapolate(int w, int h, int d, float *grid, const uint8_t *va
     free(cells);
     free(status);
 }
+
+/* FluidSimulation::_getMaximumMarkerParticleSpeed (fluidsimulation.cpp:10188-10202). */
+double flip_oracle_max_particle_speed(int n, const float *vel) {
+    double maxsq = 0.0;
+    for (int i = 0; i < n; i++) {
+        const float *v = vel + 3 * (size_t)i;
+        float d = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];    /* vmath::dot, float, left to right */
+        double distsq = d;
+        if (distsq > maxsq) maxsq = distsq;
+    }
+    return sqrt(maxsq);
+}

@@ -83,6 +83,9 @@ void flip_oracle_near_dims(int I, int J, int K, double dx, int *gi, int *gj, int
 /* GridUtils::extrapolateGrid (gridutils.h:94-163) on one w x h x d float grid (x fastest), in place. */
 void flip_oracle_extrapolate(int w, int h, int d, float *grid, const uint8_t *valid, int layers);
 
+/* FluidSimulation::_getMaximumMarkerParticleSpeed (fluidsimulation.cpp:10188-10202). */
+double flip_oracle_max_particle_speed(int n, const float *vel);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,3 +137,10 @@ def extrapolation_layers(cfl=5.0):
     """fluidsimulation.cpp:6284."""
     import math
     return int(math.ceil(math.sqrt(3) * cfl)) + 3
+
+
+def max_particle_speed(vel):
+    vel = _f32(vel)
+    f = lib().flip_oracle_max_particle_speed
+    f.restype = C.c_double
+    return float(f(C.c_int(vel.shape[0]), _p(vel)))

@@ -417,3 +417,20 @@ def test_p2g_dense_and_clustered_cells_vs_oracle(eng, oracle, method):
         ctx.p2g(sc.radius, m)
         (u, v, w), _ = ctx.get_velocity_field()
         assert bits_equal(u, ou) and bits_equal(v, ov) and bits_equal(w, ow)
+
+
+def test_maximum_particle_speed(eng, oracle):
+    """_getMaximumMarkerParticleSpeed on the device == the oracle's (and numpy's float32 arithmetic), bit for bit."""
+    rng = np.random.default_rng(17)
+    pos = (rng.random((50001, 3)) * 0.8 + 0.1).astype(np.float32)
+    vel = (rng.standard_normal((50001, 3)) * 3.0).astype(np.float32)
+    with eng.FlipContext(16, 16, 16, 1.0 / 16) as ctx:
+        ctx.set_particles(pos, vel)
+        got = ctx.maximum_particle_speed()
+        ctx.sort_particles()
+        assert ctx.maximum_particle_speed() == got
+        ctx.set_particles(pos[:0], vel[:0])
+        assert ctx.maximum_particle_speed() == 0.0
+    want = oracle.max_particle_speed(vel)
+    d = (vel[:, 0] * vel[:, 0] + vel[:, 1] * vel[:, 1]) + vel[:, 2] * vel[:, 2]
+    assert got == want == float(np.sqrt(np.float64(d.max())))
