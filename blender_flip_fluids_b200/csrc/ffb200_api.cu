@@ -578,11 +578,13 @@ int ffb200_slab_route_begin(ffb200_context *ctx, int k_begin, int k_end, float *
 }
 
 int ffb200_slab_route_ghosts_begin(ffb200_context *ctx, int k_begin, int k_end, int ghost_layers, float *block_up,
-                                   float *block_down, int block_capacity) {
+                                   float *block_down, const int *capacities) {
     return guarded("ffb200_slab_route_ghosts_begin", ctx, [&](Context &c) {
         if (ghost_layers <= 0) throw std::domain_error("ghost layer count must be positive");
-        if ((block_up || block_down) && block_capacity <= 0) throw std::domain_error("block capacity must be positive");
-        launch_route_begin(c, k_begin, k_end, block_up, block_down, block_capacity, ghost_layers);
+        if (!capacities) throw std::invalid_argument("null capacities pointer");
+        if ((block_up && (capacities[0] <= 0 || capacities[1] <= 0)) || (block_down && (capacities[2] <= 0 || capacities[3] <= 0)))
+            throw std::domain_error("section capacities must be positive");
+        launch_route_begin(c, k_begin, k_end, block_up, block_down, 0, ghost_layers, capacities);
     });
 }
 

@@ -143,7 +143,9 @@ int launch_max_speed_sq(Context &c, uint32_t *out_bits);  // bits of max float v
 // ffb200_slab.cu
 int slab_rows(Context &c);
 int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b, int hi_b, float *block_b, int cap);
-int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int ghost_layers = 0);
+// caps (ghost_layers > 0 only): {up migrants, up ghosts, down migrants, down ghosts} section capacities
+int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int ghost_layers = 0,
+                       const int *caps = nullptr);
 int launch_route_end(Context &c, int counts_host[3]);
 int launch_append(Context &c, const float *block, int count, bool as_ghost);
 

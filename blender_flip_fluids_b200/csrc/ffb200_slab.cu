@@ -74,6 +74,10 @@ __global__ void k_pack_layers(Streams src, int n, double inv_dx, int lo_a, int h
 // left as it is (migrants are packed and sent, but not removed).
 constexpr uint32_t kGhostBit = 0x80000000u;
 
+struct FaceCaps {
+    int up_m, up_g, dn_m, dn_g;      // record capacities of the migrant / ghost sections of the up and down blocks
+};
+
 __global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int k_begin, int k_end, float *block_up,
                              float *block_down, int cap, int remove_migrants, int *counters, uint32_t *holes,
                              uint8_t *leave_flag) {
@@ -99,8 +103,8 @@ __global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int
 }
 
 // The same routing with the NEXT substep's ghost exchange folded in, so that one neighbour
-// exchange per substep carries both. Blocks have two sections of `cap` records: [migrants][ghost
-// copies] and an 8-int header {migrants, overflow, ghosts, overflow, 0...}.
+// exchange per substep carries both. Blocks have two sections, [migrants][ghost copies] (their
+// capacities are per face: FaceCaps), and an 8-int header {migrants, overflow, ghosts, overflow, 0...}.
 //  * an owned particle that stays and sits within `g` cell planes of a slab face is copied into the
 //    ghost section for that neighbour (it is what k_pack_layers would select at the start of the
 //    next substep);
@@ -110,7 +114,7 @@ __global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int
 // Fixed-batch mode (remove_migrants = 0): nothing is removed or converted; ghost copies are taken
 // from the resident (pristine) batch, exactly what a start-of-substep exchange would send.
 __global__ void k_route_mark_ghosts(Streams cur, Streams dat, int n, double inv_dx, int k_begin, int k_end, int g,
-                                    float *block_up, float *block_down, int cap, int remove_migrants, int *counters,
+                                    float *block_up, float *block_down, FaceCaps caps, int remove_migrants, int *counters,
                                     uint32_t *holes, uint8_t *leave_flag) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     bool ghost = false, up = false, down = false, gup = false, gdown = false, keep = false;
@@ -125,30 +129,34 @@ __global__ void k_route_mark_ghosts(Streams cur, Streams dat, int n, double inv_
         gdown = owned_after && block_down && kc < k_begin + g;
         keep = remove_migrants && ((up && kd < k_end + g) || (down && kd >= k_begin - g));
     }
-    const bool leave = ghost || (remove_migrants && (up || down) && !keep);
     const int su = warp_slot(up, counters + 1);
     const int sd = warp_slot(down, counters + 2);
+    // a migrant that does not fit the buffer is not lost: it stays here (outside its slab for one
+    // substep; the header reports the overflow and the host enlarges the buffers)
+    const bool sent = (up && su < caps.up_m) || (down && sd < caps.dn_m);
+    keep = keep && sent;
+    const bool leave = ghost || (remove_migrants && sent && !keep);
     const int sh = warp_slot(leave, counters + 3);
     const int sgu = warp_slot(gup, counters + 4);
     const int sgd = warp_slot(gdown, counters + 5);
-    const size_t section = (size_t)cap * (cur.ns + 1);
-    if (up || down) {
+    const int rows = cur.ns + 1;
+    if (sent) {
         Streams rec = dat;
         rec.ids = cur.ids;
-        write_record(rec, j, up ? block_up : block_down, cap, up ? su : sd);
+        write_record(rec, j, up ? block_up : block_down, up ? caps.up_m : caps.dn_m, up ? su : sd);
     }
-    if (gup) write_record(cur, j, block_up + section, cap, sgu);
-    if (gdown) write_record(cur, j, block_down + section, cap, sgd);
+    if (gup) write_record(cur, j, block_up + (size_t)caps.up_m * rows, caps.up_g, sgu);
+    if (gdown) write_record(cur, j, block_down + (size_t)caps.dn_m * rows, caps.dn_g, sgd);
     if (keep) cur.ids[j] |= kGhostBit;                        // after its record (with the clean id) was written
     if (leave) holes[sh] = (uint32_t)j;
     if (j < n) leave_flag[j] = leave ? 1 : 0;
 }
 
-__global__ void k_write_header2(const int *counters, int which_m, int which_g, int cap, int rows, float *block) {
-    int *h = reinterpret_cast<int *>(block + (size_t)2 * cap * rows);
+__global__ void k_write_header2(const int *counters, int which_m, int which_g, int cap, int cap_g, int rows, float *block) {
+    int *h = reinterpret_cast<int *>(block + ((size_t)cap + cap_g) * rows);
     const int m = counters[which_m], gc = counters[which_g];
     h[0] = m; h[1] = m > cap ? 1 : 0;
-    h[2] = gc; h[3] = gc > cap ? 1 : 0;
+    h[2] = gc; h[3] = gc > cap_g ? 1 : 0;
     h[4] = h[5] = h[6] = h[7] = 0;
 }
 
@@ -236,7 +244,8 @@ struct RouteState {
 };
 static RouteState g_route;      // one routing in flight per process (one context per rank)
 
-int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int ghost_layers) {
+int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int ghost_layers,
+                       const int *caps) {
     int launches = 0;
     const int n = c.n;
     const int rows = slab_rows(c);
@@ -249,12 +258,12 @@ int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, floa
     if (ghost_layers > 0) {
         if (n > 0) {
             k_route_mark_ghosts<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, ghost_layers,
-                                                                       block_up, block_down, cap, fixed ? 0 : 1,
-                                                                       c.slab_counters, holes, leave_flag);
+                                                                       block_up, block_down, FaceCaps{caps[0], caps[1], caps[2], caps[3]},
+                                                                       fixed ? 0 : 1, c.slab_counters, holes, leave_flag);
             launches++;
         }
-        if (block_up) { k_write_header2<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, 4, cap, rows, block_up); launches++; }
-        if (block_down) { k_write_header2<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, 5, cap, rows, block_down); launches++; }
+        if (block_up) { k_write_header2<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, 4, caps[0], caps[1], rows, block_up); launches++; }
+        if (block_down) { k_write_header2<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, 5, caps[2], caps[3], rows, block_down); launches++; }
     } else {
         if (n > 0) {
             k_route_mark<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, block_up, block_down,

@@ -73,7 +73,7 @@ SIGNATURES = {
     "ffb200_slab_route": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
     "ffb200_slab_route_begin": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int],
     "ffb200_slab_route_end": [C.c_void_p, C.POINTER(C.c_int)],
-    "ffb200_slab_route_ghosts_begin": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int],
+    "ffb200_slab_route_ghosts_begin": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)],
     "ffb200_slab_append": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
     "ffb200_sort_particles": [C.c_void_p],
     "ffb200_get_binning": [C.c_void_p, _i32p, _u32p, _u32p],
@@ -251,9 +251,11 @@ class FlipContext:
         self.n = counts[0]
         return counts[0], counts[1], counts[2]
 
-    def slab_route_ghosts_begin(self, k_begin, k_end, ghost_layers, block_up, block_down, capacity):
+    def slab_route_ghosts_begin(self, k_begin, k_end, ghost_layers, block_up, block_down, capacities):
+        """capacities = (up migrants, up ghosts, down migrants, down ghosts)."""
+        caps = (C.c_int * 4)(*[int(x) for x in capacities])
         self._call("ffb200_slab_route_ghosts_begin", int(k_begin), int(k_end), int(ghost_layers), C.c_void_p(block_up or 0),
-                   C.c_void_p(block_down or 0), int(capacity))
+                   C.c_void_p(block_down or 0), caps)
 
     def slab_append(self, ptr, count, as_ghost=False):
         self._call("ffb200_slab_append", C.c_void_p(ptr), int(count), 1 if as_ghost else 0)

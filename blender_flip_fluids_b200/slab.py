@@ -138,17 +138,17 @@ class GpuBackend:
     def route_end(self):
         return self.ctx.slab_route_end()
 
-    def new_block2(self, capacity):
-        """Two-section packed buffer [migrants][ghost copies] + an 8-int header (ffb200_slab_route_ghosts_begin)."""
-        return torch.zeros(2 * capacity * self.record_floats() + 8, dtype=torch.float32, device=self.device)
+    def new_block2(self, cap_m, cap_g):
+        """Two-section packed buffer [cap_m migrants][cap_g ghost copies] + an 8-int header (ffb200_slab_route_ghosts_begin)."""
+        return torch.zeros((cap_m + cap_g) * self.record_floats() + 8, dtype=torch.float32, device=self.device)
 
-    def route_ghosts_begin(self, k_begin, k_end, ghost_layers, block_up, block_down, capacity):
+    def route_ghosts_begin(self, k_begin, k_end, ghost_layers, block_up, block_down, caps):
         self.ctx.slab_route_ghosts_begin(k_begin, k_end, ghost_layers, block_up.data_ptr() if block_up is not None else 0,
-                                         block_down.data_ptr() if block_down is not None else 0, capacity)
+                                         block_down.data_ptr() if block_down is not None else 0, caps)
 
-    def append_section(self, block, section, capacity, count, as_ghost=False):
+    def append_records(self, block, first_record, count, as_ghost=False):
         if count:
-            self.ctx.slab_append(block.data_ptr() + 4 * section * capacity * self.record_floats(), count, as_ghost)
+            self.ctx.slab_append(block.data_ptr() + 4 * first_record * self.record_floats(), count, as_ghost)
 
     def append(self, block, count, as_ghost=False):
         if count:
@@ -288,7 +288,8 @@ class SlabSimulation:
         return self._block_cap, self._blk
 
     def _swap_blocks(self, cap, b):
-        """Exchange the fixed-size packed buffers with both neighbours; returns the received counts."""
+        """Exchange the fixed-size packed buffers with both neighbours. Returns (received from below,
+        received from above, local overflow flag, headers [up_send, dn_send, up_recv, dn_recv])."""
         rows = self.backend.record_floats()
         ops = []
         if self.up is not None:
@@ -300,11 +301,18 @@ class SlabSimulation:
                 r.wait()
         hdr = torch.stack([b[k][cap * rows:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()
         self.exchanged_bytes += (int(hdr[0, 0]) + int(hdr[1, 0])) * rows * 4
-        if int(hdr[:, 1].max()) != 0 and (self.up is not None or self.down is not None):
-            return None                                     # some buffer overflowed: caller retries with a larger one
+        overflow = bool(ops) and int(hdr[:, 1].max()) != 0
         n_up = int(hdr[2, 0]) if self.up is not None else 0
         n_dn = int(hdr[3, 0]) if self.down is not None else 0
-        return n_dn, n_up
+        return n_dn, n_up, overflow, hdr
+
+    def _agree_max(self, value):
+        """max over all ranks (buffer sizes of an exchange must match on both sides of every face)."""
+        if self.world == 1:
+            return int(value)
+        t = torch.tensor([int(value)], device=self.device, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item())
 
     def _tick(self, name):
         """FFB200_SLAB_PROFILE=1: wall-clock phase breakdown (synchronising; not for benchmarking)."""
@@ -333,19 +341,24 @@ class SlabSimulation:
         # 1. the very first substep after load_resident fetches its ghost layers with an exchange of its own;
         #    afterwards they arrive with the previous substep's migration (step 5)
         if not getattr(self, "_ghosts_ready", False):
+            # buffer sizes and the retry decision are agreed by all ranks (rare path: one all-reduce each)
             n0 = be.ctx.n
-            cap, b = self._blocks(max(8192, int(0.03 * n0)))
+            cap, b = self._blocks(max(8192, int(0.05 * self._agree_max(n0))))
             while True:
                 be.pack_layers(self.ke - g, self.ke, b["up_send"] if self.up is not None else None,
                                self.kb, self.kb + g, b["dn_send"] if self.down is not None else None, cap)
-                got = self._swap_blocks(cap, b)
-                if got is not None:
+                n_dn, n_up, overflow, hdr = self._swap_blocks(cap, b)
+                if not self._agree_max(1 if overflow else 0):
                     break
                 cap, b = self._blocks(cap * 2)
-            be.append(b["dn_recv"], got[0], as_ghost=True)
-            be.append(b["up_recv"], got[1], as_ghost=True)
+            be.append(b["dn_recv"], n_dn, as_ghost=True)
+            be.append(b["up_recv"], n_up, as_ghost=True)
             self._ghosts_ready = True
             self._n_owned = n0
+            # per face, the larger of what went either way: known to BOTH ranks of the face, so both size
+            # the next exchange's buffers identically. No migrants yet: guess half a plane's worth.
+            gu, gd = max(int(hdr[0, 0]), int(hdr[2, 0])), max(int(hdr[1, 0]), int(hdr[3, 0]))
+            self._face_counts = {"up": (gu // (2 * g), gu), "dn": (gd // (2 * g), gd)}
         self._tick("ghosts")
         # 2. P2G on owned + ghost particles
         be.p2g(radius)
@@ -362,36 +375,50 @@ class SlabSimulation:
         #    dropped; the end ranks keep whatever strayed past the domain
         kb = self.kb if self.down is not None else self.INT_MIN
         ke = self.ke if self.up is not None else self.INT_MAX
-        planes = max(1, self.ke - self.kb)
-        cap2, b2 = self._blocks2(int(1.5 * self._n_owned * (g + 1) / planes) + 8192)
+        caps, b2 = self._blocks2()
         be.route_ghosts_begin(kb, ke, g, b2["up_send"] if self.up is not None else None,
-                              b2["dn_send"] if self.down is not None else None, cap2)
-        got = self._swap_blocks2(cap2, b2)        # one synchronisation serves the exchange and the routing
+                              b2["dn_send"] if self.down is not None else None, caps)
+        hdr = self._swap_blocks2(caps, b2)            # one synchronisation serves the exchange and the routing
         n_owned, _, _ = be.route_end()
-        if got is None:
-            self._block2_cap = 0                      # next call allocates larger buffers
-            raise RuntimeError("slab exchange buffer overflow: more than %d migrants or ghost copies per face" % cap2)
-        mig_dn, mig_up, gh_dn, gh_up = got
+        up, dn = self.up is not None, self.down is not None
+        # true counts of both directions per face (identical knowledge on both ranks of the face)
+        self._face_counts = {"up": (max(int(hdr[0, 0]), int(hdr[2, 0])), max(int(hdr[0, 2]), int(hdr[2, 2]))),
+                             "dn": (max(int(hdr[1, 0]), int(hdr[3, 0])), max(int(hdr[1, 2]), int(hdr[3, 2])))}
+        if (up and (hdr[0, 3] or hdr[2, 3])) or (dn and (hdr[1, 3] or hdr[3, 3])):
+            raise RuntimeError("slab exchange: the ghost copies near a face grew by more than 50 % + 4096 within one substep")
+        self.overflows = getattr(self, "overflows", 0) + int(bool(hdr[:, 1].max()))   # migrants that stayed one more substep
+        mig_up, gh_up = (min(int(hdr[2, 0]), caps[0]), int(hdr[2, 2])) if up else (0, 0)
+        mig_dn, gh_dn = (min(int(hdr[3, 0]), caps[2]), int(hdr[3, 2])) if dn else (0, 0)
         if apply_migration:
-            be.append_section(b2["dn_recv"], 0, cap2, mig_dn)
-            be.append_section(b2["up_recv"], 0, cap2, mig_up)
+            be.append_records(b2["dn_recv"], 0, mig_dn)
+            be.append_records(b2["up_recv"], 0, mig_up)
             n_owned += mig_dn + mig_up
         self._n_owned = n_owned
-        be.append_section(b2["dn_recv"], 1, cap2, gh_dn, as_ghost=True)
-        be.append_section(b2["up_recv"], 1, cap2, gh_up, as_ghost=True)
+        be.append_records(b2["dn_recv"], caps[2], gh_dn, as_ghost=True)
+        be.append_records(b2["up_recv"], caps[0], gh_up, as_ghost=True)
         self._tick("migrate")
 
-    def _blocks2(self, need):
-        cap = getattr(self, "_block2_cap", 0)
-        if cap < need:
-            cap = max(8192, int(need * 1.25))
-            self._block2_cap = cap
-            self._blk2 = {k: self.backend.new_block2(cap) for k in ("up_send", "up_recv", "dn_send", "dn_recv")}
-        return self._block2_cap, self._blk2
+    @staticmethod
+    def _bucket(x):
+        return (int(x) + 4095) // 4096 * 4096
 
-    def _swap_blocks2(self, cap, b):
-        """Exchange the two-section buffers with both neighbours; returns the received
-        (migrants from below, from above, ghosts from below, from above) or None on overflow."""
+    def _blocks2(self):
+        """Per-face section capacities (up migrants, up ghosts, down migrants, down ghosts) and buffers,
+        derived from the previous exchange's counts on that face: twice the migrants, 1.5x the ghost
+        copies, + 4096, rounded up to 4096. Everything in a buffer travels, so the fit is kept tight; a
+        migrant that does not fit stays with its sender for one substep, the counts adapt the next."""
+        (mu, gu), (md, gd) = self._face_counts["up"], self._face_counts["dn"]
+        caps = (self._bucket(2 * mu + 4096), self._bucket(1.5 * gu + 4096), self._bucket(2 * md + 4096), self._bucket(1.5 * gd + 4096))
+        if getattr(self, "_block2_caps", None) != caps:
+            self._block2_caps = caps
+            nb = self.backend.new_block2
+            self._blk2 = {"up_send": nb(caps[0], caps[1]), "up_recv": nb(caps[0], caps[1]),
+                          "dn_send": nb(caps[2], caps[3]), "dn_recv": nb(caps[2], caps[3])}
+        return caps, self._blk2
+
+    def _swap_blocks2(self, caps, b):
+        """Exchange the two-section buffers with both neighbours; returns the four 8-int headers
+        [up_send, dn_send, up_recv, dn_recv] (rows of absent neighbours are zero)."""
         rows = self.backend.record_floats()
         ops = []
         if self.up is not None:
@@ -401,12 +428,15 @@ class SlabSimulation:
         if ops:
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
-        hdr = torch.stack([b[k][2 * cap * rows:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()
+        off = {"up_send": (caps[0] + caps[1]) * rows, "up_recv": (caps[0] + caps[1]) * rows,
+               "dn_send": (caps[2] + caps[3]) * rows, "dn_recv": (caps[2] + caps[3]) * rows}
+        hdr = torch.stack([b[k][off[k]:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()
+        if self.up is None:
+            hdr[0].zero_(); hdr[2].zero_()
+        if self.down is None:
+            hdr[1].zero_(); hdr[3].zero_()
         self.exchanged_bytes += int(hdr[0, 0] + hdr[0, 2] + hdr[1, 0] + hdr[1, 2]) * rows * 4
-        if (self.up is not None or self.down is not None) and int(torch.maximum(hdr[:, 1], hdr[:, 3]).max()) != 0:
-            return None
-        up, dn = self.up is not None, self.down is not None
-        return (int(hdr[3, 0]) if dn else 0, int(hdr[2, 0]) if up else 0, int(hdr[3, 2]) if dn else 0, int(hdr[2, 2]) if up else 0)
+        return hdr
 
     def _halo_exchange_fast(self):
         plan = getattr(self, "_halo_plan", None)

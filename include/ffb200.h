@@ -153,15 +153,18 @@ int ffb200_slab_route_begin(ffb200_context *ctx, int k_begin, int k_end, float *
                             int block_capacity);
 int ffb200_slab_route_end(ffb200_context *ctx, int *counts);
 /* ffb200_slab_route_begin with the NEXT substep's ghost exchange folded in, so that one neighbour
- * exchange per substep carries migrants and ghost copies. Blocks hold two sections of
- * block_capacity records, [migrants][ghost copies], followed by an 8-int header
- * {migrants, overflow, ghosts, overflow, 0, 0, 0, 0}. Owned particles that stay within ghost_layers
- * cell planes of a face are copied into the ghost section; a migrant landing within ghost_layers
- * planes beyond the face is sent and also kept here as a ghost (its new owner would return it as
- * one); the ghosts of the substep that ended are dropped. Finish with ffb200_slab_route_end, then
- * append the received sections (ffb200_slab_append with as_ghost = 0 / 1). */
+ * exchange per substep carries migrants and ghost copies. A block holds two sections,
+ * [migrant records][ghost-copy records], followed by an 8-int header
+ * {migrants, overflow, ghosts, overflow, 0, 0, 0, 0} (true counts even on overflow).
+ * capacities = {up migrants, up ghosts, down migrants, down ghosts}: per face, so that both ranks of
+ * a face can size their buffers from numbers they both know (the previous exchange's headers).
+ * Owned particles that stay within ghost_layers cell planes of a face are copied into the ghost
+ * section; a migrant landing within ghost_layers planes beyond the face is sent and also kept here
+ * as a ghost (its new owner would return it as one); a migrant that does not fit its section stays
+ * with the sender for this substep; the ghosts of the substep that ended are dropped. Finish with
+ * ffb200_slab_route_end, then append the received sections (ffb200_slab_append, as_ghost = 0 / 1). */
 int ffb200_slab_route_ghosts_begin(ffb200_context *ctx, int k_begin, int k_end, int ghost_layers,
-                                   float *block_up, float *block_down, int block_capacity);
+                                   float *block_up, float *block_down, const int *capacities);
 /* Append `count` packed records (device buffer) to the resident particles. as_ghost marks them
  * (top id bit) as ghost copies: they take part in P2G and are dropped by the next
  * ffb200_slab_route wherever they have moved. */
