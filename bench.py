@@ -229,6 +229,11 @@ def main():
 
     apic = METHOD == "apic"
     m = engine.APIC if apic else engine.FLIP
+    # a dedicated (non-default) stream, made torch's current stream BEFORE anything binds to it: the library
+    # launches on it (GpuBackend / ffb200_set_stream), NCCL orders its transfers against it, the events time
+    # it, and at N=1 the substep is captured from it into a CUDA graph
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     if world > 1:
         from blender_flip_fluids_b200 import slab
         Kg = GRID_N * world
@@ -252,10 +257,6 @@ def main():
     dt = 1.0 * dx / V0            # ~1 cell per substep at the velocity bound (CFL limit is 5)
     ratio = 0.05
 
-    # a dedicated (non-default) stream: the library launches on it, the events time it, and at N=1 the
-    # substep is captured from it into a CUDA graph
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
     if sim is None:
         phi, near = scenes.analytic_solid_sdf(GRID_N, GRID_N, GRID_N, dx)
         ctx = engine.FlipContext(GRID_N, GRID_N, GRID_N, dx, device=local_rank)

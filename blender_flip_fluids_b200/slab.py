@@ -385,7 +385,8 @@ class SlabSimulation:
         self._face_counts = {"up": (max(int(hdr[0, 0]), int(hdr[2, 0])), max(int(hdr[0, 2]), int(hdr[2, 2]))),
                              "dn": (max(int(hdr[1, 0]), int(hdr[3, 0])), max(int(hdr[1, 2]), int(hdr[3, 2])))}
         if (up and (hdr[0, 3] or hdr[2, 3])) or (dn and (hdr[1, 3] or hdr[3, 3])):
-            raise RuntimeError("slab exchange: the ghost copies near a face grew by more than 50 % + 4096 within one substep")
+            raise RuntimeError("slab exchange: the ghost copies near a face grew by more than 50 %% + 4096 within one substep "
+                               "(rank %d, capacities %s, headers %s)" % (self.rank, caps, hdr.tolist()))
         self.overflows = getattr(self, "overflows", 0) + int(bool(hdr[:, 1].max()))   # migrants that stayed one more substep
         mig_up, gh_up = (min(int(hdr[2, 0]), caps[0]), int(hdr[2, 2])) if up else (0, 0)
         mig_dn, gh_dn = (min(int(hdr[3, 0]), caps[2]), int(hdr[3, 2])) if dn else (0, 0)
