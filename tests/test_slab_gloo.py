@@ -1,6 +1,9 @@
-"""CPU suite, world_size 2 over gloo: the z-slab driver (ghost particles, face halos, migration)
-against an undecomposed oracle run, bit-for-bit, for two substeps with particles crossing the
-slab boundary. Spawns two processes on 127.0.0.1."""
+"""CPU suite over gloo: the z-slab driver (ghost particles, face halos, migration) against an
+undecomposed oracle run, bit-for-bit, with particles crossing the slab boundaries. Two code paths:
+the generic plumbing (world size 2) and the device-plumbing protocol of step_fast -- one merged
+migrant + ghost exchange per substep, per-face buffer sizes agreed through the headers -- with the
+CUDA kernels restated in numpy (world sizes 2 and 3: a middle rank has two faces). Spawns the
+processes on 127.0.0.1."""
 import os
 import socket
 import sys
@@ -16,11 +19,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def _scene(apic):
+def _scene(apic, K=28):
     from blender_flip_fluids_b200 import scenes
-    I, J, K, dx = 12, 10, 28, 0.05
+    I, J, dx = 12, 10, 0.05
     sc = scenes.dam_break(12, apic=apic, dx=dx, dims=(I, J, K), vel="random", v0=0.6, seed=21)
-    sc.vel[:, 2] += np.where(sc.pos[:, 2] < 0.5 * K * dx, 0.9, -0.9).astype(np.float32)   # drive particles across k = 14
+    kz = np.floor(sc.pos[:, 2].astype(np.float64) / dx).astype(np.int64)
+    sc.vel[:, 2] += np.where(kz % 14 >= 7, 0.9, -0.9).astype(np.float32)   # drive particles across the slab faces (k = 14, 28)
     phi, near = scenes.analytic_solid_sdf(I, J, K, dx)
     return I, J, K, dx, sc, phi, near
 
@@ -33,16 +37,16 @@ def _streams(sc, apic, sel):
     return [torch.from_numpy(np.ascontiguousarray(c)) for c in cols]
 
 
-def _worker(rank, world, port, apic, out):
+def _worker(rank, world, port, apic, out, fast=False, K=28, steps=2):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from blender_flip_fluids_b200 import slab
-        from cpu_slab_backend import CpuOracleBackend
-        I, J, K, dx, sc, phi, near = _scene(apic)
+        from cpu_slab_backend import CpuOracleBackend, CpuOracleFastBackend
+        I, J, K, dx, sc, phi, near = _scene(apic, K)
         kb, ke = slab.slab_range(K, world, rank)
-        be = CpuOracleBackend(I, J, K, dx, kb, ke, 7, apic)
+        be = (CpuOracleFastBackend if fast else CpuOracleBackend)(I, J, K, dx, kb, ke, 7, apic)
         be.set_solid(phi, near)
         sim = slab.SlabSimulation(I, J, K, dx, rank, world, be, halo=7, ghost=2)
         kz = np.floor(sc.pos[:, 2].astype(np.float64) * (1.0 / dx)).astype(np.int64)
@@ -50,9 +54,15 @@ def _worker(rank, world, port, apic, out):
         sim.set_particles(_streams(sc, apic, sel), torch.from_numpy(sel.astype(np.int32)))
         dt = 1.5 * dx / 1.5
         moved = 0
-        for _ in range(2):
+        if fast:
+            sim.load_resident()
+        for _ in range(steps):
             before = set(sim.ids.tolist())
-            sim.step(sc.radius, 0.05, dt)
+            if fast:
+                sim.step_fast(sc.radius, 0.05, dt)
+                sim.sync_from_backend()
+            else:
+                sim.step(sc.radius, 0.05, dt)
             moved += len(set(sim.ids.tolist()) - before)
         allp, ids = sim.gather_particles()
         if rank == 0:
@@ -61,20 +71,19 @@ def _worker(rank, world, port, apic, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("apic", [False, True])
-def test_slab_two_ranks_match_single_domain(tmp_path, apic, oracle):
+def _run_and_compare(tmp_path, oracle, apic, world, fast, K, steps):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "slab.npz")
-    mp.spawn(_worker, args=(2, port, apic, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, apic, out, fast, K, steps), nprocs=world, join=True)
     got = np.load(out)
-    I, J, K, dx, sc, phi, near = _scene(apic)
+    I, J, K, dx, sc, phi, near = _scene(apic, K)
     pos, vel = sc.pos.copy(), sc.vel.copy()
     aff = [sc.affx, sc.affy, sc.affz] if apic else [None] * 3
     dt = 1.5 * dx / 1.5
-    for _ in range(2):                                      # undecomposed: P2G -> save -> G2P -> advect
+    for _ in range(steps):                                  # undecomposed: P2G -> save -> G2P -> advect
         (u, v, w), _ = oracle.p2g(I, J, K, dx, sc.radius, oracle.APIC if apic else oracle.FLIP, pos, vel, *aff)
         if apic:
             vel, ax, ay, az = oracle.g2p_apic(I, J, K, dx, pos, (u, v, w))
@@ -90,3 +99,16 @@ def test_slab_two_ranks_match_single_domain(tmp_path, apic, oracle):
     assert int(got["moved"]) > 0, "the scene must exercise migration"
     for q, wq in enumerate(want):
         assert got["streams"][q].tobytes() == np.ascontiguousarray(wq).tobytes(), f"stream {q} differs"
+
+
+@pytest.mark.parametrize("apic", [False, True])
+def test_slab_two_ranks_match_single_domain(tmp_path, apic, oracle):
+    _run_and_compare(tmp_path, oracle, apic, world=2, fast=False, K=28, steps=2)
+
+
+@pytest.mark.parametrize("world,apic", [(2, True), (3, False), (3, True)])
+def test_slab_fast_protocol_matches_single_domain(tmp_path, world, apic, oracle):
+    """step_fast's exchange protocol (merged migrant + ghost exchange, ghosts kept by the sender,
+    per-face capacities from the headers) with the kernels restated in numpy: three substeps, three
+    ranks (a middle rank exchanges on two faces), bit-identical to the undecomposed run."""
+    _run_and_compare(tmp_path, oracle, apic, world=world, fast=True, K=14 * world, steps=3)
