@@ -24,6 +24,15 @@ struct Box {
     double w, h, d;         // AABB::width/height/depth (doubles)
 };
 
+#ifndef FFB_ADV_THREADS
+#define FFB_ADV_THREADS 256
+#endif
+#ifdef FFB_ADV_MINB
+#define FFB_ADV_BOUNDS FFB_ADV_BOUNDS
+#else
+#define FFB_ADV_BOUNDS __launch_bounds__(FFB_ADV_THREADS)
+#endif
+
 struct AdvectParams {
     GridDesc g;
     MacView mac;
@@ -205,7 +214,7 @@ __device__ __noinline__ void resolve_collision(const AdvectParams &P, float ox, 
     nx = rx; ny = ry; nz = rz;
 }
 
-__global__ void __launch_bounds__(256) k_advect(const __grid_constant__ AdvectParams P) {
+__global__ void FFB_ADV_BOUNDS k_advect(const __grid_constant__ AdvectParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
@@ -317,7 +326,7 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.buffer = (double)0.2f * g.dx;
     P.collide = collide;
     P.n = c.n;
-    k_advect<<<(c.n + 255) / 256, 256, 0, c.stream>>>(P);
+    k_advect<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(P);
     FFB_CUDA(cudaGetLastError());
     if (!c.nondestructive) c.sorted = false;            // positions moved: bins are stale
     return 1;

@@ -14,6 +14,15 @@ namespace ffb200 {
 
 namespace {
 
+#ifndef FFB_G2P_THREADS
+#define FFB_G2P_THREADS 256
+#endif
+#ifdef FFB_G2P_MINB
+#define FFB_G2P_BOUNDS FFB_G2P_BOUNDS
+#else
+#define FFB_G2P_BOUNDS __launch_bounds__(FFB_G2P_THREADS)
+#endif
+
 struct G2PParams {
     GridDesc g;
     MacView cur, saved;
@@ -29,7 +38,7 @@ struct G2PParams {
     int n;
 };
 
-__global__ void __launch_bounds__(256) k_g2p_flip(const __grid_constant__ G2PParams P) {
+__global__ void FFB_G2P_BOUNDS k_g2p_flip(const __grid_constant__ G2PParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
@@ -128,7 +137,7 @@ __device__ __forceinline__ void apic_component(const G2PParams &P, const float *
     }
 }
 
-__global__ void __launch_bounds__(256) k_g2p_apic(const __grid_constant__ G2PParams P) {
+__global__ void FFB_G2P_BOUNDS k_g2p_apic(const __grid_constant__ G2PParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
@@ -196,11 +205,11 @@ int launch_g2p(Context &c, int method, double ratio) {
     P.inv_s = (float)(1.0 / (double)(float)c.g.dx);
     P.invdx = (float)(1.0f / c.g.dx);
     P.n = c.n;
-    const int blocks = (c.n + 255) / 256;
+    const int blocks = (c.n + FFB_G2P_THREADS - 1) / FFB_G2P_THREADS;
     if (method == FFB200_TRANSFER_APIC)
-        k_g2p_apic<<<blocks, 256, 0, c.stream>>>(P);
+        k_g2p_apic<<<blocks, FFB_G2P_THREADS, 0, c.stream>>>(P);
     else
-        k_g2p_flip<<<blocks, 256, 0, c.stream>>>(P);
+        k_g2p_flip<<<blocks, FFB_G2P_THREADS, 0, c.stream>>>(P);
     FFB_CUDA(cudaGetLastError());
     return 1;
 }

@@ -1355,8 +1355,11 @@ __global__ void k_p2g_edge(const __grid_constant__ P2GParams P) {
     for (int c = 0; c < 8; c++) P.partial[(size_t)c * plane + cell] = acc[c];
 }
 
+#ifndef FFB_NODES_BY
+#define FFB_NODES_BY 4
+#endif
 template <int DIR, int METHOD>
-__global__ void __launch_bounds__(128) k_p2g_nodes(const __grid_constant__ P2GParams P) {
+__global__ void __launch_bounds__(32 * FFB_NODES_BY) k_p2g_nodes(const __grid_constant__ P2GParams P) {
     const int ni = blockIdx.x * blockDim.x + threadIdx.x;
     const int nj = blockIdx.y * blockDim.y + threadIdx.y;
     const int nk = blockIdx.z * blockDim.z + threadIdx.z + P.kw0;
@@ -1460,8 +1463,8 @@ int launch_cells(Context &c, P2GParams &P, cudaStream_t st) {
         k_p2g_edge<DIR, METHOD><<<(P.edge_cap + 127) / 128, 128, 0, st>>>(P);
         launches++;
     }
-    dim3 block(32, 4, 1);
-    dim3 grid((P.gi + 31) / 32, (P.gj + 3) / 4, P.kw1 - P.kw0);
+    dim3 block(32, FFB_NODES_BY, 1);
+    dim3 grid((P.gi + 31) / 32, (P.gj + FFB_NODES_BY - 1) / FFB_NODES_BY, P.kw1 - P.kw0);
     k_p2g_nodes<DIR, METHOD><<<grid, block, 0, st>>>(P);
     launches++;
     return launches;

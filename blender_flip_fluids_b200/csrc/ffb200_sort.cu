@@ -20,6 +20,12 @@ namespace ffb200 {
 namespace {
 
 constexpr int kSortThreads = 256;
+#ifndef FFB_REORDER_THREADS
+#define FFB_REORDER_THREADS 256
+#endif
+#ifndef FFB_KEYS_THREADS
+#define FFB_KEYS_THREADS 256
+#endif
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kKeysPerThread = 16;
 constexpr int kTile = kSortThreads * kKeysPerThread;      // 4096 keys per CTA
@@ -307,11 +313,11 @@ struct ReorderArgs {
 };
 
 template <bool SEAM>
-__global__ void __launch_bounds__(256) k_reorder(const __grid_constant__ ReorderArgs a, const __grid_constant__ SeamParams sp,
+__global__ void __launch_bounds__(FFB_REORDER_THREADS) k_reorder(const __grid_constant__ ReorderArgs a, const __grid_constant__ SeamParams sp,
                                                  const uint32_t *__restrict__ key, const uint32_t *__restrict__ val,
                                                  const uint32_t *__restrict__ bin_start, const uint32_t *__restrict__ orig_old,
                                                  uint32_t *__restrict__ orig_new, int n) {
-    __shared__ int sh[SEAM ? 3 * 256 : 1];
+    __shared__ int sh[SEAM ? 3 * FFB_REORDER_THREADS : 1];
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int hidx[3] = {-1, -1, -1};
     if (j < n) {
@@ -394,7 +400,7 @@ int launch_sort(Context &c, const SeamParams *seam) {
         if (use_radix)
             k_keys<<<blocks_for(n, 256), 256, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
         else
-            k_keys_rank<<<blocks_for(n, 256), 256, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
+            k_keys_rank<<<blocks_for(n, FFB_KEYS_THREADS), FFB_KEYS_THREADS, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
         launches++;
     }
     launches += exclusive_scan_inplace(c, s.bin_start, (size_t)g.nbins + 2);
@@ -407,7 +413,7 @@ int launch_sort(Context &c, const SeamParams *seam) {
         // slot = bin_start[key] + arrival rank. The arrival order inside a bin is arbitrary (integer
         // atomics); k_reorder re-ranks the members of every multi-particle bin by original index,
         // so the final order is the deterministic (key, original index) order all the same.
-        k_place<<<blocks_for(n, 256), 256, 0, c.stream>>>(s.key[0], s.val[0], s.bin_start, s.key[1], s.val[1], n);
+        k_place<<<blocks_for(n, FFB_KEYS_THREADS), FFB_KEYS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.bin_start, s.key[1], s.val[1], n);
         launches++;
         std::swap(s.key[0], s.key[1]);
         std::swap(s.val[0], s.val[1]);
@@ -456,9 +462,9 @@ int launch_sort(Context &c, const SeamParams *seam) {
     a.nstreams = t;
     for (; t < 15; t++) { a.src[t] = nullptr; a.dst[t] = nullptr; }
     if (seam)
-        k_reorder<true><<<blocks_for(n, 256), 256, 0, c.stream>>>(a, *seam, s.key[0], s.val[0], s.bin_start, src.orig, dst.orig, n);
+        k_reorder<true><<<blocks_for(n, FFB_REORDER_THREADS), FFB_REORDER_THREADS, 0, c.stream>>>(a, *seam, s.key[0], s.val[0], s.bin_start, src.orig, dst.orig, n);
     else
-        k_reorder<false><<<blocks_for(n, 256), 256, 0, c.stream>>>(a, SeamParams{}, s.key[0], s.val[0], s.bin_start, src.orig, dst.orig, n);
+        k_reorder<false><<<blocks_for(n, FFB_REORDER_THREADS), FFB_REORDER_THREADS, 0, c.stream>>>(a, SeamParams{}, s.key[0], s.val[0], s.bin_start, src.orig, dst.orig, n);
     launches++;
     c.cur ^= 1;
     c.sorted = true;
