@@ -48,6 +48,43 @@ def _view(ptr, count, typestr, device):
     return torch.as_tensor(_DevArray(ptr, count, typestr), device=device)
 
 
+def _staged(t):
+    """gloo cannot move CUDA tensors point to point: stage them through host memory. (Used when two
+    ranks share one GPU in the tests; on a multi-GPU box the backend is NCCL and nothing is staged.)"""
+    return t.is_cuda and dist.get_backend() == "gloo"
+
+
+def _sendrecv(items):
+    """One batched neighbour exchange. items: (send tensor or None, recv tensor or None, peer)."""
+    ops, staged = [], []
+    for send, recv, peer in items:
+        if send is not None:
+            s = send.contiguous()
+            ops.append(dist.P2POp(dist.isend, s.cpu() if _staged(s) else s, peer))
+        if recv is not None:
+            if _staged(recv):
+                buf = torch.empty(recv.shape, dtype=recv.dtype)
+                staged.append((recv, buf))
+                ops.append(dist.P2POp(dist.irecv, buf, peer))
+            else:
+                ops.append(dist.P2POp(dist.irecv, recv, peer))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    for recv, buf in staged:
+        recv.copy_(buf)
+
+
+def _all_gather(outs, t):
+    if _staged(t):
+        bufs = [torch.empty(o.shape, dtype=o.dtype) for o in outs]
+        dist.all_gather(bufs, t.cpu())
+        for o, b in zip(outs, bufs):
+            o.copy_(b)
+    else:
+        dist.all_gather(outs, t)
+
+
 class GpuBackend:
     """The stages on one GPU through the C ABI, with zero-copy views for the exchanges."""
 
@@ -206,30 +243,23 @@ class SlabSimulation:
         rows = to_up.shape[0]
         dev = self.device
         cnt_out = {self.up: to_up, self.down: to_down}
-        ops, cnt_in = [], {}
+        items, cnt_in = [], {}
         for peer, blk in cnt_out.items():
             if peer is None:
                 continue
             cnt_in[peer] = torch.zeros(1, dtype=torch.int64, device=dev)
-            ops.append(dist.P2POp(dist.isend, torch.tensor([blk.shape[1]], dtype=torch.int64, device=dev), peer))
-            ops.append(dist.P2POp(dist.irecv, cnt_in[peer], peer))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        ops, recv = [], {}
+            items.append((torch.tensor([blk.shape[1]], dtype=torch.int64, device=dev), cnt_in[peer], peer))
+        _sendrecv(items)
+        items, recv = [], {}
         for peer, blk in cnt_out.items():
             if peer is None:
                 continue
             m = int(cnt_in[peer].item())
             recv[peer] = torch.empty((rows, m), dtype=torch.float32, device=dev)
             if blk.shape[1]:
-                ops.append(dist.P2POp(dist.isend, blk.contiguous(), peer))
                 self.exchanged_bytes += blk.numel() * 4
-            if m:
-                ops.append(dist.P2POp(dist.irecv, recv[peer], peer))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+            items.append((blk if blk.shape[1] else None, recv[peer] if m else None, peer))
+        _sendrecv(items)
         empty = torch.empty((rows, 0), dtype=torch.float32, device=dev)
         return recv.get(self.down, empty), recv.get(self.up, empty)
 
@@ -245,30 +275,20 @@ class SlabSimulation:
     def _halo_exchange(self):
         """Owned boundary planes of u, v, w -> the neighbours' halo planes (in place, zero copy)."""
         H = self.halo
-        ops, keep = [], []
+        items = []
         for d in range(3):
             f, kbase = self.backend.field_planes(d)
             extra = 1 if d == 2 else 0                       # w has one more plane; plane ke belongs to the upper slab
             o0, o1 = self.kb - kbase, self.ke - kbase
             if self.up is not None:
                 send = f[o1 - H:o1].contiguous()
-                recv = f[o1:o1 + H + extra]
-                buf = torch.empty_like(recv)
-                keep.append((recv, buf))
-                ops += [dist.P2POp(dist.isend, send, self.up), dist.P2POp(dist.irecv, buf, self.up)]
+                items.append((send, f[o1:o1 + H + extra], self.up))
                 self.exchanged_bytes += send.numel() * 4
             if self.down is not None:
                 send = f[o0:o0 + H + extra].contiguous()
-                recv = f[o0 - H:o0]
-                buf = torch.empty_like(recv)
-                keep.append((recv, buf))
-                ops += [dist.P2POp(dist.isend, send, self.down), dist.P2POp(dist.irecv, buf, self.down)]
+                items.append((send, f[o0 - H:o0], self.down))
                 self.exchanged_bytes += send.numel() * 4
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
-        for recv, buf in keep:
-            recv.copy_(buf)
+        _sendrecv(items)
 
     # ---- one substep, device-side plumbing (GpuBackend) ----------------------------------------------
     INT_MIN, INT_MAX = -(2 ** 31), 2 ** 31 - 1
@@ -291,17 +311,15 @@ class SlabSimulation:
         """Exchange the fixed-size packed buffers with both neighbours. Returns (received from below,
         received from above, local overflow flag, headers [up_send, dn_send, up_recv, dn_recv])."""
         rows = self.backend.record_floats()
-        ops = []
+        items = []
         if self.up is not None:
-            ops += [dist.P2POp(dist.isend, b["up_send"], self.up), dist.P2POp(dist.irecv, b["up_recv"], self.up)]
+            items.append((b["up_send"], b["up_recv"], self.up))
         if self.down is not None:
-            ops += [dist.P2POp(dist.isend, b["dn_send"], self.down), dist.P2POp(dist.irecv, b["dn_recv"], self.down)]
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+            items.append((b["dn_send"], b["dn_recv"], self.down))
+        _sendrecv(items)
         hdr = torch.stack([b[k][cap * rows:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()
         self.exchanged_bytes += (int(hdr[0, 0]) + int(hdr[1, 0])) * rows * 4
-        overflow = bool(ops) and int(hdr[:, 1].max()) != 0
+        overflow = bool(items) and int(hdr[:, 1].max()) != 0
         n_up = int(hdr[2, 0]) if self.up is not None else 0
         n_dn = int(hdr[3, 0]) if self.down is not None else 0
         return n_dn, n_up, overflow, hdr
@@ -310,7 +328,7 @@ class SlabSimulation:
         """max over all ranks (buffer sizes of an exchange must match on both sides of every face)."""
         if self.world == 1:
             return int(value)
-        t = torch.tensor([int(value)], device=self.device, dtype=torch.int64)
+        t = torch.tensor([int(value)], dtype=torch.int64, device="cpu" if dist.get_backend() == "gloo" else self.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return int(t.item())
 
@@ -421,14 +439,12 @@ class SlabSimulation:
         """Exchange the two-section buffers with both neighbours; returns the four 8-int headers
         [up_send, dn_send, up_recv, dn_recv] (rows of absent neighbours are zero)."""
         rows = self.backend.record_floats()
-        ops = []
+        items = []
         if self.up is not None:
-            ops += [dist.P2POp(dist.isend, b["up_send"], self.up), dist.P2POp(dist.irecv, b["up_recv"], self.up)]
+            items.append((b["up_send"], b["up_recv"], self.up))
         if self.down is not None:
-            ops += [dist.P2POp(dist.isend, b["dn_send"], self.down), dist.P2POp(dist.irecv, b["dn_recv"], self.down)]
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+            items.append((b["dn_send"], b["dn_recv"], self.down))
+        _sendrecv(items)
         off = {"up_send": (caps[0] + caps[1]) * rows, "up_recv": (caps[0] + caps[1]) * rows,
                "dn_send": (caps[2] + caps[3]) * rows, "dn_recv": (caps[2] + caps[3]) * rows}
         hdr = torch.stack([b[k][off[k]:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()
@@ -444,17 +460,15 @@ class SlabSimulation:
         if plan is None:
             plan = self._halo_plan = self.backend.halo_plan(self.kb, self.ke, self.halo, self.up is not None,
                                                             self.down is not None)
-        ops = []
+        items = []
         for up, down in plan:
             if up is not None:
-                ops += [dist.P2POp(dist.isend, up[0], self.up), dist.P2POp(dist.irecv, up[1], self.up)]
+                items.append((up[0], up[1], self.up))
                 self.exchanged_bytes += up[0].numel() * 4
             if down is not None:
-                ops += [dist.P2POp(dist.isend, down[0], self.down), dist.P2POp(dist.irecv, down[1], self.down)]
+                items.append((down[0], down[1], self.down))
                 self.exchanged_bytes += down[0].numel() * 4
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+        _sendrecv(items)
 
     def sync_from_backend(self):
         """Pull the resident streams back into self.streams / self.ids (tests, gather)."""
@@ -513,13 +527,13 @@ class SlabSimulation:
         ns = len(self.streams)
         blk = torch.stack(self.streams + [self.ids.view(torch.float32)], 0).contiguous()
         counts = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
-        dist.all_gather(counts, torch.tensor([blk.shape[1]], dtype=torch.int64, device=self.device))
+        _all_gather(counts, torch.tensor([blk.shape[1]], dtype=torch.int64, device=self.device))
         parts = [torch.empty((ns + 1, int(c.item())), dtype=torch.float32, device=self.device) for c in counts]
         mx = max(int(c.item()) for c in counts)
         padded = torch.zeros((ns + 1, mx), dtype=torch.float32, device=self.device)
         padded[:, :blk.shape[1]] = blk
         bufs = [torch.zeros_like(padded) for _ in range(self.world)]
-        dist.all_gather(bufs, padded)
+        _all_gather(bufs, padded)
         for r in range(self.world):
             parts[r] = bufs[r][:, :int(counts[r].item())]
         allp = torch.cat(parts, 1)
@@ -545,7 +559,7 @@ def make_slab_dam_break(I, J, K, dx, rank, world, ppc, v0, apic, seed, device):
     streams = [torch.from_numpy(np.ascontiguousarray(c)).to(device) for c in cols]
     counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     if world > 1:
-        dist.all_gather(counts, torch.tensor([n], dtype=torch.int64, device=device))
+        _all_gather(counts, torch.tensor([n], dtype=torch.int64, device=device))
     else:
         counts[0][0] = n
     base = int(sum(int(c.item()) for c in counts[:rank]))
