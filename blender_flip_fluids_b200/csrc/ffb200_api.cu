@@ -588,6 +588,14 @@ int ffb200_slab_route_ghosts_begin(ffb200_context *ctx, int k_begin, int k_end, 
     });
 }
 
+int ffb200_slab_route_end_known(ffb200_context *ctx, int leaving, int *counts) {
+    return guarded("ffb200_slab_route_end_known", ctx, [&](Context &c) {
+        if (!counts) throw std::invalid_argument("null counts pointer");
+        if (leaving < 0) throw std::domain_error("negative count of leaving particles");
+        launch_route_end(c, counts, leaving);
+    });
+}
+
 int ffb200_slab_route_end(ffb200_context *ctx, int *counts) {
     return guarded("ffb200_slab_route_end", ctx, [&](Context &c) {
         if (!counts) throw std::invalid_argument("null counts pointer");

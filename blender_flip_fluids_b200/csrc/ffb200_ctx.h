@@ -146,7 +146,7 @@ int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b,
 // caps (ghost_layers > 0 only): {up migrants, up ghosts, down migrants, down ghosts} section capacities
 int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, float *block_down, int cap, int ghost_layers = 0,
                        const int *caps = nullptr);
-int launch_route_end(Context &c, int counts_host[3]);
+int launch_route_end(Context &c, int counts_host[3], int known_holes = -1);
 int launch_append(Context &c, const float *block, int count, bool as_ghost);
 
 }  // namespace ffb200

@@ -104,7 +104,7 @@ __global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int
 
 // The same routing with the NEXT substep's ghost exchange folded in, so that one neighbour
 // exchange per substep carries both. Blocks have two sections, [migrants][ghost copies] (their
-// capacities are per face: FaceCaps), and an 8-int header {migrants, overflow, ghosts, overflow, 0...}.
+// capacities are per face: FaceCaps), and an 8-int header {migrants, overflow, ghosts, overflow, holes, 0...}.
 //  * an owned particle that stays and sits within `g` cell planes of a slab face is copied into the
 //    ghost section for that neighbour (it is what k_pack_layers would select at the start of the
 //    next substep);
@@ -157,7 +157,8 @@ __global__ void k_write_header2(const int *counters, int which_m, int which_g, i
     const int m = counters[which_m], gc = counters[which_g];
     h[0] = m; h[1] = m > cap ? 1 : 0;
     h[2] = gc; h[3] = gc > cap_g ? 1 : 0;
-    h[4] = h[5] = h[6] = h[7] = 0;
+    h[4] = counters[3];                                        // particles leaving the resident set (holes to fill)
+    h[5] = h[6] = h[7] = 0;
 }
 
 // holes below the new count, and survivors at or above it
@@ -278,15 +279,19 @@ int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, floa
     return launches;
 }
 
-int launch_route_end(Context &c, int counts_host[3]) {
+// known_holes >= 0: the caller already read the number of leaving particles from a block header (h[4] of
+// ffb200_slab_route_ghosts_begin's blocks, available after its exchange): no second synchronisation.
+int launch_route_end(Context &c, int counts_host[3], int known_holes) {
     int launches = 0;
     const int n = g_route.n;
     uint32_t *holes = c.sort.key[1], *front_hole = c.sort.val[1], *tail_stay = c.sort.key[0];
     const uint8_t *leave_flag = reinterpret_cast<const uint8_t *>(c.sort.val[0]);
     Streams cur = streams_of(c, c.cur);
-    int h[4] = {0, 0, 0, 0};
-    FFB_CUDA(cudaMemcpyAsync(h, c.slab_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    FFB_CUDA(cudaStreamSynchronize(c.stream));
+    int h[4] = {0, 0, 0, known_holes};
+    if (known_holes < 0) {
+        FFB_CUDA(cudaMemcpyAsync(h, c.slab_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+    }
     const int nholes = h[3], n_new = n - nholes;
     if (nholes > 0 && n_new > 0) {
         FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 2 * sizeof(int), c.stream));

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ffb200_slab_route": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)],
     "ffb200_slab_route_begin": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int],
     "ffb200_slab_route_end": [C.c_void_p, C.POINTER(C.c_int)],
+    "ffb200_slab_route_end_known": [C.c_void_p, C.c_int, C.POINTER(C.c_int)],
     "ffb200_slab_route_ghosts_begin": [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)],
     "ffb200_slab_append": [C.c_void_p, C.c_void_p, C.c_int, C.c_int],
     "ffb200_sort_particles": [C.c_void_p],
@@ -250,6 +251,12 @@ class FlipContext:
         self._call("ffb200_slab_route_end", counts)
         self.n = counts[0]
         return counts[0], counts[1], counts[2]
+
+    def slab_route_end_known(self, leaving):
+        counts = (C.c_int * 3)()
+        self._call("ffb200_slab_route_end_known", int(leaving), counts)
+        self.n = counts[0]
+        return counts[0]
 
     def slab_route_ghosts_begin(self, k_begin, k_end, ghost_layers, block_up, block_down, capacities):
         """capacities = (up migrants, up ghosts, down migrants, down ghosts)."""

@@ -172,8 +172,11 @@ class GpuBackend:
         self.ctx.slab_route_begin(k_begin, k_end, block_up.data_ptr() if block_up is not None else 0,
                                   block_down.data_ptr() if block_down is not None else 0, capacity)
 
-    def route_end(self):
-        return self.ctx.slab_route_end()
+    def route_end(self, leaving=None):
+        """leaving: the header's count of particles leaving the resident set, if already known."""
+        if leaving is None:
+            return self.ctx.slab_route_end()
+        return self.ctx.slab_route_end_known(leaving), None, None
 
     def new_block2(self, cap_m, cap_g):
         """Two-section packed buffer [cap_m migrants][cap_g ghost copies] + an 8-int header (ffb200_slab_route_ghosts_begin)."""
@@ -397,8 +400,8 @@ class SlabSimulation:
         be.route_ghosts_begin(kb, ke, g, b2["up_send"] if self.up is not None else None,
                               b2["dn_send"] if self.down is not None else None, caps)
         hdr = self._swap_blocks2(caps, b2)            # one synchronisation serves the exchange and the routing
-        n_owned, _, _ = be.route_end()
         up, dn = self.up is not None, self.down is not None
+        n_owned, _, _ = be.route_end(int(hdr[0, 4]) if up else (int(hdr[1, 4]) if dn else None))
         # true counts of both directions per face (identical knowledge on both ranks of the face)
         self._face_counts = {"up": (max(int(hdr[0, 0]), int(hdr[2, 0])), max(int(hdr[0, 2]), int(hdr[2, 2]))),
                              "dn": (max(int(hdr[1, 0]), int(hdr[3, 0])), max(int(hdr[1, 2]), int(hdr[3, 2])))}

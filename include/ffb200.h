@@ -155,7 +155,8 @@ int ffb200_slab_route_end(ffb200_context *ctx, int *counts);
 /* ffb200_slab_route_begin with the NEXT substep's ghost exchange folded in, so that one neighbour
  * exchange per substep carries migrants and ghost copies. A block holds two sections,
  * [migrant records][ghost-copy records], followed by an 8-int header
- * {migrants, overflow, ghosts, overflow, 0, 0, 0, 0} (true counts even on overflow).
+ * {migrants, overflow, ghosts, overflow, leaving, 0, 0, 0} (true counts even on overflow; `leaving` =
+ * particles removed from the resident set, for ffb200_slab_route_end_known).
  * capacities = {up migrants, up ghosts, down migrants, down ghosts}: per face, so that both ranks of
  * a face can size their buffers from numbers they both know (the previous exchange's headers).
  * Owned particles that stay within ghost_layers cell planes of a face are copied into the ghost
@@ -165,6 +166,11 @@ int ffb200_slab_route_end(ffb200_context *ctx, int *counts);
  * ffb200_slab_route_end, then append the received sections (ffb200_slab_append, as_ghost = 0 / 1). */
 int ffb200_slab_route_ghosts_begin(ffb200_context *ctx, int k_begin, int k_end, int ghost_layers,
                                    float *block_up, float *block_down, const int *capacities);
+/* ffb200_slab_route_end for a caller that already knows how many particles leave the resident set:
+ * header word 4 of either block written by ffb200_slab_route_ghosts_begin, which the caller reads
+ * together with the received counts after the exchange. Saves the second host synchronisation.
+ * counts[1], counts[2] (migrants sent up / down) are not filled: they are in the headers too. */
+int ffb200_slab_route_end_known(ffb200_context *ctx, int leaving, int *counts);
 /* Append `count` packed records (device buffer) to the resident particles. as_ghost marks them
  * (top id bit) as ghost copies: they take part in P2G and are dropped by the next
  * ffb200_slab_route wherever they have moved. */

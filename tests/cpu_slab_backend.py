@@ -170,7 +170,7 @@ class CpuOracleFastBackend(CpuOracleBackend):
             self._write(blk, 0, cap_m, np.nonzero(mig)[0])
             self._write(blk, cap_m, cap_g, np.nonzero(gh)[0])
             nm, ng = int(mig.sum()), int(gh.sum())
-            blk[(cap_m + cap_g) * rows:].view(torch.int32)[:] = torch.tensor([nm, int(nm > cap_m), ng, int(ng > cap_g), 0, 0, 0, 0],
+            blk[(cap_m + cap_g) * rows:].view(torch.int32)[:] = torch.tensor([nm, int(nm > cap_m), ng, int(ng > cap_g), int(leave.sum()), 0, 0, 0],
                                                                                dtype=torch.int32)
         ids = ids.copy()
         ids[keep] |= self.GHOST                                  # sent, and kept here as the new owner's ghost copy
@@ -178,7 +178,8 @@ class CpuOracleFastBackend(CpuOracleBackend):
         self._leave = leave
         self._counts = (int((up & sent).sum()), int((down & sent).sum()))
 
-    def route_end(self):
+    def route_end(self, leaving=None):
+        assert leaving is None or leaving == int(self._leave.sum())
         stay = torch.from_numpy(np.nonzero(~self._leave)[0])
         self.streams = [s.index_select(0, stay) for s in self.streams]
         self.ids = self.ids.index_select(0, stay)
