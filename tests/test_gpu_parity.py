@@ -224,14 +224,31 @@ for name in ("p2g_flip_23x21x25_seams", "p2g_apic_23x21x25_seams"):
                 assert a.tobytes() == b.tobytes()
         ks = hkey[perm].astype(np.int64)
         assert (np.diff(ks) >= 0).all() and (np.diff(perm.astype(np.int64))[np.diff(ks) == 0] > 0).all()
+# resident G2P -> advection on the reference's own fields (bit-exact with and without the stage-1 reuse)
+for name in ("scene_flip_24x20x22_nondyadic", "scene_apic_22x24x20_dyadic"):
+    meta, g = load_golden(name)
+    apic = meta["method"] == "apic"
+    aff = [g.get("s0_aff" + c) for c in "xyz"]
+    with engine.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        ctx.set_solid(g["s2_phi"], g["s2_near"])
+        ctx.set_particles(g["s0_pos"], g["s0_vel"], *aff)
+        ctx.set_velocity_field(g["s2_u"], g["s2_v"], g["s2_w"])
+        ctx.set_velocity_field(g["s2_su"], g["s2_sv"], g["s2_sw"], saved=True)
+        ctx.sort_particles()
+        ctx.g2p(1 if apic else 0, meta["ratio"])
+        ctx.advect(meta["dt"], meta["cfl"], True)
+        pos, vel, *_ = ctx.get_particles(pos=True, vel=True, affine=apic)
+    assert vel.tobytes() == g["s3_vel"].tobytes() and pos.tobytes() == g["s4_pos"].tobytes()
 print("ok")
 '''
 
 
 @pytest.mark.parametrize("env", [{"FFB200_P2G_VARIANT": "1"}, {"FFB200_P2G_VARIANT": "2"}, {"FFB200_P2G_VARIANT": "3"},
-                                 {"FFB200_SORT": "radix"}])
+                                 {"FFB200_SORT": "radix"}, {"FFB200_P2G_STREAMS": "0", "FFB200_FUSE_SEAM": "0"},
+                                 {"FFB200_REUSE_G2P": "0"}])
 def test_alternate_kernel_paths(env, tmp_path):
-    """The earlier-generation P2G kernels and the LSD radix sort stay selectable and correct."""
+    """The earlier-generation P2G kernels, the LSD radix sort and the switched-off fusions (single P2G
+    stream, stand-alone membership pass, no RK3 stage-1 reuse) stay selectable and correct."""
     import os
     import subprocess
     import sys
