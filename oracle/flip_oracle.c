@@ -682,3 +682,70 @@ double flip_oracle_max_particle_speed(int n, const float *vel) {
     }
     return sqrt(maxsq);
 }
+
+/* ---- marker-particle removal (next-row f2; oracle groundwork, no device path yet) -------------------
+ * FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7773-7851) with
+ * _getMarkerParticleSpeedLimit (:7723-7771) and MeshLevelSet::trilinearInterpolateSolidPoints
+ * (meshlevelset.h:203-216, 333-339), for the default configuration: all domain boundaries closed, no
+ * lifetime attribute. removed[i] = 1 for the particles ParticleSystem::removeParticles would drop;
+ * *num_extreme = _currentExtremeVelocityParticlesRemoved. The per-cell cap runs in particle-index
+ * order and a particle is counted BEFORE its extreme-velocity test, exactly as in the reference. */
+static float speed_limit(int n, const float *vel, double dx, double dt, double cfl, int max_frame_steps) {
+    double maxParticleSpeed = 0.0;
+    double speedLimitStep = cfl * dx / dt;
+    int counts[64];
+    for (int i = 0; i < max_frame_steps; i++) counts[i] = 0;
+    for (int i = 0; i < n; i++) {
+        const float *v = vel + 3 * (size_t)i;
+        double speed = (double)sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);      /* vmath::length */
+        int idx = (int)fmin(floor(speed / speedLimitStep), max_frame_steps - 1);
+        counts[idx]++;
+        maxParticleSpeed = speed > maxParticleSpeed ? speed : maxParticleSpeed;
+    }
+    double maxpct = 0.0005;                                   /* _maxExtremeVelocityRemovalPercent */
+    int maxabs = 35;                                          /* _maxExtremeVelocityRemovalAbsolute */
+    int maxRemovalCount = (int)fmin((int)((double)n * maxpct), maxabs);
+    double maxspeed = max_frame_steps * speedLimitStep;
+    int currentRemovalCount = 0;
+    for (int i = max_frame_steps - 1; i > 0; i--) {
+        if (currentRemovalCount + counts[i] > maxRemovalCount) break;
+        currentRemovalCount += counts[i];
+        int steps = i + 4 > max_frame_steps ? i + 4 : max_frame_steps;      /* _minTimeStepIncreaseForRemoval = 4 */
+        maxspeed = steps * speedLimitStep;
+    }
+    double lower = 0.90 * maxParticleSpeed, thr = 0.99999 * maxParticleSpeed;
+    int nlower = 0, nthr = 0;
+    for (int i = 0; i < n; i++) {
+        const float *v = vel + 3 * (size_t)i;
+        double speed = (double)sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (speed >= lower && speed < thr) nlower++;
+        if (speed >= thr) nthr++;
+    }
+    if (nthr <= 6 && nlower <= 6) maxspeed = thr < maxspeed ? thr : maxspeed;   /* _maxExtremeVelocityOutlierRemovalAbsolute */
+    return (float)maxspeed;
+}
+
+void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const float *pos, const float *vel,
+                                  const float *phi, double dt, double cfl, int max_per_cell, int extreme_removal,
+                                  uint8_t *removed, int *num_extreme) {
+    solid s;
+    s.I = I; s.J = J; s.K = K; s.dx = dx; s.phi = phi; s.near = 0; s.cfl = cfl;
+    int *count = (int *)calloc((size_t)I * J * K, sizeof(int));
+    float maxspeed = speed_limit(n, vel, dx, dt, cfl, 6);     /* _maxFrameTimeSteps = 6 */
+    double maxspeedsq = maxspeed * maxspeed;                  /* float product, widened */
+    int extreme = 0;
+    for (int i = 0; i < n; i++) {
+        const float *p = pos + 3 * (size_t)i, *v = vel + 3 * (size_t)i;
+        removed[i] = sdf_sample(&s, p) < 0.0f;
+        if (removed[i]) continue;
+        int gi = pos2idx(p[0], dx), gj = pos2idx(p[1], dx), gk = pos2idx(p[2], dx);
+        if (!in_range(gi, gj, gk, I, J, K)) { removed[i] = 1; continue; }   /* the reference would throw here */
+        size_t c = flat(gi, gj, gk, I, J);
+        if (count[c] >= max_per_cell) { removed[i] = 1; continue; }
+        count[c]++;
+        float d = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];    /* vmath::dot */
+        if (extreme_removal && d > maxspeedsq) { removed[i] = 1; extreme++; continue; }
+    }
+    *num_extreme = extreme;
+    free(count);
+}

@@ -516,9 +516,31 @@ static int mode_extrapolate() {
     return 0;
 }
 
+// remove: FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7773-7851) on given particles and solid SDF.
+static int mode_remove() {
+    int I = kvi("I"), J = kvi("J"), K = kvi("K");
+    double dx = kvd("dx"), dt = kvd("dt");
+    FluidSimulation sim(I, J, K, dx);
+    sim.disableConsoleOutput();
+    shell_sim(sim, I, J, K, dx, false);
+    sim._CFLConditionNumber = kvd("cfl", "5");
+    sim._maxMarkerParticlesPerCell = kvi("max_per_cell", "250");
+    sim._isExtremeVelocityRemovalEnabled = kvi("extreme", "1") != 0;
+    sim._solidSDF = MeshLevelSet(I, J, K, dx);
+    load_grid("in_phi", sim._solidSDF._phi);
+    size_t before = sim._markerParticles.size();
+    double t0 = now();
+    sim._removeMarkerParticles(dt);
+    double t = now() - t0;
+    dump_particles(sim._markerParticles, false, "out_");
+    printf("{\"mode\": \"remove\", \"before\": %zu, \"after\": %zu, \"extreme\": %d, \"threads\": %d, \"t_remove\": %.6f}\n",
+           before, sim._markerParticles.size(), sim._currentExtremeVelocityParticlesRemoved, ThreadUtils::getMaxThreadCount(), t);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 3) {
-        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene|extrapolate> <workdir> key=value ...\n");
+        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene|extrapolate|remove> <workdir> key=value ...\n");
         return 2;
     }
     std::string mode = argv[1];
@@ -536,6 +558,7 @@ int main(int argc, char **argv) {
     if (mode == "advect") return mode_advect();
     if (mode == "scene") return mode_scene();
     if (mode == "extrapolate") return mode_extrapolate();
+    if (mode == "remove") return mode_remove();
     fprintf(stderr, "ref_harness: unknown mode %s\n", mode.c_str());
     return 2;
 }

@@ -173,6 +173,32 @@ def fixture_extrapolate(name, scene_npz, layers, threads):
     print(name, m2)
 
 
+def fixture_remove(name, advect_npz, seed):
+    """_removeMarkerParticles on post-advection positions (reference-built solid SDF of the advect fixture):
+    extra particles inside the obstacle, one cell crowded beyond the 250 cap, a few extreme velocities."""
+    z = np.load(os.path.join(OUT, advect_npz + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    I, J, K, dx, dt = meta["I"], meta["J"], meta["K"], meta["dx"], meta["dt"]
+    rng = np.random.default_rng(seed)
+    pos = z["out_pos"].copy()
+    inside = (np.array([0.12, 0.05, 0.11]) + rng.normal(0, 0.012, (400, 3))).astype(np.float32)     # around the sphere obstacle
+    crowd = ((np.array([9.0, 8.0, 10.0]) + rng.random((330, 3))) * dx).astype(np.float32)          # one cell, > 250
+    pos = np.concatenate([pos[: len(pos) // 2], inside, pos[len(pos) // 2:], crowd])
+    pos = pos[rng.permutation(len(pos))]                                                           # index order matters
+    vel = (rng.standard_normal(pos.shape) * 0.4).astype(np.float32)
+    fast = rng.choice(len(pos), 9, replace=False)
+    vel[fast] *= np.array([40, 45, 50, 55, 60, 300, 310, 320, 2000], np.float32)[:, None]          # histogram tail + outliers
+    d = tempfile.mkdtemp(prefix="ffgold_")
+    save_inputs(d, pos=pos, vel=vel, phi=z["in_phi"])
+    info = run("remove", d, I=I, J=J, K=K, dx=float(dx), dt=float(dt), cfl=5)
+    out_pos, out_vel = np.load(os.path.join(d, "out_pos.npy")), np.load(os.path.join(d, "out_vel.npy"))
+    shutil.rmtree(d)
+    m2 = dict(I=I, J=J, K=K, dx=dx, dt=dt, cfl=5.0, particles=int(len(pos)), survivors=int(len(out_pos)), extreme=int(info["extreme"]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), in_pos=pos, in_vel=vel, in_phi=z["in_phi"],
+                        out_pos=out_pos, out_vel=out_vel)
+    print(name, m2)
+
+
 if __name__ == "__main__":
     if not os.path.exists(HARNESS):
         sys.exit("build oracle/_ref first: make -C oracle -j8 all")
@@ -189,3 +215,5 @@ if __name__ == "__main__":
     # valid-face extrapolation of the reference's own P2G output (inputs: s1_* of the scene fixtures)
     fixture_extrapolate("extrapolate_flip_24x20x22", "scene_flip_24x20x22_nondyadic", 12, (1, 3, 16))
     fixture_extrapolate("extrapolate_apic_22x24x20", "scene_apic_22x24x20_dyadic", 12, (1, 3, 16))
+    # marker-particle removal (oracle groundwork for the next row f2)
+    fixture_remove("remove_24x20x22", "advect_collide_24x20x22", 41)

@@ -124,3 +124,27 @@ def test_extrapolate_edge_cases(oracle):
     assert out[3, 3, 5] == grid[3, 3, 4] and out[3, 3, 3] == grid[3, 3, 4]
     changed = np.argwhere(out != grid)
     assert len(changed) <= 6
+
+
+def test_remove_particles_fixture(oracle):
+    """FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7723-7851): survivors of the unmodified
+    reference, in order; groundwork for SURVEY §8f row f2 (no device path yet)."""
+    meta, g = load_golden("remove_24x20x22")
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    removed, extreme = oracle.remove_particles(I, J, K, dx, g["in_pos"], g["in_vel"], g["in_phi"], meta["dt"], meta["cfl"])
+    keep = removed == 0
+    assert int(keep.sum()) == meta["survivors"] < meta["particles"]
+    assert extreme == meta["extreme"] > 0
+    assert bits_equal(g["in_pos"][keep], g["out_pos"]) and bits_equal(g["in_vel"][keep], g["out_vel"])
+    # each of the three rules removes something in this fixture: solid, crowded cell, extreme speed
+    no_extreme, n0 = oracle.remove_particles(I, J, K, dx, g["in_pos"], g["in_vel"], g["in_phi"], meta["dt"], meta["cfl"],
+                                             extreme_removal=False)
+    assert n0 == 0 and 0 < no_extreme.sum() < removed.sum()
+    no_cap, _ = oracle.remove_particles(I, J, K, dx, g["in_pos"], g["in_vel"], g["in_phi"], meta["dt"], meta["cfl"],
+                                        max_per_cell=1 << 30, extreme_removal=False)
+    assert 0 < no_cap.sum() < no_extreme.sum()
+    # per-cell cap keeps the first 250 of a cell in index order
+    ci = np.floor(g["in_pos"].astype(np.float64) / dx).astype(np.int64)
+    crowded = (ci == [9, 8, 10]).all(axis=1) & (no_cap == 0)
+    assert crowded.sum() > 250 and (no_extreme[crowded] == 0).sum() == 250
+    assert (no_extreme[np.flatnonzero(crowded)[:250]] == 0).all()
