@@ -169,6 +169,7 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->solid_clear[0]);
     dev_free(c->solid_clear[1]);
     dev_free(c->slab_counters);
+    dev_free(c->remove_words);
     dev_free(c->sort.edge_count);
     for (int q = 0; q < 3; q++) dev_free(c->k1s[q]);
     for (auto &cs : c->sort.cell) {
@@ -702,6 +703,18 @@ int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed) {
         std::memcpy(&f, &bits, sizeof(f));
         *speed = std::sqrt((double)f);                         // sqrt(maxsq), maxsq the double of a float dot product
     }, false);
+}
+
+int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_condition_number, int max_particles_per_cell,
+                                   int max_frame_time_steps, int extreme_velocity_removal, int *num_remaining,
+                                   int *num_extreme_removed) {
+    return guarded("ffb200_remove_marker_particles", ctx, [&](Context &c) {
+        int remaining = 0, extreme = 0;
+        launch_remove_particles(c, dt, cfl_condition_number, max_particles_per_cell, max_frame_time_steps,
+                                extreme_velocity_removal, &remaining, &extreme);
+        if (num_remaining) *num_remaining = remaining;
+        if (num_extreme_removed) *num_extreme_removed = extreme;
+    });
 }
 
 int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_solid) {

@@ -101,6 +101,7 @@ struct Context {
 
     float guard_abs = -1.f, guard_per = -1.f;
     int *slab_counters = nullptr;        // 8 device ints for the slab pack/route kernels
+    uint32_t *remove_words = nullptr;    // device scalars of ffb200_remove_marker_particles (lazy)
     // API-call epoch: bumped by every call that may change particles or fields. An APIC ffb200_g2p
     // records it; an ffb200_advect that finds it unchanged reuses the G2P samples as RK3 stage 1.
     unsigned long long epoch = 0, k1_epoch = ~0ull;
@@ -123,6 +124,7 @@ struct SeamParams;                        // ffb200_seam.cuh
 // P2G membership words / home marks / edge list of every particle (what k_seam_home would do next).
 int launch_sort(Context &c, const SeamParams *seam = nullptr);
 int launch_binning_dump(Context &c, int32_t *cell, uint32_t *hkey, uint32_t *perm);   // device outputs
+int launch_exclusive_scan(Context &c, uint32_t *data, size_t n);                      // in place, on c.stream
 
 // ffb200_extrapolate.cu
 int launch_extrapolate(Context &c, int layers);          // GridUtils::extrapolateGrid on u, v, w in place
@@ -139,6 +141,11 @@ int launch_g2p(Context &c, int method, double ratio);
 int launch_solid_clearance(Context &c);                  // after every change of the solid SDF
 int launch_advect(Context &c, double dt, double cfl, int collide);
 int launch_max_speed_sq(Context &c, uint32_t *out_bits);  // bits of max float v.v over the owned particles (device word)
+
+// ffb200_remove.cu
+// _removeMarkerParticles on the resident particles; updates c.n, leaves the survivors in host order
+int launch_remove_particles(Context &c, double dt, double cfl, int max_per_cell, int max_frame_steps, int extreme_on,
+                            int *remaining, int *extreme_removed);
 
 // ffb200_slab.cu
 int slab_rows(Context &c);

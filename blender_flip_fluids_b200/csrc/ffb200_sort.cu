@@ -365,6 +365,8 @@ inline int blocks_for(int n, int threads) { return (n + threads - 1) / threads; 
 
 }  // namespace
 
+int launch_exclusive_scan(Context &c, uint32_t *data, size_t n) { return exclusive_scan_inplace(c, data, n); }
+
 int launch_unpack_aos(Context &c, const float *aos, float *const dst[3], int n) {
     if (n == 0) return 0;
     k_unpack_aos<<<blocks_for(n, 256), 256, 0, c.stream>>>(aos, dst[0], dst[1], dst[2], n);

@@ -92,6 +92,7 @@ SIGNATURES = {
     "ffb200_velocity_advector_advect": [C.c_void_p, C.c_int] + [_f32p] * 5 + [C.c_double, C.c_int] + [_f32p] * 3 + [_u8p] * 3,
     "ffb200_declare_resident": [C.c_void_p, C.c_uint],
     "ffb200_get_maximum_particle_speed": [C.c_void_p, C.POINTER(C.c_double)],
+    "ffb200_remove_marker_particles": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "ffb200_extrapolate_fluid_velocities": [C.c_void_p, _f32p, _f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int],
     "ffb200_update_marker_particle_velocities": [C.c_void_p, C.c_int] + [_f32p] * 11 + [C.c_int, C.c_double],
     "ffb200_advance_marker_particles": [C.c_void_p, C.c_int] + [_f32p] * 5 + [_u8p, C.c_double, C.c_double],
@@ -304,6 +305,14 @@ class FlipContext:
         out = C.c_double()
         self._call("ffb200_get_maximum_particle_speed", C.byref(out))
         return out.value
+
+    def remove_marker_particles(self, dt, cfl=5.0, max_particles_per_cell=250, max_frame_time_steps=6, extreme_velocity_removal=True):
+        """_removeMarkerParticles on the resident particles (solid SDF of set_solid). Returns (remaining, extreme removed)."""
+        remaining, extreme = C.c_int(), C.c_int()
+        self._call("ffb200_remove_marker_particles", C.c_double(dt), C.c_double(cfl), int(max_particles_per_cell),
+                   int(max_frame_time_steps), 1 if extreme_velocity_removal else 0, C.byref(remaining), C.byref(extreme))
+        self.n = remaining.value
+        return remaining.value, extreme.value
 
     def declare_resident(self, particles=False, field=False):
         """ffb200_declare_resident: the next host-buffer call may skip uploading what the device already holds."""

@@ -207,6 +207,20 @@ int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_
  * dot product v.v, bit-identical to the reference. Synchronises the stream. On a z-slab context the ghost
  * copies are ignored (reduce the per-rank values with a max). */
 int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed);
+/* FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7773-7851) with
+ * _getMarkerParticleSpeedLimit (:7723-7771) on the resident particles, for closed domain boundaries and no
+ * lifetime attribute: drops the particles inside the solid SDF of ffb200_set_solid
+ * (MeshLevelSet::trilinearInterpolateSolidPoints, phi < 0), those beyond the first
+ * max_particles_per_cell (_maxMarkerParticlesPerCell = 250) of a cell in particle-index order, and, when
+ * extreme_velocity_removal is set (_isExtremeVelocityRemovalEnabled), those faster than the limit derived
+ * from the speed histogram over max_frame_time_steps (_maxFrameTimeSteps = 6) bins of width CFL * dx / dt.
+ * The removed set is bit-for-bit the reference's. The survivors keep their relative order and are renumbered
+ * 0..num_remaining-1 (ParticleSystem::removeParticles); ffb200_get_particles then returns num_remaining
+ * rows. num_extreme_removed is _currentExtremeVelocityParticlesRemoved. Synchronises the stream.
+ * Whole-grid contexts only. */
+int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_condition_number, int max_particles_per_cell,
+                                   int max_frame_time_steps, int extreme_velocity_removal, int *num_remaining,
+                                   int *num_extreme_removed);
 
 /* ---- stages on resident data ---------------------------------------------------------------------- */
 

@@ -451,3 +451,60 @@ def test_maximum_particle_speed(eng, oracle):
     want = oracle.max_particle_speed(vel)
     d = (vel[:, 0] * vel[:, 0] + vel[:, 1] * vel[:, 1]) + vel[:, 2] * vel[:, 2]
     assert got == want == float(np.sqrt(np.float64(d.max())))
+
+
+def test_remove_particles_golden(eng):
+    """_removeMarkerParticles on the device == the unmodified reference (survivors in order, bit for bit),
+    whatever order the particles currently have on the device."""
+    meta, g = load_golden("remove_24x20x22")
+    for presort in (False, True):
+        with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+            ctx.set_solid(g["in_phi"], np.zeros(ctx.near_dims, np.uint8))
+            ctx.set_particles(g["in_pos"], g["in_vel"])
+            if presort:
+                ctx.sort_particles()
+            remaining, extreme = ctx.remove_marker_particles(meta["dt"], meta["cfl"])
+            p, v, *_ = ctx.get_particles()
+        assert (remaining, extreme) == (meta["survivors"], meta["extreme"])
+        assert bits_equal(p, g["out_pos"]) and bits_equal(v, g["out_vel"])
+
+
+@pytest.mark.parametrize("cap,extreme_on", [(250, True), (3, True), (1, False), (0, True)])
+def test_remove_particles_vs_oracle(eng, oracle, cap, extreme_on):
+    """Small per-cell caps put most cells over the cap (the order-exact ranking path); APIC rows travel with
+    the survivors; the compacted particles feed the next P2G like freshly uploaded ones."""
+    meta, g = load_golden("remove_24x20x22")
+    I, J, K, dx, dt = meta["I"], meta["J"], meta["K"], meta["dx"], meta["dt"]
+    rng = np.random.default_rng(100 + cap)
+    n = 30011
+    pos = (rng.random((n, 3)) * [I * dx, J * dx, K * dx]).astype(np.float32)
+    pos[: n // 4] = g["in_pos"][: n // 4]
+    pos[7] = [-0.5 * dx, 0.05, 0.05]                                    # outside the grid
+    vel = (rng.standard_normal((n, 3)) * 0.5).astype(np.float32)
+    vel[rng.choice(n, 11, replace=False)] *= np.float32(90.0)
+    aff = [rng.standard_normal((n, 3)).astype(np.float32) for _ in range(3)]
+    removed, want_extreme = oracle.remove_particles(I, J, K, dx, pos, vel, g["in_phi"], dt, 5.0, max_per_cell=cap,
+                                                    extreme_removal=extreme_on)
+    keep = removed == 0
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        ctx.set_solid(g["in_phi"], np.zeros(ctx.near_dims, np.uint8))
+        ctx.set_particles(pos, vel, *aff)
+        ctx.sort_particles()
+        remaining, extreme = ctx.remove_marker_particles(dt, 5.0, max_particles_per_cell=cap, extreme_velocity_removal=extreme_on)
+        p, v, ax, ay, az = ctx.get_particles(affine=True)
+        assert (remaining, extreme) == (int(keep.sum()), want_extreme)
+        assert bits_equal(p, pos[keep]) and bits_equal(v, vel[keep])
+        assert bits_equal(ax, aff[0][keep]) and bits_equal(ay, aff[1][keep]) and bits_equal(az, aff[2][keep])
+        if remaining:
+            radius = 0.5 * dx * np.sqrt(3.0)
+            ctx.p2g(radius, 1)
+            (u, vv, w), masks = ctx.get_velocity_field()
+            with eng.FlipContext(I, J, K, dx) as fresh:
+                (fu, fv, fw), fmasks = fresh.velocity_advector_advect(pos[keep], vel[keep], *[a[keep] for a in aff],
+                                                                      radius=radius, method=1)
+            for a, b in zip(masks, fmasks):
+                assert np.array_equal(a, b)
+            assert close(u, fu) and close(vv, fv) and close(w, fw)
+        # removing again changes nothing but the extreme-speed rule (its limit follows the new maximum)
+        again, _ = ctx.remove_marker_particles(dt, 5.0, max_particles_per_cell=max(cap, 1), extreme_velocity_removal=False)
+        assert again == remaining
