@@ -415,6 +415,18 @@ void get_field_impl(ContextImpl &c, float *u, float *v, float *w, uint8_t *vu, u
     FFB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+
+RemoveRules remove_rules(double dt, double cfl, int max_per_cell, int max_frame_steps, int extreme_on, const float *open_bounds) {
+    RemoveRules r;
+    r.dt = dt;
+    r.cfl = cfl;
+    r.max_per_cell = max_per_cell;
+    r.max_frame_steps = max_frame_steps;
+    r.extreme_on = extreme_on != 0;
+    for (int q = 0; q < 6; q++) r.bounds[q] = open_bounds ? open_bounds[q] : ((q & 1) ? INFINITY : -INFINITY);
+    return r;
+}
+
 }  // namespace
 
 extern "C" {
@@ -706,12 +718,13 @@ int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed) {
 }
 
 int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_condition_number, int max_particles_per_cell,
-                                   int max_frame_time_steps, int extreme_velocity_removal, int *num_remaining,
-                                   int *num_extreme_removed) {
+                                   int max_frame_time_steps, int extreme_velocity_removal, const float *open_bounds,
+                                   int *num_remaining, int *num_extreme_removed) {
     return guarded("ffb200_remove_marker_particles", ctx, [&](Context &c) {
         int remaining = 0, extreme = 0;
-        launch_remove_particles(c, dt, cfl_condition_number, max_particles_per_cell, max_frame_time_steps,
-                                extreme_velocity_removal, &remaining, &extreme);
+        launch_remove_particles(c, remove_rules(dt, cfl_condition_number, max_particles_per_cell, max_frame_time_steps,
+                                                extreme_velocity_removal, open_bounds),
+                                &remaining, &extreme);
         if (num_remaining) *num_remaining = remaining;
         if (num_extreme_removed) *num_extreme_removed = extreme;
     });
@@ -835,6 +848,56 @@ int ffb200_advance_marker_particles(ffb200_context *ctx, int n, float *pos, cons
             get_particles_impl(c, pos, nullptr, nullptr, nullptr, nullptr);
         },
         false);
+}
+
+int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float *pos, const float *vel, const float *phi,
+                                         const uint8_t *near_solid, const float *open_bounds, const uint8_t *pre_removed,
+                                         double dt, double cfl_condition_number, int max_particles_per_cell,
+                                         int max_frame_time_steps, int extreme_velocity_removal, uint8_t *removed,
+                                         int *num_removed, int *num_extreme_removed) {
+    return guarded("ffb200_mark_removed_marker_particles", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (n < 0) throw std::domain_error("negative particle count");
+        if (n > 0 && !removed) throw std::invalid_argument("null output mask");
+        const unsigned res = c.resident_next;
+        c.resident_next = 0;
+        if (res & FFB200_RESIDENT_PARTICLES) {
+            if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
+        } else {
+            if (n > 0 && (!pos || !vel)) throw std::invalid_argument("positions and velocities are required");
+            ensure_capacity(c, n, false);
+            c.n = n;
+            c.has_affine = false;
+            c.sorted = false;
+            if (n > 0) {
+                StageTimer t(c, kH2D);
+                upload_attr(c, pos, c.soa[c.cur].p, n);
+                upload_attr(c, vel, c.soa[c.cur].v, n);
+                launch_iota(c, c.soa[c.cur].orig, n);
+                t.done(0);
+            }
+        }
+        if (!(res & FFB200_RESIDENT_SOLID)) set_solid_impl(c, phi, near_solid);
+        // byte scratch in the AoS staging buffer (12 bytes per particle of capacity): [pre-removed | removed]
+        uint8_t *bytes = reinterpret_cast<uint8_t *>(c.aos_stage);
+        uint8_t *d_pre = nullptr, *d_removed = bytes + (size_t)c.cap * 4;
+        if (pre_removed && n > 0) {
+            d_pre = bytes;
+            FFB_CUDA(cudaMemcpyAsync(d_pre, pre_removed, (size_t)n, cudaMemcpyHostToDevice, c.stream));
+        }
+        int remaining = 0, extreme = 0;
+        if (n > 0) {
+            launch_remove_mask(c, remove_rules(dt, cfl_condition_number, max_particles_per_cell, max_frame_time_steps,
+                                               extreme_velocity_removal, open_bounds),
+                               d_pre, d_removed, &remaining, &extreme);
+            StageTimer t(c, kD2H);
+            FFB_CUDA(cudaMemcpyAsync(removed, d_removed, (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+            t.done(0);
+            FFB_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        if (num_removed) *num_removed = n - remaining;
+        if (num_extreme_removed) *num_extreme_removed = extreme;
+    });
 }
 
 }  // extern "C"

@@ -143,9 +143,16 @@ int launch_advect(Context &c, double dt, double cfl, int collide);
 int launch_max_speed_sq(Context &c, uint32_t *out_bits);  // bits of max float v.v over the owned particles (device word)
 
 // ffb200_remove.cu
+struct RemoveRules {
+    double dt = 0, cfl = 5.0;
+    int max_per_cell = 250, max_frame_steps = 6, extreme_on = 1;
+    float bounds[6];                     // open-boundary planes {x-, x+, y-, y+, z-, z+}; -inf / +inf where closed
+};
 // _removeMarkerParticles on the resident particles; updates c.n, leaves the survivors in host order
-int launch_remove_particles(Context &c, double dt, double cfl, int max_per_cell, int max_frame_steps, int extreme_on,
-                            int *remaining, int *extreme_removed);
+int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, int *extreme_removed);
+// the same decisions without the compaction: one byte per ORIGINAL index (device pointers; pre_removed may be null)
+int launch_remove_mask(Context &c, const RemoveRules &r, const uint8_t *pre_removed, uint8_t *removed_by_orig, int *remaining,
+                       int *extreme_removed);
 
 // ffb200_slab.cu
 int slab_rows(Context &c);

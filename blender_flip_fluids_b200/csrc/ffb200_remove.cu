@@ -152,9 +152,16 @@ __global__ void k_speed_limit(int n, double step, int steps, uint32_t *__restric
     words[W_LIMIT] = __float_as_uint((float)maxspeed);
 }
 
-// state per slot: 0 counted candidate, 1 inside the solid (or outside the grid), 2 over the cell cap, 3 extreme speed
-__global__ void __launch_bounds__(kThreads) k_remove_classify(SolidView S, const float *__restrict__ px,
+// state per slot: 0 counted candidate, 1 dropped before counting (inside the solid, pre-removed, beyond an open
+// boundary, outside the grid), 2 over the cell cap, 3 extreme speed
+struct OpenBounds {
+    float xn, xp, yn, yp, zn, zp;       // -inf / +inf on closed sides (:7780-7788)
+};
+
+__global__ void __launch_bounds__(kThreads) k_remove_classify(SolidView S, OpenBounds B, const float *__restrict__ px,
                                                               const float *__restrict__ py, const float *__restrict__ pz,
+                                                              const uint32_t *__restrict__ orig,
+                                                              const uint8_t *__restrict__ pre_removed,
                                                               int n, int cap, uint32_t *__restrict__ state,
                                                               int *__restrict__ cell_of, uint32_t *__restrict__ count,
                                                               uint32_t *__restrict__ words) {
@@ -163,6 +170,8 @@ __global__ void __launch_bounds__(kThreads) k_remove_classify(SolidView S, const
     const float x = px[j], y = py[j], z = pz[j];
     const GridDesc &g = S.g;
     uint32_t st = solid_phi(S, x, y, z) < 0.0f ? 1u : 0u;
+    if (pre_removed && pre_removed[orig[j]] != 0) st = 1u;             // e.g. the lifetime rule (:7808-7814), decided by the caller
+    if (x < B.xn || x > B.xp || y < B.yn || y > B.yp || z < B.zn || z > B.zp) st = 1u;   // open boundaries (:7817-7823)
     int cell = -1;
     if (st == 0u) {
         const int ci = pos2idx(x, g.inv_dx), cj = pos2idx(y, g.inv_dx), ck = pos2idx(z, g.inv_dx);
@@ -226,7 +235,8 @@ __global__ void __launch_bounds__(kThreads) k_remove_overfull_rank(int cap, cons
 __global__ void __launch_bounds__(kThreads) k_remove_final(const float *__restrict__ vx, const float *__restrict__ vy,
                                                            const float *__restrict__ vz, const uint32_t *__restrict__ orig,
                                                            int n, int extreme_on, uint32_t *__restrict__ state,
-                                                           uint32_t *__restrict__ keep_by_orig, uint32_t *__restrict__ words) {
+                                                           uint32_t *__restrict__ keep_by_orig,
+                                                           uint8_t *__restrict__ removed_by_orig, uint32_t *__restrict__ words) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t keep = 0u, extreme = 0u;
     if (j < n) {
@@ -243,7 +253,9 @@ __global__ void __launch_bounds__(kThreads) k_remove_final(const float *__restri
             }
         }
         keep = st == 0u ? 1u : 0u;
-        keep_by_orig[orig[j]] = keep;
+        const uint32_t o = orig[j];
+        keep_by_orig[o] = keep;
+        if (removed_by_orig) removed_by_orig[o] = (uint8_t)(keep ^ 1u);
     }
     const uint32_t nk = warp_sum(keep), nx = warp_sum(extreme);
     if ((threadIdx.x & 31) == 0) {
@@ -279,71 +291,91 @@ __global__ void __launch_bounds__(kThreads) k_remove_compact(const __grid_consta
 
 inline int blocks_for(int n) { return (n + kThreads - 1) / kThreads; }
 
-}  // namespace
-
-int launch_remove_particles(Context &c, double dt, double cfl, int max_per_cell, int max_frame_steps, int extreme_on,
-                            int *remaining, int *extreme_removed) {
-    if (!c.has_solid) throw CudaError("ffb200_remove_marker_particles: needs ffb200_set_solid first");
+// everything up to the keep flags; the counts stay in c.remove_words
+int remove_mark(Context &c, const RemoveRules &r, const uint8_t *pre_removed, uint8_t *removed_by_orig) {
+    if (!c.has_solid) throw CudaError("ffb200_remove_marker_particles: needs the solid SDF (ffb200_set_solid) first");
     if (c.g.kbase != 0 || c.g.kloc != c.g.K)
         throw CudaError("ffb200_remove_marker_particles: not available on z-slab contexts");
-    if (max_frame_steps < 1 || max_frame_steps > kMaxSteps) throw CudaError("ffb200_remove_marker_particles: max_frame_steps out of range");
-    if (max_per_cell < 0) throw CudaError("ffb200_remove_marker_particles: negative per-cell cap");
-    if (!(dt > 0.0)) throw CudaError("ffb200_remove_marker_particles: dt must be positive");
+    if (r.max_frame_steps < 1 || r.max_frame_steps > kMaxSteps) throw CudaError("ffb200_remove_marker_particles: max_frame_time_steps out of range");
+    if (r.max_per_cell < 0) throw CudaError("ffb200_remove_marker_particles: negative per-cell cap");
+    if (!(r.dt > 0.0)) throw CudaError("ffb200_remove_marker_particles: dt must be positive");
     const int n = c.n;
-    if (n == 0) {
-        *remaining = 0;
-        *extreme_removed = 0;
-        return 0;
-    }
     if (!c.remove_words) FFB_CUDA(cudaMalloc(&c.remove_words, W_COUNT * sizeof(uint32_t)));
+    uint32_t *words = c.remove_words;
+    FFB_CUDA(cudaMemsetAsync(words, 0, W_COUNT * sizeof(uint32_t), c.stream));
+    if (n == 0) return 0;
     const GridDesc &g = c.g;
-    ParticleSoA &src = c.soa[c.cur], &dst = c.soa[c.cur ^ 1];
+    ParticleSoA &src = c.soa[c.cur];
     SortScratch &s = c.sort;
     // scratch of the (now stale) sort: the bin table doubles as the per-cell counter grid
     uint32_t *state = s.key[0], *keep_by_orig = s.key[1], *list = s.val[1], *count = s.bin_start;
     int *cell_of = reinterpret_cast<int *>(s.val[0]);
-    uint32_t *words = c.remove_words;
     const size_t cells = (size_t)g.I * g.J * g.K;
-    FFB_CUDA(cudaMemsetAsync(words, 0, W_COUNT * sizeof(uint32_t), c.stream));
     FFB_CUDA(cudaMemsetAsync(count, 0, cells * sizeof(uint32_t), c.stream));
     c.sorted = false;
 
-    const double step = cfl * g.dx / dt;                        // speedLimitStep
+    const double step = r.cfl * g.dx / r.dt;                    // speedLimitStep
     const int blocks = blocks_for(n);
     const int persistent = blocks < 8 * c.sm_count ? blocks : 8 * c.sm_count;
     int launches = 0;
-    if (extreme_on) {
-        k_speed_hist<<<persistent, kThreads, 0, c.stream>>>(src.v[0], src.v[1], src.v[2], n, step, max_frame_steps, words);
+    if (r.extreme_on) {
+        k_speed_hist<<<persistent, kThreads, 0, c.stream>>>(src.v[0], src.v[1], src.v[2], n, step, r.max_frame_steps, words);
         k_speed_outliers<<<persistent, kThreads, 0, c.stream>>>(src.v[0], src.v[1], src.v[2], n, words);
-        k_speed_limit<<<1, 32, 0, c.stream>>>(n, step, max_frame_steps, words);
+        k_speed_limit<<<1, 32, 0, c.stream>>>(n, step, r.max_frame_steps, words);
         launches += 3;
     }
     SolidView S{g, c.phi};
-    k_remove_classify<<<blocks, kThreads, 0, c.stream>>>(S, src.p[0], src.p[1], src.p[2], n, max_per_cell, state, cell_of, count, words);
-    k_remove_overfull_list<<<blocks, kThreads, 0, c.stream>>>(n, max_per_cell, state, cell_of, count, list, words);
-    k_remove_overfull_rank<<<blocks, kThreads, 0, c.stream>>>(max_per_cell, list, cell_of, src.orig, state, words);
-    k_remove_final<<<blocks, kThreads, 0, c.stream>>>(src.v[0], src.v[1], src.v[2], src.orig, n, extreme_on, state, keep_by_orig, words);
+    OpenBounds B{r.bounds[0], r.bounds[1], r.bounds[2], r.bounds[3], r.bounds[4], r.bounds[5]};
+    k_remove_classify<<<blocks, kThreads, 0, c.stream>>>(S, B, src.p[0], src.p[1], src.p[2], src.orig, pre_removed, n, r.max_per_cell,
+                                                          state, cell_of, count, words);
+    k_remove_overfull_list<<<blocks, kThreads, 0, c.stream>>>(n, r.max_per_cell, state, cell_of, count, list, words);
+    k_remove_overfull_rank<<<blocks, kThreads, 0, c.stream>>>(r.max_per_cell, list, cell_of, src.orig, state, words);
+    k_remove_final<<<blocks, kThreads, 0, c.stream>>>(src.v[0], src.v[1], src.v[2], src.orig, n, r.extreme_on, state, keep_by_orig,
+                                                       removed_by_orig, words);
     launches += 4;
-    launches += launch_exclusive_scan(c, keep_by_orig, (size_t)n);
-    CompactArgs a;
-    int t = 0;
-    for (int q = 0; q < 3; q++) { a.src[t] = src.p[q]; a.dst[t] = dst.p[q]; t++; }
-    for (int q = 0; q < 3; q++) { a.src[t] = src.v[q]; a.dst[t] = dst.v[q]; t++; }
-    if (c.has_affine)
-        for (int q = 0; q < 9; q++) { a.src[t] = src.a[q]; a.dst[t] = dst.a[q]; t++; }
-    a.nstreams = t;
-    for (; t < 15; t++) { a.src[t] = nullptr; a.dst[t] = nullptr; }
-    k_remove_compact<<<blocks, kThreads, 0, c.stream>>>(a, n, state, src.orig, keep_by_orig, dst.orig);
-    launches++;
     FFB_CUDA(cudaGetLastError());
+    return launches;
+}
 
+void read_counts(Context &c, int *remaining, int *extreme_removed) {
     uint32_t host[W_COUNT];
-    FFB_CUDA(cudaMemcpyAsync(host, words, sizeof(host), cudaMemcpyDeviceToHost, c.stream));
+    FFB_CUDA(cudaMemcpyAsync(host, c.remove_words, sizeof(host), cudaMemcpyDeviceToHost, c.stream));
     FFB_CUDA(cudaStreamSynchronize(c.stream));
-    c.cur ^= 1;
-    c.n = (int)host[W_SURVIVORS];
-    *remaining = c.n;
+    *remaining = (int)host[W_SURVIVORS];
     *extreme_removed = (int)host[W_EXTREME];
+}
+
+}  // namespace
+
+int launch_remove_mask(Context &c, const RemoveRules &r, const uint8_t *pre_removed, uint8_t *removed_by_orig, int *remaining,
+                       int *extreme_removed) {
+    const int launches = remove_mark(c, r, pre_removed, removed_by_orig);
+    read_counts(c, remaining, extreme_removed);
+    return launches;
+}
+
+int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, int *extreme_removed) {
+    int launches = remove_mark(c, r, nullptr, nullptr);
+    const int n = c.n;
+    if (n > 0) {
+        ParticleSoA &src = c.soa[c.cur], &dst = c.soa[c.cur ^ 1];
+        uint32_t *state = c.sort.key[0], *keep_by_orig = c.sort.key[1];
+        launches += launch_exclusive_scan(c, keep_by_orig, (size_t)n);
+        CompactArgs a;
+        int t = 0;
+        for (int q = 0; q < 3; q++) { a.src[t] = src.p[q]; a.dst[t] = dst.p[q]; t++; }
+        for (int q = 0; q < 3; q++) { a.src[t] = src.v[q]; a.dst[t] = dst.v[q]; t++; }
+        if (c.has_affine)
+            for (int q = 0; q < 9; q++) { a.src[t] = src.a[q]; a.dst[t] = dst.a[q]; t++; }
+        a.nstreams = t;
+        for (; t < 15; t++) { a.src[t] = nullptr; a.dst[t] = nullptr; }
+        k_remove_compact<<<blocks_for(n), kThreads, 0, c.stream>>>(a, n, state, src.orig, keep_by_orig, dst.orig);
+        launches++;
+        FFB_CUDA(cudaGetLastError());
+    }
+    read_counts(c, remaining, extreme_removed);
+    if (n > 0) c.cur ^= 1;
+    c.n = *remaining;
     return launches;
 }
 

@@ -14,12 +14,14 @@
 // Each definition marshals the reference's own host containers (std::vector<vmath::vec3>,
 // Array3d<float>, Array3d<bool>) into the C ABI of libffb200.so (include/ffb200.h) and throws
 // std::runtime_error on failure on the calling thread, so the reference's C bindings turn it
-// into err = 0 + CBindings_get_error_message (cbindings.h:48-154). Every other stage (pressure,
-// level sets, meshing, I/O, particle removal ...) stays on the reference CPU code.
+// into err = 0 + CBindings_get_error_message (cbindings.h:48-154). The marker-particle removal at the tail of the
+// advection stage (fluidsimulation.cpp:7892, its only call site) is decided on the device as well. Every other
+// stage (pressure, level sets, meshing, I/O ...) stays on the reference CPU code.
 // Compiled against the UNMODIFIED reference headers with -fno-access-control.
 // There is no fallback to the CPU originals: if the GPU call fails, the substep fails.
 #include <cmath>
 #include <cstdlib>
+#include <limits>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -152,9 +154,53 @@ void FluidSimulation::_updateMarkerParticleVelocitiesThread() {
 }
 
 // ---- advect ---------------------------------------------------------------------------------------
+// _removeMarkerParticles (fluidsimulation.cpp:7773-7851), the tail of the advection stage: the decisions are taken
+// on the device, where the advection has just left the positions (and the G2P the velocities); the host applies the
+// mask to every attribute of the particle system with the reference's own ParticleSystem::removeParticles. The
+// lifetime rule reads a host-only attribute and is evaluated here, the open-boundary planes are the reference's
+// float arithmetic on its own boundary box.
+static void remove_marker_particles_b200(FluidSimulation &sim, ffb200_context *ctx, bool particles_resident, double dt) {
+    std::vector<vmath::vec3> *pos, *vel;
+    sim._markerParticles.getAttributeValues("POSITION", pos);
+    sim._markerParticles.getAttributeValues("VELOCITY", vel);
+    const size_t n = pos->size();
+    if (n == 0) {
+        sim._currentExtremeVelocityParticlesRemoved = 0;
+        return;
+    }
+    AABB boundaryAABB = sim._getBoundaryAABB();
+    vmath::vec3 minp = boundaryAABB.getMinPoint();
+    vmath::vec3 maxp = boundaryAABB.getMaxPoint();
+    float buffer = sim._openBoundaryWidth * sim._dx;
+    const float inf = std::numeric_limits<float>::infinity();
+    const float bounds[6] = {sim._openBoundaryXNeg ? minp.x + buffer : -inf, sim._openBoundaryXPos ? maxp.x - buffer : inf,
+                             sim._openBoundaryYNeg ? minp.y + buffer : -inf, sim._openBoundaryYPos ? maxp.y - buffer : inf,
+                             sim._openBoundaryZNeg ? minp.z + buffer : -inf, sim._openBoundaryZPos ? maxp.z - buffer : inf};
+    const bool closed = !sim._openBoundaryXNeg && !sim._openBoundaryXPos && !sim._openBoundaryYNeg && !sim._openBoundaryYPos &&
+                        !sim._openBoundaryZNeg && !sim._openBoundaryZPos;
+    std::vector<uint8_t> dead;
+    if (sim._isSurfaceLifetimeAttributeEnabled || sim._isFluidParticleLifetimeAttributeEnabled) {
+        std::vector<float> *lifetimes = nullptr;
+        sim._markerParticles.getAttributeValues("LIFETIME", lifetimes);
+        dead.resize(n);
+        float eps = 1e-6f;
+        for (size_t i = 0; i < n; i++) dead[i] = lifetimes->at(i) <= sim._surfaceLifetimeAttributeDeathTime + eps ? 1 : 0;
+    }
+    std::vector<uint8_t> mask(n);
+    int removed = 0, extreme = 0;
+    check(ffb200_declare_resident(ctx, FFB200_RESIDENT_SOLID | (particles_resident ? FFB200_RESIDENT_PARTICLES : 0u)));
+    check(ffb200_mark_removed_marker_particles(ctx, (int)n, raw(pos), raw(vel), nullptr, nullptr, closed ? nullptr : bounds,
+                                               dead.empty() ? nullptr : dead.data(), dt, sim._CFLConditionNumber,
+                                               sim._maxMarkerParticlesPerCell, sim._maxFrameTimeSteps,
+                                               sim._isExtremeVelocityRemovalEnabled ? 1 : 0, mask.data(), &removed, &extreme));
+    std::vector<bool> isRemoved(n);
+    for (size_t i = 0; i < n; i++) isRemoved[i] = mask[i] != 0;
+    sim._markerParticles.removeParticles(isRemoved);
+    sim._currentExtremeVelocityParticlesRemoved = extreme;
+}
+
 // Same bracket as the reference stage (log lines, the advanceMarkerParticles timer the addon's
-// stats read, fluidsimulation.cpp:7896-7897) and the same tail call: particle removal stays on
-// the CPU and still runs inside this stage.
+// stats read, fluidsimulation.cpp:7896-7897) and the same tail: particle removal runs inside this stage.
 void FluidSimulation::_advanceMarkerParticles(double dt) {
     _logfile.logString(_logfile.getTime() + " BEGIN       Advect Marker Particles");
     StopWatch timer;
@@ -176,7 +222,8 @@ void FluidSimulation::_advanceMarkerParticles(double dt) {
             _MACVelocity.getArray3dV()->getRawArray(), _MACVelocity.getArray3dW()->getRawArray(),
             _solidSDF._phi.getRawArray(), reinterpret_cast<uint8_t *>(_nearSolidGrid.getRawArray()), dt,
             _CFLConditionNumber));
-        _removeMarkerParticles(_currentFrameDeltaTime);
+        // device velocities are the host's only if this advection found the G2P's particles resident
+        remove_marker_particles_b200(*this, ctx, resident != 0, _currentFrameDeltaTime);
     }
     timer.stop();
     _timingData.advanceMarkerParticles += timer.getTime();

@@ -92,7 +92,9 @@ SIGNATURES = {
     "ffb200_velocity_advector_advect": [C.c_void_p, C.c_int] + [_f32p] * 5 + [C.c_double, C.c_int] + [_f32p] * 3 + [_u8p] * 3,
     "ffb200_declare_resident": [C.c_void_p, C.c_uint],
     "ffb200_get_maximum_particle_speed": [C.c_void_p, C.POINTER(C.c_double)],
-    "ffb200_remove_marker_particles": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "ffb200_remove_marker_particles": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "ffb200_mark_removed_marker_particles": [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _u8p, _f32p, _u8p, C.c_double, C.c_double, C.c_int,
+                                             C.c_int, C.c_int, _u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "ffb200_extrapolate_fluid_velocities": [C.c_void_p, _f32p, _f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int],
     "ffb200_update_marker_particle_velocities": [C.c_void_p, C.c_int] + [_f32p] * 11 + [C.c_int, C.c_double],
     "ffb200_advance_marker_particles": [C.c_void_p, C.c_int] + [_f32p] * 5 + [_u8p, C.c_double, C.c_double],
@@ -306,17 +308,43 @@ class FlipContext:
         self._call("ffb200_get_maximum_particle_speed", C.byref(out))
         return out.value
 
-    def remove_marker_particles(self, dt, cfl=5.0, max_particles_per_cell=250, max_frame_time_steps=6, extreme_velocity_removal=True):
-        """_removeMarkerParticles on the resident particles (solid SDF of set_solid). Returns (remaining, extreme removed)."""
+    def remove_marker_particles(self, dt, cfl=5.0, max_particles_per_cell=250, max_frame_time_steps=6, extreme_velocity_removal=True,
+                                open_bounds=None):
+        """_removeMarkerParticles on the resident particles (solid SDF of set_solid). open_bounds: None (closed domain) or
+        the six planes (x-, x+, y-, y+, z-, z+), +-inf on closed sides. Returns (remaining, extreme removed)."""
         remaining, extreme = C.c_int(), C.c_int()
+        ob = None if open_bounds is None else np.ascontiguousarray(open_bounds, dtype=np.float32).reshape(6)
         self._call("ffb200_remove_marker_particles", C.c_double(dt), C.c_double(cfl), int(max_particles_per_cell),
-                   int(max_frame_time_steps), 1 if extreme_velocity_removal else 0, C.byref(remaining), C.byref(extreme))
+                   int(max_frame_time_steps), 1 if extreme_velocity_removal else 0, _ptr(ob), C.byref(remaining), C.byref(extreme))
         self.n = remaining.value
         return remaining.value, extreme.value
 
-    def declare_resident(self, particles=False, field=False):
+    def mark_removed_marker_particles(self, pos, vel, phi, near_solid, dt, cfl=5.0, max_particles_per_cell=250, max_frame_time_steps=6,
+                                      extreme_velocity_removal=True, open_bounds=None, pre_removed=None):
+        """_removeMarkerParticles on host arrays -> (removed mask in the caller's order, extreme removed). pos/vel None:
+        declared resident (declare_resident(particles=True)); phi/near_solid None: declare_resident(solid=True)."""
+        if pos is not None:
+            pos = _f32(pos)
+            n = pos.shape[0]
+            vel = _f32(vel, (n, 3))
+            self.n = n
+        n = self.n
+        if phi is not None:
+            phi = _f32(phi, (self.K + 1, self.J + 1, self.I + 1))
+            near_solid = np.ascontiguousarray(near_solid, dtype=np.uint8)
+        ob = None if open_bounds is None else np.ascontiguousarray(open_bounds, dtype=np.float32).reshape(6)
+        pre = None if pre_removed is None else np.ascontiguousarray(pre_removed, dtype=np.uint8).reshape(n)
+        removed = np.zeros(n, np.uint8)
+        nrem, extreme = C.c_int(), C.c_int()
+        self._call("ffb200_mark_removed_marker_particles", n, _ptr(pos), _ptr(vel), _ptr(phi), _ptr(near_solid, _u8p), _ptr(ob),
+                   _ptr(pre, _u8p), C.c_double(dt), C.c_double(cfl), int(max_particles_per_cell), int(max_frame_time_steps),
+                   1 if extreme_velocity_removal else 0, _ptr(removed, _u8p), C.byref(nrem), C.byref(extreme))
+        assert nrem.value == int(removed.sum())
+        return removed, extreme.value
+
+    def declare_resident(self, particles=False, field=False, solid=False):
         """ffb200_declare_resident: the next host-buffer call may skip uploading what the device already holds."""
-        self._call("ffb200_declare_resident", C.c_uint((1 if particles else 0) | (2 if field else 0)))
+        self._call("ffb200_declare_resident", C.c_uint((1 if particles else 0) | (2 if field else 0) | (4 if solid else 0)))
 
     def set_valid_velocities(self, validu, validv, validw):
         su, sv, sw = mac_shapes(self.I, self.J, self.K)

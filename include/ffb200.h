@@ -208,19 +208,20 @@ int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_
  * copies are ignored (reduce the per-rank values with a max). */
 int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed);
 /* FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7773-7851) with
- * _getMarkerParticleSpeedLimit (:7723-7771) on the resident particles, for closed domain boundaries and no
- * lifetime attribute: drops the particles inside the solid SDF of ffb200_set_solid
- * (MeshLevelSet::trilinearInterpolateSolidPoints, phi < 0), those beyond the first
- * max_particles_per_cell (_maxMarkerParticlesPerCell = 250) of a cell in particle-index order, and, when
- * extreme_velocity_removal is set (_isExtremeVelocityRemovalEnabled), those faster than the limit derived
- * from the speed histogram over max_frame_time_steps (_maxFrameTimeSteps = 6) bins of width CFL * dx / dt.
- * The removed set is bit-for-bit the reference's. The survivors keep their relative order and are renumbered
- * 0..num_remaining-1 (ParticleSystem::removeParticles); ffb200_get_particles then returns num_remaining
- * rows. num_extreme_removed is _currentExtremeVelocityParticlesRemoved. Synchronises the stream.
- * Whole-grid contexts only. */
+ * _getMarkerParticleSpeedLimit (:7723-7771) on the resident particles: drops the particles inside the solid SDF
+ * of ffb200_set_solid (MeshLevelSet::trilinearInterpolateSolidPoints, phi < 0), those beyond an open domain
+ * boundary, those beyond the first max_particles_per_cell (_maxMarkerParticlesPerCell = 250) of a cell in
+ * particle-index order, and, when extreme_velocity_removal is set (_isExtremeVelocityRemovalEnabled), those
+ * faster than the limit derived from the speed histogram over max_frame_time_steps (_maxFrameTimeSteps = 6)
+ * bins of width CFL * dx / dt. open_bounds is NULL for a closed domain, else the six planes
+ * {x-, x+, y-, y+, z-, z+} of :7780-7788 (boundary AABB -/+ _openBoundaryWidth * dx on open sides,
+ * -INFINITY / +INFINITY on closed ones). The removed set is bit-for-bit the reference's. The survivors keep
+ * their relative order and are renumbered 0..num_remaining-1 (ParticleSystem::removeParticles);
+ * ffb200_get_particles then returns num_remaining rows. num_extreme_removed is
+ * _currentExtremeVelocityParticlesRemoved. Synchronises the stream. Whole-grid contexts only. */
 int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_condition_number, int max_particles_per_cell,
-                                   int max_frame_time_steps, int extreme_velocity_removal, int *num_remaining,
-                                   int *num_extreme_removed);
+                                   int max_frame_time_steps, int extreme_velocity_removal, const float *open_bounds,
+                                   int *num_remaining, int *num_extreme_removed);
 
 /* ---- stages on resident data ---------------------------------------------------------------------- */
 
@@ -245,11 +246,26 @@ int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos
  * sorted order on the device; outputs are still written to the host arrays in the caller's order).
  *   FFB200_RESIDENT_PARTICLES  positions, velocities (and affine rows) equal those of the previous call
  *   FFB200_RESIDENT_FIELD      u, v, w equal those of the previous call
- * Honoured by ffb200_update_marker_particle_velocities and ffb200_advance_marker_particles; the
- * particle count must match or the call fails. */
+ * Honoured by ffb200_update_marker_particle_velocities, ffb200_advance_marker_particles and
+ * ffb200_mark_removed_marker_particles; the particle count must match or the call fails. */
 #define FFB200_RESIDENT_PARTICLES 1u
 #define FFB200_RESIDENT_FIELD 2u
+#define FFB200_RESIDENT_SOLID 4u     /* ffb200_mark_removed_marker_particles: phi equals that of the previous call */
 int ffb200_declare_resident(ffb200_context *ctx, unsigned mask);
+
+/* _removeMarkerParticles (fluidsimulation.cpp:7773-7851, called at :7892 right after the advection) on host
+ * arrays: the decisions of ffb200_remove_marker_particles, returned as one byte per particle in the caller's
+ * order (removed[i] != 0: the reference's isRemoved[i]) so that the caller can compact every attribute of its
+ * particle system (ParticleSystem::removeParticles). pre_removed (NULL or n bytes) marks particles that are
+ * dropped before the per-cell count whatever their position -- the lifetime rule of :7808-7814, which only the
+ * caller can evaluate. phi / near_solid as in ffb200_advance_marker_particles; both may be NULL after
+ * ffb200_declare_resident(FFB200_RESIDENT_SOLID), pos / vel after FFB200_RESIDENT_PARTICLES (the reference's
+ * call order: the advection has just left exactly these positions, the G2P these velocities, on the device). */
+int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float *pos, const float *vel, const float *phi,
+                                         const uint8_t *near_solid, const float *open_bounds, const uint8_t *pre_removed,
+                                         double dt, double cfl_condition_number, int max_particles_per_cell,
+                                         int max_frame_time_steps, int extreme_velocity_removal, uint8_t *removed,
+                                         int *num_removed, int *num_extreme_removed);
 
 /* _extrapolateFluidVelocities (fluidsimulation.cpp:6282-6286; the reference passes
  * num_layers = ceil(sqrt(3) * CFL) + 3): u, v, w are extrapolated in place on the host arrays.

@@ -727,7 +727,7 @@ static float speed_limit(int n, const float *vel, double dx, double dt, double c
 
 void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const float *pos, const float *vel,
                                   const float *phi, double dt, double cfl, int max_per_cell, int extreme_removal,
-                                  uint8_t *removed, int *num_extreme) {
+                                  const float *open_bounds, const uint8_t *pre_removed, uint8_t *removed, int *num_extreme) {
     solid s;
     s.I = I; s.J = J; s.K = K; s.dx = dx; s.phi = phi; s.near = 0; s.cfl = cfl;
     int *count = (int *)calloc((size_t)I * J * K, sizeof(int));
@@ -738,6 +738,12 @@ void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const f
         const float *p = pos + 3 * (size_t)i, *v = vel + 3 * (size_t)i;
         removed[i] = sdf_sample(&s, p) < 0.0f;
         if (removed[i]) continue;
+        if (pre_removed && pre_removed[i]) { removed[i] = 1; continue; }          /* lifetime rule (:7808-7814), caller-evaluated */
+        if (open_bounds && (p[0] < open_bounds[0] || p[0] > open_bounds[1] || p[1] < open_bounds[2] || p[1] > open_bounds[3] ||
+                            p[2] < open_bounds[4] || p[2] > open_bounds[5])) {   /* :7817-7823 */
+            removed[i] = 1;
+            continue;
+        }
         int gi = pos2idx(p[0], dx), gj = pos2idx(p[1], dx), gk = pos2idx(p[2], dx);
         if (!in_range(gi, gj, gk, I, J, K)) { removed[i] = 1; continue; }   /* the reference would throw here */
         size_t c = flat(gi, gj, gk, I, J);

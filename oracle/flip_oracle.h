@@ -86,10 +86,11 @@ void flip_oracle_extrapolate(int w, int h, int d, float *grid, const uint8_t *va
 /* FluidSimulation::_getMaximumMarkerParticleSpeed (fluidsimulation.cpp:10188-10202). */
 double flip_oracle_max_particle_speed(int n, const float *vel);
 
-/* FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7773-7851) for closed boundaries / no lifetimes. */
+/* FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7773-7851). open_bounds: NULL (closed domain) or the six
+ * planes {x-, x+, y-, y+, z-, z+} of :7780-7788; pre_removed: NULL or the caller-evaluated lifetime rule (:7808-7814). */
 void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const float *pos, const float *vel,
                                   const float *phi, double dt, double cfl, int max_per_cell, int extreme_removal,
-                                  uint8_t *removed, int *num_extreme);
+                                  const float *open_bounds, const uint8_t *pre_removed, uint8_t *removed, int *num_extreme);
 
 #ifdef __cplusplus
 }

@@ -146,12 +146,17 @@ def max_particle_speed(vel):
     return float(f(C.c_int(vel.shape[0]), _p(vel)))
 
 
-def remove_particles(I, J, K, dx, pos, vel, phi, dt, cfl=5.0, max_per_cell=250, extreme_removal=True):
-    """_removeMarkerParticles for closed boundaries: (removed mask, number removed for extreme velocity)."""
+def remove_particles(I, J, K, dx, pos, vel, phi, dt, cfl=5.0, max_per_cell=250, extreme_removal=True, open_bounds=None,
+                     pre_removed=None):
+    """_removeMarkerParticles: (removed mask, number removed for extreme velocity). open_bounds: None or the six planes
+    (x-, x+, y-, y+, z-, z+), +-inf where closed; pre_removed: None or a byte mask (the lifetime rule)."""
     pos, vel, phi = _f32(pos), _f32(vel), _f32(phi)
     removed = np.zeros(pos.shape[0], np.uint8)
+    ob = None if open_bounds is None else np.ascontiguousarray(open_bounds, dtype=np.float32).reshape(6)
+    pre = None if pre_removed is None else np.ascontiguousarray(pre_removed, dtype=np.uint8).reshape(pos.shape[0])
     nx = C.c_int()
     lib().flip_oracle_remove_particles(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_int(pos.shape[0]), _p(pos),
                                        _p(vel), _p(phi), C.c_double(dt), C.c_double(cfl), C.c_int(max_per_cell),
-                                       C.c_int(1 if extreme_removal else 0), _p(removed, C.c_uint8), C.byref(nx))
+                                       C.c_int(1 if extreme_removal else 0), _p(ob) if ob is not None else None,
+                                       _p(pre, C.c_uint8) if pre is not None else None, _p(removed, C.c_uint8), C.byref(nx))
     return removed, nx.value

@@ -526,6 +526,11 @@ static int mode_remove() {
     sim._CFLConditionNumber = kvd("cfl", "5");
     sim._maxMarkerParticlesPerCell = kvi("max_per_cell", "250");
     sim._isExtremeVelocityRemovalEnabled = kvi("extreme", "1") != 0;
+    const int open = kvi("open", "0");                 // bit 0..5: x-, x+, y-, y+, z-, z+
+    sim._openBoundaryXNeg = (open & 1) != 0;  sim._openBoundaryXPos = (open & 2) != 0;
+    sim._openBoundaryYNeg = (open & 4) != 0;  sim._openBoundaryYPos = (open & 8) != 0;
+    sim._openBoundaryZNeg = (open & 16) != 0; sim._openBoundaryZPos = (open & 32) != 0;
+    sim._openBoundaryWidth = kvi("open_width", "2");
     sim._solidSDF = MeshLevelSet(I, J, K, dx);
     load_grid("in_phi", sim._solidSDF._phi);
     size_t before = sim._markerParticles.size();
@@ -533,8 +538,13 @@ static int mode_remove() {
     sim._removeMarkerParticles(dt);
     double t = now() - t0;
     dump_particles(sim._markerParticles, false, "out_");
-    printf("{\"mode\": \"remove\", \"before\": %zu, \"after\": %zu, \"extreme\": %d, \"threads\": %d, \"t_remove\": %.6f}\n",
-           before, sim._markerParticles.size(), sim._currentExtremeVelocityParticlesRemoved, ThreadUtils::getMaxThreadCount(), t);
+    // the boundary box the open-boundary planes are measured from (the planes themselves are the caller's arithmetic)
+    AABB box = sim._getBoundaryAABB();
+    vmath::vec3 bmin = box.getMinPoint(), bmax = box.getMaxPoint();
+    printf("{\"mode\": \"remove\", \"before\": %zu, \"after\": %zu, \"extreme\": %d, \"threads\": %d, \"t_remove\": %.6f, "
+           "\"box_min\": [%.9g, %.9g, %.9g], \"box_max\": [%.9g, %.9g, %.9g]}\n",
+           before, sim._markerParticles.size(), sim._currentExtremeVelocityParticlesRemoved, ThreadUtils::getMaxThreadCount(), t,
+           bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z);
     return 0;
 }
 

@@ -173,7 +173,7 @@ def fixture_extrapolate(name, scene_npz, layers, threads):
     print(name, m2)
 
 
-def fixture_remove(name, advect_npz, seed):
+def fixture_remove(name, advect_npz, seed, open_mask=0, open_width=2):
     """_removeMarkerParticles on post-advection positions (reference-built solid SDF of the advect fixture):
     extra particles inside the obstacle, one cell crowded beyond the 250 cap, a few extreme velocities."""
     z = np.load(os.path.join(OUT, advect_npz + ".npz"))
@@ -190,12 +190,19 @@ def fixture_remove(name, advect_npz, seed):
     vel[fast] *= np.array([40, 45, 50, 55, 60, 300, 310, 320, 2000], np.float32)[:, None]          # histogram tail + outliers
     d = tempfile.mkdtemp(prefix="ffgold_")
     save_inputs(d, pos=pos, vel=vel, phi=z["in_phi"])
-    info = run("remove", d, I=I, J=J, K=K, dx=float(dx), dt=float(dt), cfl=5)
+    info = run("remove", d, I=I, J=J, K=K, dx=float(dx), dt=float(dt), cfl=5, open=open_mask, open_width=open_width)
     out_pos, out_vel = np.load(os.path.join(d, "out_pos.npy")), np.load(os.path.join(d, "out_vel.npy"))
     shutil.rmtree(d)
-    m2 = dict(I=I, J=J, K=K, dx=dx, dt=dt, cfl=5.0, particles=int(len(pos)), survivors=int(len(out_pos)), extreme=int(info["extreme"]))
+    m2 = dict(I=I, J=J, K=K, dx=dx, dt=dt, cfl=5.0, particles=int(len(pos)), survivors=int(len(out_pos)), extreme=int(info["extreme"]),
+              open_mask=open_mask)
+    # the six planes of fluidsimulation.cpp:7780-7788 from the reference's own boundary box: float(min) + float(width * dx)
+    buf = np.float32(open_width * dx)
+    lo, hi = np.array(info["box_min"], np.float32) + buf, np.array(info["box_max"], np.float32) - buf
+    planes = np.array([lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]], np.float32)
+    closed = np.array([-np.inf, np.inf] * 3, np.float32)
+    bounds = np.where([(open_mask >> q) & 1 for q in range(6)], planes, closed).astype(np.float32)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), in_pos=pos, in_vel=vel, in_phi=z["in_phi"],
-                        out_pos=out_pos, out_vel=out_vel)
+                        in_bounds=bounds, out_pos=out_pos, out_vel=out_vel)
     print(name, m2)
 
 
@@ -217,3 +224,4 @@ if __name__ == "__main__":
     fixture_extrapolate("extrapolate_apic_22x24x20", "scene_apic_22x24x20_dyadic", 12, (1, 3, 16))
     # marker-particle removal (oracle groundwork for the next row f2)
     fixture_remove("remove_24x20x22", "advect_collide_24x20x22", 41)
+    fixture_remove("remove_open_24x20x22", "advect_collide_24x20x22", 43, open_mask=2 | 16 | 8)      # x+, z-, y+ open

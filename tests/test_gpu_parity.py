@@ -453,20 +453,49 @@ def test_maximum_particle_speed(eng, oracle):
     assert got == want == float(np.sqrt(np.float64(d.max())))
 
 
-def test_remove_particles_golden(eng):
+@pytest.mark.parametrize("name", ["remove_24x20x22", "remove_open_24x20x22"])
+def test_remove_particles_golden(eng, name):
     """_removeMarkerParticles on the device == the unmodified reference (survivors in order, bit for bit),
-    whatever order the particles currently have on the device."""
-    meta, g = load_golden("remove_24x20x22")
+    whatever order the particles currently have on the device; closed domain and three open sides."""
+    meta, g = load_golden(name)
+    bounds = g["in_bounds"] if meta["open_mask"] else None
     for presort in (False, True):
         with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
             ctx.set_solid(g["in_phi"], np.zeros(ctx.near_dims, np.uint8))
             ctx.set_particles(g["in_pos"], g["in_vel"])
             if presort:
                 ctx.sort_particles()
-            remaining, extreme = ctx.remove_marker_particles(meta["dt"], meta["cfl"])
+            remaining, extreme = ctx.remove_marker_particles(meta["dt"], meta["cfl"], open_bounds=bounds)
             p, v, *_ = ctx.get_particles()
         assert (remaining, extreme) == (meta["survivors"], meta["extreme"])
         assert bits_equal(p, g["out_pos"]) and bits_equal(v, g["out_vel"])
+
+
+def test_mark_removed_host_entry_point(eng, oracle):
+    """ffb200_mark_removed_marker_particles: the mask in the caller's order, with uploads and with everything declared
+    resident after an advection-like sequence; open sides and a pre-removed (lifetime) mask against the oracle."""
+    meta, g = load_golden("remove_open_24x20x22")
+    I, J, K, dx, dt = meta["I"], meta["J"], meta["K"], meta["dx"], meta["dt"]
+    pos, vel, phi = g["in_pos"], g["in_vel"], g["in_phi"]
+    pre = (np.arange(len(pos)) % 5 == 0).astype(np.uint8)
+    want = {}
+    for key, kw in {"open": dict(open_bounds=g["in_bounds"]), "pre": dict(pre_removed=pre, max_per_cell=4)}.items():
+        want[key] = oracle.remove_particles(I, J, K, dx, pos, vel, phi, dt, 5.0, **kw)
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        near = np.zeros(ctx.near_dims, np.uint8)
+        removed, extreme = ctx.mark_removed_marker_particles(pos, vel, phi, near, dt, open_bounds=g["in_bounds"])
+        assert np.array_equal(removed, want["open"][0]) and extreme == want["open"][1] == meta["extreme"]
+        assert bits_equal(pos[removed == 0], g["out_pos"])
+        # resident: particles sorted on the device (what an advection leaves), nothing uploaded but the pre-removed mask
+        ctx.sort_particles()
+        ctx.declare_resident(particles=True, solid=True)
+        removed, extreme = ctx.mark_removed_marker_particles(None, None, None, None, dt, max_particles_per_cell=4, pre_removed=pre)
+        assert np.array_equal(removed, want["pre"][0]) and extreme == want["pre"][1]
+        # a wrong resident claim fails loudly
+        ctx.declare_resident(particles=True, solid=True)
+        ctx.n += 1
+        with pytest.raises(RuntimeError):
+            ctx.mark_removed_marker_particles(None, None, None, None, dt)
 
 
 @pytest.mark.parametrize("cap,extreme_on", [(250, True), (3, True), (1, False), (0, True)])

@@ -126,9 +126,29 @@ def test_extrapolate_edge_cases(oracle):
     assert len(changed) <= 6
 
 
+def test_remove_particles_open_boundaries_fixture(oracle):
+    """Same with three open domain sides (fluidsimulation.cpp:7780-7823), and the caller-evaluated pre-removal mask."""
+    meta, g = load_golden("remove_open_24x20x22")
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    args = (I, J, K, dx, g["in_pos"], g["in_vel"], g["in_phi"], meta["dt"], meta["cfl"])
+    removed, extreme = oracle.remove_particles(*args, open_bounds=g["in_bounds"])
+    keep = removed == 0
+    assert int(keep.sum()) == meta["survivors"] and extreme == meta["extreme"]
+    assert bits_equal(g["in_pos"][keep], g["out_pos"]) and bits_equal(g["in_vel"][keep], g["out_vel"])
+    closed, _ = oracle.remove_particles(*args)
+    assert (closed == 0).sum() > keep.sum() + 100                     # the open sides really remove particles
+    # a pre-removed particle is dropped without taking a slot of its cell: same as deleting it beforehand
+    pre = (np.arange(len(removed)) % 7 == 0).astype(np.uint8)
+    with_pre, _ = oracle.remove_particles(*args, max_per_cell=3, extreme_removal=False, pre_removed=pre)
+    sub = pre == 0
+    without, _ = oracle.remove_particles(I, J, K, dx, g["in_pos"][sub], g["in_vel"][sub], g["in_phi"], meta["dt"], meta["cfl"],
+                                         max_per_cell=3, extreme_removal=False)
+    assert (with_pre[pre == 1] == 1).all() and np.array_equal(with_pre[sub], without)
+
+
 def test_remove_particles_fixture(oracle):
     """FluidSimulation::_removeMarkerParticles (fluidsimulation.cpp:7723-7851): survivors of the unmodified
-    reference, in order; groundwork for SURVEY §8f row f2 (no device path yet)."""
+    reference, in order."""
     meta, g = load_golden("remove_24x20x22")
     I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
     removed, extreme = oracle.remove_particles(I, J, K, dx, g["in_pos"], g["in_vel"], g["in_phi"], meta["dt"], meta["cfl"])
