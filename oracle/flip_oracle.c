@@ -755,3 +755,78 @@ void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const f
     *num_extreme = extreme;
     free(count);
 }
+
+/* ---- liquid SDF from particles ------------------------------------------
+ * ParticleLevelSet::_computeSignedDistanceFromParticles, particlelevelset.cpp:335-398, with
+ * _initializeBlockGrid (:400-437), _computeGridCountDataThread (:515-569: which 10^3 blocks a particle is
+ * handed to) and _computeExactBandProducerThread (:620-668: block-local distances). phi is the
+ * cell-centred Array3d<float>(I, J, K), initial value _getMaxDistance() = (float)(3.0 * dx). The result
+ * is a minimum, so neither the particle order nor the thread count matters. */
+void flip_oracle_liquid_sdf(int I, int J, int K, double dx, double radius, int n, const float *pos, float *phi) {
+    const int W = 10;                                         /* _blockwidth */
+    const float maxd = (float)(3.0 * dx);                     /* :331-333 */
+    size_t cells = (size_t)I * J * K;
+    for (size_t c = 0; c < cells; c++) phi[c] = maxd;
+    if (n == 0) return;
+    int bi = (I + W - 1) / W, bj = (J + W - 1) / W, bk = (K + W - 1) / W;
+    size_t nb = (size_t)bi * bj * bk;
+    uint8_t *home = (uint8_t *)calloc(nb, 1), *active = (uint8_t *)calloc(nb, 1);
+    float blockdx = (float)(W * dx);                          /* float blockdx = _blockwidth * _dx; */
+    for (int p = 0; p < n; p++) {                             /* _initializeActiveBlocksThread :439-450 */
+        int a = pos2idx(pos[3 * p], blockdx), b = pos2idx(pos[3 * p + 1], blockdx), c = pos2idx(pos[3 * p + 2], blockdx);
+        if (in_range(a, b, c, bi, bj, bk)) home[flat(a, b, c, bi, bj)] = 1;
+    }
+    for (int k = 0; k < bk; k++)                              /* GridUtils::featherGrid26 */
+        for (int j = 0; j < bj; j++)
+            for (int i = 0; i < bi; i++) {
+                if (!home[flat(i, j, k, bi, bj)]) continue;
+                for (int c = -1; c <= 1; c++)
+                    for (int b = -1; b <= 1; b++)
+                        for (int a = -1; a <= 1; a++)
+                            if (in_range(i + a, j + b, k + c, bi, bj, bk)) active[flat(i + a, j + b, k + c, bi, bj)] = 1;
+            }
+    float r = (float)radius;                                  /* float r = block.radius; */
+    float sr = 2.0f * r;                                      /* _searchRadiusFactor * (float)radius */
+    double chunk = W * dx;                                    /* _blockwidth * _dx, a double, in the producer */
+    for (int p = 0; p < n; p++) {
+        float x = pos[3 * p], y = pos[3 * p + 1], z = pos[3 * p + 2];
+        int b0 = pos2idx(x, blockdx), b1 = pos2idx(y, blockdx), b2 = pos2idx(z, blockdx);
+        float bx = idx2posf(b0, blockdx), by = idx2posf(b1, blockdx), bz = idx2posf(b2, blockdx);
+        int lo[3], hi[3];
+        if (x - sr > bx && y - sr > by && z - sr > bz && x + sr < bx + blockdx && y + sr < by + blockdx && z + sr < bz + blockdx) {
+            lo[0] = hi[0] = b0; lo[1] = hi[1] = b1; lo[2] = hi[2] = b2;
+        } else {
+            lo[0] = pos2idx(x - sr, blockdx); lo[1] = pos2idx(y - sr, blockdx); lo[2] = pos2idx(z - sr, blockdx);
+            hi[0] = pos2idx(x + sr, blockdx); hi[1] = pos2idx(y + sr, blockdx); hi[2] = pos2idx(z + sr, blockdx);
+        }
+        for (int ck = lo[2]; ck <= hi[2]; ck++)
+            for (int cj = lo[1]; cj <= hi[1]; cj++)
+                for (int ci = lo[0]; ci <= hi[0]; ci++) {
+                    if (!in_range(ci, cj, ck, bi, bj, bk) || !active[flat(ci, cj, ck, bi, bj)]) continue;   /* getBlockID == -1 */
+                    float lx = x - idx2posf(ci, chunk), ly = y - idx2posf(cj, chunk), lz = z - idx2posf(ck, chunk);
+                    int i0 = pos2idx(lx - sr, dx), j0 = pos2idx(ly - sr, dx), k0 = pos2idx(lz - sr, dx);
+                    int i1 = pos2idx(lx + sr, dx), j1 = pos2idx(ly + sr, dx), k1 = pos2idx(lz + sr, dx);
+                    if (i0 < 0) i0 = 0;
+                    if (j0 < 0) j0 = 0;
+                    if (k0 < 0) k0 = 0;
+                    if (i1 > W - 1) i1 = W - 1;
+                    if (j1 > W - 1) j1 = W - 1;
+                    if (k1 > W - 1) k1 = W - 1;
+                    double hw = 0.5 * dx;
+                    for (int k = k0; k <= k1; k++)
+                        for (int j = j0; j <= j1; j++)
+                            for (int i = i0; i <= i1; i++) {
+                                int gi = ci * W + i, gj = cj * W + j, gk = ck * W + k;
+                                if (!in_range(gi, gj, gk, I, J, K)) continue;                  /* write-out :377-379 */
+                                /* GridIndexToCellCenter(i, j, k, dx): (float)i*dx + hw in double, narrowed by vec3 */
+                                float cx = (float)((double)(float)i * dx + hw), cy = (float)((double)(float)j * dx + hw),
+                                      cz = (float)((double)(float)k * dx + hw);
+                                float dist = vlen(cx - lx, cy - ly, cz - lz) - r;
+                                size_t f = flat(gi, gj, gk, I, J);
+                                if (dist < phi[f]) phi[f] = dist;
+                            }
+                }
+    }
+    free(home);
+    free(active);
+}

@@ -92,6 +92,10 @@ void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const f
                                   const float *phi, double dt, double cfl, int max_per_cell, int extreme_removal,
                                   const float *open_bounds, const uint8_t *pre_removed, uint8_t *removed, int *num_extreme);
 
+/* ParticleLevelSet::calculateSignedDistanceField (particlelevelset.cpp:161-168, 335-668): cell-centred liquid SDF
+ * phi[K][J][I] from the marker positions; radius = _liquidSDFParticleRadius (fluidsimulation.cpp:4351). */
+void flip_oracle_liquid_sdf(int I, int J, int K, double dx, double radius, int n, const float *pos, float *phi);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,3 +160,14 @@ def remove_particles(I, J, K, dx, pos, vel, phi, dt, cfl=5.0, max_per_cell=250, 
                                        C.c_int(1 if extreme_removal else 0), _p(ob) if ob is not None else None,
                                        _p(pre, C.c_uint8) if pre is not None else None, _p(removed, C.c_uint8), C.byref(nx))
     return removed, nx.value
+
+
+def liquid_sdf(I, J, K, dx, pos, radius=None):
+    """ParticleLevelSet::calculateSignedDistanceField: phi[K, J, I] (cell centred). radius defaults to the
+    reference's _liquidSDFParticleRadius = 0.5 * dx * sqrt(3) (_liquidSDFParticleScale = 1)."""
+    pos = _f32(pos)
+    radius = 0.5 * dx * np.sqrt(3.0) if radius is None else radius
+    phi = np.empty((K, J, I), np.float32)
+    lib().flip_oracle_liquid_sdf(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius), C.c_int(pos.shape[0]),
+                                 _p(pos), _p(phi))
+    return phi

@@ -15,6 +15,7 @@
 // One JSON line with timings is printed on stdout.
 
 #include "fluidsimulation.h"
+#include "particlelevelset.h"
 #include "velocityadvector.h"
 #include "macvelocityfield.h"
 #include "particlesystem.h"
@@ -548,9 +549,29 @@ static int mode_remove() {
     return 0;
 }
 
+// liquidsdf: ParticleLevelSet::_computeSignedDistanceFromParticles (particlelevelset.cpp:335-398), what
+// calculateSignedDistanceField (:161-168, called from fluidsimulation.cpp:5599) runs on the marker positions.
+static int mode_liquidsdf() {
+    int I = kvi("I"), J = kvi("J"), K = kvi("K");
+    double dx = kvd("dx"), radius = kvd("radius");
+    std::vector<vmath::vec3> points = load_vec3("in_pos");
+    int reps = kvi("reps", "1");
+    double t = 0;
+    for (int r = 0; r < reps; r++) {
+        ParticleLevelSet ls(I, J, K, dx);
+        double t0 = now();
+        ls._computeSignedDistanceFromParticles(points, radius);
+        t = now() - t0;
+        if (r == 0) save_grid("out_phi", ls._phi);
+    }
+    printf("{\"mode\": \"liquidsdf\", \"particles\": %zu, \"threads\": %d, \"t_sdf\": %.6f}\n", points.size(),
+           ThreadUtils::getMaxThreadCount(), t);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 3) {
-        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene|extrapolate|remove> <workdir> key=value ...\n");
+        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene|extrapolate|remove|liquidsdf> <workdir> key=value ...\n");
         return 2;
     }
     std::string mode = argv[1];
@@ -569,6 +590,7 @@ int main(int argc, char **argv) {
     if (mode == "scene") return mode_scene();
     if (mode == "extrapolate") return mode_extrapolate();
     if (mode == "remove") return mode_remove();
+    if (mode == "liquidsdf") return mode_liquidsdf();
     fprintf(stderr, "ref_harness: unknown mode %s\n", mode.c_str());
     return 2;
 }

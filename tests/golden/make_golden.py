@@ -173,6 +173,28 @@ def fixture_extrapolate(name, scene_npz, layers, threads):
     print(name, m2)
 
 
+def fixture_liquid_sdf(name, source_npz, key, scale, threads):
+    """ParticleLevelSet::_computeSignedDistanceFromParticles on the positions of another fixture (not stored again);
+    radius = scale * _liquidSDFParticleRadius (scale 2 = the smooth surface-tension kernel, fluidsimulation.cpp:5594-5597).
+    The result is a minimum over particles: it must not depend on the reference's thread count."""
+    z = np.load(os.path.join(OUT, source_npz + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    radius = float(scale * 0.5 * dx * np.sqrt(3.0))
+    outs = []
+    for t in threads:
+        d = tempfile.mkdtemp(prefix="ffgold_")
+        save_inputs(d, pos=z[key])
+        run("liquidsdf", d, I=I, J=J, K=K, dx=float(dx), radius=radius, threads=t)
+        outs.append(np.load(os.path.join(d, "out_phi.npy")))
+        shutil.rmtree(d)
+    for o in outs[1:]:
+        assert o.tobytes() == outs[0].tobytes(), "reference liquid SDF depends on the thread count"
+    m2 = dict(I=I, J=J, K=K, dx=dx, radius=radius, source=source_npz, key=key, threads=list(threads))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), out_phi=outs[0])
+    print(name, m2, "cells below the far value:", int((outs[0] < np.float32(3.0 * dx)).sum()))
+
+
 def fixture_remove(name, advect_npz, seed, open_mask=0, open_width=2):
     """_removeMarkerParticles on post-advection positions (reference-built solid SDF of the advect fixture):
     extra particles inside the obstacle, one cell crowded beyond the 250 cap, a few extreme velocities."""
@@ -225,3 +247,6 @@ if __name__ == "__main__":
     # marker-particle removal (oracle groundwork for the next row f2)
     fixture_remove("remove_24x20x22", "advect_collide_24x20x22", 41)
     fixture_remove("remove_open_24x20x22", "advect_collide_24x20x22", 43, open_mask=2 | 16 | 8)      # x+, z-, y+ open
+    # liquid SDF from particles (oracle groundwork for row f3)
+    fixture_liquid_sdf("liquid_sdf_23x21x25_seams", "p2g_flip_23x21x25_seams", "in_pos", 1.0, (1, 3, 16))
+    fixture_liquid_sdf("liquid_sdf_22x24x20_radius2", "scene_apic_22x24x20_dyadic", "s0_pos", 2.0, (1, 16))

@@ -168,3 +168,24 @@ def test_remove_particles_fixture(oracle):
     crowded = (ci == [9, 8, 10]).all(axis=1) & (no_cap == 0)
     assert crowded.sum() > 250 and (no_extreme[crowded] == 0).sum() == 250
     assert (no_extreme[np.flatnonzero(crowded)[:250]] == 0).all()
+
+
+LIQUID_SDF = ["liquid_sdf_23x21x25_seams", "liquid_sdf_22x24x20_radius2"]
+
+
+@pytest.mark.parametrize("name", LIQUID_SDF)
+def test_liquid_sdf_fixture(oracle, name):
+    """ParticleLevelSet::calculateSignedDistanceField (particlelevelset.cpp:161-168, 335-668): the reference's cell-centred
+    liquid SDF (identical for 1, 3 and 16 reference threads) on fixture positions; groundwork for SURVEY §8f row f3."""
+    meta, e = load_golden(name)
+    _, src = load_golden(meta["source"])
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    pos = src[meta["key"]]
+    phi = oracle.liquid_sdf(I, J, K, dx, pos, meta["radius"])
+    assert bits_equal(phi, e["out_phi"])
+    far = np.float32(3.0 * dx)
+    assert phi.max() == far and (phi < 0).sum() > 1000 and (phi == far).sum() > 1000
+    # a minimum over particles: any particle order gives the same field
+    perm = np.random.default_rng(2).permutation(len(pos))
+    assert bits_equal(oracle.liquid_sdf(I, J, K, dx, pos[perm], meta["radius"]), phi)
+    assert bits_equal(oracle.liquid_sdf(I, J, K, dx, pos[:0], meta["radius"]), np.full_like(phi, far))
