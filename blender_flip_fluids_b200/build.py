@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libffb200.so")
-SOURCES = ["ffb200_api.cu", "ffb200_sort.cu", "ffb200_p2g.cu", "ffb200_g2p.cu", "ffb200_advect.cu", "ffb200_slab.cu", "ffb200_extrapolate.cu", "ffb200_remove.cu"]
+SOURCES = ["ffb200_api.cu", "ffb200_sort.cu", "ffb200_p2g.cu", "ffb200_g2p.cu", "ffb200_advect.cu", "ffb200_slab.cu", "ffb200_extrapolate.cu", "ffb200_remove.cu", "ffb200_liquid_sdf.cu"]
 
 # -fmad=false: the reference is built without FMA contraction; wherever results are compared
 # bit-for-bit a*b+c must round twice. Explicit fmaf()/fma() calls are still honoured.

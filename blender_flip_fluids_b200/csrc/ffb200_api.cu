@@ -170,6 +170,8 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->solid_clear[1]);
     dev_free(c->slab_counters);
     dev_free(c->remove_words);
+    dev_free(c->liquid_phi);
+    dev_free(c->liquid_blocks);
     dev_free(c->sort.edge_count);
     for (int q = 0; q < 3; q++) dev_free(c->k1s[q]);
     for (auto &cs : c->sort.cell) {
@@ -897,6 +899,49 @@ int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float
         }
         if (num_removed) *num_removed = n - remaining;
         if (num_extreme_removed) *num_extreme_removed = extreme;
+    });
+}
+
+int ffb200_liquid_sdf(ffb200_context *ctx, double particle_radius) {
+    return guarded("ffb200_liquid_sdf", ctx, [&](Context &c) { launch_liquid_sdf(c, particle_radius); }, false);
+}
+
+int ffb200_get_liquid_sdf(ffb200_context *ctx, float *phi) {
+    return guarded("ffb200_get_liquid_sdf", ctx, [&](Context &c) {
+        if (!phi) throw std::invalid_argument("null output pointer");
+        if (!c.liquid_phi) throw std::logic_error("no liquid SDF on the device (ffb200_liquid_sdf first)");
+        const size_t cells = (size_t)c.g.I * c.g.J * c.g.K;
+        FFB_CUDA(cudaMemcpyAsync(phi, c.liquid_phi, cells * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+    }, false);
+}
+
+int ffb200_calculate_signed_distance_field(ffb200_context *ctx, int n, const float *pos, double particle_radius, float *phi) {
+    return guarded("ffb200_calculate_signed_distance_field", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (n < 0) throw std::domain_error("negative particle count");
+        if (!phi) throw std::invalid_argument("null output pointer");
+        const unsigned res = c.resident_next;
+        c.resident_next = 0;
+        if (res & FFB200_RESIDENT_PARTICLES) {
+            if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
+        } else {
+            if (n > 0 && !pos) throw std::invalid_argument("null position pointer");
+            ensure_capacity(c, n, false);                      // positions only, like the advection entry point
+            c.n = n;
+            c.has_affine = false;
+            c.sorted = false;
+            if (n > 0) {
+                StageTimer t(c, kH2D);
+                upload_attr(c, pos, c.soa[c.cur].p, n);
+                launch_iota(c, c.soa[c.cur].orig, n);
+                t.done(0);
+            }
+        }
+        launch_liquid_sdf(c, particle_radius);
+        const size_t cells = (size_t)c.g.I * c.g.J * c.g.K;
+        FFB_CUDA(cudaMemcpyAsync(phi, c.liquid_phi, cells * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
     });
 }
 

@@ -102,6 +102,8 @@ struct Context {
     float guard_abs = -1.f, guard_per = -1.f;
     int *slab_counters = nullptr;        // 8 device ints for the slab pack/route kernels
     uint32_t *remove_words = nullptr;    // device scalars of ffb200_remove_marker_particles (lazy)
+    int *liquid_phi = nullptr;           // I*J*K cell-centred liquid SDF (ffb200_liquid_sdf; floats once decoded, lazy)
+    uint8_t *liquid_blocks = nullptr;    // home + active masks of its 10^3 blocks
     // API-call epoch: bumped by every call that may change particles or fields. An APIC ffb200_g2p
     // records it; an ffb200_advect that finds it unchanged reuses the G2P samples as RK3 stage 1.
     unsigned long long epoch = 0, k1_epoch = ~0ull;
@@ -153,6 +155,9 @@ int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, in
 // the same decisions without the compaction: one byte per ORIGINAL index (device pointers; pre_removed may be null)
 int launch_remove_mask(Context &c, const RemoveRules &r, const uint8_t *pre_removed, uint8_t *removed_by_orig, int *remaining,
                        int *extreme_removed);
+
+// ffb200_liquid_sdf.cu
+int launch_liquid_sdf(Context &c, double radius);        // ParticleLevelSet::calculateSignedDistanceField -> c.liquid_phi
 
 // ffb200_slab.cu
 int slab_rows(Context &c);

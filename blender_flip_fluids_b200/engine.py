@@ -92,6 +92,9 @@ SIGNATURES = {
     "ffb200_velocity_advector_advect": [C.c_void_p, C.c_int] + [_f32p] * 5 + [C.c_double, C.c_int] + [_f32p] * 3 + [_u8p] * 3,
     "ffb200_declare_resident": [C.c_void_p, C.c_uint],
     "ffb200_get_maximum_particle_speed": [C.c_void_p, C.POINTER(C.c_double)],
+    "ffb200_liquid_sdf": [C.c_void_p, C.c_double],
+    "ffb200_get_liquid_sdf": [C.c_void_p, _f32p],
+    "ffb200_calculate_signed_distance_field": [C.c_void_p, C.c_int, _f32p, C.c_double, _f32p],
     "ffb200_remove_marker_particles": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "ffb200_mark_removed_marker_particles": [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _u8p, _f32p, _u8p, C.c_double, C.c_double, C.c_int,
                                              C.c_int, C.c_int, _u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)],
@@ -307,6 +310,26 @@ class FlipContext:
         out = C.c_double()
         self._call("ffb200_get_maximum_particle_speed", C.byref(out))
         return out.value
+
+    def liquid_sdf(self, radius=None, download=True):
+        """ParticleLevelSet::calculateSignedDistanceField on the resident positions -> phi[K, J, I] (or None)."""
+        radius = 0.5 * self.dx * np.sqrt(3.0) if radius is None else radius
+        self._call("ffb200_liquid_sdf", C.c_double(radius))
+        if not download:
+            return None
+        phi = np.empty((self.K, self.J, self.I), np.float32)
+        self._call("ffb200_get_liquid_sdf", _ptr(phi))
+        return phi
+
+    def calculate_signed_distance_field(self, pos, radius=None):
+        """Host-array flavour; pos None: declared resident (declare_resident(particles=True))."""
+        radius = 0.5 * self.dx * np.sqrt(3.0) if radius is None else radius
+        if pos is not None:
+            pos = _f32(pos)
+            self.n = pos.shape[0]
+        phi = np.empty((self.K, self.J, self.I), np.float32)
+        self._call("ffb200_calculate_signed_distance_field", self.n, _ptr(pos), C.c_double(radius), _ptr(phi))
+        return phi
 
     def remove_marker_particles(self, dt, cfl=5.0, max_particles_per_cell=250, max_frame_time_steps=6, extreme_velocity_removal=True,
                                 open_bounds=None):

@@ -223,6 +223,16 @@ int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_co
                                    int max_frame_time_steps, int extreme_velocity_removal, const float *open_bounds,
                                    int *num_remaining, int *num_extreme_removed);
 
+/* ParticleLevelSet::calculateSignedDistanceField (particlelevelset.cpp:161-168, 335-668; called from
+ * FluidSimulation::_updateLiquidLevelSet, fluidsimulation.cpp:5599) on the resident positions: the cell-centred
+ * liquid SDF, phi = min(3 dx, min over particles of |cell centre - p| - particle_radius) restricted to the
+ * (particle, 10^3-block) pairs and block-local float frames of the reference, bit for bit (a minimum does not
+ * depend on the order). particle_radius = _liquidSDFParticleRadius = 0.5 * dx * sqrt(3) (x2 with the smooth
+ * surface-tension kernel), below 5 dx. The field stays on the device; ffb200_get_liquid_sdf copies its
+ * I*J*K floats (x fastest) to the host. Whole-grid contexts only. */
+int ffb200_liquid_sdf(ffb200_context *ctx, double particle_radius);
+int ffb200_get_liquid_sdf(ffb200_context *ctx, float *phi);
+
 /* ---- stages on resident data ---------------------------------------------------------------------- */
 
 int ffb200_p2g(ffb200_context *ctx, double particle_radius, int transfer_method);
@@ -266,6 +276,10 @@ int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float
                                          double dt, double cfl_condition_number, int max_particles_per_cell,
                                          int max_frame_time_steps, int extreme_velocity_removal, uint8_t *removed,
                                          int *num_removed, int *num_extreme_removed);
+
+/* ParticleLevelSet::calculateSignedDistanceField on host positions -> phi (I*J*K floats, the layout of
+ * Array3d<float>::getRawArray()). Uploads the positions unless FFB200_RESIDENT_PARTICLES was declared. */
+int ffb200_calculate_signed_distance_field(ffb200_context *ctx, int n, const float *pos, double particle_radius, float *phi);
 
 /* _extrapolateFluidVelocities (fluidsimulation.cpp:6282-6286; the reference passes
  * num_layers = ceil(sqrt(3) * CFL) + 3): u, v, w are extrapolated in place on the host arrays.

@@ -537,3 +537,37 @@ def test_remove_particles_vs_oracle(eng, oracle, cap, extreme_on):
         # removing again changes nothing but the extreme-speed rule (its limit follows the new maximum)
         again, _ = ctx.remove_marker_particles(dt, 5.0, max_particles_per_cell=max(cap, 1), extreme_velocity_removal=False)
         assert again == remaining
+
+
+@pytest.mark.parametrize("name", ["liquid_sdf_23x21x25_seams", "liquid_sdf_22x24x20_radius2"])
+def test_liquid_sdf_golden(eng, name):
+    """ParticleLevelSet::calculateSignedDistanceField on the device == the unmodified reference, bit for bit;
+    resident and host-array entry points, unsorted and sorted particles."""
+    meta, e = load_golden(name)
+    _, src = load_golden(meta["source"])
+    pos = src[meta["key"]]
+    with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        ctx.set_particles(pos, np.zeros_like(pos))
+        assert bits_equal(ctx.liquid_sdf(meta["radius"]), e["out_phi"])
+        ctx.sort_particles()
+        assert bits_equal(ctx.liquid_sdf(meta["radius"]), e["out_phi"])
+        assert bits_equal(ctx.calculate_signed_distance_field(pos[::-1].copy(), meta["radius"]), e["out_phi"])
+        ctx.declare_resident(particles=True)
+        assert bits_equal(ctx.calculate_signed_distance_field(None, meta["radius"]), e["out_phi"])
+        far = np.float32(3.0 * meta["dx"])
+        assert bits_equal(ctx.calculate_signed_distance_field(pos[:0], meta["radius"]), np.full_like(e["out_phi"], far))
+
+
+def test_liquid_sdf_vs_oracle_boundaries(eng, oracle):
+    """Particles on and beyond the grid boundary, block seams and a grid that is not a multiple of the block width."""
+    I, J, K, dx = 23, 31, 12, 0.013
+    rng = np.random.default_rng(77)
+    pos = (rng.random((40000, 3)) * [I * dx, J * dx, K * dx]).astype(np.float32)
+    pos[:3000] = (rng.random((3000, 3)) * [I * dx * 1.2, J * dx * 1.2, K * dx * 1.2] - 0.1 * I * dx).astype(np.float32)
+    seams = rng.integers(0, 3, (4000, 3)) * np.float32(10 * dx)
+    pos[3000:7000] = (seams + rng.normal(0, 0.02 * dx, (4000, 3))).astype(np.float32)
+    for radius in (0.5 * dx * np.sqrt(3.0), dx * np.sqrt(3.0), 0.3 * dx):
+        want = oracle.liquid_sdf(I, J, K, dx, pos, radius)
+        with eng.FlipContext(I, J, K, dx) as ctx:
+            got = ctx.calculate_signed_distance_field(pos, radius)
+        assert bits_equal(got, want)
