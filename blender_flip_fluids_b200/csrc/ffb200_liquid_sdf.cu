@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(256) k_sdf_home(SdfParams P, uint8_t *__restri
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const int a = pos2idx(P.px[j], P.inv_blockdx), b = pos2idx(P.py[j], P.inv_blockdx), c = pos2idx(P.pz[j], P.inv_blockdx);
-    if (in_range3(a, b, c, P.bi, P.bj, P.bk)) home[a + P.bi * (b + P.bj * c)] = 1;
+    if (in_range3(a, b, c, P.bi, P.bj, P.bk)) {
+        uint8_t *h = home + (a + P.bi * (b + P.bj * c));
+        if (*h == 0) *h = 1;                                   // thousands of particles per block: read before the contended store
+    }
 }
 
 // GridUtils::featherGrid26

@@ -237,6 +237,9 @@ __global__ void __launch_bounds__(kThreads) k_remove_final(const float *__restri
                                                            int n, int extreme_on, uint32_t *__restrict__ state,
                                                            uint32_t *__restrict__ keep_by_orig,
                                                            uint8_t *__restrict__ removed_by_orig, uint32_t *__restrict__ words) {
+    __shared__ uint32_t sh_count[2];
+    if (threadIdx.x < 2) sh_count[threadIdx.x] = 0u;
+    __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t keep = 0u, extreme = 0u;
     if (j < n) {
@@ -257,10 +260,16 @@ __global__ void __launch_bounds__(kThreads) k_remove_final(const float *__restri
         keep_by_orig[o] = keep;
         if (removed_by_orig) removed_by_orig[o] = (uint8_t)(keep ^ 1u);
     }
+    // one global atomic per CTA: every warp has survivors, and same-address atomics serialise in L2
     const uint32_t nk = warp_sum(keep), nx = warp_sum(extreme);
     if ((threadIdx.x & 31) == 0) {
-        if (nk) atomicAdd(&words[W_SURVIVORS], nk);
-        if (nx) atomicAdd(&words[W_EXTREME], nx);
+        if (nk) atomicAdd(&sh_count[0], nk);
+        if (nx) atomicAdd(&sh_count[1], nx);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sh_count[0]) atomicAdd(&words[W_SURVIVORS], sh_count[0]);
+        if (sh_count[1]) atomicAdd(&words[W_EXTREME], sh_count[1]);
     }
 }
 
@@ -357,7 +366,8 @@ int launch_remove_mask(Context &c, const RemoveRules &r, const uint8_t *pre_remo
 int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, int *extreme_removed) {
     int launches = remove_mark(c, r, nullptr, nullptr);
     const int n = c.n;
-    if (n > 0) {
+    read_counts(c, remaining, extreme_removed);
+    if (*remaining != n) {                                   // the usual substep removes nothing: no compaction then
         ParticleSoA &src = c.soa[c.cur], &dst = c.soa[c.cur ^ 1];
         uint32_t *state = c.sort.key[0], *keep_by_orig = c.sort.key[1];
         launches += launch_exclusive_scan(c, keep_by_orig, (size_t)n);
@@ -372,10 +382,9 @@ int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, in
         k_remove_compact<<<blocks_for(n), kThreads, 0, c.stream>>>(a, n, state, src.orig, keep_by_orig, dst.orig);
         launches++;
         FFB_CUDA(cudaGetLastError());
+        c.cur ^= 1;
+        c.n = *remaining;
     }
-    read_counts(c, remaining, extreme_removed);
-    if (n > 0) c.cur ^= 1;
-    c.n = *remaining;
     return launches;
 }
 
