@@ -15,6 +15,7 @@
 // never lose one). A last pass decodes the grid in place.
 #include "ffb200_ctx.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace ffb200 {
@@ -118,6 +119,99 @@ __global__ void __launch_bounds__(kThreads) k_sdf_scatter(SdfParams P, const uin
                 if (active[ci + P.bi * (cj + P.bj * ck)]) sdf_block(P, ci, cj, ck, x, y, z, phi);
 }
 
+// ---- variant 1 (FFB200_SDF_VARIANT=1; written at the end of round 1, its decomposition proven bit-exact on the CPU by
+// tests/test_oracle_golden.py:test_liquid_sdf_axes_decomposition, NOT yet run on hardware: the default stays k_sdf_scatter) --
+//
+// The reference's block set and its block-local cell boxes are products of per-axis ranges, and each squared
+// distance term depends only on (axis, block index along the axis, local cell index). A particle is therefore
+// reduced to three short lists in shared memory -- (global cell index | block offset << 24, (centre - local
+// coordinate)^2) -- and the 3-D work is their product, gated by a 27-bit active-block mask: no conversions, no
+// block arithmetic and no per-block loop nest inside, which is what held k_sdf_scatter at 9.8 active lanes. A
+// squared-distance pre-filter against the value already loaded skips the IEEE square root wherever the candidate
+// provably cannot lower the cell (sqrt and the subtraction are monotone; the margins cover every rounding).
+constexpr int kAxisMax = 12;           // entries per axis: 2 sr / dx + 3 <= 12, i.e. sr <= 4.5 dx
+
+__device__ __forceinline__ int sdf_axis_list(const SdfParams &P, float x, bool simple, int nb, int ncell, int *__restrict__ sh_g,
+                                             float *__restrict__ sh_sq, int &lo_out) {
+    const GridDesc &g = P.g;
+    const int b = pos2idx(x, P.inv_blockdx);
+    int lo = b, hi = b;
+    if (!simple) {
+        lo = pos2idx(x - P.sr, P.inv_blockdx);
+        hi = pos2idx(x + P.sr, P.inv_blockdx);
+    }
+    lo = max(lo, 0);
+    hi = min(hi, nb - 1);
+    lo_out = lo;
+    int n = 0;
+    for (int c = lo; c <= hi; c++) {
+        const float l = x - idx2posf(c, P.chunk);
+        int i0 = max(pos2idx(l - P.sr, g.inv_dx), 0);
+        int i1 = min(min(pos2idx(l + P.sr, g.inv_dx), kBlockWidth - 1), ncell - 1 - c * kBlockWidth);
+        for (int i = i0; i <= i1 && n < kAxisMax; i++) {
+            const float d = (float)((double)(float)i * g.dx + P.hw) - l;
+            sh_g[n * kThreads] = (c * kBlockWidth + i) | ((c - lo) << 24);
+            sh_sq[n * kThreads] = d * d;
+            n++;
+        }
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(kThreads) k_sdf_scatter_axes(SdfParams P, const uint8_t *__restrict__ active, int *phi) {
+    __shared__ int sh_g[3 * kAxisMax * kThreads];
+    __shared__ float sh_sq[3 * kAxisMax * kThreads];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n) return;
+    const GridDesc &g = P.g;
+    const float x = P.px[t], y = P.py[t], z = P.pz[t];
+    const float sr = P.sr, blockdx = P.blockdx;
+    const int b0 = pos2idx(x, P.inv_blockdx), b1 = pos2idx(y, P.inv_blockdx), b2 = pos2idx(z, P.inv_blockdx);
+    const double bdx = (double)blockdx;
+    const float bx = idx2posf(b0, bdx), by = idx2posf(b1, bdx), bz = idx2posf(b2, bdx);
+    const bool simple = x - sr > bx && y - sr > by && z - sr > bz && x + sr < bx + blockdx && y + sr < by + blockdx &&
+                        z + sr < bz + blockdx;
+    int *gx = sh_g + threadIdx.x, *gy = gx + kAxisMax * kThreads, *gz = gy + kAxisMax * kThreads;
+    float *qx = sh_sq + threadIdx.x, *qy = qx + kAxisMax * kThreads, *qz = qy + kAxisMax * kThreads;
+    int lo0, lo1, lo2;
+    const int nx = sdf_axis_list(P, x, simple, P.bi, g.I, gx, qx, lo0);
+    const int ny = sdf_axis_list(P, y, simple, P.bj, g.J, gy, qy, lo1);
+    const int nz = sdf_axis_list(P, z, simple, P.bk, g.K, gz, qz, lo2);
+    if (nx == 0 || ny == 0 || nz == 0) return;
+    // active blocks among the (at most 3 x 3 x 3) blocks the lists touch: bit u0 + 3 (u1 + 3 u2)
+    const int hu0 = min(gx[(nx - 1) * kThreads] >> 24, 2), hu1 = min(gy[(ny - 1) * kThreads] >> 24, 2), hu2 = min(gz[(nz - 1) * kThreads] >> 24, 2);
+    unsigned mask = 0u;
+    for (int w = 0; w <= hu2; w++)
+        for (int v = 0; v <= hu1; v++)
+            for (int u = 0; u <= hu0; u++)
+                if (active[(lo0 + u) + P.bi * ((lo1 + v) + P.bj * (lo2 + w))]) mask |= 1u << (u + 3 * (v + 3 * w));
+    if (mask == 0u) return;
+    const float r = P.r;
+    for (int c = 0; c < nz; c++) {
+        const int ez = gz[c * kThreads];
+        const float sz = qz[c * kThreads];
+        for (int b = 0; b < ny; b++) {
+            const int ey = gy[b * kThreads];
+            const unsigned m3 = (mask >> (3 * ((ey >> 24) + 3 * (ez >> 24)))) & 7u;
+            if (m3 == 0u) continue;
+            const float sy = qy[b * kThreads];
+            int *row = phi + (size_t)g.I * ((size_t)(ey & 0xffffff) + (size_t)g.J * (size_t)(ez & 0xffffff));
+            for (int a = 0; a < nx; a++) {
+                const int ex = gx[a * kThreads];
+                if (!((m3 >> (ex >> 24)) & 1u)) continue;
+                const float d2 = qx[a * kThreads] + sy + sz;                 // (x*x + y*y) + z*z, vmath::length's order
+                int *cell = row + (ex & 0xffffff);
+                const int seen = *cell;
+                const float cur = __int_as_float(order_bits(seen));
+                const float reach = (cur + r) * 1.00001f;
+                if (reach > 0.0f && d2 > reach * reach * 1.00001f) continue;   // sqrt(d2) - r >= cur for certain
+                const int e = order_bits(__float_as_int(sqrtf(d2) - r));
+                if (e < seen) atomicMin(cell, e);
+            }
+        }
+    }
+}
+
 __global__ void k_sdf_decode(int *phi, size_t cells) {
     float *out = reinterpret_cast<float *>(phi);
     for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < cells; c += (size_t)gridDim.x * blockDim.x)
@@ -162,7 +256,11 @@ int launch_liquid_sdf(Context &c, double radius) {
         FFB_CUDA(cudaMemsetAsync(home, 0, blocks, c.stream));
         k_sdf_home<<<(c.n + 255) / 256, 256, 0, c.stream>>>(P, home);
         k_sdf_feather<<<(int)((blocks + 127) / 128), 128, 0, c.stream>>>(home, active, P.bi, P.bj, P.bk);
-        k_sdf_scatter<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, c.stream>>>(P, active, c.liquid_phi);
+        static const int variant = [] { const char *e = std::getenv("FFB200_SDF_VARIANT"); return e ? std::atoi(e) : 0; }();
+        if (variant == 1 && 2.0 * (double)P.sr / g.dx + 3.0 <= (double)kAxisMax && g.I < (1 << 24) && g.J < (1 << 24) && g.K < (1 << 24))
+            k_sdf_scatter_axes<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, c.stream>>>(P, active, c.liquid_phi);
+        else
+            k_sdf_scatter<<<(c.n + kThreads - 1) / kThreads, kThreads, 0, c.stream>>>(P, active, c.liquid_phi);
         launches += 3;
     }
     k_sdf_decode<<<fill_blocks, 256, 0, c.stream>>>(c.liquid_phi, cells);

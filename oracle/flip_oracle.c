@@ -830,3 +830,94 @@ void flip_oracle_liquid_sdf(int I, int J, int K, double dx, double radius, int n
     free(home);
     free(active);
 }
+
+/* The same field evaluated the way the device's per-axis variant does (k_sdf_scatter_axes): the reference's
+ * block set and its block-local cell boxes are both products of per-axis ranges, and each distance term depends
+ * only on (axis, block index along that axis, local cell index). So a particle is reduced to three short lists
+ * of (global cell index, centre - local coordinate, block offset) and the 3-D work is their product, gated by
+ * the 3x3x3 active-block mask; a squared-distance pre-filter skips the square root where the candidate cannot
+ * lower the cell. This function exists to prove that decomposition (and the filter) bit-exact against
+ * flip_oracle_liquid_sdf on the CPU. Returns the number of candidates the filter skipped. */
+#define SDF_AXIS_MAX 24
+typedef struct { int n; int g[SDF_AXIS_MAX]; float d[SDF_AXIS_MAX]; int u[SDF_AXIS_MAX]; int lo; } sdf_axis;
+
+static void sdf_axis_list(sdf_axis *a, float x, int simple, int W, int nb, int ncell, float blockdx, double chunk, double dx,
+                          float sr) {
+    int b = pos2idx(x, blockdx);
+    int lo = b, hi = b;
+    if (!simple) { lo = pos2idx(x - sr, blockdx); hi = pos2idx(x + sr, blockdx); }
+    if (lo < 0) lo = 0;
+    if (hi > nb - 1) hi = nb - 1;
+    a->n = 0;
+    a->lo = lo;
+    double hw = 0.5 * dx;
+    for (int c = lo; c <= hi; c++) {
+        float l = x - idx2posf(c, chunk);
+        int i0 = pos2idx(l - sr, dx), i1 = pos2idx(l + sr, dx);
+        if (i0 < 0) i0 = 0;
+        if (i1 > W - 1) i1 = W - 1;
+        if (i1 > ncell - 1 - c * W) i1 = ncell - 1 - c * W;
+        for (int i = i0; i <= i1 && a->n < SDF_AXIS_MAX; i++) {
+            a->g[a->n] = c * W + i;
+            a->d[a->n] = (float)((double)(float)i * dx + hw) - l;
+            a->u[a->n] = c - lo;
+            a->n++;
+        }
+    }
+}
+
+long long flip_oracle_liquid_sdf_axes(int I, int J, int K, double dx, double radius, int n, const float *pos, float *phi) {
+    const int W = 10;
+    const float maxd = (float)(3.0 * dx);
+    size_t cells = (size_t)I * J * K;
+    long long skipped = 0;
+    for (size_t c = 0; c < cells; c++) phi[c] = maxd;
+    if (n == 0) return 0;
+    int bi = (I + W - 1) / W, bj = (J + W - 1) / W, bk = (K + W - 1) / W;
+    size_t nb = (size_t)bi * bj * bk;
+    uint8_t *home = (uint8_t *)calloc(nb, 1), *active = (uint8_t *)calloc(nb, 1);
+    float blockdx = (float)(W * dx);
+    for (int p = 0; p < n; p++) {
+        int a = pos2idx(pos[3 * p], blockdx), b = pos2idx(pos[3 * p + 1], blockdx), c = pos2idx(pos[3 * p + 2], blockdx);
+        if (in_range(a, b, c, bi, bj, bk)) home[flat(a, b, c, bi, bj)] = 1;
+    }
+    for (int k = 0; k < bk; k++)
+        for (int j = 0; j < bj; j++)
+            for (int i = 0; i < bi; i++) {
+                if (!home[flat(i, j, k, bi, bj)]) continue;
+                for (int c = -1; c <= 1; c++)
+                    for (int b = -1; b <= 1; b++)
+                        for (int a = -1; a <= 1; a++)
+                            if (in_range(i + a, j + b, k + c, bi, bj, bk)) active[flat(i + a, j + b, k + c, bi, bj)] = 1;
+            }
+    float r = (float)radius, sr = 2.0f * r;
+    double chunk = W * dx;
+    for (int p = 0; p < n; p++) {
+        float x = pos[3 * p], y = pos[3 * p + 1], z = pos[3 * p + 2];
+        int b0 = pos2idx(x, blockdx), b1 = pos2idx(y, blockdx), b2 = pos2idx(z, blockdx);
+        float bx = idx2posf(b0, blockdx), by = idx2posf(b1, blockdx), bz = idx2posf(b2, blockdx);
+        int simple = x - sr > bx && y - sr > by && z - sr > bz && x + sr < bx + blockdx && y + sr < by + blockdx && z + sr < bz + blockdx;
+        sdf_axis ax, ay, az;
+        sdf_axis_list(&ax, x, simple, W, bi, I, blockdx, chunk, dx, sr);
+        sdf_axis_list(&ay, y, simple, W, bj, J, blockdx, chunk, dx, sr);
+        sdf_axis_list(&az, z, simple, W, bk, K, blockdx, chunk, dx, sr);
+        for (int c = 0; c < az.n; c++)
+            for (int b = 0; b < ay.n; b++) {
+                float sy = ay.d[b] * ay.d[b], sz = az.d[c] * az.d[c];
+                for (int a = 0; a < ax.n; a++) {
+                    int ci = ax.lo + ax.u[a], cj = ay.lo + ay.u[b], ck = az.lo + az.u[c];
+                    if (!active[flat(ci, cj, ck, bi, bj)]) continue;
+                    size_t f = flat(ax.g[a], ay.g[b], az.g[c], I, J);
+                    float d2 = ax.d[a] * ax.d[a] + sy + sz;
+                    float cur = phi[f];
+                    float A = (cur + r) * 1.00001f;
+                    if (A > 0.0f && d2 > A * A * 1.00001f) { skipped++; continue; }     /* cannot lower the cell */
+                    float dist = sqrtf(d2) - r;
+                    if (dist < cur) phi[f] = dist;
+                }
+            }
+    }
+    free(home);
+    free(active);
+    return skipped;
+}

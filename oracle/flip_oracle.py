@@ -171,3 +171,14 @@ def liquid_sdf(I, J, K, dx, pos, radius=None):
     lib().flip_oracle_liquid_sdf(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius), C.c_int(pos.shape[0]),
                                  _p(pos), _p(phi))
     return phi
+
+
+def liquid_sdf_axes(I, J, K, dx, pos, radius=None):
+    """liquid_sdf through the per-axis decomposition of the device variant: (phi, candidates skipped by the filter)."""
+    pos = _f32(pos)
+    radius = 0.5 * dx * np.sqrt(3.0) if radius is None else radius
+    phi = np.empty((K, J, I), np.float32)
+    f = lib().flip_oracle_liquid_sdf_axes
+    f.restype = C.c_longlong
+    skipped = f(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius), C.c_int(pos.shape[0]), _p(pos), _p(phi))
+    return phi, int(skipped)

@@ -571,3 +571,41 @@ def test_liquid_sdf_vs_oracle_boundaries(eng, oracle):
         with eng.FlipContext(I, J, K, dx) as ctx:
             got = ctx.calculate_signed_distance_field(pos, radius)
         assert bits_equal(got, want)
+
+
+SDF_VARIANT_CHECK = r'''
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from conftest import load_golden
+from blender_flip_fluids_b200 import engine
+from oracle import flip_oracle as fo
+for name in ("liquid_sdf_23x21x25_seams", "liquid_sdf_22x24x20_radius2"):
+    meta, e = load_golden(name)
+    _, src = load_golden(meta["source"])
+    with engine.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        got = ctx.calculate_signed_distance_field(src[meta["key"]], meta["radius"])
+    assert got.tobytes() == e["out_phi"].tobytes(), name
+I, J, K, dx = 23, 31, 12, 0.013
+rng = np.random.default_rng(77)
+pos = (rng.random((40000, 3)) * [I * dx, J * dx, K * dx]).astype(np.float32)
+pos[:3000] = (rng.random((3000, 3)) * [I * dx * 1.2, J * dx * 1.2, K * dx * 1.2] - 0.1 * I * dx).astype(np.float32)
+pos[3000:7000] = (rng.integers(0, 3, (4000, 3)) * np.float32(10 * dx) + rng.normal(0, 0.02 * dx, (4000, 3))).astype(np.float32)
+for radius in (0.5 * dx * np.sqrt(3.0), dx * np.sqrt(3.0), 0.3 * dx):
+    with engine.FlipContext(I, J, K, dx) as ctx:
+        got = ctx.calculate_signed_distance_field(pos, radius)
+    assert got.tobytes() == fo.liquid_sdf(I, J, K, dx, pos, radius).tobytes(), radius
+print("ok")
+'''
+
+
+@pytest.mark.skipif(__import__("os").environ.get("FFB200_TEST_EXPERIMENTAL") != "1",
+                    reason="FFB200_SDF_VARIANT=1 (per-axis liquid-SDF scatter) was written after the round's GPU budget was spent; "
+                           "its decomposition is proven on the CPU (test_liquid_sdf_axes_decomposition); set "
+                           "FFB200_TEST_EXPERIMENTAL=1 to run it on hardware")
+def test_liquid_sdf_variant1_experimental():
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e["FFB200_SDF_VARIANT"] = "1"
+    r = subprocess.run([sys.executable, "-c", SDF_VARIANT_CHECK, root], capture_output=True, text=True, env=e, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

@@ -189,3 +189,21 @@ def test_liquid_sdf_fixture(oracle, name):
     perm = np.random.default_rng(2).permutation(len(pos))
     assert bits_equal(oracle.liquid_sdf(I, J, K, dx, pos[perm], meta["radius"]), phi)
     assert bits_equal(oracle.liquid_sdf(I, J, K, dx, pos[:0], meta["radius"]), np.full_like(phi, far))
+
+
+def test_liquid_sdf_axes_decomposition(oracle):
+    """The per-axis evaluation with the squared-distance pre-filter (what the device's opt-in k_sdf_scatter_axes does) is
+    bit-identical to the pinned restatement, on the fixtures and on a boundary / block-seam stress cloud."""
+    for name in LIQUID_SDF:
+        meta, e = load_golden(name)
+        _, src = load_golden(meta["source"])
+        phi, skipped = oracle.liquid_sdf_axes(meta["I"], meta["J"], meta["K"], meta["dx"], src[meta["key"]], meta["radius"])
+        assert bits_equal(phi, e["out_phi"]) and skipped > 0
+    I, J, K, dx = 23, 31, 12, 0.013
+    rng = np.random.default_rng(77)
+    pos = (rng.random((20000, 3)) * [I * dx, J * dx, K * dx]).astype(np.float32)
+    pos[:2000] = (rng.random((2000, 3)) * [I * dx * 1.2, J * dx * 1.2, K * dx * 1.2] - 0.1 * I * dx).astype(np.float32)
+    pos[2000:5000] = (rng.integers(0, 3, (3000, 3)) * np.float32(10 * dx) + rng.normal(0, 0.02 * dx, (3000, 3))).astype(np.float32)
+    for radius in (0.5 * dx * np.sqrt(3.0), dx * np.sqrt(3.0), 0.3 * dx, 2.2 * dx):
+        phi, _ = oracle.liquid_sdf_axes(I, J, K, dx, pos, radius)
+        assert bits_equal(phi, oracle.liquid_sdf(I, J, K, dx, pos, radius)), radius
