@@ -188,7 +188,7 @@ static void p2g_direction(int dir, int I, int J, int K, double dx, double radius
     d.bk = (d.gk + CHUNK - 1) / CHUNK;
     float h = (float)(0.5 * dx);                              /* vec3(0.0, 0.5*_dx, 0.5*_dx) narrows */
     d.off[0] = d.off[1] = d.off[2] = h;
-    d.off[dir] = 0.0f;
+    if (dir < 3) d.off[dir] = 0.0f;                           /* dir 3: cell-centred scalar grid, offset (h, h, h) */
     size_t nf = (size_t)d.gi * d.gj * d.gk;
     d.scalar = (float *)calloc(nf, sizeof(float));
     d.weight = (float *)calloc(nf, sizeof(float));
@@ -221,7 +221,7 @@ static void p2g_direction(int dir, int I, int J, int K, double dx, double radius
             lo[0] = pos2idx(x - sr, blockdx); lo[1] = pos2idx(y - sr, blockdx); lo[2] = pos2idx(z - sr, blockdx);
             hi[0] = pos2idx(x + sr, blockdx); hi[1] = pos2idx(y + sr, blockdx); hi[2] = pos2idx(z + sr, blockdx);
         }
-        float velocity = vel[3 * p + dir];
+        float velocity = dir < 3 ? vel[3 * p + dir] : vel[p]; /* dir 3: one scalar attribute per particle */
         for (int bk = lo[2]; bk <= hi[2]; bk++)
             for (int bj = lo[1]; bj <= hi[1]; bj++)
                 for (int bi = lo[0]; bi <= hi[0]; bi++) {
@@ -920,4 +920,15 @@ long long flip_oracle_liquid_sdf_axes(int I, int J, int K, double dx, double rad
     free(home);
     free(active);
     return skipped;
+}
+
+/* ---- scalar attribute P2G ------------------------------------------------
+ * AttributeToGridTransfer<float>::transfer (attributetogridtransfer.h:52-157, 213-520): the FLIP-kernel splat
+ * of VelocityAdvector with one scalar per particle, onto the cell-centred I x J x K grid (gridOffset =
+ * (dx/2, dx/2, dx/2) at every call site, e.g. fluidsimulation.cpp:7001-7012), normalised, valid = weight > 1e-6.
+ * Same block structure, same block-local float frames, same ascending-index summation order as the velocity
+ * transfer, so it is p2g_direction with a fourth "direction". The caller pre-fills grid and mask with 0. */
+void flip_oracle_attribute_p2g(int I, int J, int K, double dx, double radius, int n, const float *pos, const float *attr,
+                               float *grid, uint8_t *valid) {
+    p2g_direction(3, I, J, K, dx, radius, FLIP_ORACLE_FLIP, n, pos, attr, NULL, grid, valid, NULL);
 }

@@ -96,6 +96,11 @@ void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const f
  * phi[K][J][I] from the marker positions; radius = _liquidSDFParticleRadius (fluidsimulation.cpp:4351). */
 void flip_oracle_liquid_sdf(int I, int J, int K, double dx, double radius, int n, const float *pos, float *phi);
 
+/* AttributeToGridTransfer<float>::transfer (attributetogridtransfer.h:52-157): scalar attribute -> cell-centred grid
+ * grid[K][J][I], normalised, valid = weight > 1e-6. */
+void flip_oracle_attribute_p2g(int I, int J, int K, double dx, double radius, int n, const float *pos, const float *attr,
+                               float *grid, uint8_t *valid);
+
 /* flip_oracle_liquid_sdf evaluated through per-axis lists with a squared-distance pre-filter (the device's
  * k_sdf_scatter_axes): must be bit-identical; returns the number of candidates the filter skipped. */
 long long flip_oracle_liquid_sdf_axes(int I, int J, int K, double dx, double radius, int n, const float *pos, float *phi);

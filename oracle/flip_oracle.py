@@ -182,3 +182,13 @@ def liquid_sdf_axes(I, J, K, dx, pos, radius=None):
     f.restype = C.c_longlong
     skipped = f(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius), C.c_int(pos.shape[0]), _p(pos), _p(phi))
     return phi, int(skipped)
+
+
+def attribute_p2g(I, J, K, dx, pos, attr, radius):
+    """AttributeToGridTransfer<float>::transfer: (grid[K, J, I], valid[K, J, I])."""
+    pos = _f32(pos)
+    attr = np.ascontiguousarray(attr, dtype=np.float32).reshape(pos.shape[0])
+    grid, valid = np.zeros((K, J, I), np.float32), np.zeros((K, J, I), np.uint8)
+    lib().flip_oracle_attribute_p2g(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius), C.c_int(pos.shape[0]),
+                                    _p(pos), _p(attr), _p(grid), _p(valid, C.c_uint8))
+    return grid, valid

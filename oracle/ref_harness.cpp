@@ -16,6 +16,9 @@
 
 #include "fluidsimulation.h"
 #include "particlelevelset.h"
+#include "gridutils.h"
+#include "threadutils.h"
+#include "attributetogridtransfer.h"
 #include "velocityadvector.h"
 #include "macvelocityfield.h"
 #include "particlesystem.h"
@@ -569,9 +572,38 @@ static int mode_liquidsdf() {
     return 0;
 }
 
+// attribute: AttributeToGridTransfer<float>::transfer (attributetogridtransfer.h:52-157) the way
+// _updateMarkerParticleAgeAttributeGrid calls it (fluidsimulation.cpp:6990-7015): cell-centred grid, offset dx/2.
+static int mode_attribute() {
+    int I = kvi("I"), J = kvi("J"), K = kvi("K");
+    double dx = kvd("dx"), radius = kvd("radius");
+    std::vector<vmath::vec3> positions = load_vec3("in_pos");
+    Npy a = npy_load(P("in_attr"));
+    std::vector<float> attributes((float *)a.data.data(), (float *)a.data.data() + positions.size());
+    Array3d<float> grid(I, J, K, 0.0f);
+    Array3d<bool> valid(I, J, K, false);
+    AttributeTransferParameters<float> params;
+    params.positions = &positions;
+    params.attributes = &attributes;
+    params.attributeGrid = &grid;
+    params.validGrid = &valid;
+    params.gridOffset = vmath::vec3(0.5 * dx, 0.5 * dx, 0.5 * dx);
+    params.particleRadius = radius;
+    params.dx = dx;
+    double t0 = now();
+    AttributeToGridTransfer<float> transfer;
+    transfer.transfer(params);
+    double t = now() - t0;
+    save_grid("out_grid", grid);
+    save_mask("out_valid", valid);
+    printf("{\"mode\": \"attribute\", \"particles\": %zu, \"threads\": %d, \"t_transfer\": %.6f}\n", positions.size(),
+           ThreadUtils::getMaxThreadCount(), t);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 3) {
-        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene|extrapolate|remove|liquidsdf> <workdir> key=value ...\n");
+        fprintf(stderr, "usage: ref_harness <p2g|g2p|advect|scene|extrapolate|remove|liquidsdf|attribute> <workdir> key=value ...\n");
         return 2;
     }
     std::string mode = argv[1];
@@ -591,6 +623,7 @@ int main(int argc, char **argv) {
     if (mode == "extrapolate") return mode_extrapolate();
     if (mode == "remove") return mode_remove();
     if (mode == "liquidsdf") return mode_liquidsdf();
+    if (mode == "attribute") return mode_attribute();
     fprintf(stderr, "ref_harness: unknown mode %s\n", mode.c_str());
     return 2;
 }

@@ -195,6 +195,29 @@ def fixture_liquid_sdf(name, source_npz, key, scale, threads):
     print(name, m2, "cells below the far value:", int((outs[0] < np.float32(3.0 * dx)).sum()))
 
 
+def fixture_attribute(name, source_npz, key, radius_cells, seed, threads):
+    """AttributeToGridTransfer<float>::transfer of a random per-particle scalar on the positions of another fixture
+    (not stored again; the attribute is regenerated from the seed), cell-centred grid, offset dx/2."""
+    z = np.load(os.path.join(OUT, source_npz + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    pos = z[key]
+    attr = (np.random.default_rng(seed).random(len(pos)) * 10.0).astype(np.float32)
+    radius = float(np.float32(radius_cells) * dx)            # float radius = _ageAttributeRadius * _dx; (fluidsimulation.cpp:6997)
+    outs = []
+    for t in threads:
+        d = tempfile.mkdtemp(prefix="ffgold_")
+        save_inputs(d, pos=pos, attr=attr)
+        run("attribute", d, I=I, J=J, K=K, dx=float(dx), radius=radius, threads=t)
+        outs.append((np.load(os.path.join(d, "out_grid.npy")), np.load(os.path.join(d, "out_valid.npy")).astype(np.uint8)))
+        shutil.rmtree(d)
+    for g, v in outs[1:]:
+        assert g.tobytes() == outs[0][0].tobytes() and v.tobytes() == outs[0][1].tobytes(), "thread-count dependent"
+    m2 = dict(I=I, J=J, K=K, dx=dx, radius=radius, source=source_npz, key=key, seed=seed, threads=list(threads))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), out_grid=outs[0][0], out_valid=outs[0][1])
+    print(name, m2, "valid cells:", int(outs[0][1].sum()))
+
+
 def fixture_remove(name, advect_npz, seed, open_mask=0, open_width=2):
     """_removeMarkerParticles on post-advection positions (reference-built solid SDF of the advect fixture):
     extra particles inside the obstacle, one cell crowded beyond the 250 cap, a few extreme velocities."""
@@ -250,3 +273,5 @@ if __name__ == "__main__":
     # liquid SDF from particles (oracle groundwork for row f3)
     fixture_liquid_sdf("liquid_sdf_23x21x25_seams", "p2g_flip_23x21x25_seams", "in_pos", 1.0, (1, 3, 16))
     fixture_liquid_sdf("liquid_sdf_22x24x20_radius2", "scene_apic_22x24x20_dyadic", "s0_pos", 2.0, (1, 16))
+    # scalar attribute P2G (oracle groundwork for row f4)
+    fixture_attribute("attribute_23x21x25_seams_r2", "p2g_flip_23x21x25_seams", "in_pos", 2.0, 9, (1, 16))

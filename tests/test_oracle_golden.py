@@ -207,3 +207,18 @@ def test_liquid_sdf_axes_decomposition(oracle):
     for radius in (0.5 * dx * np.sqrt(3.0), dx * np.sqrt(3.0), 0.3 * dx, 2.2 * dx):
         phi, _ = oracle.liquid_sdf_axes(I, J, K, dx, pos, radius)
         assert bits_equal(phi, oracle.liquid_sdf(I, J, K, dx, pos, radius)), radius
+
+
+def test_attribute_p2g_fixture(oracle):
+    """AttributeToGridTransfer<float>::transfer (attributetogridtransfer.h:52-157): the reference's cell-centred attribute
+    grid + valid mask at a radius of 2 dx (identical for 1 and 16 reference threads); groundwork for SURVEY §8f row f4."""
+    meta, e = load_golden("attribute_23x21x25_seams_r2")
+    _, src = load_golden(meta["source"])
+    pos = src[meta["key"]]
+    attr = (np.random.default_rng(meta["seed"]).random(len(pos)) * 10.0).astype(np.float32)
+    grid, valid = oracle.attribute_p2g(meta["I"], meta["J"], meta["K"], meta["dx"], pos, attr, meta["radius"])
+    assert np.array_equal(valid, e["out_valid"]) and bits_equal(grid, e["out_grid"])
+    assert valid.sum() > 5000 and np.abs(grid[valid == 0]).max() < 1e-4      # weight <= 1e-6: unnormalised leftovers, not valid
+    # a constant attribute comes back as that constant wherever the grid is valid (normalised weights)
+    ones, v1 = oracle.attribute_p2g(meta["I"], meta["J"], meta["K"], meta["dx"], pos, np.full(len(pos), 3.0, np.float32), meta["radius"])
+    assert np.array_equal(v1, valid) and np.abs(ones[valid == 1] - 3.0).max() < 1e-5
