@@ -863,6 +863,11 @@ int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float
         if (n > 0 && !removed) throw std::invalid_argument("null output mask");
         const unsigned res = c.resident_next;
         c.resident_next = 0;
+        if (n == 0 && !(res & FFB200_RESIDENT_PARTICLES)) {     // nothing to decide; the resident set is left alone
+            if (num_removed) *num_removed = 0;
+            if (num_extreme_removed) *num_extreme_removed = 0;
+            return;
+        }
         if (res & FFB200_RESIDENT_PARTICLES) {
             if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
         } else {
