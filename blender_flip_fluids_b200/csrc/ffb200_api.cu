@@ -911,6 +911,10 @@ int ffb200_liquid_sdf(ffb200_context *ctx, double particle_radius) {
     return guarded("ffb200_liquid_sdf", ctx, [&](Context &c) { launch_liquid_sdf(c, particle_radius); }, false);
 }
 
+int ffb200_postprocess_liquid_sdf(ffb200_context *ctx) {
+    return guarded("ffb200_postprocess_liquid_sdf", ctx, [&](Context &c) { launch_liquid_sdf_postprocess(c); }, false);
+}
+
 int ffb200_get_liquid_sdf(ffb200_context *ctx, float *phi) {
     return guarded("ffb200_get_liquid_sdf", ctx, [&](Context &c) {
         if (!phi) throw std::invalid_argument("null output pointer");

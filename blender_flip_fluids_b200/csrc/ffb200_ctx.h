@@ -158,6 +158,7 @@ int launch_remove_mask(Context &c, const RemoveRules &r, const uint8_t *pre_remo
 
 // ffb200_liquid_sdf.cu
 int launch_liquid_sdf(Context &c, double radius);        // ParticleLevelSet::calculateSignedDistanceField -> c.liquid_phi
+int launch_liquid_sdf_postprocess(Context &c);           // ParticleLevelSet::postProcessSignedDistanceField, in place
 
 // ffb200_slab.cu
 int slab_rows(Context &c);

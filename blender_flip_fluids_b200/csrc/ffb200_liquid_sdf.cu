@@ -218,7 +218,38 @@ __global__ void k_sdf_decode(int *phi, size_t cells) {
         out[c] = __int_as_float(order_bits(phi[c]));
 }
 
+// ParticleLevelSet::postProcessSignedDistanceField (particlelevelset.cpp:170-195) with
+// MeshLevelSet::getDistanceAtCellCenter (meshlevelset.cpp:152-162); one thread per cell. Written at the end of round 1
+// with k_sdf_scatter_axes: pinned on the CPU, not yet run on hardware.
+__global__ void __launch_bounds__(256) k_sdf_postprocess(GridDesc g, float *__restrict__ phi, const float *__restrict__ solid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= g.I) return;
+    const size_t f = (size_t)i + (size_t)g.I * ((size_t)j + (size_t)g.J * (size_t)k);
+    const int w = g.I + 1;
+    const size_t sj = (size_t)w, sk = (size_t)w * (size_t)(g.J + 1);
+    const float *s = solid + ((size_t)i + sj * (size_t)j + sk * (size_t)k);
+    const float eps = (float)(0.005 * g.dx);
+    float val = phi[f];
+    if ((double)val < 0.5 * g.dx) {
+        const float centre = 0.125f * (s[0] + s[1] + s[sj] + s[sj + 1] + s[sk] + s[sk + 1] + s[sk + sj] + s[sk + sj + 1]);
+        if (centre < 0.0f) val = (float)(-0.5 * g.dx);
+    }
+    if (fabsf(val) < eps) val = val > 0.0f ? eps : -eps;
+    phi[f] = val;
+}
+
 }  // namespace
+
+int launch_liquid_sdf_postprocess(Context &c) {
+    const GridDesc &g = c.g;
+    if (g.kbase != 0 || g.kloc != g.K) throw CudaError("ffb200_postprocess_liquid_sdf: not available on z-slab contexts");
+    if (!c.liquid_phi) throw CudaError("ffb200_postprocess_liquid_sdf: no liquid SDF on the device (ffb200_liquid_sdf first)");
+    if (!c.has_solid) throw CudaError("ffb200_postprocess_liquid_sdf: needs the solid SDF (ffb200_set_solid) first");
+    dim3 grid((g.I + 255) / 256, g.J, g.K);
+    k_sdf_postprocess<<<grid, 256, 0, c.stream>>>(g, reinterpret_cast<float *>(c.liquid_phi), c.phi);
+    FFB_CUDA(cudaGetLastError());
+    return 1;
+}
 
 int launch_liquid_sdf(Context &c, double radius) {
     const GridDesc &g = c.g;

@@ -94,6 +94,7 @@ SIGNATURES = {
     "ffb200_get_maximum_particle_speed": [C.c_void_p, C.POINTER(C.c_double)],
     "ffb200_liquid_sdf": [C.c_void_p, C.c_double],
     "ffb200_get_liquid_sdf": [C.c_void_p, _f32p],
+    "ffb200_postprocess_liquid_sdf": [C.c_void_p],
     "ffb200_calculate_signed_distance_field": [C.c_void_p, C.c_int, _f32p, C.c_double, _f32p],
     "ffb200_remove_marker_particles": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "ffb200_mark_removed_marker_particles": [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _u8p, _f32p, _u8p, C.c_double, C.c_double, C.c_int,
@@ -317,6 +318,13 @@ class FlipContext:
         self._call("ffb200_liquid_sdf", C.c_double(radius))
         if not download:
             return None
+        phi = np.empty((self.K, self.J, self.I), np.float32)
+        self._call("ffb200_get_liquid_sdf", _ptr(phi))
+        return phi
+
+    def postprocess_liquid_sdf(self):
+        """ParticleLevelSet::postProcessSignedDistanceField on the device field -> phi[K, J, I]."""
+        self._call("ffb200_postprocess_liquid_sdf")
         phi = np.empty((self.K, self.J, self.I), np.float32)
         self._call("ffb200_get_liquid_sdf", _ptr(phi))
         return phi

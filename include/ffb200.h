@@ -232,6 +232,11 @@ int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_co
  * I*J*K floats (x fastest) to the host. Whole-grid contexts only. */
 int ffb200_liquid_sdf(ffb200_context *ctx, double particle_radius);
 int ffb200_get_liquid_sdf(ffb200_context *ctx, float *phi);
+/* ParticleLevelSet::postProcessSignedDistanceField (particlelevelset.cpp:170-195, called at fluidsimulation.cpp:5616) on
+ * the device field of ffb200_liquid_sdf, against the solid SDF of ffb200_set_solid: cells whose centre lies in the
+ * solid go to -dx/2, magnitudes below 0.005 dx are clamped away from zero. (Experimental in round 1: pinned against
+ * the reference on the CPU, its kernel has not run on hardware yet.) */
+int ffb200_postprocess_liquid_sdf(ffb200_context *ctx);
 
 /* ---- stages on resident data ---------------------------------------------------------------------- */
 

@@ -932,3 +932,26 @@ void flip_oracle_attribute_p2g(int I, int J, int K, double dx, double radius, in
                                float *grid, uint8_t *valid) {
     p2g_direction(3, I, J, K, dx, radius, FLIP_ORACLE_FLIP, n, pos, attr, NULL, grid, valid, NULL);
 }
+
+/* ParticleLevelSet::postProcessSignedDistanceField (particlelevelset.cpp:170-195): liquid cells whose centre is inside
+ * the solid (MeshLevelSet::getDistanceAtCellCenter, meshlevelset.cpp:152-162: 0.125f * the 8 corner nodes summed in
+ * i-fastest order) are pushed to -dx/2; magnitudes below 0.005 dx are clamped away from zero. In place on phi[K][J][I];
+ * solid is the node-centred (K+1)(J+1)(I+1) SDF. */
+void flip_oracle_liquid_sdf_postprocess(int I, int J, int K, double dx, float *phi, const float *solid) {
+    float eps = (float)(0.005 * dx);
+    int w = I + 1, h = J + 1;
+    for (int k = 0; k < K; k++)
+        for (int j = 0; j < J; j++)
+            for (int i = 0; i < I; i++) {
+                size_t f = flat(i, j, k, I, J);
+                if ((double)phi[f] < 0.5 * dx) {
+                    float c = 0.125f * (solid[flat(i, j, k, w, h)] + solid[flat(i + 1, j, k, w, h)] + solid[flat(i, j + 1, k, w, h)] +
+                                        solid[flat(i + 1, j + 1, k, w, h)] + solid[flat(i, j, k + 1, w, h)] +
+                                        solid[flat(i + 1, j, k + 1, w, h)] + solid[flat(i, j + 1, k + 1, w, h)] +
+                                        solid[flat(i + 1, j + 1, k + 1, w, h)]);
+                    if (c < 0) phi[f] = (float)(-0.5f * dx);
+                }
+                float val = phi[f];
+                if (fabsf(val) < eps) phi[f] = val > 0 ? eps : -eps;
+            }
+}

@@ -96,6 +96,9 @@ void flip_oracle_remove_particles(int I, int J, int K, double dx, int n, const f
  * phi[K][J][I] from the marker positions; radius = _liquidSDFParticleRadius (fluidsimulation.cpp:4351). */
 void flip_oracle_liquid_sdf(int I, int J, int K, double dx, double radius, int n, const float *pos, float *phi);
 
+/* ParticleLevelSet::postProcessSignedDistanceField (particlelevelset.cpp:170-195), in place. */
+void flip_oracle_liquid_sdf_postprocess(int I, int J, int K, double dx, float *phi, const float *solid);
+
 /* AttributeToGridTransfer<float>::transfer (attributetogridtransfer.h:52-157): scalar attribute -> cell-centred grid
  * grid[K][J][I], normalised, valid = weight > 1e-6. */
 void flip_oracle_attribute_p2g(int I, int J, int K, double dx, double radius, int n, const float *pos, const float *attr,

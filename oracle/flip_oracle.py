@@ -192,3 +192,11 @@ def attribute_p2g(I, J, K, dx, pos, attr, radius):
     lib().flip_oracle_attribute_p2g(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius), C.c_int(pos.shape[0]),
                                     _p(pos), _p(attr), _p(grid), _p(valid, C.c_uint8))
     return grid, valid
+
+
+def liquid_sdf_postprocess(I, J, K, dx, phi, solid):
+    """ParticleLevelSet::postProcessSignedDistanceField: returns the processed copy of phi[K, J, I]."""
+    out = np.ascontiguousarray(phi, dtype=np.float32).reshape(K, J, I).copy()
+    solid = _f32(solid)
+    lib().flip_oracle_liquid_sdf_postprocess(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), _p(out), _p(solid))
+    return out

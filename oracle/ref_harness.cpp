@@ -565,7 +565,15 @@ static int mode_liquidsdf() {
         double t0 = now();
         ls._computeSignedDistanceFromParticles(points, radius);
         t = now() - t0;
-        if (r == 0) save_grid("out_phi", ls._phi);
+        if (r == 0) {
+            save_grid("out_phi", ls._phi);
+            if (npy_exists(P("in_phi"))) {                 // + postProcessSignedDistanceField against a solid SDF
+                MeshLevelSet solid(I, J, K, dx);
+                load_grid("in_phi", solid._phi);
+                ls.postProcessSignedDistanceField(solid);
+                save_grid("out_phi_post", ls._phi);
+            }
+        }
     }
     printf("{\"mode\": \"liquidsdf\", \"particles\": %zu, \"threads\": %d, \"t_sdf\": %.6f}\n", points.size(),
            ThreadUtils::getMaxThreadCount(), t);

@@ -173,7 +173,7 @@ def fixture_extrapolate(name, scene_npz, layers, threads):
     print(name, m2)
 
 
-def fixture_liquid_sdf(name, source_npz, key, scale, threads):
+def fixture_liquid_sdf(name, source_npz, key, scale, threads, solid_key=None):
     """ParticleLevelSet::_computeSignedDistanceFromParticles on the positions of another fixture (not stored again);
     radius = scale * _liquidSDFParticleRadius (scale 2 = the smooth surface-tension kernel, fluidsimulation.cpp:5594-5597).
     The result is a minimum over particles: it must not depend on the reference's thread count."""
@@ -184,14 +184,16 @@ def fixture_liquid_sdf(name, source_npz, key, scale, threads):
     outs = []
     for t in threads:
         d = tempfile.mkdtemp(prefix="ffgold_")
-        save_inputs(d, pos=z[key])
+        save_inputs(d, pos=z[key], phi=None if solid_key is None else z[solid_key])
         run("liquidsdf", d, I=I, J=J, K=K, dx=float(dx), radius=radius, threads=t)
         outs.append(np.load(os.path.join(d, "out_phi.npy")))
+        post = np.load(os.path.join(d, "out_phi_post.npy")) if solid_key is not None else None    # + postProcessSignedDistanceField
         shutil.rmtree(d)
     for o in outs[1:]:
         assert o.tobytes() == outs[0].tobytes(), "reference liquid SDF depends on the thread count"
-    m2 = dict(I=I, J=J, K=K, dx=dx, radius=radius, source=source_npz, key=key, threads=list(threads))
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), out_phi=outs[0])
+    m2 = dict(I=I, J=J, K=K, dx=dx, radius=radius, source=source_npz, key=key, threads=list(threads), solid_key=solid_key)
+    extra = {} if post is None else dict(out_phi_post=post)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), out_phi=outs[0], **extra)
     print(name, m2, "cells below the far value:", int((outs[0] < np.float32(3.0 * dx)).sum()))
 
 
@@ -273,5 +275,6 @@ if __name__ == "__main__":
     # liquid SDF from particles (oracle groundwork for row f3)
     fixture_liquid_sdf("liquid_sdf_23x21x25_seams", "p2g_flip_23x21x25_seams", "in_pos", 1.0, (1, 3, 16))
     fixture_liquid_sdf("liquid_sdf_22x24x20_radius2", "scene_apic_22x24x20_dyadic", "s0_pos", 2.0, (1, 16))
+    fixture_liquid_sdf("liquid_sdf_post_24x20x22", "remove_24x20x22", "in_pos", 1.0, (1, 16), solid_key="in_phi")
     # scalar attribute P2G (oracle groundwork for row f4)
     fixture_attribute("attribute_23x21x25_seams_r2", "p2g_flip_23x21x25_seams", "in_pos", 2.0, 9, (1, 16))

@@ -594,12 +594,19 @@ for radius in (0.5 * dx * np.sqrt(3.0), dx * np.sqrt(3.0), 0.3 * dx):
     with engine.FlipContext(I, J, K, dx) as ctx:
         got = ctx.calculate_signed_distance_field(pos, radius)
     assert got.tobytes() == fo.liquid_sdf(I, J, K, dx, pos, radius).tobytes(), radius
+meta, e = load_golden("liquid_sdf_post_24x20x22")
+_, src = load_golden(meta["source"])
+with engine.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+    ctx.set_solid(src[meta["solid_key"]], np.zeros(ctx.near_dims, np.uint8))
+    ctx.set_particles(src[meta["key"]], np.zeros_like(src[meta["key"]]))
+    assert ctx.liquid_sdf(meta["radius"]).tobytes() == e["out_phi"].tobytes()
+    assert ctx.postprocess_liquid_sdf().tobytes() == e["out_phi_post"].tobytes()
 print("ok")
 '''
 
 
 @pytest.mark.skipif(__import__("os").environ.get("FFB200_TEST_EXPERIMENTAL") != "1",
-                    reason="FFB200_SDF_VARIANT=1 (per-axis liquid-SDF scatter) was written after the round's GPU budget was spent; "
+                    reason="FFB200_SDF_VARIANT=1 (per-axis liquid-SDF scatter) and the SDF post-process kernel were written after the round's GPU budget was spent; "
                            "its decomposition is proven on the CPU (test_liquid_sdf_axes_decomposition); set "
                            "FFB200_TEST_EXPERIMENTAL=1 to run it on hardware")
 def test_liquid_sdf_variant1_experimental():

@@ -170,7 +170,7 @@ def test_remove_particles_fixture(oracle):
     assert (no_extreme[np.flatnonzero(crowded)[:250]] == 0).all()
 
 
-LIQUID_SDF = ["liquid_sdf_23x21x25_seams", "liquid_sdf_22x24x20_radius2"]
+LIQUID_SDF = ["liquid_sdf_23x21x25_seams", "liquid_sdf_22x24x20_radius2", "liquid_sdf_post_24x20x22"]
 
 
 @pytest.mark.parametrize("name", LIQUID_SDF)
@@ -189,6 +189,11 @@ def test_liquid_sdf_fixture(oracle, name):
     perm = np.random.default_rng(2).permutation(len(pos))
     assert bits_equal(oracle.liquid_sdf(I, J, K, dx, pos[perm], meta["radius"]), phi)
     assert bits_equal(oracle.liquid_sdf(I, J, K, dx, pos[:0], meta["radius"]), np.full_like(phi, far))
+    if meta.get("solid_key"):
+        # ParticleLevelSet::postProcessSignedDistanceField (particlelevelset.cpp:170-195) against the fixture's solid SDF
+        post = oracle.liquid_sdf_postprocess(I, J, K, dx, phi, src[meta["solid_key"]])
+        assert bits_equal(post, e["out_phi_post"])
+        assert (post == np.float32(-0.5 * dx)).sum() > 500 and np.abs(post).min() >= np.float32(0.005 * dx)
 
 
 def test_liquid_sdf_axes_decomposition(oracle):
