@@ -462,3 +462,39 @@ class FlipContext:
                    _ptr(near, _u8p), C.c_double(dt), C.c_double(cfl))
         self.n = n
         return out
+
+
+class AttributeTransfer:
+    """AttributeToGridTransfer<float>::transfer (attributetogridtransfer.h:52-157) by composition, until the P2G kernels
+    get a cell-centred fourth direction: the transfer onto the I x J x K cell-centred grid (offset dx/2 on every axis) is,
+    operation for operation, the U-direction FLIP transfer of VelocityAdvector on an (I-1) x J x K grid with the particle x
+    shifted by float(dx/2) and the attribute in the x velocity (proven bit-exact on the CPU restatements by
+    tests/test_oracle_golden.py::test_attribute_p2g_is_a_shifted_u_transfer). Radii up to the device P2G's limit
+    (below 2 dx: the age / lifetime / density / colour attributes use 1 dx). EXPERIMENTAL in round 1: built from
+    hardware-validated kernels, but this composition itself has not run on hardware yet."""
+
+    def __init__(self, I, J, K, dx, device=0):
+        if I < 2:
+            raise ValueError("the grid must be at least two cells wide")
+        self.I, self.J, self.K, self.dx = I, J, K, dx
+        self.ctx = FlipContext(I - 1, J, K, dx, device)
+
+    def close(self):
+        self.ctx.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def transfer(self, pos, attr, radius):
+        """-> (grid[K, J, I] float32, valid[K, J, I] uint8)."""
+        pos = _f32(pos)
+        n = pos.shape[0]
+        shifted = pos.copy()
+        shifted[:, 0] = pos[:, 0] - np.float32(0.5 * self.dx)          # vec3 p = _positions[i] - offset, in float
+        vel = np.zeros((n, 3), np.float32)
+        vel[:, 0] = np.ascontiguousarray(attr, dtype=np.float32).reshape(n)
+        (u, _, _), (vu, _, _) = self.ctx.velocity_advector_advect(shifted, vel, radius=radius, method=FLIP)
+        return u, vu

@@ -278,3 +278,4 @@ if __name__ == "__main__":
     fixture_liquid_sdf("liquid_sdf_post_24x20x22", "remove_24x20x22", "in_pos", 1.0, (1, 16), solid_key="in_phi")
     # scalar attribute P2G (oracle groundwork for row f4)
     fixture_attribute("attribute_23x21x25_seams_r2", "p2g_flip_23x21x25_seams", "in_pos", 2.0, 9, (1, 16))
+    fixture_attribute("attribute_24x20x22_r1", "scene_flip_24x20x22_nondyadic", "s0_pos", 1.0, 10, (1, 16))   # _ageAttributeRadius

@@ -616,3 +616,18 @@ def test_liquid_sdf_variant1_experimental():
     e["FFB200_SDF_VARIANT"] = "1"
     r = subprocess.run([sys.executable, "-c", SDF_VARIANT_CHECK, root], capture_output=True, text=True, env=e, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("FFB200_TEST_EXPERIMENTAL") != "1",
+                    reason="engine.AttributeTransfer composes hardware-validated kernels, but the composition itself was written "
+                           "after the round's GPU budget was spent; set FFB200_TEST_EXPERIMENTAL=1 to run it on hardware")
+def test_attribute_transfer_composition_experimental(eng):
+    """AttributeToGridTransfer<float>::transfer through the U-direction FLIP P2G of a grid one cell narrower."""
+    meta, e = load_golden("attribute_24x20x22_r1")
+    _, src = load_golden(meta["source"])
+    pos = src[meta["key"]]
+    attr = (np.random.default_rng(meta["seed"]).random(len(pos)) * 10.0).astype(np.float32)
+    with eng.AttributeTransfer(meta["I"], meta["J"], meta["K"], meta["dx"]) as tr:
+        grid, valid = tr.transfer(pos, attr, meta["radius"])
+    assert np.array_equal(valid, e["out_valid"])
+    assert close(grid, e["out_grid"])
