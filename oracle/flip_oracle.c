@@ -176,9 +176,22 @@ static void splat_apic(p2g_dir *d, double dx, int bi, int bj, int bk,
     }
 }
 
+static void p2g_direction_n(int dir, int I, int J, int K, double dx, double radius, int method, int n,
+                            const float *pos, const float *vel, const float *aff,
+                            float *out, uint8_t *valid, float *wsum, int vec3_norm, int stride);
+
 static void p2g_direction(int dir, int I, int J, int K, double dx, double radius, int method, int n,
                           const float *pos, const float *vel, const float *aff,
                           float *out, uint8_t *valid, float *wsum) {
+    p2g_direction_n(dir, I, J, K, dx, radius, method, n, pos, vel, aff, out, valid, wsum, 0, 1);
+}
+
+/* vec3_norm: normalise with vmath's vec3 /= float (multiply by float(1.0 / w), vmath.cpp:105-111) instead of a float
+ * division; stride: distance in floats between the scalar payloads of consecutive particles (dir 3 only) and between
+ * consecutive outputs (one channel of an interleaved vec3 grid). */
+static void p2g_direction_n(int dir, int I, int J, int K, double dx, double radius, int method, int n,
+                            const float *pos, const float *vel, const float *aff,
+                            float *out, uint8_t *valid, float *wsum, int vec3_norm, int stride) {
     p2g_dir d;
     d.gi = I + (dir == 0);
     d.gj = J + (dir == 1);
@@ -221,7 +234,7 @@ static void p2g_direction(int dir, int I, int J, int K, double dx, double radius
             lo[0] = pos2idx(x - sr, blockdx); lo[1] = pos2idx(y - sr, blockdx); lo[2] = pos2idx(z - sr, blockdx);
             hi[0] = pos2idx(x + sr, blockdx); hi[1] = pos2idx(y + sr, blockdx); hi[2] = pos2idx(z + sr, blockdx);
         }
-        float velocity = dir < 3 ? vel[3 * p + dir] : vel[p]; /* dir 3: one scalar attribute per particle */
+        float velocity = dir < 3 ? vel[3 * p + dir] : vel[(size_t)stride * p]; /* dir 3: one scalar attribute per particle */
         for (int bk = lo[2]; bk <= hi[2]; bk++)
             for (int bj = lo[1]; bj <= hi[1]; bj++)
                 for (int bi = lo[0]; bi <= hi[0]; bi++) {
@@ -233,8 +246,11 @@ static void p2g_direction(int dir, int I, int J, int K, double dx, double radius
     }
     for (size_t f = 0; f < nf; f++) {                         /* normalise :527-531, write-out :140-168 */
         float s = d.scalar[f], wt = d.weight[f];
-        if (wt > eps) s /= wt;
-        out[f] = s;
+        if (wt > eps) {
+            if (vec3_norm) s *= (float)(1.0 / (double)wt);
+            else s /= wt;
+        }
+        out[(size_t)stride * f] = s;
         valid[f] = wt > eps ? 1 : 0;
         if (wsum) wsum[f] = wt;
     }
@@ -954,4 +970,13 @@ void flip_oracle_liquid_sdf_postprocess(int I, int J, int K, double dx, float *p
                 float val = phi[f];
                 if (fabsf(val) < eps) phi[f] = val > 0 ? eps : -eps;
             }
+}
+
+/* AttributeToGridTransfer<vmath::vec3>::transfer (colour, whitewater proximity): three channels accumulated like
+ * scalars (vec3 * float and vec3 += are per component), normalised with vec3 /= float. attr and grid are packed
+ * float[3] per particle / cell. */
+void flip_oracle_attribute_p2g_vec3(int I, int J, int K, double dx, double radius, int n, const float *pos, const float *attr,
+                                    float *grid, uint8_t *valid) {
+    for (int ch = 0; ch < 3; ch++)
+        p2g_direction_n(3, I, J, K, dx, radius, FLIP_ORACLE_FLIP, n, pos, attr + ch, NULL, grid + ch, valid, NULL, 1, 3);
 }

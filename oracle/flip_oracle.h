@@ -104,6 +104,10 @@ void flip_oracle_liquid_sdf_postprocess(int I, int J, int K, double dx, float *p
 void flip_oracle_attribute_p2g(int I, int J, int K, double dx, double radius, int n, const float *pos, const float *attr,
                                float *grid, uint8_t *valid);
 
+/* AttributeToGridTransfer<vmath::vec3>::transfer: packed float[3] attributes -> grid[K][J][I][3], one valid mask. */
+void flip_oracle_attribute_p2g_vec3(int I, int J, int K, double dx, double radius, int n, const float *pos, const float *attr,
+                                    float *grid, uint8_t *valid);
+
 /* flip_oracle_liquid_sdf evaluated through per-axis lists with a squared-distance pre-filter (the device's
  * k_sdf_scatter_axes): must be bit-identical; returns the number of candidates the filter skipped. */
 long long flip_oracle_liquid_sdf_axes(int I, int J, int K, double dx, double radius, int n, const float *pos, float *phi);

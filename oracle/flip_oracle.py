@@ -200,3 +200,13 @@ def liquid_sdf_postprocess(I, J, K, dx, phi, solid):
     solid = _f32(solid)
     lib().flip_oracle_liquid_sdf_postprocess(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), _p(out), _p(solid))
     return out
+
+
+def attribute_p2g_vec3(I, J, K, dx, pos, attr, radius):
+    """AttributeToGridTransfer<vmath::vec3>::transfer: (grid[K, J, I, 3], valid[K, J, I])."""
+    pos = _f32(pos)
+    attr = np.ascontiguousarray(attr, dtype=np.float32).reshape(pos.shape[0], 3)
+    grid, valid = np.zeros((K, J, I, 3), np.float32), np.zeros((K, J, I), np.uint8)
+    lib().flip_oracle_attribute_p2g_vec3(C.c_int(I), C.c_int(J), C.c_int(K), C.c_double(dx), C.c_double(radius),
+                                         C.c_int(pos.shape[0]), _p(pos), _p(attr), _p(grid), _p(valid, C.c_uint8))
+    return grid, valid

@@ -604,6 +604,27 @@ static int mode_attribute() {
     double t = now() - t0;
     save_grid("out_grid", grid);
     save_mask("out_valid", valid);
+    if (npy_exists(P("in_attr3"))) {                       // the vec3 flavour (colour, whitewater proximity) on the same positions
+        std::vector<vmath::vec3> attributes3 = load_vec3("in_attr3");
+        Array3d<vmath::vec3> grid3(I, J, K, vmath::vec3());
+        Array3d<bool> valid3(I, J, K, false);
+        AttributeTransferParameters<vmath::vec3> p3;
+        p3.positions = &positions;
+        p3.attributes = &attributes3;
+        p3.attributeGrid = &grid3;
+        p3.validGrid = &valid3;
+        p3.gridOffset = vmath::vec3(0.5 * dx, 0.5 * dx, 0.5 * dx);
+        p3.particleRadius = radius;
+        p3.dx = dx;
+        AttributeToGridTransfer<vmath::vec3> transfer3;
+        transfer3.transfer(p3);
+        std::vector<vmath::vec3> flat((size_t)I * J * K);
+        for (int k = 0; k < K; k++)
+            for (int j = 0; j < J; j++)
+                for (int i = 0; i < I; i++) flat[(size_t)i + (size_t)I * ((size_t)j + (size_t)J * k)] = grid3(i, j, k);
+        save_vec3("out_grid3", flat);
+        save_mask("out_valid3", valid3);
+    }
     printf("{\"mode\": \"attribute\", \"particles\": %zu, \"threads\": %d, \"t_transfer\": %.6f}\n", positions.size(),
            ThreadUtils::getMaxThreadCount(), t);
     return 0;

@@ -205,18 +205,22 @@ def fixture_attribute(name, source_npz, key, radius_cells, seed, threads):
     I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
     pos = z[key]
     attr = (np.random.default_rng(seed).random(len(pos)) * 10.0).astype(np.float32)
+    attr3 = np.random.default_rng(seed + 1000).random((len(pos), 3)).astype(np.float32)    # the vec3 flavour (colour), same positions
     radius = float(np.float32(radius_cells) * dx)            # float radius = _ageAttributeRadius * _dx; (fluidsimulation.cpp:6997)
     outs = []
     for t in threads:
         d = tempfile.mkdtemp(prefix="ffgold_")
-        save_inputs(d, pos=pos, attr=attr)
+        save_inputs(d, pos=pos, attr=attr, attr3=attr3)
         run("attribute", d, I=I, J=J, K=K, dx=float(dx), radius=radius, threads=t)
-        outs.append((np.load(os.path.join(d, "out_grid.npy")), np.load(os.path.join(d, "out_valid.npy")).astype(np.uint8)))
+        outs.append((np.load(os.path.join(d, "out_grid.npy")), np.load(os.path.join(d, "out_valid.npy")).astype(np.uint8),
+                     np.load(os.path.join(d, "out_grid3.npy")).reshape(K, J, I, 3), np.load(os.path.join(d, "out_valid3.npy")).astype(np.uint8)))
         shutil.rmtree(d)
-    for g, v in outs[1:]:
-        assert g.tobytes() == outs[0][0].tobytes() and v.tobytes() == outs[0][1].tobytes(), "thread-count dependent"
+    for o in outs[1:]:
+        assert all(a.tobytes() == b.tobytes() for a, b in zip(o, outs[0])), "thread-count dependent"
+    assert outs[0][1].tobytes() == outs[0][3].tobytes()       # one weight field, one mask
     m2 = dict(I=I, J=J, K=K, dx=dx, radius=radius, source=source_npz, key=key, seed=seed, threads=list(threads))
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), out_grid=outs[0][0], out_valid=outs[0][1])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(m2), out_grid=outs[0][0], out_valid=outs[0][1],
+                        out_grid3=outs[0][2])
     print(name, m2, "valid cells:", int(outs[0][1].sum()))
 
 

@@ -245,6 +245,10 @@ def test_attribute_p2g_fixture(oracle, name):
     grid, valid = oracle.attribute_p2g(meta["I"], meta["J"], meta["K"], meta["dx"], pos, attr, meta["radius"])
     assert np.array_equal(valid, e["out_valid"]) and bits_equal(grid, e["out_grid"])
     assert valid.sum() > 1500 and np.abs(grid[valid == 0]).max() < 1e-4      # weight <= 1e-6: unnormalised leftovers, not valid
+    # AttributeToGridTransfer<vmath::vec3> (colour): same sums per channel, but normalised by vec3 /= float (x * float(1/w))
+    attr3 = np.random.default_rng(meta["seed"] + 1000).random((len(pos), 3)).astype(np.float32)
+    grid3, valid3 = oracle.attribute_p2g_vec3(meta["I"], meta["J"], meta["K"], meta["dx"], pos, attr3, meta["radius"])
+    assert np.array_equal(valid3, valid) and bits_equal(grid3, e["out_grid3"])
     # a constant attribute comes back as that constant wherever the grid is valid (normalised weights)
     ones, v1 = oracle.attribute_p2g(meta["I"], meta["J"], meta["K"], meta["dx"], pos, np.full(len(pos), 3.0, np.float32), meta["radius"])
     assert np.array_equal(v1, valid) and np.abs(ones[valid == 1] - 3.0).max() < 1e-5
