@@ -218,7 +218,8 @@ int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed);
  * -INFINITY / +INFINITY on closed ones). The removed set is bit-for-bit the reference's. The survivors keep
  * their relative order and are renumbered 0..num_remaining-1 (ParticleSystem::removeParticles);
  * ffb200_get_particles then returns num_remaining rows. num_extreme_removed is
- * _currentExtremeVelocityParticlesRemoved. Synchronises the stream. Whole-grid contexts only. */
+ * _currentExtremeVelocityParticlesRemoved. Synchronises the stream. Whole-grid contexts only;
+ * 1 <= max_frame_time_steps <= 64, max_particles_per_cell >= 0, dt > 0 (anything else fails with a message). */
 int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_condition_number, int max_particles_per_cell,
                                    int max_frame_time_steps, int extreme_velocity_removal, const float *open_bounds,
                                    int *num_remaining, int *num_extreme_removed);
