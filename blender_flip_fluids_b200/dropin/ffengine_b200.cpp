@@ -159,6 +159,17 @@ void FluidSimulation::_updateMarkerParticleVelocitiesThread() {
 // mask to every attribute of the particle system with the reference's own ParticleSystem::removeParticles. The
 // lifetime rule reads a host-only attribute and is evaluated here, the open-boundary planes are the reference's
 // float arithmetic on its own boundary box.
+// _updateMarkerParticleVelocities (fluidsimulation.cpp:6931-6944) runs _constrainMarkerParticleVelocities on the HOST
+// after the G2P: with an enabled inflow that constrains fluid velocities (:6922-6929) the host velocities are no
+// longer the ones the G2P left on the device, and the removal's speed rules must see the host's.
+static bool host_velocities_may_differ(FluidSimulation &sim) {
+    for (size_t i = 0; i < sim._meshFluidSources.size(); i++) {
+        MeshFluidSource *source = sim._meshFluidSources[i];
+        if (source->isEnabled() && source->isInflow() && source->isConstrainedFluidVelocityEnabled()) return true;
+    }
+    return false;
+}
+
 static void remove_marker_particles_b200(FluidSimulation &sim, ffb200_context *ctx, bool particles_resident, double dt) {
     std::vector<vmath::vec3> *pos, *vel;
     sim._markerParticles.getAttributeValues("POSITION", pos);
@@ -223,7 +234,7 @@ void FluidSimulation::_advanceMarkerParticles(double dt) {
             _solidSDF._phi.getRawArray(), reinterpret_cast<uint8_t *>(_nearSolidGrid.getRawArray()), dt,
             _CFLConditionNumber));
         // device velocities are the host's only if this advection found the G2P's particles resident
-        remove_marker_particles_b200(*this, ctx, resident != 0, _currentFrameDeltaTime);
+        remove_marker_particles_b200(*this, ctx, resident != 0 && !host_velocities_may_differ(*this), _currentFrameDeltaTime);
     }
     timer.stop();
     _timingData.advanceMarkerParticles += timer.getTime();
