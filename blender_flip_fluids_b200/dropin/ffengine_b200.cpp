@@ -240,3 +240,20 @@ void FluidSimulation::_advanceMarkerParticles(double dt) {
     _timingData.advanceMarkerParticles += timer.getTime();
     _logfile.logString(_logfile.getTime() + " COMPLETE    Advect Marker Particles");
 }
+
+// ---- liquid SDF from particles (next symbol; compiled only with -DFFB200_DROPIN_LIQUID_SDF until it has run on hardware) ----
+// ParticleLevelSet::calculateSignedDistanceField (particlelevelset.cpp:161-168), called from _updateLiquidLevelSet
+// (fluidsimulation.cpp:5599) on a std::thread that _stepFluid joins at once (:10082-10083), so never concurrently with
+// the stages above. It leaves positions only on the device: the resident-input tracking is reset.
+#ifdef FFB200_DROPIN_LIQUID_SDF
+#include "particlelevelset.h"
+void ParticleLevelSet::calculateSignedDistanceField(ParticleSystem &particles, double radius) {
+    std::vector<vmath::vec3> *positions;
+    particles.getAttributeValues("POSITION", positions);
+    ffb200_context *ctx = context_for(_isize, _jsize, _ksize, _dx);
+    g_fresh_p2g_field = nullptr;
+    g_resident_particles = nullptr;
+    g_resident_field = nullptr;
+    check(ffb200_calculate_signed_distance_field(ctx, (int)positions->size(), raw(positions), radius, _phi.getRawArray()));
+}
+#endif
