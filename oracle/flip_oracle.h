@@ -6,9 +6,10 @@
  *
  * Pinning: the reference has no tests or golden vectors of its own, so
  * this restatement is pinned against the UNMODIFIED reference built from its own sources
- * (oracle/_ref/libffengine_ref.so through oracle/ref_harness.cpp): tests/test_oracle_pin.py
- * checks bit-equality in this container, and tests/golden/ holds reference-generated
- * fixtures (tests/golden/make_golden.py) that travel to the GPU box.
+ * (oracle/_ref/libffengine_ref.so through oracle/ref_harness.cpp): tests/golden/ holds the
+ * reference-generated fixtures (tests/golden/make_golden.py, index in tests/golden/README.md)
+ * that travel to the GPU box, and tests/test_oracle_golden.py checks every function below
+ * against them bit for bit.
  *
  * Layouts are the reference's host layouts: particle attributes are packed float[3] per
  * particle (vmath::vec3, vmath.h:37-61); grids are dense x-fastest, flat = i + w*(j + h*k)

@@ -1,7 +1,7 @@
 """ctypes loader for the C oracle (oracle/flip_oracle.c) -- TEST INFRASTRUCTURE.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module;
-the product package never does (tests/test_layout.py enforces it).
+the product package never does (tests/test_abi.py::test_product_never_imports_oracle enforces it).
 """
 from __future__ import annotations
 
