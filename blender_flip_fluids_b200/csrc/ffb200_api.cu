@@ -22,10 +22,14 @@ char g_error[4096] = "";
 void set_error(const char *fn, const char *what) { snprintf(g_error, sizeof(g_error), "%s - %s", fn, what); }
 
 template <class F>
-int guarded(const char *fn, ffb200_context *ctx, F &&body, bool mutates = true) {
+int guarded(const char *fn, ffb200_context *ctx, F &&body, bool mutates = true, bool declares = false) {
     try {
         if (!ctx) throw std::invalid_argument("null context");
         Context &c = *reinterpret_cast<Context *>(ctx);
+        // an ffb200_declare_resident holds for the IMMEDIATELY following call only, whatever that call is and
+        // however it ends: latched here, before any argument check of the body can throw
+        c.resident_arg = declares ? 0u : c.resident_next;
+        if (!declares) c.resident_next = 0;
         FFB_CUDA(cudaSetDevice(c.device));
         if (mutates) c.epoch++;                               // anything cached about particles / field is stale
         body(c);
@@ -702,7 +706,7 @@ int ffb200_extrapolate_velocity_field(ffb200_context *ctx, int num_layers) {
 }
 
 int ffb200_declare_resident(ffb200_context *ctx, unsigned mask) {
-    return guarded("ffb200_declare_resident", ctx, [&](Context &c) { c.resident_next = mask; }, false);
+    return guarded("ffb200_declare_resident", ctx, [&](Context &c) { c.resident_next = mask; }, false, true);
 }
 
 int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed) {
@@ -736,6 +740,18 @@ int ffb200_set_solid(ffb200_context *ctx, const float *phi, const uint8_t *near_
     return guarded("ffb200_set_solid", ctx, [&](Context &c) { set_solid_impl(impl(c), phi, near_solid); });
 }
 
+int ffb200_set_solid_device(ffb200_context *ctx, const float *d_phi, const uint8_t *d_near_solid) {
+    return guarded("ffb200_set_solid_device", ctx, [&](Context &c) {
+        if (!d_phi || !d_near_solid) throw std::invalid_argument("null solid SDF / near-solid pointer");
+        const GridDesc &g = c.g;
+        const size_t plane = (size_t)(g.I + 1) * (g.J + 1);
+        FFB_CUDA(cudaMemcpyAsync(c.phi, d_phi, plane * (g.kloc + 1) * 4, cudaMemcpyDeviceToDevice, c.stream));
+        FFB_CUDA(cudaMemcpyAsync(c.near_solid, d_near_solid, (size_t)c.ni * c.nj * c.nk, cudaMemcpyDeviceToDevice, c.stream));
+        launch_solid_clearance(c);
+        c.has_solid = true;
+    });
+}
+
 int ffb200_p2g(ffb200_context *ctx, double particle_radius, int transfer_method) {
     return guarded("ffb200_p2g", ctx, [&](Context &c) { p2g_impl(impl(c), particle_radius, transfer_method); });
 }
@@ -760,9 +776,15 @@ int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos
                                     float *u, float *v, float *w, uint8_t *validu, uint8_t *validv, uint8_t *validw) {
     return guarded("ffb200_velocity_advector_advect", ctx, [&](Context &cc) {
         ContextImpl &c = impl(cc);
-        set_particles_impl(c, n, pos, vel, affx, affy, affz);
+        const unsigned res = c.resident_arg;
+        if (res & FFB200_RESIDENT_PARTICLES) {                 // the caller vouches: the device holds exactly these particles
+            if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
+        } else {
+            set_particles_impl(c, n, pos, vel, affx, affy, affz);
+        }
         p2g_impl(c, particle_radius, transfer_method);
-        get_field_impl(c, u, v, w, validu, validv, validw);
+        // null outputs stay on the device (ffb200_get_velocity_field fetches them later)
+        if (u || v || w || validu || validv || validw) get_field_impl(c, u, v, w, validu, validv, validw);
     });
 }
 
@@ -796,20 +818,27 @@ int ffb200_update_marker_particle_velocities(ffb200_context *ctx, int n, const f
     return guarded("ffb200_update_marker_particle_velocities", ctx, [&](Context &cc) {
         ContextImpl &c = impl(cc);
         const bool apic = transfer_method == FFB200_TRANSFER_APIC;
-        if (apic && (!affx || !affy || !affz)) throw std::invalid_argument("APIC needs affine output buffers");
-        if (!apic && (!su || !sv || !sw)) throw std::invalid_argument("FLIP needs the saved velocity field");
-        const unsigned res = c.resident_next;
-        c.resident_next = 0;
+        const unsigned res = c.resident_arg;
+        const bool lazy = (res & FFB200_RESIDENT_PARTICLES) && !vel;      // outputs stay on the device
+        if (apic && !lazy && (!affx || !affy || !affz)) throw std::invalid_argument("APIC needs affine output buffers");
+        if (!apic && !(res & FFB200_RESIDENT_SAVED_FIELD) && (!su || !sv || !sw))
+            throw std::invalid_argument("FLIP needs the saved velocity field");
         if (res & FFB200_RESIDENT_PARTICLES) {                 // the caller vouches: same particles as the previous call
             if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
         } else {
             set_particles_impl(c, n, pos, vel, nullptr, nullptr, nullptr);
         }
-        if (!(res & FFB200_RESIDENT_FIELD)) upload_field(c, false, u, v, w);
-        if (!apic) upload_field(c, true, su, sv, sw);
+        if (!(res & FFB200_RESIDENT_FIELD)) {
+            StageTimer t(c, kH2D);
+            upload_field(c, false, u, v, w);
+            t.done(0);
+        }
+        if (!apic && !(res & FFB200_RESIDENT_SAVED_FIELD)) upload_field(c, true, su, sv, sw);
         sort_impl(c);                                          // spatial order for the gathers (no-op if still sorted)
         g2p_impl(c, transfer_method, ratio_pic_flip);
-        get_particles_impl(c, nullptr, vel, apic ? affx : nullptr, apic ? affy : nullptr, apic ? affz : nullptr);
+        // resident particles with null outputs: the results stay on the device until ffb200_get_particles asks
+        if (vel || !(res & FFB200_RESIDENT_PARTICLES))
+            get_particles_impl(c, nullptr, vel, apic ? affx : nullptr, apic ? affy : nullptr, apic ? affz : nullptr);
     });
 }
 
@@ -822,9 +851,8 @@ int ffb200_advance_marker_particles(ffb200_context *ctx, int n, float *pos, cons
         "ffb200_advance_marker_particles", ctx,
         [&](Context &cc) {
             ContextImpl &c = impl(cc);
-            if (n > 0 && !pos) throw std::invalid_argument("null position pointer");
-            const unsigned res = c.resident_next;
-            c.resident_next = 0;
+            const unsigned res = c.resident_arg;
+            if (n > 0 && !pos && !(res & FFB200_RESIDENT_PARTICLES)) throw std::invalid_argument("null position pointer");
             const unsigned both = FFB200_RESIDENT_PARTICLES | FFB200_RESIDENT_FIELD;
             if ((res & both) != both) c.epoch++;
             if (res & FFB200_RESIDENT_PARTICLES) {
@@ -847,7 +875,7 @@ int ffb200_advance_marker_particles(ffb200_context *ctx, int n, float *pos, cons
             sort_impl(c);
             advect_impl(c, dt, cfl_condition_number, 1);
             c.epoch++;
-            get_particles_impl(c, pos, nullptr, nullptr, nullptr, nullptr);
+            if (pos) get_particles_impl(c, pos, nullptr, nullptr, nullptr, nullptr);   // null + resident: stays on the device
         },
         false);
 }
@@ -861,8 +889,7 @@ int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float
         ContextImpl &c = impl(cc);
         if (n < 0) throw std::domain_error("negative particle count");
         if (n > 0 && !removed) throw std::invalid_argument("null output mask");
-        const unsigned res = c.resident_next;
-        c.resident_next = 0;
+        const unsigned res = c.resident_arg;
         if (n == 0 && !(res & FFB200_RESIDENT_PARTICLES)) {     // nothing to decide; the resident set is left alone
             if (num_removed) *num_removed = 0;
             if (num_extreme_removed) *num_extreme_removed = 0;
@@ -930,8 +957,7 @@ int ffb200_calculate_signed_distance_field(ffb200_context *ctx, int n, const flo
         ContextImpl &c = impl(cc);
         if (n < 0) throw std::domain_error("negative particle count");
         if (!phi) throw std::invalid_argument("null output pointer");
-        const unsigned res = c.resident_next;
-        c.resident_next = 0;
+        const unsigned res = c.resident_arg;
         if (res & FFB200_RESIDENT_PARTICLES) {
             if (n != c.n) throw std::logic_error("FFB200_RESIDENT_PARTICLES: the particle count differs from the resident set");
         } else {

@@ -111,6 +111,7 @@ struct Context {
     float *k1s[3] = {nullptr, nullptr, nullptr};
     int k1s_cap = 0;
     unsigned resident_next = 0;          // ffb200_declare_resident: inputs the next host-buffer call may skip uploading
+    unsigned resident_arg = 0;           // ... as latched for the call in progress (cleared for every other call)
     bool nondestructive = false;         // G2P/advect write to the spare SoA buffer (fixed-batch benchmarking)
     ffb200_timing timing = {};
 };

@@ -25,7 +25,10 @@ namespace ffb200 {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxSteps = 64;
+// _maxFrameTimeSteps bins of the speed histogram (the reference sizes it from the setting, :7727). The addon's
+// 'Max Substeps' goes to 100 in its normal UI; 4096 bins are 16 KB of shared memory. Beyond that the limit is
+// only enforced when the extreme-velocity rule -- the histogram's only user -- is enabled.
+constexpr int kMaxSteps = 4096;
 
 // device scalars of one removal (uint32 words)
 enum Word {
@@ -305,7 +308,8 @@ int remove_mark(Context &c, const RemoveRules &r, const uint8_t *pre_removed, ui
     if (!c.has_solid) throw CudaError("ffb200_remove_marker_particles: needs the solid SDF (ffb200_set_solid) first");
     if (c.g.kbase != 0 || c.g.kloc != c.g.K)
         throw CudaError("ffb200_remove_marker_particles: not available on z-slab contexts");
-    if (r.max_frame_steps < 1 || r.max_frame_steps > kMaxSteps) throw CudaError("ffb200_remove_marker_particles: max_frame_time_steps out of range");
+    if (r.extreme_on && (r.max_frame_steps < 1 || r.max_frame_steps > kMaxSteps))
+        throw CudaError("ffb200_remove_marker_particles: max_frame_time_steps must be in [1, 4096] for the extreme-velocity rule");
     if (r.max_per_cell < 0) throw CudaError("ffb200_remove_marker_particles: negative per-cell cap");
     if (!(r.dt > 0.0)) throw CudaError("ffb200_remove_marker_particles: dt must be positive");
     const int n = c.n;
@@ -347,11 +351,12 @@ int remove_mark(Context &c, const RemoveRules &r, const uint8_t *pre_removed, ui
 }
 
 void read_counts(Context &c, int *remaining, int *extreme_removed) {
-    uint32_t host[W_COUNT];
-    FFB_CUDA(cudaMemcpyAsync(host, c.remove_words, sizeof(host), cudaMemcpyDeviceToHost, c.stream));
+    static_assert(W_EXTREME == W_SURVIVORS + 1, "the two counts are read with one copy");
+    uint32_t host[2];
+    FFB_CUDA(cudaMemcpyAsync(host, c.remove_words + W_SURVIVORS, sizeof(host), cudaMemcpyDeviceToHost, c.stream));
     FFB_CUDA(cudaStreamSynchronize(c.stream));
-    *remaining = (int)host[W_SURVIVORS];
-    *extreme_removed = (int)host[W_EXTREME];
+    *remaining = (int)host[0];
+    *extreme_removed = (int)host[1];
 }
 
 }  // namespace

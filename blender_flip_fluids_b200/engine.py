@@ -86,6 +86,7 @@ SIGNATURES = {
     "ffb200_set_valid_velocities": [C.c_void_p, _u8p, _u8p, _u8p],
     "ffb200_extrapolate_velocity_field": [C.c_void_p, C.c_int],
     "ffb200_set_solid": [C.c_void_p, _f32p, _u8p],
+    "ffb200_set_solid_device": [C.c_void_p, C.c_void_p, C.c_void_p],
     "ffb200_p2g": [C.c_void_p, C.c_double, C.c_int],
     "ffb200_g2p": [C.c_void_p, C.c_int, C.c_double],
     "ffb200_advect": [C.c_void_p, C.c_double, C.c_double, C.c_int],
@@ -373,9 +374,10 @@ class FlipContext:
         assert nrem.value == int(removed.sum())
         return removed, extreme.value
 
-    def declare_resident(self, particles=False, field=False, solid=False):
+    def declare_resident(self, particles=False, field=False, solid=False, saved=False):
         """ffb200_declare_resident: the next host-buffer call may skip uploading what the device already holds."""
-        self._call("ffb200_declare_resident", C.c_uint((1 if particles else 0) | (2 if field else 0) | (4 if solid else 0)))
+        self._call("ffb200_declare_resident", C.c_uint((1 if particles else 0) | (2 if field else 0) | (4 if solid else 0) |
+                                                       (8 if saved else 0)))
 
     def set_valid_velocities(self, validu, validv, validw):
         su, sv, sw = mac_shapes(self.I, self.J, self.K)
@@ -400,6 +402,10 @@ class FlipContext:
         self._call("ffb200_set_solid", _ptr(phi), _ptr(near, _u8p))
         self.synchronize()
 
+    def set_solid_device(self, phi_ptr, near_ptr):
+        """ffb200_set_solid with device pointers (stored node planes of phi, whole near-solid grid)."""
+        self._call("ffb200_set_solid_device", C.c_void_p(int(phi_ptr)), C.c_void_p(int(near_ptr)))
+
     # ---- stages on resident data ----------------------------------------------------------------
     def p2g(self, radius, method):
         self._call("ffb200_p2g", C.c_double(radius), int(method))
@@ -412,12 +418,18 @@ class FlipContext:
 
     # ---- reference-named host-buffer operators --------------------------------------------------------
     def velocity_advector_advect(self, pos, vel, affx=None, affy=None, affz=None, radius=None, method=FLIP, out=None):
-        """VelocityAdvector::advect on host arrays -> ((u,v,w), (validU,validV,validW))."""
-        pos = _f32(pos)
-        n = pos.shape[0]
-        vel, affx, affy, affz = (_f32(a, (n, 3)) for a in (vel, affx, affy, affz))
+        """VelocityAdvector::advect on host arrays -> ((u,v,w), (validU,validV,validW)).
+        pos None (after declare_resident(particles=True)): the resident particles; out False: the field stays resident."""
+        if pos is None:
+            n = self.n
+        else:
+            pos = _f32(pos)
+            n = pos.shape[0]
+            vel, affx, affy, affz = (_f32(a, (n, 3)) for a in (vel, affx, affy, affz))
         radius = 0.5 * self.dx * np.sqrt(3.0) if radius is None else radius
-        if out is None:
+        if out is False:
+            out = (None,) * 6
+        elif out is None:
             su, sv, sw = mac_shapes(self.I, self.J, self.K)
             out = (np.zeros(su, np.float32), np.zeros(sv, np.float32), np.zeros(sw, np.float32),
                    np.zeros(su, np.uint8), np.zeros(sv, np.uint8), np.zeros(sw, np.uint8))
@@ -434,6 +446,13 @@ class FlipContext:
 
         inplace=True updates ``vel`` itself, as the reference does (fluidsimulation.cpp:6782);
         aff_out=(ax, ay, az) supplies the APIC output buffers (e.g. pinned memory)."""
+        apic = method == APIC
+        if pos is None:                       # resident particles (declare_resident(particles=True)): results stay on the device
+            u, v, w = (None, None, None) if mac is None else (_f32(a) for a in mac)
+            su, sv, sw = (None, None, None) if saved is None else (_f32(a) for a in saved)
+            self._call("ffb200_update_marker_particle_velocities", self.n, None, None, None, None, None, _ptr(u), _ptr(v), _ptr(w),
+                       _ptr(su), _ptr(sv), _ptr(sw), int(method), C.c_double(ratio_pic_flip))
+            return None
         pos = _f32(pos)
         n = pos.shape[0]
         vel = _f32(vel, (n, 3))
@@ -441,7 +460,6 @@ class FlipContext:
             vel = vel.copy()
         u, v, w = (_f32(a) for a in mac)
         su, sv, sw = (None, None, None) if saved is None else (_f32(a) for a in saved)
-        apic = method == APIC
         if apic and aff_out is not None:
             ax, ay, az = (_f32(a, (n, 3)) for a in aff_out)
         else:
@@ -453,6 +471,13 @@ class FlipContext:
 
     def advance_marker_particles(self, pos, mac, phi=None, near_solid=None, dt=1.0 / 60.0, cfl=5.0, inplace=False):
         """RK3 + collision on host arrays -> new positions (inplace=True overwrites ``pos``)."""
+        if pos is None:                       # resident particles and field: the advected positions stay on the device
+            phi = _f32(phi)
+            near = None if near_solid is None else np.ascontiguousarray(near_solid, dtype=np.uint8)
+            u, v, w = (None, None, None) if mac is None else (_f32(a) for a in mac)
+            self._call("ffb200_advance_marker_particles", self.n, None, _ptr(u), _ptr(v), _ptr(w), _ptr(phi), _ptr(near, _u8p),
+                       C.c_double(dt), C.c_double(cfl))
+            return None
         out = _f32(pos) if inplace else _f32(pos).copy()
         n = out.shape[0]
         u, v, w = (_f32(a) for a in mac)

@@ -151,3 +151,110 @@ def analytic_solid_sdf(I: int, J: int, K: int, dx: float, sphere: tuple[float, f
         g[:, :, :-1] |= near[:, :, 1:]
         near = g
     return phi, near
+
+
+# ---- decomposition-independent generator (large scenes, any rank count) ------------------------------
+#
+# The jitter / velocity / affine values of a particle are a pure function of (seed, global particle
+# id, component): a counter-based integer hash, evaluated with the same integer and float64
+# operations by numpy on the host and by torch on the device, so a z-slab rank, a single GPU and
+# the CPU reference arm all produce bit-identical particles for the planes they hold without ever
+# materialising the whole scene in one place.
+
+_SITE8 = [(0.25, 0.25, 0.25), (0.75, 0.25, 0.25), (0.25, 0.75, 0.25), (0.75, 0.75, 0.25),
+          (0.25, 0.25, 0.75), (0.75, 0.25, 0.75), (0.25, 0.75, 0.75), (0.75, 0.75, 0.75)]
+HASH_COMPONENTS = 16          # 3 jitter + 3 velocity + 9 affine, padded
+
+
+def _hash_u01(xp, ids, comp, seed):
+    """lowbias32-style integer hash of (seed, id, comp) -> float64 in [0, 1) with 24 random bits.
+    `ids` is an int64 array/tensor (numpy or torch); all intermediates are int64 holding 32-bit values."""
+    M = 0xFFFFFFFF
+    lo = ids & M
+    hi = (ids >> 32) & M
+    x = (lo * 0x9E3779B1 + hi * 0x7F4A7C15 + (comp * 0x85EBCA77 + seed * 0xC2B2AE3D + 0x27D4EB2F)) & M
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & M
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & M
+    x = x ^ (x >> 16)
+    return (x >> 8).to(xp.float64) * (1.0 / 16777216.0) if xp.__name__ == "torch" else (x >> 8).astype(np.float64) * (1.0 / 16777216.0)
+
+
+def dam_break_extent(I, J, K):
+    """Fluid cell box of the SURVEY 8d dam break: [3, 0.4 I) x [3, 0.8 J) x [3, K - 3)."""
+    return 3, max(4, int(0.4 * I)), 3, max(4, int(0.8 * J)), 3, K - 3
+
+
+def dam_break_count(I, J, K, ppc=8, k0=None, k1=None):
+    i0, i1, j0, j1, kk0, kk1 = dam_break_extent(I, J, K)
+    k0 = kk0 if k0 is None else max(kk0, k0)
+    k1 = kk1 if k1 is None else min(kk1, k1)
+    return max(0, k1 - k0) * (j1 - j0) * (i1 - i0) * ppc
+
+
+def dam_break_planes(I, J, K, dx, k0, k1, apic=True, v0=0.5, seed=1234, jitter=0.05, xp=np, device=None, chunk_planes=8):
+    """Particles of the cell planes [k0, k1) of the hashed dam break I x J x K (8 per cell, the reference's
+    sub-cell sites, fluidsimulation.cpp:8045-8055), as SoA float32 streams [px,py,pz,vx,vy,vz(,9 affine)]
+    plus int64 global ids, in (k, j, i, site) order. xp = numpy (host) or torch (`device`)."""
+    i0, i1, j0, j1, kk0, kk1 = dam_break_extent(I, J, K)
+    k0, k1 = max(kk0, k0), min(kk1, k1)
+    ni, nj = i1 - i0, j1 - j0
+    per_plane = ni * nj * 8
+    nstream = 15 if apic else 6
+    is_torch = xp.__name__ == "torch"
+    n = max(0, k1 - k0) * per_plane
+    if is_torch:
+        out = [xp.empty(n, dtype=xp.float32, device=device) for _ in range(nstream)]
+        ids_out = xp.empty(n, dtype=xp.int64, device=device)
+        ar = lambda m: xp.arange(m, dtype=xp.int64, device=device)
+        site = xp.tensor(_SITE8, dtype=xp.float64, device=device)
+        f64 = lambda t: t.to(xp.float64)
+        f32 = lambda t: t.to(xp.float32)
+    else:
+        out = [np.empty(n, np.float32) for _ in range(nstream)]
+        ids_out = np.empty(n, np.int64)
+        ar = lambda m: np.arange(m, dtype=np.int64)
+        site = np.array(_SITE8, np.float64)
+        f64 = lambda t: t.astype(np.float64)
+        f32 = lambda t: t.astype(np.float32)
+    for ka in range(k0, k1, chunk_planes):
+        kb = min(k1, ka + chunk_planes)
+        m = (kb - ka) * per_plane
+        local = ar(m)
+        s = local % 8
+        c = local // 8
+        ci = c % ni + i0
+        cj = (c // ni) % nj + j0
+        ck = c // (ni * nj) + ka
+        gid = local + (ka - kk0) * per_plane
+        o = (ka - k0) * per_plane
+        cell = (ci, cj, ck)
+        for a in range(3):
+            u = _hash_u01(xp, gid, a, seed)
+            p = (f64(cell[a]) + site[s, a]) * dx + (2.0 * u - 1.0) * (jitter * dx)
+            out[a][o:o + m] = f32(p)
+        for a in range(3):
+            u = _hash_u01(xp, gid, 3 + a, seed)
+            out[3 + a][o:o + m] = f32((2.0 * u - 1.0) * v0)
+        if apic:
+            for a in range(9):
+                u = _hash_u01(xp, gid, 6 + a, seed)
+                out[6 + a][o:o + m] = f32((2.0 * u - 1.0) * (0.1 / dx))
+        ids_out[o:o + m] = gid
+    return out, ids_out
+
+
+def analytic_solid_sdf_planes(I, J, K, dx, k0, k1, xp=np, device=None):
+    """Node planes [k0, k1] (inclusive) of analytic_solid_sdf's wall SDF (no sphere), float32 [(k1-k0+1), J+1, I+1]:
+    the same double expression, narrowed once, so slabs and the full array agree bit for bit."""
+    inset = 0.5 * (3.0 * dx + 1e-4)
+    if xp.__name__ == "torch":
+        ar = lambda a, b: xp.arange(a, b, dtype=xp.float64, device=device)
+        z, y, x = xp.meshgrid(ar(k0, k1 + 1) * dx, ar(0, J + 1) * dx, ar(0, I + 1) * dx, indexing="ij")
+        d = xp.minimum(xp.minimum(xp.minimum(x - inset, I * dx - inset - x), xp.minimum(y - inset, J * dx - inset - y)),
+                       xp.minimum(z - inset, K * dx - inset - z))
+        return d.to(xp.float32)
+    z, y, x = np.meshgrid(np.arange(k0, k1 + 1) * dx, np.arange(J + 1) * dx, np.arange(I + 1) * dx, indexing="ij")
+    d = np.minimum.reduce([x - inset, I * dx - inset - x, y - inset, J * dx - inset - y, z - inset, K * dx - inset - z])
+    return d.astype(np.float32)

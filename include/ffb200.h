@@ -219,7 +219,8 @@ int ffb200_get_maximum_particle_speed(ffb200_context *ctx, double *speed);
  * their relative order and are renumbered 0..num_remaining-1 (ParticleSystem::removeParticles);
  * ffb200_get_particles then returns num_remaining rows. num_extreme_removed is
  * _currentExtremeVelocityParticlesRemoved. Synchronises the stream. Whole-grid contexts only;
- * 1 <= max_frame_time_steps <= 64, max_particles_per_cell >= 0, dt > 0 (anything else fails with a message). */
+ * max_particles_per_cell >= 0, dt > 0; with the extreme-velocity rule on, 1 <= max_frame_time_steps <= 4096 (the
+ * addon UI allows 100; the setting sizes the speed histogram, fluidsimulation.cpp:7727). Anything else fails with a message. */
 int ffb200_remove_marker_particles(ffb200_context *ctx, double dt, double cfl_condition_number, int max_particles_per_cell,
                                    int max_frame_time_steps, int extreme_velocity_removal, const float *open_bounds,
                                    int *num_remaining, int *num_extreme_removed);
@@ -238,6 +239,11 @@ int ffb200_get_liquid_sdf(ffb200_context *ctx, float *phi);
  * solid go to -dx/2, magnitudes below 0.005 dx are clamped away from zero. (Experimental in round 1: pinned against
  * the reference on the CPU, its kernel has not run on hardware yet.) */
 int ffb200_postprocess_liquid_sdf(ffb200_context *ctx);
+
+/* ffb200_set_solid with DEVICE pointers: d_phi holds the context's stored node planes only
+ * ((I+1)(J+1)(kloc+1) floats, first plane = the context's first stored cell plane), d_near_solid the whole
+ * ceil(I/3) x ceil(J/3) x ceil(K/3) byte grid. For scenes too large to stage through host arrays per rank. */
+int ffb200_set_solid_device(ffb200_context *ctx, const float *d_phi, const uint8_t *d_near_solid);
 
 /* ---- stages on resident data ---------------------------------------------------------------------- */
 
@@ -262,11 +268,21 @@ int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos
  * sorted order on the device; outputs are still written to the host arrays in the caller's order).
  *   FFB200_RESIDENT_PARTICLES  positions, velocities (and affine rows) equal those of the previous call
  *   FFB200_RESIDENT_FIELD      u, v, w equal those of the previous call
- * Honoured by ffb200_update_marker_particle_velocities, ffb200_advance_marker_particles and
- * ffb200_mark_removed_marker_particles; the particle count must match or the call fails. */
+ *   FFB200_RESIDENT_SAVED_FIELD the device's saved field (ffb200_save_velocity_field) is the caller's _savedVelocityField
+ * Honoured by ffb200_velocity_advector_advect, ffb200_update_marker_particle_velocities,
+ * ffb200_advance_marker_particles, ffb200_mark_removed_marker_particles and
+ * ffb200_calculate_signed_distance_field; the particle count must match or the call fails. The declaration is
+ * consumed -- or dropped -- by the very next call on the context, whichever entry point that is.
+ *
+ * Residency across stages AND substeps (the generation protocol the interposer runs): with
+ * FFB200_RESIDENT_PARTICLES the particle pointers of those entry points may be NULL. Inputs are then taken
+ * from the device and OUTPUTS STAY THERE (G2P velocities / affine rows, advected positions); the host copy is
+ * stale until ffb200_get_particles fetches what host code actually reads. Null field outputs of
+ * ffb200_velocity_advector_advect likewise stay resident (ffb200_get_velocity_field). */
 #define FFB200_RESIDENT_PARTICLES 1u
 #define FFB200_RESIDENT_FIELD 2u
 #define FFB200_RESIDENT_SOLID 4u     /* ffb200_mark_removed_marker_particles: phi equals that of the previous call */
+#define FFB200_RESIDENT_SAVED_FIELD 8u
 int ffb200_declare_resident(ffb200_context *ctx, unsigned mask);
 
 /* _removeMarkerParticles (fluidsimulation.cpp:7773-7851, called at :7892 right after the advection) on host
