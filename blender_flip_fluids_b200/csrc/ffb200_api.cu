@@ -934,6 +934,56 @@ int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float
     });
 }
 
+int ffb200_remove_marker_particles_masked(ffb200_context *ctx, const float *open_bounds, const uint8_t *pre_removed, double dt,
+                                          double cfl_condition_number, int max_particles_per_cell, int max_frame_time_steps,
+                                          int extreme_velocity_removal, uint8_t *removed, int *num_remaining,
+                                          int *num_extreme_removed) {
+    return guarded("ffb200_remove_marker_particles_masked", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        const int n = c.n;
+        if (n > 0 && !removed) throw std::invalid_argument("null output mask");
+        uint8_t *bytes = reinterpret_cast<uint8_t *>(c.aos_stage);     // 12 bytes per particle of capacity: [pre-removed | removed]
+        uint8_t *d_pre = nullptr, *d_removed = bytes + (size_t)c.cap * 4;
+        if (pre_removed && n > 0) {
+            d_pre = bytes;
+            FFB_CUDA(cudaMemcpyAsync(d_pre, pre_removed, (size_t)n, cudaMemcpyHostToDevice, c.stream));
+        }
+        int remaining = n, extreme = 0;
+        if (n > 0) {
+            launch_remove_particles(c, remove_rules(dt, cfl_condition_number, max_particles_per_cell, max_frame_time_steps,
+                                                    extreme_velocity_removal, open_bounds),
+                                    &remaining, &extreme, d_pre, d_removed);
+            if (remaining != n) {                                  // the usual substep removes nothing: no mask traffic then
+                StageTimer t(c, kD2H);
+                FFB_CUDA(cudaMemcpyAsync(removed, d_removed, (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+                t.done(0);
+                FFB_CUDA(cudaStreamSynchronize(c.stream));
+            } else {
+                std::memset(removed, 0, (size_t)n);
+            }
+        }
+        if (num_remaining) *num_remaining = remaining;
+        if (num_extreme_removed) *num_extreme_removed = extreme;
+    });
+}
+
+int ffb200_pin_host_memory(ffb200_context *ctx, void *ptr, size_t bytes) {
+    return guarded("ffb200_pin_host_memory", ctx, [&](Context &) {
+        if (!ptr || bytes == 0) throw std::invalid_argument("null host range");
+        cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+        if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return; }
+        if (e != cudaSuccess) { cudaGetLastError(); throw CudaError(std::string("cudaHostRegister failed: ") + cudaGetErrorString(e)); }
+    }, false);
+}
+
+int ffb200_unpin_host_memory(ffb200_context *ctx, void *ptr) {
+    return guarded("ffb200_unpin_host_memory", ctx, [&](Context &) {
+        if (!ptr) throw std::invalid_argument("null host pointer");
+        cudaError_t e = cudaHostUnregister(ptr);
+        if (e != cudaSuccess) cudaGetLastError();                  // not registered (any more): nothing to undo
+    }, false);
+}
+
 int ffb200_liquid_sdf(ffb200_context *ctx, double particle_radius) {
     return guarded("ffb200_liquid_sdf", ctx, [&](Context &c) { launch_liquid_sdf(c, particle_radius); }, false);
 }

@@ -152,7 +152,8 @@ struct RemoveRules {
     float bounds[6];                     // open-boundary planes {x-, x+, y-, y+, z-, z+}; -inf / +inf where closed
 };
 // _removeMarkerParticles on the resident particles; updates c.n, leaves the survivors in host order
-int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, int *extreme_removed);
+int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, int *extreme_removed,
+                            const uint8_t *pre_removed = nullptr, uint8_t *removed_by_orig = nullptr);
 // the same decisions without the compaction: one byte per ORIGINAL index (device pointers; pre_removed may be null)
 int launch_remove_mask(Context &c, const RemoveRules &r, const uint8_t *pre_removed, uint8_t *removed_by_orig, int *remaining,
                        int *extreme_removed);

@@ -368,8 +368,9 @@ int launch_remove_mask(Context &c, const RemoveRules &r, const uint8_t *pre_remo
     return launches;
 }
 
-int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, int *extreme_removed) {
-    int launches = remove_mark(c, r, nullptr, nullptr);
+int launch_remove_particles(Context &c, const RemoveRules &r, int *remaining, int *extreme_removed, const uint8_t *pre_removed,
+                            uint8_t *removed_by_orig) {
+    int launches = remove_mark(c, r, pre_removed, removed_by_orig);
     const int n = c.n;
     read_counts(c, remaining, extreme_removed);
     if (*remaining != n) {                                   // the usual substep removes nothing: no compaction then

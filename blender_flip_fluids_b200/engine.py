@@ -98,6 +98,10 @@ SIGNATURES = {
     "ffb200_postprocess_liquid_sdf": [C.c_void_p],
     "ffb200_calculate_signed_distance_field": [C.c_void_p, C.c_int, _f32p, C.c_double, _f32p],
     "ffb200_remove_marker_particles": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "ffb200_remove_marker_particles_masked": [C.c_void_p, _f32p, _u8p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _u8p,
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "ffb200_pin_host_memory": [C.c_void_p, C.c_void_p, C.c_size_t],
+    "ffb200_unpin_host_memory": [C.c_void_p, C.c_void_p],
     "ffb200_mark_removed_marker_particles": [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _u8p, _f32p, _u8p, C.c_double, C.c_double, C.c_int,
                                              C.c_int, C.c_int, _u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "ffb200_extrapolate_fluid_velocities": [C.c_void_p, _f32p, _f32p, _f32p, _u8p, _u8p, _u8p, C.c_int, C.c_int],
@@ -350,6 +354,23 @@ class FlipContext:
                    int(max_frame_time_steps), 1 if extreme_velocity_removal else 0, _ptr(ob), C.byref(remaining), C.byref(extreme))
         self.n = remaining.value
         return remaining.value, extreme.value
+
+    def remove_marker_particles_masked(self, dt, cfl=5.0, max_particles_per_cell=250, max_frame_time_steps=6,
+                                       extreme_velocity_removal=True, open_bounds=None, pre_removed=None):
+        """_removeMarkerParticles on the RESIDENT particles, compacting the device set and returning the mask (in the
+        order the ids had before the call) for the host's own compaction -> (removed mask, extreme removed)."""
+        n = self.n
+        ob = None if open_bounds is None else np.ascontiguousarray(open_bounds, dtype=np.float32).reshape(6)
+        pre = None if pre_removed is None else np.ascontiguousarray(pre_removed, dtype=np.uint8).reshape(n)
+        removed = np.ones(max(n, 1), np.uint8)
+        remaining, extreme = C.c_int(), C.c_int()
+        self._call("ffb200_remove_marker_particles_masked", _ptr(ob), _ptr(pre, _u8p), C.c_double(dt), C.c_double(cfl),
+                   int(max_particles_per_cell), int(max_frame_time_steps), 1 if extreme_velocity_removal else 0,
+                   _ptr(removed, _u8p), C.byref(remaining), C.byref(extreme))
+        removed = removed[:n]
+        assert remaining.value == n - int(removed.sum())
+        self.n = remaining.value
+        return removed, extreme.value
 
     def mark_removed_marker_particles(self, pos, vel, phi, near_solid, dt, cfl=5.0, max_particles_per_cell=250, max_frame_time_steps=6,
                                       extreme_velocity_removal=True, open_bounds=None, pre_removed=None):

@@ -39,6 +39,7 @@
 #ifndef FFB200_H
 #define FFB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -298,6 +299,23 @@ int ffb200_mark_removed_marker_particles(ffb200_context *ctx, int n, const float
                                          double dt, double cfl_condition_number, int max_particles_per_cell,
                                          int max_frame_time_steps, int extreme_velocity_removal, uint8_t *removed,
                                          int *num_removed, int *num_extreme_removed);
+
+/* The same decisions for RESIDENT particles and a resident solid SDF (the advection has just left both on the
+ * device), applied on both sides: the device set is compacted exactly as ffb200_remove_marker_particles does
+ * (survivors keep their order, ids renumbered 0..num_remaining-1) and `removed` (n bytes, the count before the
+ * call) tells the host which entries of its own attribute vectors to drop (ParticleSystem::removeParticles),
+ * so that host index i and device id i stay the same particle without the arrays crossing PCIe. When nothing
+ * is removed -- the usual substep -- `removed` is cleared on the host and no mask is downloaded. */
+int ffb200_remove_marker_particles_masked(ffb200_context *ctx, const float *open_bounds, const uint8_t *pre_removed, double dt,
+                                          double cfl_condition_number, int max_particles_per_cell, int max_frame_time_steps,
+                                          int extreme_velocity_removal, uint8_t *removed, int *num_remaining,
+                                          int *num_extreme_removed);
+
+/* Page-lock / release a host range the caller keeps alive (cudaHostRegister): the interposer pins the reference's
+ * long-lived MAC field arrays once, so that the per-substep field transfers run at pinned-memory speed out of the
+ * reference's own containers. Pinning an already pinned range succeeds. */
+int ffb200_pin_host_memory(ffb200_context *ctx, void *ptr, size_t bytes);
+int ffb200_unpin_host_memory(ffb200_context *ctx, void *ptr);
 
 /* ParticleLevelSet::calculateSignedDistanceField on host positions -> phi (I*J*K floats, the layout of
  * Array3d<float>::getRawArray()). Uploads the positions unless FFB200_RESIDENT_PARTICLES was declared. */

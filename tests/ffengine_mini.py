@@ -22,6 +22,24 @@ class MarkerParticleAffineData(C.Structure):    # fluidsimulation.h:159-164
     _fields_ = [("size", C.c_int), ("affineX", C.c_char_p), ("affineY", C.c_char_p), ("affineZ", C.c_char_p)]
 
 
+class MeshStats(C.Structure):                   # fluidsimulation.h:62-67
+    _fields_ = [("enabled", C.c_int), ("vertices", C.c_int), ("triangles", C.c_int), ("bytes", C.c_uint)]
+
+
+class TimingStats(C.Structure):                 # fluidsimulation.h:69-78
+    _fields_ = [(k, C.c_double) for k in ("total", "mesh", "advection", "particles", "pressure", "diffuse", "viscosity", "objects")]
+
+
+class FrameStats(C.Structure):                  # fluidsimulation.h:80-150: 50 mesh records, the timing block last
+    _fields_ = [("frame", C.c_int), ("substeps", C.c_int), ("delta_time", C.c_double), ("fluid_particles", C.c_int),
+                ("diffuse_particles", C.c_int), ("performance_score", C.c_int), ("pressure_solver_enabled", C.c_int),
+                ("pressure_solver_success", C.c_int), ("pressure_solver_error", C.c_double),
+                ("pressure_solver_iterations", C.c_int), ("pressure_solver_max_iterations", C.c_int),
+                ("viscosity_solver_enabled", C.c_int), ("viscosity_solver_success", C.c_int),
+                ("viscosity_solver_error", C.c_double), ("viscosity_solver_iterations", C.c_int),
+                ("viscosity_solver_max_iterations", C.c_int), ("mesh", MeshStats * 50), ("timing", TimingStats)]
+
+
 class Engine:
     def __init__(self, lib_path, isize, jsize, ksize, dx):
         self.lib = C.CDLL(lib_path)
@@ -60,6 +78,24 @@ class Engine:
     def add_body_force(self, x, y, z): self._void("FluidSimulation_add_body_force", x, y, z, argtypes=[C.c_double] * 3)  # :2599
     def initialize(self): self._void("FluidSimulation_initialize")                                     # :97
     def update(self, dt): self._void("FluidSimulation_update", dt, argtypes=[C.c_double])              # :115
+
+    def enable_surface_velocity_attribute(self): self._void("FluidSimulation_enable_surface_velocity_attribute")      # :1070
+    def enable_surface_velocity_attribute_against_obstacles(self):                                     # :1091
+        self._void("FluidSimulation_enable_surface_velocity_attribute_against_obstacles")
+    def enable_fluid_particle_lifetime_attribute(self): self._void("FluidSimulation_enable_fluid_particle_lifetime_attribute")  # :938
+
+    def set_fluid_boundary_collisions(self, active6):                                                  # :226 (x-, x+, y-, y+, z-, z+)
+        arr = (C.c_int * 6)(*[int(bool(a)) for a in active6])
+        self._void("FluidSimulation_set_fluid_boundary_collisions", arr, argtypes=[C.POINTER(C.c_int)])
+
+    def frame_stats(self):                                                                             # :4618 (struct by value)
+        f = self.lib.FluidSimulation_get_frame_stats_data
+        f.restype = FrameStats
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        err = C.c_int(0)
+        st = f(self.obj, C.byref(err))
+        self._check(err, "FluidSimulation_get_frame_stats_data")
+        return st
 
     def load_marker_particle_data(self, pos, vel):                                                     # :4872
         pos, vel = np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(vel, np.float32)

@@ -92,7 +92,12 @@ def test_dropin_reexports_reference_abi():
     assert defined == {"_ZN16VelocityAdvector6advectE26VelocityAdvectorParameters",
                        "_ZN15FluidSimulation37_updateMarkerParticleVelocitiesThreadEv",
                        "_ZN15FluidSimulation23_advanceMarkerParticlesEd",
-                       "_ZN15FluidSimulation27_extrapolateFluidVelocitiesER16MACVelocityFieldR26ValidVelocityComponentGrid"}
+                       "_ZN15FluidSimulation27_extrapolateFluidVelocitiesER16MACVelocityFieldR26ValidVelocityComponentGrid",
+                       "_ZN16ParticleLevelSet28calculateSignedDistanceFieldER14ParticleSystemd",
+                       "_ZN15FluidSimulation30_getMaximumMarkerParticleSpeedEv",
+                       # bookkeeping hooks that forward to the reference's definition (dlsym RTLD_NEXT)
+                       "_ZN14ParticleSystem25getAttributeValuesVector3ER23ParticleSystemAttribute",
+                       "_ZN15FluidSimulation10initializeEv"}
     needed = subprocess.run(["readelf", "-d", dropin], capture_output=True, text=True, check=True).stdout
     assert "libffb200.so" in needed and "libffengine_cpu.so" in needed
     refsyms = subprocess.run(["nm", "-D", "--defined-only", ref], capture_output=True, text=True, check=True).stdout
@@ -123,3 +128,35 @@ def test_bench_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_dropin_without_usable_device_reports_error_flag(tmp_path):
+    """No CUDA device (this CPU box) or an ordinal that does not exist (FFB200_DEVICE=99 on a GPU box): the drop-in
+    has no CPU fallback, so FluidSimulation_update must fail -- as err = 0 + message (cbindings.h:48-154), with the
+    process alive and the particle getters still answering, never as std::terminate."""
+    dropin = os.path.join(ROOT, "blender_flip_fluids_b200", "lib", "libffengine_b200.so")
+    if not os.path.exists(dropin):
+        pytest.skip("drop-in not built (needs /root/reference)")
+    code = '''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from blender_flip_fluids_b200 import scenes
+from ffengine_mini import Engine
+sc = scenes.dam_break(16, apic=False, dx=0.02, vel="swirl", v0=0.4, seed=17)
+e = Engine(%r, 16, 16, 16, sc.dx)
+e.disable_console_output(); e.disable_surface_reconstruction(); e.set_max_thread_count(2)
+e.load_marker_particle_data(sc.pos, sc.vel)
+e.initialize()
+try:
+    e.update(1.0 / 60.0)
+    print("UPDATED")
+except RuntimeError as ex:
+    print("ERR", ex)
+print("ALIVE", e.num_marker_particles(), e.positions().shape[0])
+e.close()
+''' % (ROOT, os.path.join(ROOT, "tests"), dropin)
+    env = dict(os.environ, FFB200_DEVICE="99")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "ERR FluidSimulation_update - ffb200_create" in r.stdout and "UPDATED" not in r.stdout, r.stdout[-1500:]
+    assert "ALIVE 2160 2160" in r.stdout

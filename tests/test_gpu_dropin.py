@@ -1,13 +1,15 @@
-"""Drop-in test (-m gpu): the same small simulation driven through the reference's own
+"""Drop-in tests (-m gpu): the same small simulation driven through the reference's own
 `FluidSimulation_*` C ABI, once with the unmodified reference library and once with
-libffengine_b200.so (P2G, valid-face extrapolation, G2P and advection on the GPU, everything else
-reference CPU code).
+libffengine_b200.so (liquid SDF, P2G, valid-face extrapolation, G2P, advection + removal and the CFL
+speed on the GPU with the particles RESIDENT across stages and substeps, everything else reference
+CPU code).
 
-With FFB200_EXACT_P2G=1 the GPU P2G sums every face in the reference's order, and since G2P
-and advection are bit-exact, the WHOLE simulation must come out bit-identical. With the
-default (fast) P2G the grid differs by summation order (~1e-7 relative), which the pressure
-solve amplifies slightly: positions are compared at 1e-4 of the domain size.
+With FFB200_EXACT_P2G=1 the GPU P2G sums every face in the reference's order, and since the other
+stages are bit-exact, the WHOLE simulation must come out bit-identical. With the default (fast)
+P2G the grid differs by summation order (~1e-7 relative), which the pressure solve amplifies
+slightly: positions are compared at 1e-4 of the domain size.
 """
+import json
 import os
 import subprocess
 import sys
@@ -23,26 +25,84 @@ DROPIN = os.path.join(ROOT, "blender_flip_fluids_b200", "lib", "libffengine_b200
 RUN = os.path.join(ROOT, "tests", "dropin_run.py")
 
 
-def _run(lib, out, method, env_extra=None):
+def _libs():
+    # built by __graft_entry__.build() where the reference sources exist and shipped with the tree: a GPU box
+    # without them is a broken deployment, not a reason to skip
+    assert os.path.exists(REF), "oracle/_ref/libffengine_ref.so is missing (run __graft_entry__.build() where /root/reference exists)"
+    assert os.path.exists(DROPIN), "blender_flip_fluids_b200/lib/libffengine_b200.so is missing"
+
+
+def _run(lib, out, method, env_extra=None, frames=2, n=24, features="", expect_fail=False):
     env = dict(os.environ)
     env.update(env_extra or {})
-    r = subprocess.run([sys.executable, RUN, lib, out, method, "2"], capture_output=True, text=True, env=env)
+    r = subprocess.run([sys.executable, RUN, lib, out, method, str(frames), str(n), features], capture_output=True, text=True,
+                       env=env, timeout=900)
+    if expect_fail:
+        return r
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    return np.load(out)
+    stats = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("STATS ")][-1][6:])
+    return np.load(out), stats
+
+
+def _identical(a, b, what):
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert a[k].shape == b[k].shape, f"{what}: {k} shape {a[k].shape} vs {b[k].shape}"
+        assert a[k].tobytes() == b[k].tobytes(), f"{what}: {k} is not bit-identical to the reference"
 
 
 @pytest.mark.parametrize("method", ["flip", "apic"])
 def test_dropin_matches_reference(tmp_path, method):
-    if not (os.path.exists(REF) and os.path.exists(DROPIN)):
-        pytest.skip("reference / drop-in libraries not built (need /root/reference at build time)")
-    ref = _run(REF, str(tmp_path / "ref.npz"), method)
-    exact = _run(DROPIN, str(tmp_path / "exact.npz"), method, {"FFB200_EXACT_P2G": "1"})
-    for k in ref.files:
-        assert ref[k].shape == exact[k].shape
-        assert ref[k].tobytes() == exact[k].tobytes(), f"{k}: exact-mode drop-in is not bit-identical to the reference"
-    fast = _run(DROPIN, str(tmp_path / "fast.npz"), method)
+    _libs()
+    ref, _ = _run(REF, str(tmp_path / "ref.npz"), method)
+    exact, _ = _run(DROPIN, str(tmp_path / "exact.npz"), method, {"FFB200_EXACT_P2G": "1"})
+    _identical(ref, exact, "exact-mode drop-in (resident particles)")
+    eager, _ = _run(DROPIN, str(tmp_path / "eager.npz"), method, {"FFB200_EXACT_P2G": "1", "FFB200_DROPIN_LAZY": "0", "FFB200_DROPIN_PIN": "0"})
+    _identical(ref, eager, "exact-mode drop-in (every result downloaded at once, pageable)")
+    fast, _ = _run(DROPIN, str(tmp_path / "fast.npz"), method)
     assert ref["pos"].shape == fast["pos"].shape
     size = 24 * 0.02
     assert np.abs(fast["pos"].astype(np.float64) - ref["pos"]).max() <= 1e-4 * size
     vscale = np.abs(ref["vel"]).max()
     assert np.abs(fast["vel"].astype(np.float64) - ref["vel"]).max() <= 2e-3 * vscale
+
+
+@pytest.mark.parametrize("features,frames", [("open,surfvel", 3), ("lifetime", 2), ("open,lifetime,surfvel", 2)])
+def test_dropin_feature_scenes(tmp_path, features, frames):
+    """Branches the plain scene never takes: an open domain side (removal planes), the lifetime rule (a host-only
+    attribute evaluated by the interposer; loaded particles carry lifetime 0, so the rule removes the whole set at
+    once) and the surface-velocity attribute against obstacles -- the SECOND VelocityAdvector::advect +
+    _extrapolateFluidVelocities call site (fluidsimulation.cpp:6951-6977), whose host readers also exercise the
+    lazy download through the accessor hook. Bit-identical in exact mode, particle counts included."""
+    _libs()
+    ref, rs = _run(REF, str(tmp_path / "ref.npz"), "flip", frames=frames, features=features)
+    got, gs = _run(DROPIN, str(tmp_path / "got.npz"), "flip", {"FFB200_EXACT_P2G": "1"}, frames=frames, features=features)
+    _identical(ref, got, f"drop-in with {features}")
+    assert rs["fluid_particles"] == gs["fluid_particles"]
+
+
+def test_dropin_config1_64cubed_flip(tmp_path):
+    """BASELINE.json configs[0] as written: dam break 64^3, ~8 particles per cell, FLIP ratio 0.95 (PIC 0.05), one
+    substep through FluidSimulation_update (fluidsimulation_c.cpp:115) -- bit-identical to the unmodified reference
+    in exact mode, and the timing block of FluidSimulation_get_frame_stats_data (:4618) filled by the interposed
+    stages (the addon's stats read it)."""
+    _libs()
+    ref, rs = _run(REF, str(tmp_path / "ref.npz"), "flip", frames=1, n=64)
+    got, gs = _run(DROPIN, str(tmp_path / "got.npz"), "flip", {"FFB200_EXACT_P2G": "1"}, frames=1, n=64)
+    assert ref["pos"].shape[0] > 400000
+    _identical(ref, got, "config #1")
+    assert gs["substeps"] == rs["substeps"] >= 1 and gs["fluid_particles"] == rs["fluid_particles"]
+    t = gs["timing"]
+    assert t["total"] > 0 and t["advection"] > 0 and t["particles"] > 0 and t["pressure"] > 0, t
+    assert t["advection"] < rs["timing"]["advection"], (t, rs["timing"])    # P2G + extrapolation: GPU vs 4 CPU threads
+
+
+@pytest.mark.parametrize("stage", ["liquid_sdf", "p2g", "extrapolate", "g2p", "advect", "max_speed"])
+def test_dropin_stage_failure_surfaces_as_error_flag(tmp_path, stage):
+    """A failing stage -- three of them run on std::threads the reference joins at once (fluidsimulation.cpp:5663-5669,
+    5611-5618) -- must come back as err = 0 + message from FluidSimulation_update (cbindings.h:48-154), not as
+    std::terminate: the process stays alive and reports the stage."""
+    _libs()
+    r = _run(DROPIN, str(tmp_path / "x.npz"), "flip", {"FFB200_DROPIN_INJECT": stage}, frames=1, expect_fail=True)
+    assert r.returncode == 1 and "RuntimeError" in r.stderr, (r.returncode, r.stderr[-800:])
+    assert "FluidSimulation_update" in r.stderr and f"injected failure in {stage}" in r.stderr, r.stderr[-800:]

@@ -605,23 +605,19 @@ print("ok")
 '''
 
 
-@pytest.mark.skipif(__import__("os").environ.get("FFB200_TEST_EXPERIMENTAL") != "1",
-                    reason="FFB200_SDF_VARIANT=1 (per-axis liquid-SDF scatter) and the SDF post-process kernel were written after the round's GPU budget was spent; "
-                           "its decomposition is proven on the CPU (test_liquid_sdf_axes_decomposition); set "
-                           "FFB200_TEST_EXPERIMENTAL=1 to run it on hardware")
-def test_liquid_sdf_variant1_experimental():
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_liquid_sdf_variants_and_postprocess(variant):
+    """Both scatter kernels (1 = per-axis lists, the default; 0 = the first version) and the post-process kernel
+    against the reference-generated fixtures, bit for bit (a fresh process per variant: the switch is read once)."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ)
-    e["FFB200_SDF_VARIANT"] = "1"
+    e["FFB200_SDF_VARIANT"] = variant
     r = subprocess.run([sys.executable, "-c", SDF_VARIANT_CHECK, root], capture_output=True, text=True, env=e, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
-@pytest.mark.skipif(__import__("os").environ.get("FFB200_TEST_EXPERIMENTAL") != "1",
-                    reason="engine.AttributeTransfer composes hardware-validated kernels, but the composition itself was written "
-                           "after the round's GPU budget was spent; set FFB200_TEST_EXPERIMENTAL=1 to run it on hardware")
-def test_attribute_transfer_composition_experimental(eng):
+def test_attribute_transfer_composition(eng):
     """AttributeToGridTransfer<float>::transfer through the U-direction FLIP P2G of a grid one cell narrower."""
     meta, e = load_golden("attribute_24x20x22_r1")
     _, src = load_golden(meta["source"])
