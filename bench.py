@@ -1,24 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- FLIP substep particle-updates/s (P2G + G2P + advect) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 512]
 
-One "step" is one pass of the hot path over the scene's particles: cell binning + sort, P2G
-(U, V, W), velocity-field save, G2P, RK3 advection with collision. The workload at N=1 is
-BASELINE.json configs[1]: dam break 128^3, APIC, RK3 (4.64 M particles, synthetic, seeded).
-At N>1 the domain is 128 x 128 x (128*N), z-slab sharded, one rank per GPU (weak scaling).
+One "step" is one pass of the hot path over the scene's particles: cell binning + sort, P2G (U, V, W),
+velocity-field save, G2P, RK3 advection with collision.
 
-`value`   device-resident throughput: particle arrays and grids live in HBM, K steps timed
-          with CUDA events between barriers, max over ranks.
-`e2e`     the same metric through the reference-facing host-buffer entry points of the C ABI
-          (ffb200_velocity_advector_advect / _update_marker_particle_velocities /
-          _advance_marker_particles) with PINNED HOST buffers, H2D/D2H inside the timed region.
-`roofline` the dominant kernel (k_p2g): algorithmic bytes per launch / its live CUDA-event
-          duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-`cpu_baseline` the unmodified reference engine (oracle/_ref, built from /root/reference) timed
-          on this box's host cores for the same three stages on a bounded sample.
+WORKLOAD (every N, strong scaling): BASELINE.json configs[3] -- dam break 512 x 512 x 512, APIC transfer,
+8 particles per cell (330 341 088 particles), z-slab sharded across the N ranks (N = 1: one context holds the
+whole scene, ~133 GB of the 180 GB). Particles come from a counter-based hash of (seed, global particle id)
+(blender_flip_fluids_b200/scenes.py), so every decomposition -- and the CPU reference arm -- sees
+bit-identical particles. The batch EVOLVES: every step sorts the particles the previous step advected, ranks
+migrate particles for real. Where the reference's CPU pressure projection would hand back a field, the MAC
+field is overwritten with an analytic divergence-free field (Taylor-Green vortex, tangential at the walls),
+so the set circulates instead of compressing. Same launch mode (eager) at every N.
 
-`--impl reference` times only that CPU reference arm and prints its own JSON line.
+`value`    device-resident throughput: particles and grids live in HBM, K steps timed with CUDA events on the
+           launching stream between barriers, max over ranks.
+`e2e`      the same step through the reference-facing host-buffer entry points of the C ABI with the particles
+           RESIDENT (the protocol the libffengine interposer runs): per step the P2G's faces + valid masks go to
+           pinned host memory, the projected field comes back from pinned host memory, the CFL speed is read back.
+`roofline` whole-substep algorithmic bytes / step time against MEASURED_PEAKS.json, with the
+           per-stage figures beside it.
+`checksum` order-independent hash of the owned particles (global id, position and velocity bits) after the K+W
+           steps and of the P2G field of the final state: equal across N iff the slab path reproduces the single-GPU
+           bits.
+`secondary` (N = 1) BASELINE.json configs[1]: dam break 128^3 APIC (4 637 952 particles): evolving and fixed batch,
+           eager launches and CUDA-graph replay (the round-1 headline configuration, kept for comparison).
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference engine (oracle/_ref/ref_harness, built from
+           /root/reference) on this box's host cores, all threads, on a bounded sample of the same scene (a slab of
+           16 interior cell planes; the reference at 330 M particles would need minutes per step).
 """
 from __future__ import annotations
 
@@ -41,14 +52,18 @@ sys.path.insert(0, ROOT)
 
 METRIC = "FLIP substep particle-updates/sec (P2G+G2P+advect)"
 UNIT = "particle-updates/s"
-GRID_N = 128
+GRID_PRIMARY = 512
+GRID_SECONDARY = 128
 METHOD = "apic"
 PPC = 8
-V0 = 0.5                      # |v| component bound of the synthetic velocities
+V0 = 0.5                      # |v| component bound of the synthetic velocities and the amplitude of the analytic field
+SEED = 1234
+RATIO = 0.05
+HALO, GHOST = 7, 2
+SAMPLE_PLANES = 16            # fluid cell planes of the CPU reference sample
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
-# --------------------------------------------------------------------------------------------------
 def algorithmic_bytes(method: str, ppc: float):
     """compulsory bytes per particle-update, per stage."""
     if method == "apic":
@@ -62,6 +77,11 @@ def measured_peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_string(n, total):
+    return (f"dam break {n}x{n}x{n} (BASELINE configs[{3 if n == 512 else 1}]), {METHOD.upper()} transfer, RK3 advection + "
+            f"collision, ppc {PPC}, {total} particles, hashed generator seed {SEED}")
 
 
 class ClockSampler(threading.Thread):
@@ -83,8 +103,7 @@ class ClockSampler(threading.Thread):
         if self.nv is None:
             return
         nv = self.nv
-        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -105,38 +124,65 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------------
-def build_scene(world: int, rank: int):
-    """Rank's share of the dam break 128 x 128 x (128*world): particles of its z-slab."""
-    from blender_flip_fluids_b200 import scenes
-    K = GRID_N * world
-    sc = scenes.dam_break(GRID_N, ppc=PPC, apic=(METHOD == "apic"), vel="random", v0=V0, dims=(GRID_N, GRID_N, K),
-                          seed=1234)
-    return sc, K
-
-
-def reference_arm(steps: int, warmup: int, sample_planes: int = 32, threads: int = 0):
-    """Time the UNMODIFIED reference (oracle/_ref/ref_harness) on host cores: P2G, G2P, advect on
-    a z-slice sample of the bench scene. Returns (value, info)."""
+def reference_arm(n_grid: int, steps: int, warmup: int, threads: int = 0):
+    """Time the UNMODIFIED reference (oracle/_ref/ref_harness) on host cores: VelocityAdvector::advect,
+    _updateMarkerParticleVelocitiesThread, _advanceMarkerParticlesThread on a bounded sample of the bench scene:
+    SAMPLE_PLANES interior cell planes of the n^3 dam break (same x/y extent, same hashed particles, same analytic
+    field; the x/y walls are solid as in the scene, the z neighbours are fluid, so the collision gate fires at the
+    scene's rate), or the whole scene when it has no more planes than that. Returns (value, info)."""
     if not os.path.exists(HARNESS):
         raise RuntimeError("oracle/_ref/ref_harness missing: run __graft_entry__.build() where /root/reference exists")
     from blender_flip_fluids_b200 import scenes
-    sc = scenes.dam_break(GRID_N, ppc=PPC, apic=(METHOD == "apic"), vel="random", v0=V0, seed=1234)
-    n_grid, dx = GRID_N, sc.dx
-    keep = sc.pos[:, 2] < (3 + sample_planes) * dx                     # z-planes 3 .. 3+sample_planes
-    pos, vel = sc.pos[keep], sc.vel[keep]
-    aff = [a[keep] for a in (sc.affx, sc.affy, sc.affz)]
-    rng = np.random.default_rng(99)
-    shp = [(n_grid, n_grid, n_grid + 1), (n_grid, n_grid + 1, n_grid), (n_grid + 1, n_grid, n_grid)]
-    mac = [(rng.uniform(-V0, V0, size=s)).astype(np.float32) for s in shp]
-    phi, near = scenes.analytic_solid_sdf(n_grid, n_grid, n_grid, dx)
+    n, dx = n_grid, 1.0 / n_grid
+    e = scenes.dam_break_extent(n, n, n)
+    whole = (e[5] - e[4]) <= 4 * SAMPLE_PLANES
+    if whole:
+        K, k0, k1, shift = n, e[4], e[5], 0
+    else:
+        K = SAMPLE_PLANES + 6
+        k0 = (n - SAMPLE_PLANES) // 2
+        k1, shift = k0 + SAMPLE_PLANES, k0 - 3                       # scene plane k -> sample plane k - shift
+    streams, _ = scenes.dam_break_planes(n, n, n, dx, k0, k1, apic=(METHOD == "apic"), v0=V0, seed=SEED, xp=np)
+    pos = np.stack(streams[0:3], axis=1)
+    pos[:, 2] = (pos[:, 2].astype(np.float64) - shift * dx).astype(np.float32)
+    vel = np.stack(streams[3:6], axis=1)
+    aff = [np.stack(streams[6 + 3 * q:9 + 3 * q], axis=1) for q in range(3)] if METHOD == "apic" else None
+    # analytic field (benchscene.taylor_green_field restated with numpy: the same doubles, narrowed once)
+    xu, yu = np.arange(n + 1) * dx, (np.arange(n) + 0.5) * dx
+    u2 = (V0 * np.sin(math.pi * xu)[None, :] * np.cos(math.pi * yu)[:, None]).astype(np.float32)
+    xv, yv = (np.arange(n) + 0.5) * dx, np.arange(n + 1) * dx
+    v2 = (-V0 * np.cos(math.pi * xv)[None, :] * np.sin(math.pi * yv)[:, None]).astype(np.float32)
+    mac = [np.ascontiguousarray(np.broadcast_to(u2[None], (K, n, n + 1))), np.ascontiguousarray(np.broadcast_to(v2[None], (K, n + 1, n))),
+           np.zeros((K + 1, n, n), np.float32)]
+    if whole:
+        phi, near = scenes.analytic_solid_sdf(n, n, n, dx)
+    else:
+        # x / y walls of the scene; the sample's z faces are interior planes of the scene (far from its z walls)
+        inset = 0.5 * (3.0 * dx + 1e-4)
+        y, x = np.meshgrid(np.arange(n + 1) * dx, np.arange(n + 1) * dx, indexing="ij")
+        d2 = np.minimum.reduce([x - inset, n * dx - inset - x, y - inset, n * dx - inset - y])
+        zdist = np.minimum(np.arange(k0 - 3, k0 - 3 + K + 1) * dx - inset, n * dx - inset - np.arange(k0 - 3, k0 - 3 + K + 1) * dx)
+        phi = np.minimum(d2[None], zdist[:, None, None]).astype(np.float32)
+        gi, gk = math.ceil(n / 3), math.ceil(K / 3)
+        near = np.zeros((gk, gi, gi), np.uint8)
+        band = np.abs(phi[:K, :n, :n]) < np.float32(3.0 * dx)
+        kk, jj, ii = np.nonzero(band)
+        near[kk // 3, jj // 3, ii // 3] = 1
+        for _ in range(2):
+            g = near.copy()
+            g[:, 1:, :] |= near[:, :-1, :]; g[:, :-1, :] |= near[:, 1:, :]
+            g[:, :, 1:] |= near[:, :, :-1]; g[:, :, :-1] |= near[:, :, 1:]
+            g[1:] |= near[:-1]; g[:-1] |= near[1:]
+            near = g
     d = tempfile.mkdtemp(prefix="ffb200_ref_")
     try:
-        for k, a in dict(pos=pos, vel=vel, affx=aff[0], affy=aff[1], affz=aff[2], u=mac[0], v=mac[1], w=mac[2],
-                         phi=phi, near=near).items():
+        arrs = dict(pos=pos, vel=vel, u=mac[0], v=mac[1], w=mac[2], phi=phi, near=near)
+        if aff:
+            arrs.update(affx=aff[0], affy=aff[1], affz=aff[2])
+        for k, a in arrs.items():
             np.save(os.path.join(d, f"in_{k}.npy"), a)
         reps = steps + warmup
-        common = [f"I={n_grid}", f"J={n_grid}", f"K={n_grid}", f"dx={dx!r}", f"method={METHOD}", f"reps={reps}",
-                  f"threads={threads}"]
+        common = [f"I={n}", f"J={n}", f"K={K}", f"dx={dx!r}", f"method={METHOD}", f"reps={reps}", f"threads={threads}"]
         dt = 1.0 * dx / V0
 
         def run(mode, *extra):
@@ -144,20 +190,23 @@ def reference_arm(steps: int, warmup: int, sample_planes: int = 32, threads: int
             return json.loads(r.stdout.strip().splitlines()[-1])
 
         a = run("p2g")
-        b = run("g2p", "ratio=0.05")
+        b = run("g2p", f"ratio={RATIO}")
         c = run("advect", f"dt={dt!r}", "cfl=5")
     finally:
         shutil.rmtree(d, ignore_errors=True)
     per_step = [x + y + z for x, y, z in zip(a["times"], b["times"], c["times"])][warmup:]
     total = sum(per_step)
-    n = int(pos.shape[0])
-    info = {"particles": n, "threads": a["threads"], "t_p2g": statistics.mean(a["times"][warmup:]),
+    m = int(pos.shape[0])
+    full = scenes.dam_break_count(n, n, n, PPC)
+    info = {"particles": m, "threads": a["threads"], "t_p2g": statistics.mean(a["times"][warmup:]),
             "t_g2p": statistics.mean(b["times"][warmup:]), "t_advect": statistics.mean(c["times"][warmup:]),
-            "ms_per_step": 1e3 * total / len(per_step),
-            "sample": f"dam break {n_grid}^3 {METHOD.upper()} ppc{PPC}, z-planes 3..{3 + sample_planes} "
-                      f"({n} particles), stage-level VelocityAdvector::advect + _updateMarkerParticleVelocitiesThread "
-                      f"+ _advanceMarkerParticlesThread (no extrapolation/removal) via oracle/_ref/ref_harness"}
-    return n * len(per_step) / total, info
+            "ms_per_step": 1e3 * total / len(per_step), "same_config": True, "scene_particles": full,
+            "sample": (f"the whole scene ({m} particles)" if whole else
+                       f"{SAMPLE_PLANES} interior cell planes k={k0}..{k1 - 1} of the scene ({m} of {full} particles, same hashed particles "
+                       f"and analytic field, x/y walls solid, z neighbours fluid); the rate is per particle, i.e. extrapolated to the "
+                       f"full scene") + "; stage-level VelocityAdvector::advect + _updateMarkerParticleVelocitiesThread + "
+                      "_advanceMarkerParticlesThread (no extrapolation/removal) of the unmodified reference via oracle/_ref/ref_harness"}
+    return m * len(per_step) / total, info
 
 
 def host_cpu():
@@ -174,19 +223,155 @@ def host_cpu():
 
 
 # --------------------------------------------------------------------------------------------------
+class Runner:
+    """One rank's share of the n^3 hashed dam break, resident, with the step in its modes."""
+
+    def __init__(self, n, rank, world, local_rank, stream):
+        import torch
+        from blender_flip_fluids_b200 import benchscene, engine, slab
+        self.torch, self.engine, self.bs = torch, engine, benchscene
+        self.n, self.rank, self.world = n, rank, world
+        self.dx = 1.0 / n
+        self.dev = torch.device("cuda", local_rank)
+        self.stream = stream
+        self.m = engine.APIC if METHOD == "apic" else engine.FLIP
+        self.apic = METHOD == "apic"
+        self.radius = 0.5 * self.dx * math.sqrt(3.0)
+        self.dt = self.dx / V0            # ~1 cell per substep at the velocity bound (CFL limit is 5)
+        self.kb, self.ke = slab.slab_range(n, world, rank)
+        if world > 1:
+            self.backend = slab.GpuBackend(n, n, n, self.dx, self.kb, self.ke, HALO, local_rank, self.apic)
+            self.ctx = self.backend.ctx
+            self.sim = slab.SlabSimulation(n, n, n, self.dx, rank, world, self.backend, halo=HALO, ghost=GHOST)
+        else:
+            self.ctx = engine.FlipContext(n, n, n, self.dx, device=local_rank)
+            self.ctx.set_stream(stream.cuda_stream)
+            self.sim = None
+        benchscene.set_wall_solid(self.ctx, n, n, n, self.dx, self.dev)
+        self.n_local = benchscene.fill_dam_break(self.ctx, n, n, n, self.dx, self.kb, self.ke, self.apic, V0, SEED, self.dev,
+                                                 headroom=1.15 if world == 1 else 1.35)
+        if self.sim is not None:
+            self.sim.adopt_resident(self.n_local)
+        b = self.ctx.device_buffers()
+        self.tg = benchscene.taylor_green_field(n, n, n, self.dx, b.kbase, b.kloc, V0, self.dev)
+        self.fv = benchscene.field_views(self.ctx, self.dev)
+        self.fixed = False
+
+    def set_fixed(self, on):
+        self.fixed = bool(on)
+        self.ctx.set_fixed_batch(self.fixed)
+
+    def step(self):
+        if self.sim is not None:
+            self.sim.step_fast(self.radius, RATIO, self.dt, apply_migration=not self.fixed,
+                               projected_field=None if self.fixed else self.tg)
+            return
+        c = self.ctx
+        c.p2g(self.radius, self.m)            # bins + sort + seam words + U, V, W transfers
+        c.save_velocity_field()               # _saveVelocityField; the CPU pressure solve would sit here ...
+        if not self.fixed:
+            for a, t in zip(self.fv, self.tg):    # ... and hand back a divergence-free field
+                a.copy_(t.view(-1))
+        c.g2p(self.m, RATIO)
+        c.advect(self.dt, 5.0, True)
+
+    def time_steps(self, steps, barrier, replay=None):
+        torch = self.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(self.stream)
+        if replay is not None:
+            for _ in range(steps // 2):
+                replay()
+        else:
+            for _ in range(steps):
+                self.step()
+        ev1.record(self.stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        return ms / (2 * (steps // 2) if replay is not None else steps)
+
+    def capture(self):
+        """Two consecutive substeps (the sort flips the double buffer: two return it to where it started) in one
+        CUDA graph. Single GPU only (no host decision in the step)."""
+        torch = self.torch
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=self.stream):
+            self.step()
+            self.step()
+        torch.cuda.set_stream(self.stream)
+        graph.replay()
+        torch.cuda.synchronize()
+        return graph
+
+    def stage_times(self, reps=3):
+        stage = {"sort_ms": 0.0, "p2g_prep_ms": 0.0, "p2g_ms": 0.0, "g2p_ms": 0.0, "advect_ms": 0.0}
+        launches = 0
+        for _ in range(reps):
+            self.step()
+            t = self.ctx.timing()
+            for k in stage:
+                stage[k] += t[k] / reps
+            launches = sum(t[k] for k in ("sort_launches", "p2g_prep_launches", "p2g_launches", "g2p_launches", "advect_launches"))
+        return stage, launches
+
+    def checksums(self):
+        """(owned particle count, particle checksum, P2G field checksum of the current state), this rank's share."""
+        cnt, ph = self.bs.particle_checksum(self.ctx, self.apic, self.dev)
+        # the transfer of the current particles onto the faces this rank owns (ghost copies are in place after a step)
+        if self.sim is not None:
+            if not getattr(self.sim, "_ghosts_ready", False):
+                return cnt, ph, None
+            self.backend.p2g(self.radius)
+        else:
+            self.ctx.p2g(self.radius, self.m)
+        fh = self.bs.field_checksum(self.ctx, self.dev, self.kb, self.ke, top_w=(self.rank == self.world - 1))
+        return cnt, ph, fh
+
+    def close(self):
+        self.sim = None
+        self.fv = self.tg = None
+        self.ctx.close()
+        self.torch.cuda.empty_cache()
+
+
+def roofline_block(n_local, ms_per_step, stage, peak, peak_src, traffic):
+    balg = algorithmic_bytes(METHOD, PPC)
+    total_b = sum(balg.values()) * n_local
+    ach = total_b / (ms_per_step * 1e-3) / 1e9
+
+    def st(key, ms):
+        a = balg[key] * n_local / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"algorithmic_bytes": balg[key] * n_local, "ms": ms, "achieved": a, "frac": a / peak}
+
+    return {"kernel": "whole substep: sort + P2G (k_p2g_* x3 directions) + G2P + advect, per GPU",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": total_b, "launch_ms": ms_per_step,
+            "algorithmic_bytes_per_particle": sum(balg.values()),
+            "stages": {"p2g (3 directions on 3 streams, incl. cell lists and node gather)": st("p2g", stage["p2g_ms"]),
+                       "g2p (one kernel)": st("g2p", stage["g2p_ms"]), "advect (one kernel)": st("advect", stage["advect_ms"]),
+                       "sort + membership (no algorithmic bytes)": {"ms": stage["sort_ms"] + stage["p2g_prep_ms"]}},
+            "stage_ms": stage}
+
+
+# --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=GRID_PRIMARY)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-checksum", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    n = args.grid
 
     # stdout carries exactly one JSON line: everything libraries write to fd 1 meanwhile (NCCL prints its
     # version banner there) is sent to stderr
@@ -197,25 +382,31 @@ def main():
     def emit(obj):
         os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
+    from blender_flip_fluids_b200 import scenes
+    n_scene = scenes.dam_break_count(n, n, n, PPC)
+    base_config = {"workload": workload_string(n, n_scene), "dt": (1.0 / n) / V0, "pic_flip_ratio": RATIO}
+
     if args.impl == "reference":
         if rank != 0:
             return 0
         model, cores = host_cpu()
-        value, info = reference_arm(steps, warmup)
+        ref_steps = min(steps, 6)                 # each rep is seconds of CPU work; the rate does not depend on the count
+        value, info = reference_arm(n, ref_steps, 1)
+        cfg = dict(base_config, cpu_model=model, timed_reps=ref_steps)
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-                "warmup": warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32 (fp64 gathers)", "data": "synthetic",
-                "config": {"workload": f"dam break {GRID_N}^3, {METHOD.upper()} transfer, RK3 advection, ppc {PPC}",
-                           "cpu_model": model},
+                "warmup": warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32 (fp64 gathers)", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "reference",
-                                 "sample": info["sample"], "stage_s": {k: info[k] for k in ("t_p2g", "t_g2p", "t_advect")}},
+                                 "sample": info["sample"], "same_config": True, "sample_particles": info["particles"],
+                                 "scene_particles": info["scene_particles"],
+                                 "stage_s": {k: info[k] for k in ("t_p2g", "t_g2p", "t_advect")}},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
 
     import torch
     import torch.distributed as dist
-    from blender_flip_fluids_b200 import engine, scenes
+    from blender_flip_fluids_b200 import engine
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -227,209 +418,110 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    apic = METHOD == "apic"
-    m = engine.APIC if apic else engine.FLIP
+    def allsum(vals):
+        if world == 1:
+            return [int(v) for v in vals]
+        t = torch.tensor([int(v) & 0x7FFFFFFFFFFFFFFF for v in vals], device="cuda", dtype=torch.int64)
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return [int(sum(int(p[i]) for p in parts) & 0x7FFFFFFFFFFFFFFF) for i in range(len(vals))]
+
     # a dedicated (non-default) stream, made torch's current stream BEFORE anything binds to it: the library
-    # launches on it (GpuBackend / ffb200_set_stream), NCCL orders its transfers against it, the events time
-    # it, and at N=1 the substep is captured from it into a CUDA graph
+    # launches on it (GpuBackend / ffb200_set_stream), NCCL orders its transfers against it, the events time it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    if world > 1:
-        from blender_flip_fluids_b200 import slab
-        Kg = GRID_N * world
-        kb, ke = slab.slab_range(Kg, world, rank)
-        backend = slab.GpuBackend(GRID_N, GRID_N, Kg, 1.0 / GRID_N, kb, ke, 7, local_rank, apic)
-        sim = slab.SlabSimulation(GRID_N, GRID_N, Kg, 1.0 / GRID_N, rank, world, backend, halo=7, ghost=2)
-        pristine = slab.make_slab_dam_break(GRID_N, GRID_N, Kg, 1.0 / GRID_N, rank, world, PPC, V0, apic, 1234,
-                                            backend.device)[:2]
-        sim.set_particles(*pristine)
-        backend.reserve(int(sim.num_particles() * 1.3))
-        phi, near = scenes.analytic_solid_sdf(GRID_N, GRID_N, Kg, 1.0 / GRID_N)
-        backend.set_solid(phi, near)
-        sc = None
-        n_local = sim.num_particles()
-    else:
-        sc, K = build_scene(1, 0)
-        sim = None
-        n_local = sc.n
-    dx = 1.0 / GRID_N
-    radius = 0.5 * dx * math.sqrt(3.0)
-    dt = 1.0 * dx / V0            # ~1 cell per substep at the velocity bound (CFL limit is 5)
-    ratio = 0.05
+    peak, peak_src = measured_peaks()
 
-    if sim is None:
-        phi, near = scenes.analytic_solid_sdf(GRID_N, GRID_N, GRID_N, dx)
-        ctx = engine.FlipContext(GRID_N, GRID_N, GRID_N, dx, device=local_rank)
-        ctx.set_stream(stream.cuda_stream)
-        ctx.set_solid(phi, near)
-        ctx.set_particles(sc.pos, sc.vel, sc.affx, sc.affy, sc.affz)
-        ctx.set_fixed_batch(True)     # every step re-bins, re-sorts and processes the same resident batch
-
-        def step():
-            ctx.p2g(radius, m)            # bins + sort + seam words + U, V, W transfers
-            ctx.save_velocity_field()     # _saveVelocityField; the CPU pressure solve would sit here
-            ctx.g2p(m, ratio)
-            ctx.advect(dt, 5.0, True)
-    else:
-        ctx = sim.backend.ctx
-        sim.load_resident()
-        ctx.set_fixed_batch(True)     # G2P/advect write to the spare buffer; migrants are packed and sent, not applied
-
-        def step():
-            # fixed batch: every step starts from the same resident particle streams (the tensors are
-            # not modified by step(), which builds new ones) and does the full exchange + stage work
-            sim.step_fast(radius, ratio, dt, apply_migration=False)
-
-    # ---- device-resident timing ----------------------------------------------------------------
+    run = Runner(n, rank, world, local_rank, stream)
+    n_local = run.n_local
     for _ in range(warmup):
-        step()
+        run.step()
     barrier()
-    if sim is not None and getattr(sim, "_profile", False):
-        sim._phase = {}                   # FFB200_SLAB_PROFILE=1: steady-state phases only
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"sort_ms": 0.0, "p2g_prep_ms": 0.0, "p2g_ms": 0.0, "g2p_ms": 0.0, "advect_ms": 0.0}
-    launches = 0
-    # N=1: the substep is a fixed sequence of ~25 launches with no host decision in it, so two
-    # consecutive substeps (the sort flips the double buffer: two return it to where it started) are
-    # captured into one CUDA graph and replayed; launch gaps between the small kernels disappear.
-    # FFB200_BENCH_GRAPH=0 times eager launches instead. N>1 has host decisions (exchange counts): eager.
-    replay, graphed = None, False
-    if sim is None and os.environ.get("FFB200_BENCH_GRAPH", "1") != "0":
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=stream):
-                step()
-                step()
-            torch.cuda.set_stream(stream)
-            for _ in range(2):
-                graph.replay()
-            torch.cuda.synchronize()
-            replay, graphed = graph.replay, True
-        except Exception as e:                                  # capture is an optimisation, never a requirement
-            sys.stderr.write(f"CUDA graph capture unavailable ({e}); timing eager launches\n")
-            torch.cuda.set_stream(stream)
-            torch.cuda.synchronize()
-    barrier()
-    ev0.record(stream)
-    if replay is not None:
-        for _ in range(steps // 2):
-            replay()
-        if steps % 2:
-            step()
-            step()          # keep the double buffer where the graph expects it ...
-    else:
-        for _ in range(steps):
-            step()
-    ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    if replay is not None and steps % 2:
-        ms_total *= steps / (steps + 1.0)                       # ... and do not count the extra substep
+    ms_per_step = run.time_steps(steps, barrier)
     sampler.stop_flag = True
     sampler.join()
-    # per-stage durations (the library records CUDA events around every stage): one more step
-    for _ in range(3):
-        step()
-        t = ctx.timing()
-        for k in stage:
-            stage[k] += t[k] / 3.0
-        launches = t["sort_launches"] + t["p2g_prep_launches"] + t["p2g_launches"] + t["g2p_launches"] + t["advect_launches"]
+    checks = None
+    if not args.no_checksum:
+        cnt, ph, fh = run.checksums()
+        tot = allsum([cnt, ph, fh or 0])
+        checks = {"after_steps": warmup + steps, "particles": tot[0], "particle_hash": f"{tot[1]:016x}", "p2g_field_hash": f"{tot[2]:016x}",
+                  "what": "sums mod 2^63 over the owned particles of hash(global id, position bits, velocity bits), and over the "
+                          "owned faces of hash(face index) * value bits of the P2G of that state; decomposition independent"}
+    stage, launches = run.stage_times()
     if world > 1:
-        tt = torch.tensor([ms_total, float(n_local)], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([ms_per_step, float(n_local)], device="cuda", dtype=torch.float64)
         mx = tt.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_total, n_total = float(mx[0]), int(round(float(sm[1])))
+        ms_per_step, n_total = float(mx[0]), int(round(float(sm[1])))
     else:
         n_total = n_local
-    ms_per_step = ms_total / steps
     value = n_total / (ms_per_step * 1e-3)
-
-    # ---- roofline of the dominant kernel (k_p2g, 3 launches per step) -------------------------------
-    peak, peak_src = measured_peaks()
-    balg = algorithmic_bytes(METHOD, PPC)
-    p2g_launch_ms = stage["p2g_ms"] / 3.0
-    p2g_bytes_per_launch = balg["p2g"] / 3.0 * n_local
-    achieved = p2g_bytes_per_launch / (p2g_launch_ms * 1e-3) / 1e9 if p2g_launch_ms > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "p2g_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "step_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"kernel": "P2G transfer of one MAC direction: k_p2g_cell_list + k_p2g_cells + k_p2g_edge + k_p2g_nodes <dir, APIC>",
-                "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": p2g_bytes_per_launch, "launch_ms": p2g_launch_ms,
-                "whole_step": {"algorithmic_bytes_per_particle": sum(balg.values()),
-                               "achieved_gbs": sum(balg.values()) * n_local / (ms_per_step * 1e-3) / 1e9,
-                               "frac": sum(balg.values()) * n_local / (ms_per_step * 1e-3) / 1e9 / peak},
-                "stage_ms": stage}
+            traffic = json.load(f).get("dram_bytes_per_step")
+    roofline = roofline_block(n_total / world, ms_per_step, stage, peak, peak_src, traffic)
 
-    # ---- e2e: host buffers through the reference-facing entry points -----------------------------------
+    # ---- fixed-batch figure beside it (the round-1 mode: every step re-sorts the same resident batch) ------------
+    fixed_rec = None
+    if world == 1:
+        run.set_fixed(True)
+        for _ in range(3):
+            run.step()
+        ms_fixed = run.time_steps(max(4, steps // 2), barrier)
+        fixed_rec = {"ms_per_step": ms_fixed, "value": n_total / (ms_fixed * 1e-3),
+                     "batch": "fixed resident batch (each step re-bins, re-sorts and transfers the same particles; results go "
+                              "to the spare SoA buffer; the already sorted input is the reorder's best case)"}
+        run.set_fixed(False)
+
+    # ---- e2e: host buffers through the reference-facing entry points, particles resident ---------------------------
     e2e = None
-    if not args.no_e2e and sim is None:
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        h_pos, h_vel = pin(sc.pos), pin(sc.vel)
-        h_aff = [pin(a) for a in (sc.affx, sc.affy, sc.affz)]
-        su, sv, sw = engine.mac_shapes(GRID_N, GRID_N, GRID_N)
-        h_mac = [torch.zeros(s, dtype=torch.float32).pin_memory() for s in (su, sv, sw)]
-        h_valid = [torch.zeros(s, dtype=torch.uint8).pin_memory() for s in (su, sv, sw)]
-        h_phi, h_near = pin(phi), pin(near)
-        out = tuple(t.numpy() for t in h_mac) + tuple(t.numpy() for t in h_valid)
-        n = sc.n
-        ngrid = sum(int(np.prod(s)) for s in (su, sv, sw))
+    if not args.no_e2e:
+        b = run.ctx.device_buffers()
+        if world == 1:
+            shapes = engine.mac_shapes(n, n, n)
+            h_out = [torch.empty(s, dtype=torch.float32).pin_memory() for s in shapes]
+            h_valid = [torch.empty(s, dtype=torch.uint8).pin_memory() for s in shapes]
+            h_in = [t.cpu().pin_memory() for t in run.tg]
+            out = tuple(t.numpy() for t in h_out) + tuple(t.numpy() for t in h_valid)
+            mac_in = tuple(t.numpy() for t in h_in)
+            ctx = run.ctx
 
-        aff_np = [t.numpy() for t in h_aff]
+            def e2e_step():
+                # the interposed call sites of FluidSimulation::_stepFluid with the particles resident: faces + masks out
+                # (the host pressure solve's input), projected field in, advected state stays, CFL speed out
+                ctx.declare_resident(particles=True)
+                ctx.velocity_advector_advect(None, None, radius=run.radius, method=run.m, out=out)
+                ctx.declare_resident(particles=True)
+                ctx.update_marker_particle_velocities(None, None, mac_in, method=run.m, ratio_pic_flip=RATIO)
+                ctx.declare_resident(particles=True, field=True)
+                ctx.advance_marker_particles(None, None, None, None, dt=run.dt, cfl=5.0)
+                return ctx.maximum_particle_speed()
 
-        def e2e_step():
-            # the three interposed call sites of FluidSimulation::_stepFluid, host arrays in and out
-            pos, vel = h_pos.numpy(), h_vel.numpy()
-            (u, v, w), _ = ctx.velocity_advector_advect(pos, vel, *aff_np, radius=radius, method=m, out=out)
-            # as in the reference substep, the same particle arrays go to the G2P and the advection, and the
-            # same field to the advection: declared, so each distinct input crosses PCIe once per step
-            # (particles at the P2G, the field -- the CPU would have projected it -- at the G2P)
-            ctx.declare_resident(particles=True)
-            ctx.update_marker_particle_velocities(pos, vel, (u, v, w), method=m, ratio_pic_flip=ratio, inplace=True,
-                                                  aff_out=aff_np)
-            ctx.declare_resident(particles=True, field=True)
-            ctx.advance_marker_particles(pos, (u, v, w), h_phi.numpy(), h_near.numpy(), dt=dt, cfl=5.0, inplace=True)
+            ngrid = sum(int(np.prod(s)) for s in shapes)
+            h2d, d2h = ngrid * 4, ngrid * 5 + 8
+            path = ("ffb200_velocity_advector_advect (resident particles; faces + valid masks to pinned host) + "
+                    "ffb200_update_marker_particle_velocities (projected field from pinned host; results stay resident) + "
+                    "ffb200_advance_marker_particles (resident) + ffb200_get_maximum_particle_speed (CFL input to the host)")
+        else:
+            own = run.sim._owned_field_views()
+            h_out = [torch.empty(v.shape, dtype=torch.float32).pin_memory() for v in own]
+            h_in = [t.cpu().pin_memory() for t in run.tg]
 
-        ctx.set_fixed_batch(False)        # host-buffer calls: inputs arrive from the host every step
-        h2d = n * 60 + ngrid * 4 + (phi.nbytes + near.nbytes)
-        d2h = ngrid * 5 + n * 48 + n * 12
-        for _ in range(2):
-            e2e_step()
-        torch.cuda.synchronize()
-        k_e2e = max(3, min(steps, 5))
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        t_e2e = (time.perf_counter() - t0) / k_e2e
-        e2e = {"value": n / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": t_e2e * 1e3, "steps": k_e2e,
-               "path": "ffb200_velocity_advector_advect + ffb200_update_marker_particle_velocities + "
-                       "ffb200_advance_marker_particles, pinned host buffers; particles uploaded once per step "
-                       "(ffb200_declare_resident), field uploaded at the G2P, every output downloaded"}
-    elif sim is not None and not args.no_e2e:
-        # N > 1: inputs come from pinned host memory every step and the advected state goes back
-        host_in = [t.cpu().pin_memory() for t in pristine[0]] + [pristine[1].cpu().pin_memory()]
-        host_out = [torch.empty_like(t).pin_memory() for t in host_in[:6]]
-        n = n_local
+            def e2e_step():
+                run.sim.step_fast(run.radius, RATIO, run.dt, apply_migration=True, projected_field=h_in, p2g_download=h_out)
+                return run.ctx.maximum_particle_speed()
 
-        def e2e_step():
-            dev = [t.to(backend.device, non_blocking=True) for t in host_in]
-            sim.set_particles(dev[:-1], dev[-1])
-            sim.load_resident()
-            sim.step_fast(radius, ratio, dt, apply_migration=False)
-            views, _ = backend.particle_views()
-            for q in range(6):
-                m = min(views[q].shape[0], host_out[q].shape[0])
-                host_out[q][:m].copy_(views[q][:m], non_blocking=True)
-
+            h2d = sum(t.numel() for t in h_in) * 4
+            d2h = sum(t.numel() for t in h_out) * 4 + 8
+            path = ("per rank: SlabSimulation.step_fast with the owned planes of the transferred field copied to pinned host, "
+                    "the projected field (stored planes incl. halo) copied from pinned host, particles resident and migrating "
+                    "over NCCL, CFL speed read back")
         for _ in range(2):
             e2e_step()
         barrier()
@@ -439,41 +531,73 @@ def main():
             e2e_step()
         barrier()
         t_e2e = (time.perf_counter() - t0) / k_e2e
-        tt = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        nstream = len(host_in)
-        e2e = {"value": n_total / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": int(n * 4 * nstream),
-               "d2h_bytes_per_step": int(n * 24), "ms_per_step": float(tt[0]) * 1e3, "steps": k_e2e,
-               "path": "per rank: particle streams H2D from pinned host -> SlabSimulation.step (ghosts, P2G, halo, "
-                       "G2P, advect, migration) -> positions+velocities D2H"}
+        if world > 1:
+            tt = torch.tensor([t_e2e, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            t_e2e, h2d, d2h = float(mx[0]), float(sm[1]), float(sm[2])
+        e2e = {"value": n_total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": t_e2e * 1e3, "steps": k_e2e, "path": path,
+               "particles": "resident across stages and substeps (uploaded once, outside the timed region); what the host "
+                            "pipeline needs every substep crosses PCIe inside it"}
+    run.close()
+
+    # ---- secondary record: BASELINE configs[1], 128^3 APIC (N = 1 only) ----------------------------------------------
+    secondary = None
+    if world == 1 and not args.no_secondary and n != GRID_SECONDARY:
+        try:
+            r2 = Runner(GRID_SECONDARY, 0, 1, local_rank, stream)
+            rec = {"workload": workload_string(GRID_SECONDARY, r2.n_local)}
+            k2 = max(20, steps)
+            for mode in ("evolving", "fixed"):
+                r2.set_fixed(mode == "fixed")
+                for _ in range(3):
+                    r2.step()
+                eager = r2.time_steps(k2, barrier)
+                st, ln = r2.stage_times()
+                graphed = None
+                try:
+                    g = r2.capture()
+                    graphed = r2.time_steps(k2, barrier, replay=g.replay)
+                    del g
+                except Exception as ex:                                  # capture is an optimisation, never a requirement
+                    sys.stderr.write(f"CUDA graph capture unavailable ({ex})\n")
+                    torch.cuda.set_stream(stream)
+                    torch.cuda.synchronize()
+                best = min(eager, graphed) if graphed else eager
+                rec[mode] = {"ms_per_step_eager": eager, "ms_per_step_graph": graphed, "value_eager": r2.n_local / (eager * 1e-3),
+                             "value_graph": (r2.n_local / (graphed * 1e-3)) if graphed else None, "launches_per_step": ln,
+                             "roofline": roofline_block(r2.n_local, best, st, peak, peak_src, None)}
+            r2.close()
+            secondary = rec
+        except Exception as ex:
+            secondary = {"error": str(ex)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, info = reference_arm(3, 1)
+            v, info = reference_arm(n, 2, 1)
             cpu = {"value": v, "unit": UNIT, "cores": info["threads"], "kind": "reference", "sample": info["sample"],
+                   "same_config": True, "sample_particles": info["particles"], "scene_particles": info["scene_particles"],
                    "cpu_model": host_cpu()[0], "stage_s": {k: info[k] for k in ("t_p2g", "t_g2p", "t_advect")}}
         except Exception as e:                                   # the checker is optional for the headline
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
-    if sim is not None and getattr(sim, "_profile", False) and rank == 0:
-        tot = sum(sim._phase.values())
-        sys.stderr.write("slab phases (ms/step, synchronised): " + ", ".join(
-            f"{k} {1e3 * v / max(1, steps + 3):.3f}" for k, v in sim._phase.items()) + "\n")
     if rank == 0:
+        cfg = dict(base_config,
+                   parallelism="single GPU" if world == 1 else f"z-slab x{world} ({n // world} planes per rank, halo {HALO}, ghost "
+                               f"particle layers {GHOST}), face halo + particle migration over NCCL, one process per GPU",
+                   l2="inputs larger than L2 (particle streams + grids >> 126 MB per step)",
+                   batch="evolving: each step sorts and transfers the particles the previous step advected (ranks migrate them); "
+                         "the MAC field is replaced by an analytic divergence-free field where the CPU projection would return one",
+                   launch="eager launches (every N)")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (fp64 index/gather arithmetic)", "data": "synthetic",
-                "config": {"workload": f"dam break {GRID_N}x{GRID_N}x{GRID_N * world}, {METHOD.upper()} transfer, RK3 "
-                                       f"advection + collision, ppc {PPC}, {n_total} particles",
-                           "parallelism": "single GPU" if world == 1 else f"z-slab x{world}, halo + migration over NCCL",
-                           "l2": "inputs larger than L2 (particle streams + grids > 126 MB per step)",
-                           "batch": "fixed resident batch: each step re-bins, re-sorts and transfers the same particles; "
-                                    "G2P/advect results go to the spare SoA buffer",
-                           "launch": "two substeps captured in one CUDA graph, replayed" if graphed else "eager launches",
-                           "dt": dt, "pic_flip_ratio": ratio},
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (fp64 index/gather arithmetic)", "data": "synthetic", "config": cfg,
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches * steps, "roofline": roofline,
-                "cpu_baseline": cpu}
+                "checksum": checks, "fixed_batch": fixed_rec, "secondary": secondary, "cpu_baseline": cpu}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -116,17 +116,18 @@ def particle_checksum(ctx, apic, device):
     return int(own.sum().item()), int(acc.sum().item() & 0x7FFFFFFFFFFFFFFF)
 
 
-def field_checksum(ctx, device, k_lo, k_hi):
+def field_checksum(ctx, device, k_lo, k_hi, top_w=False):
     """Position-weighted 64-bit checksum of the velocity-field bits on the cell planes [k_lo, k_hi) this rank owns
-    (w: face planes [k_lo, k_hi) too; the top plane K belongs to the last rank and is added by the caller's range)."""
+    (w: face planes [k_lo, k_hi); top_w adds w's last plane K, which belongs to the last rank)."""
     b = ctx.device_buffers()
     total = 0
     for d in range(3):
         plane = b.face_plane[d]
         f = _view(b.field[d], b.face_count[d], "<f4", device).view(-1, plane)
-        lo, hi = k_lo - b.kbase, k_hi - b.kbase
+        k_top = k_hi + (1 if (d == 2 and top_w) else 0)
+        lo, hi = k_lo - b.kbase, k_top - b.kbase
         bits = f[lo:hi].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
-        gidx = (torch.arange(k_lo, k_hi, dtype=torch.int64, device=device)[:, None] * plane +
+        gidx = (torch.arange(k_lo, k_top, dtype=torch.int64, device=device)[:, None] * plane +
                 torch.arange(plane, dtype=torch.int64, device=device)[None, :])
         total += int((((gidx * 0x9E3779B1 + (d + 1)) & 0xFFFFFFFF) * bits & 0x7FFFFFFFFFFF).sum().item())
     return total & 0x7FFFFFFFFFFFFFFF

@@ -345,7 +345,14 @@ class SlabSimulation:
         self._phase[name] = self._phase.get(name, 0.0) + now - self._t_last
         self._t_last = now
 
-    def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True, apply_migration=True):
+    def adopt_resident(self, n_owned):
+        """The backend's resident streams were filled in place (benchscene.fill_dam_break): they are the authoritative
+        particle state of this rank from now on."""
+        self._resident = True
+        self._ghosts_ready = False
+        self._n_owned = int(n_owned)
+
+    def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True, apply_migration=True, projected_field=None, p2g_download=None):
         """One substep with device-side plumbing. apply_migration=False is the fixed-batch
         benchmark mode (context in ffb200_set_fixed_batch): ghosts are added and removed and
         migrants are selected, packed and exchanged as usual, but the resident batch itself is
@@ -387,6 +394,14 @@ class SlabSimulation:
         # 3. face halos (zero copy, straight into the halo planes), saved copy
         self._halo_exchange_fast()
         be.save_field()
+        if p2g_download is not None:
+            # e2e: the owned planes of the transferred field go to (pinned) host memory -- the CPU pressure solve's input
+            for dst, src in zip(p2g_download, self._owned_field_views()):
+                dst.copy_(src, non_blocking=True)
+        if projected_field is not None:
+            # the field the host's projection would hand back (stored planes incl. halo; device or pinned host tensors)
+            for dst, src in zip(self._stored_field_views(), projected_field):
+                dst.copy_(src.view(-1), non_blocking=True)
         self._tick("halo+save")
         # 4. G2P + advection; the marked ghost copies ride along (a few %) and are dropped below
         be.g2p(ratio)
@@ -465,6 +480,23 @@ class SlabSimulation:
             hdr[1].zero_(); hdr[3].zero_()
         self.exchanged_bytes += int(hdr[0, 0] + hdr[0, 2] + hdr[1, 0] + hdr[1, 2]) * rows * 4
         return hdr
+
+    def _stored_field_views(self):
+        v = getattr(self, "_stored_views", None)
+        if v is None:
+            b = self.backend.ctx.device_buffers()
+            v = self._stored_views = [_view(b.field[d], b.face_count[d], "<f4", self.device) for d in range(3)]
+        return v
+
+    def _owned_field_views(self):
+        v = getattr(self, "_owned_views", None)
+        if v is None:
+            v = []
+            for d in range(3):
+                f, kbase = self.backend.field_planes(d)
+                v.append(f[self.kb - kbase:self.ke - kbase + (1 if d == 2 and self.up is None else 0)])
+            self._owned_views = v
+        return v
 
     def _halo_exchange_fast(self):
         plan = getattr(self, "_halo_plan", None)

@@ -115,7 +115,7 @@ def test_bench_reference_arm_prints_one_json_line():
     harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
     if not os.path.exists(harness):
         pytest.skip("reference harness not built (needs /root/reference)")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3", "--grid", "128"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -124,6 +124,13 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "particle-updates/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the same scene as the GPU arm names (identical workload string), on a stated sample of it
+    sys.path.insert(0, ROOT)
+    import bench
+    from blender_flip_fluids_b200 import scenes
+    assert d["config"]["workload"] == bench.workload_string(128, scenes.dam_break_count(128, 128, 128, 8))
+    assert d["cpu_baseline"]["same_config"] is True and d["cpu_baseline"]["scene_particles"] == 4637952
+    assert 0 < d["cpu_baseline"]["sample_particles"] <= 4637952 and d["scaling"] == "strong"
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=env)
