@@ -366,6 +366,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-checksum", action="store_true")
+    ap.add_argument("--no-tolerance", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -467,6 +468,33 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_step")
     roofline = roofline_block(n_total / world, ms_per_step, stage, peak, peak_src, traffic)
 
+    # ---- tolerance mode beside it: fp32 gathers within the north star's 1e-5 (ffb200_set_precision), same evolving batch ----
+    tol_rec = None
+    if not args.no_tolerance:
+        run.ctx.set_precision(True)
+        for _ in range(2):
+            run.step()
+        run.ctx.tolerance_stats(reset=True)
+        ms_tol = run.time_steps(steps, barrier)
+        ts = run.ctx.tolerance_stats()
+        stage_tol, _ = run.stage_times()
+        run.ctx.set_precision(False)
+        if world > 1:
+            tt = torch.tensor([ms_tol, float(ts["advected"]), float(ts["advected_exact"])], device="cuda", dtype=torch.float64)
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms_tol, ts = float(mx[0]), {"advected": int(sm[1]), "advected_exact": int(sm[2])}
+        tol_rec = {"ms_per_step": ms_tol, "value": n_total / (ms_tol * 1e-3),
+                   "exact_fallback_rate": ts["advected_exact"] / max(1, ts["advected"]),
+                   "roofline": roofline_block(n_total / world, ms_tol, stage_tol, peak, peak_src, None),
+                   "what": "G2P and RK3 with the trilinear interpolant in fp32 from float-pair cell coordinates (no fp64, no "
+                           "conversion instructions); particles whose collision decisions are not clear-cut run the exact code "
+                           "(the fallback rate); binning, sort and valid masks are mode independent. Parity: "
+                           "tests/test_gpu_parity.py::test_tolerance_mode_* (1e-5 on every fixture and oracle scene). "
+                           "`value` above is the EXACT mode."}
+
     # ---- fixed-batch figure beside it (the round-1 mode: every step re-sorts the same resident batch) ------------
     fixed_rec = None
     if world == 1:
@@ -551,8 +579,9 @@ def main():
             r2 = Runner(GRID_SECONDARY, 0, 1, local_rank, stream)
             rec = {"workload": workload_string(GRID_SECONDARY, r2.n_local)}
             k2 = max(20, steps)
-            for mode in ("evolving", "fixed"):
+            for mode in ("evolving", "evolving_tolerance", "fixed"):
                 r2.set_fixed(mode == "fixed")
+                r2.ctx.set_precision(mode == "evolving_tolerance")
                 for _ in range(3):
                     r2.step()
                 eager = r2.time_steps(k2, barrier)
@@ -597,7 +626,8 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 (fp64 index/gather arithmetic)", "data": "synthetic", "config": cfg,
                 "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches * steps, "roofline": roofline,
-                "checksum": checks, "fixed_batch": fixed_rec, "secondary": secondary, "cpu_baseline": cpu}
+                "checksum": checks, "tolerance_mode": tol_rec, "fixed_batch": fixed_rec, "secondary": secondary,
+                "cpu_baseline": cpu}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

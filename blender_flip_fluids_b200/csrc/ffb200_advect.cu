@@ -233,6 +233,94 @@ __global__ void FFB_ADV_BOUNDS k_advect(const __grid_constant__ AdvectParams P) 
     P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
 }
 
+// ---- tolerance mode ---------------------------------------------------------------------------------------------
+//
+// RK3 through the fp32 evaluation of ffb200_common.cuh. The approximate end point differs from the exact one by a few
+// float ulps of the coordinate plus ~1e-6 of the displacement; that is far inside the 1e-5 the north star allows for
+// positions, but the collision code takes DISCRETE decisions on it (cell range, 3dx near-solid gate, clearance
+// shortcut, SDF sign along the march), and a flipped decision moves a particle by up to 0.1 dx. So the approximate
+// end point is only accepted where every decision is clear-cut with a guard band around it:
+//   * its cell and its 3dx gate cell are at least kBand cells away from their planes and inside the grid,
+//   * and either no gate cell (start or end) is marked near-solid, or the per-cell clearance proves, with one cell
+//     of slack more than the exact shortcut needs, that the march would find nothing, with both end points inside
+//     the boundary box by its 1e-4 margin.
+// Everything else -- the particles that can actually touch a solid -- takes the exact path in full: the reference's
+// fp64 RK3 and _resolveCollision, bit for bit. `stats` counts both populations.
+constexpr float kBand = 4e-3f;            // cells; covers 8 ulps of a coordinate up to 2^11 cells plus the RK3 error
+
+__device__ __forceinline__ bool clear_of_planes(float f, float band) { return f > band && f < 1.0f - band; }
+
+__device__ __noinline__ void exact_advect(const AdvectParams &P, float x0, float y0, float z0, float &x1, float &y1, float &z1) {
+    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
+    mac_eval(P.g, P.mac, x0, y0, z0, k1x, k1y, k1z);
+    mac_eval(P.g, P.mac, x0 + k1x * P.c2, y0 + k1y * P.c2, z0 + k1z * P.c2, k2x, k2y, k2z);
+    mac_eval(P.g, P.mac, x0 + k2x * P.c3, y0 + k2y * P.c3, z0 + k2z * P.c3, k3x, k3y, k3z);
+    x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
+    y1 = y0 + ((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * P.c9;
+    z1 = z0 + ((k1z * 2.0f + k2z * 3.0f) + k3z * 4.0f) * P.c9;
+    if (P.collide) resolve_collision(P, x0, y0, z0, x1, y1, z1);
+}
+
+__global__ void FFB_ADV_BOUNDS k_advect_fast(const __grid_constant__ AdvectParams P, const __grid_constant__ FastGrid fg,
+                                             float inv_near, unsigned long long *__restrict__ stats) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
+    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
+    if (P.k1x) {
+        k1x = P.k1x[j]; k1y = P.k1y[j]; k1z = P.k1z[j];
+    } else {
+        fast_mac_eval(P.g, fg, P.mac, x0, y0, z0, k1x, k1y, k1z);
+    }
+    fast_mac_eval(P.g, fg, P.mac, x0 + k1x * P.c2, y0 + k1y * P.c2, z0 + k1z * P.c2, k2x, k2y, k2z);
+    fast_mac_eval(P.g, fg, P.mac, x0 + k2x * P.c3, y0 + k2y * P.c3, z0 + k2z * P.c3, k3x, k3y, k3z);
+    float x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
+    float y1 = y0 + ((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * P.c9;
+    float z1 = z0 + ((k1z * 2.0f + k2z * 3.0f) + k3z * 4.0f) * P.c9;
+    bool accept = !P.collide;
+    if (P.collide) {
+        const GridDesc &g = P.g;
+        // end point: cell and gate cell, both clear of their planes and inside the grid
+        const FastAxis ex = fast_axis(x1, fg), ey = fast_axis(y1, fg), ez = fast_axis(z1, fg);
+        bool sure = clear_of_planes(ex.f, kBand) && clear_of_planes(ey.f, kBand) && clear_of_planes(ez.f, kBand) &&
+                    in_range3(ex.i, ey.i, ez.i, g.I, g.J, g.K);
+        // 3dx gate cells: a float product is enough with the band around it (magic-number floor, no conversion)
+        const float tx = x1 * inv_near, ty = y1 * inv_near, tz = z1 * inv_near;
+        const float mx = tx + kMagic, my = ty + kMagic, mz = tz + kMagic;
+        float qx = tx - (mx - kMagic), qy = ty - (my - kMagic), qz = tz - (mz - kMagic);    // in [-0.5, 0.5]
+        int ni = __float_as_int(mx) - kMagicBits, nj = __float_as_int(my) - kMagicBits, nk = __float_as_int(mz) - kMagicBits;
+        if (qx < 0.0f) { qx += 1.0f; ni -= 1; }
+        if (qy < 0.0f) { qy += 1.0f; nj -= 1; }
+        if (qz < 0.0f) { qz += 1.0f; nk -= 1; }
+        sure = sure && clear_of_planes(qx, kBand) && clear_of_planes(qy, kBand) && clear_of_planes(qz, kBand);
+        if (sure) {
+            const bool near_new = !in_range3(ni, nj, nk, P.ni, P.nj, P.nk) || P.near_solid[ni + P.ni * (nj + P.nj * nk)] != 0;
+            if (!near_new && !near_solid(P, x0, y0, z0)) {
+                accept = true;                                   // the reference returns before looking at the SDF (:7654-7658)
+            } else {
+                // clearance shortcut of resolve_collision with one more cell of slack (the start cell comes from the
+                // float-pair floor, which may differ from the double floor within 2^-44 of a plane)
+                const FastAxis sx = fast_axis(x0, fg), sy = fast_axis(y0, fg), sz = fast_axis(z0, fg);
+                if (in_range3(sx.i, sy.i, sz.i - g.kbase, g.I, g.J, g.kloc)) {
+                    const int reach = max(max(abs(ex.i - sx.i), abs(ey.i - sy.i)), abs(ez.i - sz.i)) + 2;
+                    const int c = P.clear[(size_t)sx.i + (size_t)g.I * ((size_t)sy.i + (size_t)g.J * (sz.i - g.kbase))];
+                    accept = c > reach && box_inside_margin(P.box, x0, y0, z0) && box_inside_margin(P.box, x1, y1, z1);
+                }
+            }
+        }
+    }
+    if (!accept) exact_advect(P, x0, y0, z0, x1, y1, z1);
+    P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
+    {
+        const unsigned active = __activemask();
+        const unsigned slow = __ballot_sync(active, !accept);
+        if ((threadIdx.x & 31) == (__ffs(active) - 1)) {
+            atomicAdd(stats + 2, (unsigned long long)__popc(active));
+            if (slow) atomicAdd(stats + 3, (unsigned long long)__popc(slow));
+        }
+    }
+}
+
 // clearance pass 1: 0 for a cell with any of its 8 SDF nodes <= margin (or outside the stored slab), else the cap
 __global__ void k_solid_unsafe(const float *__restrict__ phi, uint8_t *__restrict__ clear, int I, int J, int kloc, float margin,
                                int cap) {
@@ -326,7 +414,11 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.buffer = (double)0.2f * g.dx;
     P.collide = collide;
     P.n = c.n;
-    k_advect<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(P);
+    if (c.precision == FFB200_PRECISION_TOLERANCE)
+        k_advect_fast<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(
+            P, make_fast_grid(g), (float)P.inv_near, tolerance_stats(c));
+    else
+        k_advect<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(P);
     FFB_CUDA(cudaGetLastError());
     if (!c.nondestructive) c.sorted = false;            // positions moved: bins are stale
     return 1;

@@ -176,6 +176,7 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->remove_words);
     dev_free(c->liquid_phi);
     dev_free(c->liquid_blocks);
+    dev_free(c->tol_stats);
     dev_free(c->sort.edge_count);
     for (int q = 0; q < 3; q++) dev_free(c->k1s[q]);
     for (auto &cs : c->sort.cell) {
@@ -266,6 +267,12 @@ int create_impl(ffb200_context **out, int I, int J, int K, double dx, int device
 }
 
 ContextImpl &impl(Context &c) { return static_cast<ContextImpl &>(c); }
+
+float below(double lim) {                                     // largest float f with (double)f < lim
+    float f = (float)lim;
+    if ((double)f >= lim) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
 
 void upload_attr(ContextImpl &c, const float *host, float *const dst[3], int n) {
     FFB_CUDA(cudaMemcpyAsync(c.aos_stage, host, (size_t)n * 12, cudaMemcpyHostToDevice, c.stream));
@@ -435,7 +442,46 @@ RemoveRules remove_rules(double dt, double cfl, int max_per_cell, int max_frame_
 
 }  // namespace
 
+namespace ffb200 {
+
+FastGrid make_fast_grid(const GridDesc &g) {
+    FastGrid f;
+    f.inv_hi = (float)g.inv_dx;
+    f.inv_lo = (float)(g.inv_dx - (double)f.inv_hi);
+    f.xmax = below(g.dx * g.I);                               // Grid3d::isPositionInGrid: x < dx * I in double (grid3d.h:134-136)
+    f.ymax = below(g.dx * g.J);
+    f.zmax = below(g.dx * g.K);
+    return f;
+}
+
+unsigned long long *tolerance_stats(Context &c) {
+    if (!c.tol_stats) {
+        FFB_CUDA(cudaMalloc(reinterpret_cast<void **>(&c.tol_stats), 4 * sizeof(unsigned long long)));
+        FFB_CUDA(cudaMemsetAsync(c.tol_stats, 0, 4 * sizeof(unsigned long long), c.stream));
+    }
+    return c.tol_stats;
+}
+
+}  // namespace ffb200
+
 extern "C" {
+
+int ffb200_set_precision(ffb200_context *ctx, int mode) {
+    return guarded("ffb200_set_precision", ctx, [&](Context &c) {
+        if (mode != FFB200_PRECISION_EXACT && mode != FFB200_PRECISION_TOLERANCE) throw std::domain_error("unknown precision mode");
+        c.precision = mode;
+    });
+}
+
+int ffb200_get_tolerance_stats(ffb200_context *ctx, unsigned long long *counts, int reset) {
+    return guarded("ffb200_get_tolerance_stats", ctx, [&](Context &c) {
+        if (!counts) throw std::invalid_argument("null output pointer");
+        unsigned long long *d = tolerance_stats(c);
+        FFB_CUDA(cudaMemcpyAsync(counts, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+        FFB_CUDA(cudaStreamSynchronize(c.stream));
+        if (reset) FFB_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), c.stream));
+    }, false);
+}
 
 int ffb200_create(ffb200_context **ctx, int isize, int jsize, int ksize, double dx, int device) {
     return create_impl(ctx, isize, jsize, ksize, dx, device, 0, ksize, 0);

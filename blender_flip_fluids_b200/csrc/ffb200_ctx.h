@@ -112,9 +112,15 @@ struct Context {
     int k1s_cap = 0;
     unsigned resident_next = 0;          // ffb200_declare_resident: inputs the next host-buffer call may skip uploading
     unsigned resident_arg = 0;           // ... as latched for the call in progress (cleared for every other call)
+    int precision = FFB200_PRECISION_EXACT;   // ffb200_set_precision: exact (reference arithmetic) or tolerance (fp32 gathers, 1e-5)
+    unsigned long long *tol_stats = nullptr;  // device: {particles advected on the fp32 path, particles sent to the exact code, ...}
     bool nondestructive = false;         // G2P/advect write to the spare SoA buffer (fixed-batch benchmarking)
     ffb200_timing timing = {};
 };
+
+// float-pair 1/dx and float grid bounds of the tolerance path (ffb200_common.cuh)
+FastGrid make_fast_grid(const GridDesc &g);
+unsigned long long *tolerance_stats(Context &c);         // 4 device counters, allocated on first use
 
 // ---- launchers (each returns the number of kernels it launched) -------------------------------
 

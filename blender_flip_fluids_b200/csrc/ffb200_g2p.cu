@@ -157,6 +157,106 @@ __global__ void FFB_G2P_BOUNDS k_g2p_apic(const __grid_constant__ G2PParams P) {
     P.ovx[j] = v0; P.ovy[j] = v1; P.ovz[j] = v2;
 }
 
+// ---- tolerance mode (ffb200_common.cuh, "tolerance mode") ---------------------------------------------------
+//
+// The same updates with the trilinear interpolant evaluated in fp32 from float-pair cell coordinates: no fp64 and
+// no conversion instruction on the common path. Velocities and affine rows agree with the exact kernels within a
+// few fp32 ulps of the field's magnitude (the 1e-5 of the north star leaves two orders of margin). The affine rows
+// are the gradient of the interpolant and jump across cell planes, so a component whose gradient frame sits within
+// 1e-6 cells of a plane -- where the float-pair floor could disagree with the reference's double floor -- is
+// evaluated by the exact apic_component instead.
+struct FastCount {
+    unsigned long long fast, exact;
+};
+
+__device__ __forceinline__ void fast_count(unsigned long long *counter, bool slow) {
+    const unsigned m = __ballot_sync(__activemask(), slow);
+    if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1) && m) atomicAdd(counter, (unsigned long long)__popc(m));
+}
+
+__device__ __forceinline__ bool near_plane(float f) { return f < 1e-6f || f > 1.0f - 1e-6f; }
+
+template <int DIR>
+__device__ __noinline__ void exact_apic_fallback(const G2PParams &P, const float *__restrict__ f, float px, float py, float pz,
+                                                 bool in_grid, float &vel, float &ox, float &oy, float &oz) {
+    const GridDesc &g = P.g;
+    const double x = px, y = py, z = pz, hdx = 0.5 * g.dx;
+    const AxisCoord cx = axis_coord(DIR == 0 ? x : x - hdx, g), cy = axis_coord(DIR == 1 ? y : y - hdx, g),
+                    cz = axis_coord(DIR == 2 ? z : z - hdx, g);
+    apic_component<DIR>(P, f, px, py, pz, in_grid, cx, cy, cz, vel, ox, oy, oz);
+}
+
+template <int DIR>
+__device__ __forceinline__ void fast_apic_component(const G2PParams &P, const float *__restrict__ f, float px, float py, float pz,
+                                                    bool in_grid, const FastAxis &vx, const FastAxis &vy, const FastAxis &vz,
+                                                    const FastAxis &gx, const FastAxis &gy, const FastAxis &gz, float &vel,
+                                                    float &ox, float &oy, float &oz, bool &slow) {
+    if (near_plane(gx.f) || near_plane(gy.f) || near_plane(gz.f)) {          // rare: the reference's own arithmetic
+        exact_apic_fallback<DIR>(P, f, px, py, pz, in_grid, vel, ox, oy, oz);
+        slow = true;
+        return;
+    }
+    float v[8];
+    fast_faces<DIR>(P.g, f, gx.i, gy.i, gz.i, v);
+    fast_gradient(v, gx.f, gy.f, gz.f, P.invdx, ox, oy, oz);
+    if (!in_grid) {
+        vel = 0.0f;
+        return;
+    }
+    if (vx.i != gx.i || vy.i != gy.i || vz.i != gz.i) fast_faces<DIR>(P.g, f, vx.i, vy.i, vz.i, v);   // an ulp from a plane
+    vel = fast_trilerp(v, vx.f, vy.f, vz.f);
+}
+
+__global__ void FFB_G2P_BOUNDS k_g2p_apic_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg,
+                                               unsigned long long *__restrict__ stats) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const float px = P.px[j], py = P.py[j], pz = P.pz[j];
+    const bool in_grid = fast_in_grid(px, py, pz, fg);
+    const FastFrames F = fast_frames(px, py, pz, fg);
+    // the affine rows use the reference's FLOAT-shifted coordinates (p - (float)(0.5f * dx), fluidsimulation.cpp:6717)
+    const FastAxis gxs = fast_axis(px - P.h, fg), gys = fast_axis(py - P.h, fg), gzs = fast_axis(pz - P.h, fg);
+    float v0, v1, v2, ax, ay, az;
+    bool slow = false;
+    fast_apic_component<0>(P, P.cur.u, px, py, pz, in_grid, F.xu, F.ys, F.zs, F.xu, gys, gzs, v0, ax, ay, az, slow);
+    P.a[0][j] = ax; P.a[1][j] = ay; P.a[2][j] = az;
+    fast_apic_component<1>(P, P.cur.v, px, py, pz, in_grid, F.xs, F.yu, F.zs, gxs, F.yu, gzs, v1, ax, ay, az, slow);
+    P.a[3][j] = ax; P.a[4][j] = ay; P.a[5][j] = az;
+    fast_apic_component<2>(P, P.cur.w, px, py, pz, in_grid, F.xs, F.ys, F.zu, gxs, gys, F.zu, v2, ax, ay, az, slow);
+    P.a[6][j] = ax; P.a[7][j] = ay; P.a[8][j] = az;
+    P.ovx[j] = v0; P.ovy[j] = v1; P.ovz[j] = v2;
+    fast_count(stats + 1, slow);
+}
+
+__global__ void FFB_G2P_BOUNDS k_g2p_flip_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n) return;
+    const float px = P.px[j], py = P.py[j], pz = P.pz[j];
+    float pic[3] = {0.0f, 0.0f, 0.0f}, old[3] = {0.0f, 0.0f, 0.0f};
+    if (fast_in_grid(px, py, pz, fg)) {
+        const FastFrames F = fast_frames(px, py, pz, fg);
+        float v[8];
+        fast_faces<0>(P.g, P.cur.u, F.xu.i, F.ys.i, F.zs.i, v);
+        pic[0] = fast_trilerp(v, F.xu.f, F.ys.f, F.zs.f);
+        fast_faces<0>(P.g, P.saved.u, F.xu.i, F.ys.i, F.zs.i, v);
+        old[0] = fast_trilerp(v, F.xu.f, F.ys.f, F.zs.f);
+        fast_faces<1>(P.g, P.cur.v, F.xs.i, F.yu.i, F.zs.i, v);
+        pic[1] = fast_trilerp(v, F.xs.f, F.yu.f, F.zs.f);
+        fast_faces<1>(P.g, P.saved.v, F.xs.i, F.yu.i, F.zs.i, v);
+        old[1] = fast_trilerp(v, F.xs.f, F.yu.f, F.zs.f);
+        fast_faces<2>(P.g, P.cur.w, F.xs.i, F.ys.i, F.zu.i, v);
+        pic[2] = fast_trilerp(v, F.xs.f, F.ys.f, F.zu.f);
+        fast_faces<2>(P.g, P.saved.w, F.xs.i, F.ys.i, F.zu.i, v);
+        old[2] = fast_trilerp(v, F.xs.f, F.ys.f, F.zu.f);
+    }
+    const float v0 = P.vx[j], v1 = P.vy[j], v2 = P.vz[j];
+    const float f0 = (v0 + pic[0]) - old[0], f1 = (v1 + pic[1]) - old[1], f2 = (v2 + pic[2]) - old[2];
+    P.ovx[j] = pic[0] * P.rp + f0 * P.rf;
+    P.ovy[j] = pic[1] * P.rp + f1 * P.rf;
+    P.ovz[j] = pic[2] * P.rp + f2 * P.rf;
+    P.k1[0][j] = pic[0]; P.k1[1][j] = pic[1]; P.k1[2][j] = pic[2];
+}
+
 // FluidSimulation::_getMaximumMarkerParticleSpeed (fluidsimulation.cpp:10188-10202): max over the particles of
 // the float dot product v.v (left to right); a max is order independent, so the reduction is bit-exact.
 // Non-negative floats order like their bit patterns: integer atomicMax.
@@ -206,7 +306,13 @@ int launch_g2p(Context &c, int method, double ratio) {
     P.invdx = (float)(1.0f / c.g.dx);
     P.n = c.n;
     const int blocks = (c.n + FFB_G2P_THREADS - 1) / FFB_G2P_THREADS;
-    if (method == FFB200_TRANSFER_APIC)
+    if (c.precision == FFB200_PRECISION_TOLERANCE) {
+        const FastGrid fg = make_fast_grid(c.g);
+        if (method == FFB200_TRANSFER_APIC)
+            k_g2p_apic_fast<<<blocks, FFB_G2P_THREADS, 0, c.stream>>>(P, fg, tolerance_stats(c));
+        else
+            k_g2p_flip_fast<<<blocks, FFB_G2P_THREADS, 0, c.stream>>>(P, fg);
+    } else if (method == FFB200_TRANSFER_APIC)
         k_g2p_apic<<<blocks, FFB_G2P_THREADS, 0, c.stream>>>(P);
     else
         k_g2p_flip<<<blocks, FFB_G2P_THREADS, 0, c.stream>>>(P);

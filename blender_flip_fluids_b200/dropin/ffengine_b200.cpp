@@ -241,7 +241,6 @@ void after_device_write(bool pos, bool vel, bool aff) {
 MACVelocityField *g_pending_p2g_field = nullptr;
 ffb200_context *g_pending_ctx = nullptr;
 MACVelocityField *g_resident_field = nullptr;    // the field object our G2P uploaded last (advection reuses it)
-bool g_saved_on_device = false;                  // the device's saved field is _savedVelocityField's content
 
 void flush_pending_field() {
     if (!g_pending_p2g_field) return;
@@ -337,7 +336,6 @@ void FluidSimulation::initialize() {
         g_res = Residency();
         g_pending_p2g_field = nullptr;
         g_resident_field = nullptr;
-        g_saved_on_device = false;
         g_has_deferred = false;
     }
     unpin_all();
@@ -395,7 +393,6 @@ void VelocityAdvector::advect(VelocityAdvectorParameters params) {
         g_pending_p2g_field = params.vfield;
         g_pending_ctx = ctx;
         g_resident_field = nullptr;
-        g_saved_on_device = false;
         if (g_profile.path) g_profile.particles += (long)g_res.count;
     });
 }
@@ -420,12 +417,9 @@ void FluidSimulation::_extrapolateFluidVelocities(MACVelocityField &MACGrid, Val
             reinterpret_cast<uint8_t *>(validVelocities.validV.getRawArray()),
             reinterpret_cast<uint8_t *>(validVelocities.validW.getRawArray()), numLayers, fresh ? 1 : 0));
         g_resident_field = nullptr;
-        g_saved_on_device = false;
-        if (&MACGrid == &_MACVelocity) {
-            // _saveVelocityField (fluidsimulation.cpp:5671-5679) copies exactly this field next: keep the device's copy too
-            check(ffb200_save_velocity_field(ctx));
-            g_saved_on_device = true;
-        }
+        // (The device's copy is NOT kept as the FLIP "saved" field: the host constrains _savedVelocityField against
+        // the solids after saving it, _constrainVelocityFields fluidsimulation.cpp:6444-6453, and this member runs a
+        // second time on the projected field, :6268. The G2P uploads the host's saved field.)
     });
 }
 
@@ -441,16 +435,14 @@ void FluidSimulation::_updateMarkerParticleVelocitiesThread() {
     const bool apic = _velocityTransferMethod == VelocityTransferMethod::APIC;
     ensure_resident(ctx, _markerParticles, apic);
     pin_field(ctx, _MACVelocity);
-    const bool saved = !apic && g_saved_on_device;
-    g_saved_on_device = false;
-    check(ffb200_declare_resident(ctx, FFB200_RESIDENT_PARTICLES | (saved ? FFB200_RESIDENT_SAVED_FIELD : 0u)));
+    check(ffb200_declare_resident(ctx, FFB200_RESIDENT_PARTICLES));
     // the projected field goes up, the results stay on the device
     check(ffb200_update_marker_particle_velocities(
         ctx, (int)g_res.count, nullptr, nullptr, nullptr, nullptr, nullptr, _MACVelocity.getArray3dU()->getRawArray(),
         _MACVelocity.getArray3dV()->getRawArray(), _MACVelocity.getArray3dW()->getRawArray(),
-        (apic || saved) ? nullptr : _savedVelocityField.getArray3dU()->getRawArray(),
-        (apic || saved) ? nullptr : _savedVelocityField.getArray3dV()->getRawArray(),
-        (apic || saved) ? nullptr : _savedVelocityField.getArray3dW()->getRawArray(),
+        apic ? nullptr : _savedVelocityField.getArray3dU()->getRawArray(),
+        apic ? nullptr : _savedVelocityField.getArray3dV()->getRawArray(),
+        apic ? nullptr : _savedVelocityField.getArray3dW()->getRawArray(),
         apic ? FFB200_TRANSFER_APIC : FFB200_TRANSFER_FLIP, _ratioPICFLIP));
     g_resident_field = &_MACVelocity;
     after_device_write(false, true, apic);

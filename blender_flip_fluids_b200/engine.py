@@ -87,6 +87,8 @@ SIGNATURES = {
     "ffb200_extrapolate_velocity_field": [C.c_void_p, C.c_int],
     "ffb200_set_solid": [C.c_void_p, _f32p, _u8p],
     "ffb200_set_solid_device": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "ffb200_set_precision": [C.c_void_p, C.c_int],
+    "ffb200_get_tolerance_stats": [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int],
     "ffb200_p2g": [C.c_void_p, C.c_double, C.c_int],
     "ffb200_g2p": [C.c_void_p, C.c_int, C.c_double],
     "ffb200_advect": [C.c_void_p, C.c_double, C.c_double, C.c_int],
@@ -422,6 +424,16 @@ class FlipContext:
             raise ValueError(f"near-solid mask must have shape {self.near_dims}, got {near.shape}")
         self._call("ffb200_set_solid", _ptr(phi), _ptr(near, _u8p))
         self.synchronize()
+
+    def set_precision(self, tolerance):
+        """ffb200_set_precision: False = exact (bit-identical gathers), True = tolerance (fp32 gathers, 1e-5)."""
+        self._call("ffb200_set_precision", 1 if tolerance else 0)
+
+    def tolerance_stats(self, reset=False):
+        """-> dict(g2p_exact_components, advected, advected_exact) since the last reset."""
+        c = (C.c_ulonglong * 4)()
+        self._call("ffb200_get_tolerance_stats", c, 1 if reset else 0)
+        return {"g2p_exact": int(c[1]), "advected": int(c[2]), "advected_exact": int(c[3])}
 
     def set_solid_device(self, phi_ptr, near_ptr):
         """ffb200_set_solid with device pointers (stored node planes of phi, whole near-solid grid)."""

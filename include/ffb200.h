@@ -241,6 +241,21 @@ int ffb200_get_liquid_sdf(ffb200_context *ctx, float *phi);
  * the reference on the CPU, its kernel has not run on hardware yet.) */
 int ffb200_postprocess_liquid_sdf(ffb200_context *ctx);
 
+/* Arithmetic of the gathers (G2P, advection). FFB200_PRECISION_EXACT (default) repeats the reference's fp64
+ * index / fraction / blend operation for operation: particle velocities, APIC rows and advected positions are
+ * bit-identical to the reference. FFB200_PRECISION_TOLERANCE evaluates the same trilinear interpolant in fp32
+ * from float-pair cell coordinates (no fp64, no conversion instructions) and meets the north star's 1e-5
+ * relative bar instead; every discrete decision of the advection -- collision gate, clearance shortcut, boundary
+ * clamp -- is taken with a guard band, and particles whose decisions are not clear-cut (those that can touch a
+ * solid) run the exact code in full. Binning, sort order and valid-face masks do not depend on the mode.
+ * ffb200_get_tolerance_stats: counts[0] unused, counts[1] G2P particles with a component sent to the exact
+ * code (gradient frame within 1e-6 cells of a plane), counts[2] particles advected in tolerance mode,
+ * counts[3] those of them that took the exact path; reset != 0 clears the counters. */
+#define FFB200_PRECISION_EXACT 0
+#define FFB200_PRECISION_TOLERANCE 1
+int ffb200_set_precision(ffb200_context *ctx, int mode);
+int ffb200_get_tolerance_stats(ffb200_context *ctx, unsigned long long *counts, int reset);
+
 /* ffb200_set_solid with DEVICE pointers: d_phi holds the context's stored node planes only
  * ((I+1)(J+1)(kloc+1) floats, first plane = the context's first stored cell plane), d_near_solid the whole
  * ceil(I/3) x ceil(J/3) x ceil(K/3) byte grid. For scenes too large to stage through host arrays per rank. */

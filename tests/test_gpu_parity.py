@@ -627,3 +627,104 @@ def test_attribute_transfer_composition(eng):
         grid, valid = tr.transfer(pos, attr, meta["radius"])
     assert np.array_equal(valid, e["out_valid"])
     assert close(grid, e["out_grid"])
+
+
+# ---- tolerance mode (ffb200_set_precision(FFB200_PRECISION_TOLERANCE)): fp32 gathers, the north star's 1e-5 bar ----
+
+def _tol_pos(a, b, rtol=RTOL):
+    """positions: |a - b| <= 1e-5 * max(|b|, max|b|), the bar of close(), per array."""
+    return close(a, b, rtol)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_tolerance_mode_scene_chain(eng, name):
+    """The reference-generated whole-substep fixtures (reference-built solid SDFs, dyadic and non-dyadic dx) with the
+    fp32 gathers: velocities, APIC rows and advected positions within 1e-5; P2G (mode independent) unchanged."""
+    meta, g = load_golden(name)
+    I, J, K, dx = meta["I"], meta["J"], meta["K"], meta["dx"]
+    apic = meta["method"] == "apic"
+    mac = (g["s2_u"], g["s2_v"], g["s2_w"])
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        ctx.set_precision(True)
+        if apic:
+            vel, ax, ay, az = ctx.update_marker_particle_velocities(g["s0_pos"], g["s0_vel"], mac, method=eng.APIC)
+            assert close(ax, g["s3_affx"]) and close(ay, g["s3_affy"]) and close(az, g["s3_affz"])
+        else:
+            vel = ctx.update_marker_particle_velocities(g["s0_pos"], g["s0_vel"], mac,
+                                                        saved=(g["s2_su"], g["s2_sv"], g["s2_sw"]), method=eng.FLIP,
+                                                        ratio_pic_flip=meta["ratio"])
+        assert close(vel, g["s3_vel"])
+        ctx.tolerance_stats(reset=True)
+        out = ctx.advance_marker_particles(g["s0_pos"], mac, g["s2_phi"], g["s2_near"], dt=meta["dt"], cfl=meta["cfl"])
+        st = ctx.tolerance_stats()
+    assert _tol_pos(out, g["s4_pos"])
+    assert st["advected"] == g["s0_pos"].shape[0] and 0 <= st["advected_exact"] <= st["advected"]
+
+
+def test_tolerance_mode_collision_fixture(eng):
+    """The collision-heavy fixture: every particle that touches the solid must have taken the exact path (its
+    projected position is a discrete outcome: anything else would be off by ~0.1 dx, 4 orders above the bar)."""
+    meta, g = load_golden("advect_collide_24x20x22")
+    with eng.FlipContext(meta["I"], meta["J"], meta["K"], meta["dx"]) as ctx:
+        exact = ctx.advance_marker_particles(g["in_pos"], (g["in_u"], g["in_v"], g["in_w"]), g["in_phi"], g["in_near"],
+                                             dt=meta["dt"], cfl=meta["cfl"])
+        assert bits_equal(exact, g["out_pos"])
+        ctx.set_precision(True)
+        ctx.tolerance_stats(reset=True)
+        out = ctx.advance_marker_particles(g["in_pos"], (g["in_u"], g["in_v"], g["in_w"]), g["in_phi"], g["in_near"],
+                                           dt=meta["dt"], cfl=meta["cfl"])
+        st = ctx.tolerance_stats()
+        ctx.set_precision(False)
+        again = ctx.advance_marker_particles(g["in_pos"], (g["in_u"], g["in_v"], g["in_w"]), g["in_phi"], g["in_near"],
+                                             dt=meta["dt"], cfl=meta["cfl"])
+    assert _tol_pos(out, g["out_pos"])
+    assert bits_equal(again, g["out_pos"])                     # the switch goes both ways
+    assert st["advected"] == g["in_pos"].shape[0]
+    print("tolerance-mode fallback rate on the collision fixture:", st["advected_exact"] / max(1, st["advected"]))
+
+
+@pytest.mark.parametrize("method", ["flip", "apic"])
+@pytest.mark.parametrize("n,dx", [(32, 1.0 / 32), (30, 0.004 * 250 / 30), (40, 0.0123)])
+def test_tolerance_mode_vs_oracle(eng, oracle, method, n, dx):
+    """Dam break with a sphere obstacle on a white-noise-like P2G field (the worst case for an fp32 fraction, SURVEY hard
+    part 3), dyadic and non-dyadic dx: G2P and advection in tolerance mode against the oracle at 1e-5, through the
+    resident stages (k1 reuse included) and with collisions on and off."""
+    from blender_flip_fluids_b200 import scenes
+    apic = method == "apic"
+    sc = scenes.dam_break(n, apic=apic, dx=dx, vel="random", v0=0.5, seed=11)
+    I = J = K = n
+    m = eng.APIC if apic else eng.FLIP
+    aff = (sc.affx, sc.affy, sc.affz)
+    (ou, ov, ow), _ = oracle.p2g(I, J, K, dx, sc.radius, m, sc.pos, sc.vel, *aff)
+    phi, near = scenes.analytic_solid_sdf(I, J, K, dx, sphere=(0.3 * n * dx, 0.3 * n * dx, 0.5 * n * dx, 0.12 * n * dx))
+    dt = 2.5 * dx / 0.5
+    saved = (ou * 0.9, ov * 0.9, ow * 0.9)
+    res = {}
+    with eng.FlipContext(I, J, K, dx) as ctx:
+        ctx.set_precision(True)
+        ctx.set_solid(phi, near)
+        for collide in (True, False):
+            ctx.set_particles(sc.pos, sc.vel, *aff)
+            ctx.set_velocity_field(ou, ov, ow)
+            ctx.set_velocity_field(*saved, saved=True)
+            ctx.sort_particles()
+            ctx.g2p(m, 0.05)
+            _, vel, ax, ay, az = ctx.get_particles(pos=False, vel=True, affine=apic)
+            ctx.tolerance_stats(reset=True)
+            ctx.advect(dt, 5.0, collide)
+            res[collide] = (ctx.get_particles(pos=True, vel=False)[0], ctx.tolerance_stats())
+    if apic:
+        ovel, oax, oay, oaz = oracle.g2p_apic(I, J, K, dx, sc.pos, (ou, ov, ow))
+        assert close(ax, oax) and close(ay, oay) and close(az, oaz)
+    else:
+        ovel = oracle.g2p_flip(I, J, K, dx, sc.pos, sc.vel, (ou, ov, ow), saved, 0.05)
+    assert close(vel, ovel)
+    for collide in (True, False):
+        opos = oracle.advect(I, J, K, dx, sc.pos, (ou, ov, ow), phi, near, dt, 5.0, collide)
+        pos1, st = res[collide]
+        assert _tol_pos(pos1, opos), f"collide={collide}"
+        assert st["advected"] == sc.n
+        if not collide:
+            assert st["advected_exact"] == 0
+        else:
+            assert 0 < st["advected_exact"] < sc.n            # wall/obstacle particles fall back, the interior does not
