@@ -479,7 +479,11 @@ int ffb200_get_tolerance_stats(ffb200_context *ctx, unsigned long long *counts, 
         unsigned long long *d = tolerance_stats(c);
         FFB_CUDA(cudaMemcpyAsync(counts, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
         FFB_CUDA(cudaStreamSynchronize(c.stream));
-        if (reset) FFB_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), c.stream));
+        counts[2] = c.tol_advected;
+        if (reset) {
+            FFB_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), c.stream));
+            c.tol_advected = 0;
+        }
     }, false);
 }
 
