@@ -13,6 +13,7 @@
 // neighbours, which keeps warps mostly convergent on the gate.
 #include "ffb200_ctx.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace ffb200 {
@@ -138,6 +139,23 @@ __device__ __forceinline__ bool near_solid(const AdvectParams &P, float x, float
     return P.near_solid[i + P.ni * (j + P.nj * k)] != 0;
 }
 
+// The early exits of _resolveCollision (:7646-7658) and the clearance shortcut: true when the march must run.
+// n is clamped into the boundary box first, as the reference does, when its cell is outside the grid.
+__device__ __noinline__ bool collision_gate(const AdvectParams &P, float ox, float oy, float oz, float &nx, float &ny, float &nz) {
+    const GridDesc &g = P.g;
+    const int gi = pos2idx(nx, g.inv_dx), gj = pos2idx(ny, g.inv_dx), gk = pos2idx(nz, g.inv_dx);
+    if (!in_range3(gi, gj, gk, g.I, g.J, g.K)) box_nearest_inside(P.box, nx, ny, nz);
+    if (!near_solid(P, ox, oy, oz) && !near_solid(P, nx, ny, nz)) return false;
+    const int oi = pos2idx(ox, g.inv_dx), oj = pos2idx(oy, g.inv_dx), ok = pos2idx(oz, g.inv_dx);
+    const int ni2 = pos2idx(nx, g.inv_dx), nj2 = pos2idx(ny, g.inv_dx), nk2 = pos2idx(nz, g.inv_dx);
+    if (in_range3(oi, oj, ok - g.kbase, g.I, g.J, g.kloc)) {
+        const int reach = max(max(abs(ni2 - oi), abs(nj2 - oj)), abs(nk2 - ok)) + 1;
+        const int c = P.clear[(size_t)oi + (size_t)g.I * ((size_t)oj + (size_t)g.J * (ok - g.kbase))];
+        if (c > reach && box_inside_margin(P.box, ox, oy, oz) && box_inside_margin(P.box, nx, ny, nz)) return false;
+    }
+    return true;
+}
+
 __device__ __noinline__ void resolve_collision(const AdvectParams &P, float ox, float oy, float oz, float &nx, float &ny,
                                                float &nz) {
     const GridDesc &g = P.g;
@@ -214,7 +232,11 @@ __device__ __noinline__ void resolve_collision(const AdvectParams &P, float ox, 
     nx = rx; ny = ry; nz = rz;
 }
 
-__global__ void FFB_ADV_BOUNDS k_advect(const __grid_constant__ AdvectParams P) {
+// With `list` the particles whose collision march must run are appended to it instead (k_advect_exact_list, pass 2, runs
+// them in full warps): the march is 10-50 SDF samples for a few percent of the particles, and inline it leaves every
+// warp that holds one of them idling on a lane or two.
+__global__ void FFB_ADV_BOUNDS k_advect(const __grid_constant__ AdvectParams P, uint32_t *__restrict__ list,
+                                        unsigned long long *__restrict__ stats) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
@@ -229,8 +251,25 @@ __global__ void FFB_ADV_BOUNDS k_advect(const __grid_constant__ AdvectParams P) 
     float x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
     float y1 = y0 + ((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * P.c9;
     float z1 = z0 + ((k1z * 2.0f + k2z * 3.0f) + k3z * 4.0f) * P.c9;
-    if (P.collide) resolve_collision(P, x0, y0, z0, x1, y1, z1);
-    P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
+    bool defer = false;
+    if (P.collide) {
+        if (list) defer = collision_gate(P, x0, y0, z0, x1, y1, z1);
+        else resolve_collision(P, x0, y0, z0, x1, y1, z1);
+    }
+    if (!defer) {
+        P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
+    }
+    if (list) {
+        const unsigned active = __activemask();
+        const unsigned rej = __ballot_sync(active, defer);
+        if (rej) {
+            const int lane = threadIdx.x & 31, leader = __ffs(rej) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(stats + 0, (unsigned long long)__popc(rej));
+            base = __shfl_sync(active, base, leader);
+            if (defer) list[base + __popc(rej & ((1u << lane) - 1u))] = (uint32_t)j;
+        }
+    }
 }
 
 // ---- tolerance mode ---------------------------------------------------------------------------------------------
@@ -250,9 +289,10 @@ constexpr float kBand = 4e-3f;            // cells; covers 8 ulps of a coordinat
 
 __device__ __forceinline__ bool clear_of_planes(float f, float band) { return f > band && f < 1.0f - band; }
 
-__device__ __noinline__ void exact_advect(const AdvectParams &P, float x0, float y0, float z0, float &x1, float &y1, float &z1) {
-    float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
-    mac_eval(P.g, P.mac, x0, y0, z0, k1x, k1y, k1z);
+__device__ __noinline__ void exact_advect(const AdvectParams &P, float x0, float y0, float z0, float &x1, float &y1, float &z1,
+                                          bool have_k1 = false, float k1x = 0.0f, float k1y = 0.0f, float k1z = 0.0f) {
+    float k2x, k2y, k2z, k3x, k3y, k3z;
+    if (!have_k1) mac_eval(P.g, P.mac, x0, y0, z0, k1x, k1y, k1z);
     mac_eval(P.g, P.mac, x0 + k1x * P.c2, y0 + k1y * P.c2, z0 + k1z * P.c2, k2x, k2y, k2z);
     mac_eval(P.g, P.mac, x0 + k2x * P.c3, y0 + k2y * P.c3, z0 + k2z * P.c3, k3x, k3y, k3z);
     x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
@@ -261,8 +301,14 @@ __device__ __noinline__ void exact_advect(const AdvectParams &P, float x0, float
     if (P.collide) resolve_collision(P, x0, y0, z0, x1, y1, z1);
 }
 
-__global__ void FFB_ADV_BOUNDS k_advect_fast(const __grid_constant__ AdvectParams P, const __grid_constant__ FastGrid fg,
-                                             float inv_near, unsigned long long *__restrict__ stats) {
+// Pass 1: every particle on the fp32 path. Accepted end points are written; the others are appended to a compact
+// list (warp-aggregated slot allocation) for pass 2 -- running the exact code inline instead leaves the warps of a
+// near-wall region with a handful of active lanes each (13.8 of 32 measured), which cost more than the whole exact kernel.
+#ifndef FFB_ADV_FAST_MINB
+#define FFB_ADV_FAST_MINB 4
+#endif
+__global__ void __launch_bounds__(FFB_ADV_THREADS, FFB_ADV_FAST_MINB) k_advect_fast(const __grid_constant__ AdvectParams P, const __grid_constant__ FastGrid fg,
+                                             float inv_near, uint32_t *__restrict__ list, unsigned long long *__restrict__ stats) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
@@ -274,9 +320,9 @@ __global__ void FFB_ADV_BOUNDS k_advect_fast(const __grid_constant__ AdvectParam
     }
     fast_mac_eval(P.g, fg, P.mac, x0 + k1x * P.c2, y0 + k1y * P.c2, z0 + k1z * P.c2, k2x, k2y, k2z);
     fast_mac_eval(P.g, fg, P.mac, x0 + k2x * P.c3, y0 + k2y * P.c3, z0 + k2z * P.c3, k3x, k3y, k3z);
-    float x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
-    float y1 = y0 + ((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * P.c9;
-    float z1 = z0 + ((k1z * 2.0f + k2z * 3.0f) + k3z * 4.0f) * P.c9;
+    const float x1 = x0 + ((k1x * 2.0f + k2x * 3.0f) + k3x * 4.0f) * P.c9;
+    const float y1 = y0 + ((k1y * 2.0f + k2y * 3.0f) + k3y * 4.0f) * P.c9;
+    const float z1 = z0 + ((k1z * 2.0f + k2z * 3.0f) + k3z * 4.0f) * P.c9;
     bool accept = !P.collide;
     if (P.collide) {
         const GridDesc &g = P.g;
@@ -309,15 +355,37 @@ __global__ void FFB_ADV_BOUNDS k_advect_fast(const __grid_constant__ AdvectParam
             }
         }
     }
-    if (!accept) exact_advect(P, x0, y0, z0, x1, y1, z1);
-    P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
-    {
-        // one same-address atomic per warp that HAS a fallback lane (a counter bumped by every warp costs ~0.5 ns per
-        // warp in L2 serialisation -- 10 ms at 330 M particles, measured); the advected total is kept by the host
-        const unsigned active = __activemask();
-        const unsigned slow = __ballot_sync(active, !accept);
-        if (slow && (threadIdx.x & 31) == (__ffs(active) - 1)) atomicAdd(stats + 3, (unsigned long long)__popc(slow));
+    if (accept) {
+        P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
     }
+    const unsigned active = __activemask();
+    const unsigned rej = __ballot_sync(active, !accept);
+    if (rej) {
+        const int lane = threadIdx.x & 31, leader = __ffs(rej) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(stats + 0, (unsigned long long)__popc(rej));
+        base = __shfl_sync(active, base, leader);
+        if (!accept) list[base + __popc(rej & ((1u << lane) - 1u))] = (uint32_t)j;
+    }
+}
+
+// Pass 2: the listed particles through the reference's own arithmetic, one thread each, full warps.
+// exact_k1: the k1 streams hold the exact G2P samples (exact mode); in tolerance mode they are fp32 values and stage 1 is
+// evaluated again.
+__global__ void FFB_ADV_BOUNDS k_advect_exact_list(const __grid_constant__ AdvectParams P, const uint32_t *__restrict__ list,
+                                                   unsigned long long *__restrict__ stats, int exact_k1) {
+    const unsigned long long count = stats[0];
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < count;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t j = list[t];
+        float x1, y1, z1;
+        if (exact_k1 && P.k1x)
+            exact_advect(P, P.px[j], P.py[j], P.pz[j], x1, y1, z1, true, P.k1x[j], P.k1y[j], P.k1z[j]);
+        else
+            exact_advect(P, P.px[j], P.py[j], P.pz[j], x1, y1, z1);
+        P.opx[j] = x1; P.opy[j] = y1; P.opz[j] = z1;
+    }
+    if (!exact_k1 && blockIdx.x == 0 && threadIdx.x == 0) stats[3] += count;   // tolerance mode: fallback total (single writer)
 }
 
 // clearance pass 1: 0 for a cell with any of its 8 SDF nodes <= margin (or outside the stored slab), else the cap
@@ -414,11 +482,35 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.collide = collide;
     P.n = c.n;
     if (c.precision == FFB200_PRECISION_TOLERANCE) c.tol_advected += (unsigned long long)c.n;
-    if (c.precision == FFB200_PRECISION_TOLERANCE)
+    if (c.precision == FFB200_PRECISION_TOLERANCE) {
+        unsigned long long *stats = tolerance_stats(c);
+        uint32_t *list = c.sort.val[1];                        // sort scratch, free between the P2G and the next sort
+        FFB_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long), c.stream));
         k_advect_fast<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(
-            P, make_fast_grid(g), (float)P.inv_near, tolerance_stats(c));
-    else
-        k_advect<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(P);
+            P, make_fast_grid(g), (float)P.inv_near, list, stats);
+        if (collide) {
+            const int want = (c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS;
+            k_advect_exact_list<<<std::min(want, c.sm_count * 8), FFB_ADV_THREADS, 0, c.stream>>>(P, list, stats, 0);
+        }
+        FFB_CUDA(cudaGetLastError());
+        if (!c.nondestructive) c.sorted = false;
+        return collide ? 2 : 1;
+    }
+    // exact mode: the march of the few particles that need one runs as a second pass over a compact list
+    // (FFB200_ADVECT_TWO_PASS=0: inline, the round-1 kernel)
+    static const bool two_pass = [] { const char *e = std::getenv("FFB200_ADVECT_TWO_PASS"); return e ? std::atoi(e) != 0 : true; }();
+    if (two_pass && collide) {
+        unsigned long long *stats = tolerance_stats(c);
+        uint32_t *list = c.sort.val[1];
+        FFB_CUDA(cudaMemsetAsync(stats, 0, sizeof(unsigned long long), c.stream));
+        k_advect<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(P, list, stats);
+        const int want = (c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS;
+        k_advect_exact_list<<<std::min(want, c.sm_count * 8), FFB_ADV_THREADS, 0, c.stream>>>(P, list, stats, 1);
+        FFB_CUDA(cudaGetLastError());
+        if (!c.nondestructive) c.sorted = false;
+        return 2;
+    }
+    k_advect<<<(c.n + FFB_ADV_THREADS - 1) / FFB_ADV_THREADS, FFB_ADV_THREADS, 0, c.stream>>>(P, nullptr, nullptr);
     FFB_CUDA(cudaGetLastError());
     if (!c.nondestructive) c.sorted = false;            // positions moved: bins are stale
     return 1;

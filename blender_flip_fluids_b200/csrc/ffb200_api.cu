@@ -451,6 +451,10 @@ FastGrid make_fast_grid(const GridDesc &g) {
     f.xmax = below(g.dx * g.I);                               // Grid3d::isPositionInGrid: x < dx * I in double (grid3d.h:134-136)
     f.ymax = below(g.dx * g.J);
     f.zmax = below(g.dx * g.K);
+    f.I = g.I; f.J = g.J; f.K = g.K; f.kbase = g.kbase;
+    f.sju = g.I + 1; f.sku = (g.I + 1) * g.J;
+    f.sjv = g.I;     f.skv = g.I * (g.J + 1);
+    f.sjw = g.I;     f.skw = g.I * g.J;
     return f;
 }
 

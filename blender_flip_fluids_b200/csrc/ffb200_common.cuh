@@ -192,6 +192,8 @@ __device__ __forceinline__ void mac_eval(const GridDesc &g, const MacView &m, fl
 struct FastGrid {
     float inv_hi, inv_lo;           // 1/dx as a float pair: inv_hi + inv_lo == 1/dx to ~2^-48
     float xmax, ymax, zmax;         // largest floats strictly below dx*I, dx*J, dx*K (Grid3d::isPositionInGrid in float)
+    int I, J, K, kbase;             // the interior fast path uses 32-bit face offsets (face counts below 2^31: checked by the host)
+    int sju, sku, sjv, skv, sjw, skw;   // row / plane strides of u, v, w
 };
 
 struct FastAxis {
@@ -276,9 +278,23 @@ __device__ __forceinline__ bool fast_in_grid(float x, float y, float z, const Fa
     return x >= 0.0f && y >= 0.0f && z >= 0.0f && x <= fg.xmax && y <= fg.ymax && z <= fg.zmax;
 }
 
-// MACVelocityField::evaluateVelocityAtPositionLinear in fp32 (zero outside the grid)
-__device__ __forceinline__ void fast_mac_eval(const GridDesc &g, const FastGrid &fg, const MacView &m, float x, float y, float z,
-                                              float &ox, float &oy, float &oz) {
+// eight faces at p + {0,1} + {0,sj} + {0,sk}, index c = di + 2 dj + 4 dk; unconditional (interior cells only)
+__device__ __forceinline__ void load8(const float *__restrict__ p, int sj, int sk, float v[8]) {
+    v[0] = __ldg(p);           v[1] = __ldg(p + 1);
+    v[2] = __ldg(p + sj);      v[3] = __ldg(p + sj + 1);
+    v[4] = __ldg(p + sk);      v[5] = __ldg(p + sk + 1);
+    v[6] = __ldg(p + sk + sj); v[7] = __ldg(p + sk + sj + 1);
+}
+
+// A cell whose 3 x 3 x 3 neighbourhood lies inside the grid: every face any staggered frame of a point in this cell
+// can touch exists, so the 24 loads of an evaluation need no range test and are issued back to back.
+__device__ __forceinline__ bool fast_interior(int i, int j, int k, const FastGrid &fg) {
+    return (unsigned)(i - 1) < (unsigned)(fg.I - 2) && (unsigned)(j - 1) < (unsigned)(fg.J - 2) && (unsigned)(k - 1) < (unsigned)(fg.K - 2);
+}
+
+// generic path (grid border, outside): per-face range tests, zero outside the grid
+static __device__ __noinline__ void fast_mac_eval_border(const GridDesc &g, const FastGrid &fg, const MacView &m, float x, float y, float z,
+                                                  float &ox, float &oy, float &oz) {
     if (!fast_in_grid(x, y, z, fg)) {
         ox = oy = oz = 0.0f;
         return;
@@ -291,6 +307,25 @@ __device__ __forceinline__ void fast_mac_eval(const GridDesc &g, const FastGrid 
     oy = fast_trilerp(v, F.xs.f, F.yu.f, F.zs.f);
     fast_faces<2>(g, m.w, F.xs.i, F.ys.i, F.zu.i, v);
     oz = fast_trilerp(v, F.xs.f, F.ys.f, F.zu.f);
+}
+
+// MACVelocityField::evaluateVelocityAtPositionLinear in fp32 (zero outside the grid)
+__device__ __forceinline__ void fast_mac_eval(const GridDesc &g, const FastGrid &fg, const MacView &m, float x, float y, float z,
+                                              float &ox, float &oy, float &oz) {
+    const FastAxis xu = fast_axis(x, fg), yu = fast_axis(y, fg), zu = fast_axis(z, fg);
+    if (fast_interior(xu.i, yu.i, zu.i, fg)) {
+        const FastAxis xs = fast_shift(xu), ys = fast_shift(yu), zs = fast_shift(zu);
+        const int ks = zs.i - fg.kbase, kk = zu.i - fg.kbase;
+        float a[8], b[8], c[8];
+        load8(m.u + (xu.i + fg.sju * ys.i + fg.sku * ks), fg.sju, fg.sku, a);
+        load8(m.v + (xs.i + fg.sjv * yu.i + fg.skv * ks), fg.sjv, fg.skv, b);
+        load8(m.w + (xs.i + fg.sjw * ys.i + fg.skw * kk), fg.sjw, fg.skw, c);
+        ox = fast_trilerp(a, xu.f, ys.f, zs.f);
+        oy = fast_trilerp(b, xs.f, yu.f, zs.f);
+        oz = fast_trilerp(c, xs.f, ys.f, zu.f);
+        return;
+    }
+    fast_mac_eval_border(g, fg, m, x, y, z, ox, oy, oz);
 }
 
 // ---- error handling -------------------------------------------------------------------------

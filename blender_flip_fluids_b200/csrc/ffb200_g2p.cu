@@ -207,49 +207,109 @@ __device__ __forceinline__ void fast_apic_component(const G2PParams &P, const fl
     vel = fast_trilerp(v, vx.f, vy.f, vz.f);
 }
 
-__global__ void FFB_G2P_BOUNDS k_g2p_apic_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg,
-                                               unsigned long long *__restrict__ stats) {
+// border cells, points outside the grid, gradient frames within 1e-6 cells of a plane: the per-component code above
+__device__ __noinline__ bool g2p_apic_fast_generic(const G2PParams &P, const FastGrid &fg, float px, float py, float pz, int j) {
+    float vel[3], aff[9];
+    bool slow = false;
+    const bool in_grid = fast_in_grid(px, py, pz, fg);
+    const FastFrames F = fast_frames(px, py, pz, fg);
+    const FastAxis gxs = fast_axis(px - P.h, fg), gys = fast_axis(py - P.h, fg), gzs = fast_axis(pz - P.h, fg);
+    fast_apic_component<0>(P, P.cur.u, px, py, pz, in_grid, F.xu, F.ys, F.zs, F.xu, gys, gzs, vel[0], aff[0], aff[1], aff[2], slow);
+    fast_apic_component<1>(P, P.cur.v, px, py, pz, in_grid, F.xs, F.yu, F.zs, gxs, F.yu, gzs, vel[1], aff[3], aff[4], aff[5], slow);
+    fast_apic_component<2>(P, P.cur.w, px, py, pz, in_grid, F.xs, F.ys, F.zu, gxs, gys, F.zu, vel[2], aff[6], aff[7], aff[8], slow);
+#pragma unroll
+    for (int q = 0; q < 9; q++) P.a[q][j] = aff[q];
+    P.ovx[j] = vel[0]; P.ovy[j] = vel[1]; P.ovz[j] = vel[2];
+    return slow;
+}
+
+#ifndef FFB_G2P_FAST_MINB
+#define FFB_G2P_FAST_MINB 4
+#endif
+__global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FAST_MINB)
+    k_g2p_apic_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg, unsigned long long *__restrict__ stats) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
-    const bool in_grid = fast_in_grid(px, py, pz, fg);
-    const FastFrames F = fast_frames(px, py, pz, fg);
+    const FastAxis xu = fast_axis(px, fg), yu = fast_axis(py, fg), zu = fast_axis(pz, fg);
+    const FastAxis xs = fast_shift(xu), ys = fast_shift(yu), zs = fast_shift(zu);
     // the affine rows use the reference's FLOAT-shifted coordinates (p - (float)(0.5f * dx), fluidsimulation.cpp:6717)
     const FastAxis gxs = fast_axis(px - P.h, fg), gys = fast_axis(py - P.h, fg), gzs = fast_axis(pz - P.h, fg);
-    float v0, v1, v2, ax, ay, az;
     bool slow = false;
-    fast_apic_component<0>(P, P.cur.u, px, py, pz, in_grid, F.xu, F.ys, F.zs, F.xu, gys, gzs, v0, ax, ay, az, slow);
-    P.a[0][j] = ax; P.a[1][j] = ay; P.a[2][j] = az;
-    fast_apic_component<1>(P, P.cur.v, px, py, pz, in_grid, F.xs, F.yu, F.zs, gxs, F.yu, gzs, v1, ax, ay, az, slow);
-    P.a[3][j] = ax; P.a[4][j] = ay; P.a[5][j] = az;
-    fast_apic_component<2>(P, P.cur.w, px, py, pz, in_grid, F.xs, F.ys, F.zu, gxs, gys, F.zu, v2, ax, ay, az, slow);
-    P.a[6][j] = ax; P.a[7][j] = ay; P.a[8][j] = az;
-    P.ovx[j] = v0; P.ovy[j] = v1; P.ovz[j] = v2;
+    // interior cell, both shifts agree on the cell, every gradient frame clear of its planes: 24 loads back to back
+    const bool quick = fast_interior(xu.i, yu.i, zu.i, fg) && gxs.i == xs.i && gys.i == ys.i && gzs.i == zs.i &&
+                       !(near_plane(xu.f) || near_plane(yu.f) || near_plane(zu.f) || near_plane(gxs.f) || near_plane(gys.f) ||
+                         near_plane(gzs.f));
+    if (quick) {
+        const int ks = zs.i - fg.kbase, kk = zu.i - fg.kbase;
+        float a[8], b[8], c[8];
+        load8(P.cur.u + (xu.i + fg.sju * ys.i + fg.sku * ks), fg.sju, fg.sku, a);
+        load8(P.cur.v + (xs.i + fg.sjv * yu.i + fg.skv * ks), fg.sjv, fg.skv, b);
+        load8(P.cur.w + (xs.i + fg.sjw * ys.i + fg.skw * kk), fg.sjw, fg.skw, c);
+        float g0, g1, g2;
+        P.ovx[j] = fast_trilerp(a, xu.f, ys.f, zs.f);
+        fast_gradient(a, xu.f, gys.f, gzs.f, P.invdx, g0, g1, g2);
+        P.a[0][j] = g0; P.a[1][j] = g1; P.a[2][j] = g2;
+        P.ovy[j] = fast_trilerp(b, xs.f, yu.f, zs.f);
+        fast_gradient(b, gxs.f, yu.f, gzs.f, P.invdx, g0, g1, g2);
+        P.a[3][j] = g0; P.a[4][j] = g1; P.a[5][j] = g2;
+        P.ovz[j] = fast_trilerp(c, xs.f, ys.f, zu.f);
+        fast_gradient(c, gxs.f, gys.f, zu.f, P.invdx, g0, g1, g2);
+        P.a[6][j] = g0; P.a[7][j] = g1; P.a[8][j] = g2;
+    } else {
+        slow = g2p_apic_fast_generic(P, fg, px, py, pz, j);
+    }
     fast_count(stats + 1, slow);
 }
 
-__global__ void FFB_G2P_BOUNDS k_g2p_flip_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg) {
+__device__ __noinline__ void g2p_flip_fast_generic(const G2PParams &P, const FastGrid &fg, float px, float py, float pz, float pic[3],
+                                                    float old[3]) {
+    pic[0] = pic[1] = pic[2] = old[0] = old[1] = old[2] = 0.0f;
+    if (!fast_in_grid(px, py, pz, fg)) return;
+    const FastFrames F = fast_frames(px, py, pz, fg);
+    float v[8];
+    fast_faces<0>(P.g, P.cur.u, F.xu.i, F.ys.i, F.zs.i, v);
+    pic[0] = fast_trilerp(v, F.xu.f, F.ys.f, F.zs.f);
+    fast_faces<0>(P.g, P.saved.u, F.xu.i, F.ys.i, F.zs.i, v);
+    old[0] = fast_trilerp(v, F.xu.f, F.ys.f, F.zs.f);
+    fast_faces<1>(P.g, P.cur.v, F.xs.i, F.yu.i, F.zs.i, v);
+    pic[1] = fast_trilerp(v, F.xs.f, F.yu.f, F.zs.f);
+    fast_faces<1>(P.g, P.saved.v, F.xs.i, F.yu.i, F.zs.i, v);
+    old[1] = fast_trilerp(v, F.xs.f, F.yu.f, F.zs.f);
+    fast_faces<2>(P.g, P.cur.w, F.xs.i, F.ys.i, F.zu.i, v);
+    pic[2] = fast_trilerp(v, F.xs.f, F.ys.f, F.zu.f);
+    fast_faces<2>(P.g, P.saved.w, F.xs.i, F.ys.i, F.zu.i, v);
+    old[2] = fast_trilerp(v, F.xs.f, F.ys.f, F.zu.f);
+}
+
+__global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FAST_MINB)
+    k_g2p_flip_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
-    float pic[3] = {0.0f, 0.0f, 0.0f}, old[3] = {0.0f, 0.0f, 0.0f};
-    if (fast_in_grid(px, py, pz, fg)) {
-        const FastFrames F = fast_frames(px, py, pz, fg);
-        float v[8];
-        fast_faces<0>(P.g, P.cur.u, F.xu.i, F.ys.i, F.zs.i, v);
-        pic[0] = fast_trilerp(v, F.xu.f, F.ys.f, F.zs.f);
-        fast_faces<0>(P.g, P.saved.u, F.xu.i, F.ys.i, F.zs.i, v);
-        old[0] = fast_trilerp(v, F.xu.f, F.ys.f, F.zs.f);
-        fast_faces<1>(P.g, P.cur.v, F.xs.i, F.yu.i, F.zs.i, v);
-        pic[1] = fast_trilerp(v, F.xs.f, F.yu.f, F.zs.f);
-        fast_faces<1>(P.g, P.saved.v, F.xs.i, F.yu.i, F.zs.i, v);
-        old[1] = fast_trilerp(v, F.xs.f, F.yu.f, F.zs.f);
-        fast_faces<2>(P.g, P.cur.w, F.xs.i, F.ys.i, F.zu.i, v);
-        pic[2] = fast_trilerp(v, F.xs.f, F.ys.f, F.zu.f);
-        fast_faces<2>(P.g, P.saved.w, F.xs.i, F.ys.i, F.zu.i, v);
-        old[2] = fast_trilerp(v, F.xs.f, F.ys.f, F.zu.f);
-    }
     const float v0 = P.vx[j], v1 = P.vy[j], v2 = P.vz[j];
+    const FastAxis xu = fast_axis(px, fg), yu = fast_axis(py, fg), zu = fast_axis(pz, fg);
+    float pic[3], old[3];
+    if (fast_interior(xu.i, yu.i, zu.i, fg)) {
+        const FastAxis xs = fast_shift(xu), ys = fast_shift(yu), zs = fast_shift(zu);
+        const int ks = zs.i - fg.kbase, kk = zu.i - fg.kbase;
+        const int ou = xu.i + fg.sju * ys.i + fg.sku * ks, ov = xs.i + fg.sjv * yu.i + fg.skv * ks, ow = xs.i + fg.sjw * ys.i + fg.skw * kk;
+        float a[8], b[8], c[8];
+        load8(P.cur.u + ou, fg.sju, fg.sku, a);
+        load8(P.cur.v + ov, fg.sjv, fg.skv, b);
+        load8(P.cur.w + ow, fg.sjw, fg.skw, c);
+        pic[0] = fast_trilerp(a, xu.f, ys.f, zs.f);
+        pic[1] = fast_trilerp(b, xs.f, yu.f, zs.f);
+        pic[2] = fast_trilerp(c, xs.f, ys.f, zu.f);
+        load8(P.saved.u + ou, fg.sju, fg.sku, a);
+        load8(P.saved.v + ov, fg.sjv, fg.skv, b);
+        load8(P.saved.w + ow, fg.sjw, fg.skw, c);
+        old[0] = fast_trilerp(a, xu.f, ys.f, zs.f);
+        old[1] = fast_trilerp(b, xs.f, yu.f, zs.f);
+        old[2] = fast_trilerp(c, xs.f, ys.f, zu.f);
+    } else {
+        g2p_flip_fast_generic(P, fg, px, py, pz, pic, old);
+    }
     const float f0 = (v0 + pic[0]) - old[0], f1 = (v1 + pic[1]) - old[1], f2 = (v2 + pic[2]) - old[2];
     P.ovx[j] = pic[0] * P.rp + f0 * P.rf;
     P.ovy[j] = pic[1] * P.rp + f1 * P.rf;
