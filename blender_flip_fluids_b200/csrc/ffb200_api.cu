@@ -177,6 +177,8 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->liquid_phi);
     dev_free(c->liquid_blocks);
     dev_free(c->tol_stats);
+    dev_free(c->cell.wsum); dev_free(c->cell.home); dev_free(c->cell.active);
+    dev_free(c->sort.seam_cell);
     dev_free(c->sort.edge_count);
     for (int q = 0; q < 3; q++) dev_free(c->k1s[q]);
     for (auto &cs : c->sort.cell) {
@@ -1036,6 +1038,52 @@ int ffb200_unpin_host_memory(ffb200_context *ctx, void *ptr) {
         cudaError_t e = cudaHostUnregister(ptr);
         if (e != cudaSuccess) cudaGetLastError();                  // not registered (any more): nothing to undo
     }, false);
+}
+
+int ffb200_attribute_to_grid_transfer(ffb200_context *ctx, int n, const float *pos, const float *attr, int num_components,
+                                      double particle_radius, int normalize, float *grid, uint8_t *valid) {
+    return guarded("ffb200_attribute_to_grid_transfer", ctx, [&](Context &cc) {
+        ContextImpl &c = impl(cc);
+        if (num_components != 1 && num_components != 3) throw std::domain_error("1 (scalar) or 3 (vmath::vec3) attribute components");
+        if (!(particle_radius > 0.0)) throw std::domain_error("particle radius must be positive");
+        if (n < 0) throw std::domain_error("negative particle count");
+        if (!grid || !valid) throw std::invalid_argument("null output pointer");
+        if (n > 0 && (!pos || !attr)) throw std::invalid_argument("null position / attribute pointer");
+        ensure_capacity(c, n, false);
+        c.n = n;
+        c.has_affine = false;
+        c.sorted = false;
+        const size_t cells = (size_t)c.g.I * c.g.J * c.g.K;
+        if (n > 0) {
+            // the payload rides in the velocity streams through the sort
+            ParticleSoA &s = c.soa[c.cur];
+            StageTimer t(c, kH2D);
+            upload_attr(c, pos, s.p, n);
+            if (num_components == 3)
+                upload_attr(c, attr, s.v, n);
+            else
+                FFB_CUDA(cudaMemcpyAsync(s.v[0], attr, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+            launch_iota(c, s.orig, n);
+            t.done(0);
+        }
+        sort_impl(c);
+        float *d_out = nullptr;
+        uint8_t *d_valid = nullptr;
+        FFB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_out), cells * num_components * sizeof(float)));
+        FFB_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_valid), cells));
+        try {
+            launch_attribute_p2g(c, particle_radius, num_components, normalize, d_out, d_valid);
+            FFB_CUDA(cudaMemcpyAsync(grid, d_out, cells * num_components * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+            FFB_CUDA(cudaMemcpyAsync(valid, d_valid, cells, cudaMemcpyDeviceToHost, c.stream));
+            FFB_CUDA(cudaStreamSynchronize(c.stream));
+        } catch (...) {
+            cudaFree(d_out);
+            cudaFree(d_valid);
+            throw;
+        }
+        cudaFree(d_out);
+        cudaFree(d_valid);
+    });
 }
 
 int ffb200_liquid_sdf(ffb200_context *ctx, double particle_radius) {

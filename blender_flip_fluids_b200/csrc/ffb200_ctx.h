@@ -55,6 +55,8 @@ struct SortScratch {
     uint32_t *scan_partials = nullptr;   // block sums for the scans
     size_t scan_partials_cap = 0;
     uint32_t *seam = nullptr;            // 3 words per slot [dir*cap + slot]: 10^3-block membership
+    uint32_t *seam_cell = nullptr;       // membership words of the cell-centred attribute grid (lazy)
+    int seam_cell_cap = 0;
     // cell-partial splat scratch, one set per MAC direction so that the three transfers can run
     // concurrently (direction 0 on the context stream, 1 and 2 on auxiliary streams)
     struct CellScratch {
@@ -92,6 +94,7 @@ struct Context {
     size_t h_stage_bytes = 0;
     SortScratch sort;
     FaceGrid face[3];
+    FaceGrid cell;                       // the cell-centred grid of the attribute transfer (block masks + weight sums; lazy)
 
     float *phi = nullptr;                // (I+1)(J+1)(kloc+1) node-centred solid SDF
     uint8_t *near_solid = nullptr;       // ni*nj*nk
@@ -143,6 +146,7 @@ int launch_extrapolate(Context &c, int layers);          // GridUtils::extrapola
 void p2g_seam_begin(Context &c, double radius, SeamParams &sp);   // clears marks / counters, fills sp
 int launch_p2g_prepare(Context &c, double radius, bool seam_done);   // [membership words +] block masks
 int launch_p2g(Context &c, double radius, int method);  // the three transfer kernels
+int launch_attribute_p2g(Context &c, double radius, int ncomp, int normalize, float *d_out, uint8_t *d_valid);   // AttributeToGridTransfer<T>
 
 // ffb200_g2p.cu
 int launch_g2p(Context &c, int method, double ratio);

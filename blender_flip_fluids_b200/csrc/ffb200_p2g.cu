@@ -63,6 +63,9 @@ struct P2GParams {
     double chunk;                // _chunkWidth * _dx
     int wm;                      // half-cell window half width
     float guard_abs, guard_per;
+    int out_stride = 1;          // floats between consecutive outputs (one channel of an interleaved vec3 grid)
+    int vec3_norm = 0;           // normalise with vmath's vec3 /= float: x * (float)(1.0 / w) (vmath.cpp:105-111)
+    int no_norm = 0;             // AttributeTransferParameters::normalize == false: keep the weighted sum
 };
 
 __global__ void __launch_bounds__(256) k_seam_home(const __grid_constant__ SeamParams s) {
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(256) k_p2g(const __grid_constant__ P2GParams P
         f.h1[a] = h1 > H[a] - 1 ? H[a] - 1 : h1;
     }
     if (!P.active[f.nb[0] + P.bi * (f.nb[1] + P.bj * f.nb[2])]) {
-        P.out[fidx] = 0.0f;
+        P.out[fidx * (size_t)P.out_stride] = 0.0f;
         P.wsum[fidx] = 0.0f;
         P.valid[fidx] = 0;
         return;
@@ -277,10 +280,23 @@ __global__ void __launch_bounds__(256) k_p2g(const __grid_constant__ P2GParams P
     const float eps = 1e-6f;
     if (fabsf(sw - eps) <= P.guard_abs + P.guard_per * (float)cnt) exact_face<DIR, METHOD>(P, f, sw, swv);
     float s = swv;
-    if (sw > eps) s /= sw;                                     // :527-531
-    P.out[fidx] = s;                                           // write-out :155-162
+    if (sw > eps && !P.no_norm) s = P.vec3_norm ? s * finv(sw) : s / sw;   // :527-531; attributetogridtransfer.h vec3 flavour
+    P.out[fidx * (size_t)P.out_stride] = s;                    // write-out :155-162
     P.wsum[fidx] = sw;
     P.valid[fidx] = sw > eps ? 1 : 0;
+}
+
+// Membership word and home-block mark of the cell-centred "fourth direction" (offset (dx/2, dx/2, dx/2)) of
+// AttributeToGridTransfer<T>::transfer (attributetogridtransfer.h:213-330: the same block structure as the velocity
+// transfer), for its own radius. FLIP kernel only, so no edge flags.
+__global__ void __launch_bounds__(256) k_seam_cell(const __grid_constant__ SeamParams s, uint32_t *__restrict__ words,
+                                                   uint8_t *__restrict__ home, int bi, int bj, int bk) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= s.n) return;
+    const AxisSeam X = axis_seam(s.px[j] - s.h, s), Y = axis_seam(s.py[j] - s.h, s), Z = axis_seam(s.pz[j] - s.h, s);
+    if (in_range3(X.home, Y.home, Z.home, bi, bj, bk)) home[X.home + bi * (Y.home + bj * Z.home)] = 1;
+    const bool simple = X.simple && Y.simple && Z.simple;
+    words[j] = simple ? (X.fs | (Y.fs << 10) | (Z.fs << 20)) : (X.fn | (Y.fn << 10) | (Z.fn << 20));
 }
 
 // ---- shared-memory brick kernel -------------------------------------------------------------------
@@ -1680,6 +1696,94 @@ int launch_p2g(Context &c, double radius, int method) {
     launches += launch_dir<0>(c, deferred, method, variant, c.stream);
     if (forked)
         for (int d = 1; d < 3; d++) FFB_CUDA(cudaStreamWaitEvent(c.stream, c.sort.cell[d].done, 0));
+    FFB_CUDA(cudaGetLastError());
+    return launches;
+}
+
+// AttributeToGridTransfer<T>::transfer on the sorted resident particles: the payload channels are the velocity
+// streams v[0 .. ncomp), the result goes to d_out (ncomp interleaved floats per cell) and d_valid. Any radius: the
+// gather's half-cell window is clamped to the bin grid.
+int launch_attribute_p2g(Context &c, double radius, int ncomp, int normalize, float *d_out, uint8_t *d_valid) {
+    const GridDesc &g = c.g;
+    if (g.kbase != 0 || g.kloc != g.K) throw CudaError("ffb200_attribute_to_grid_transfer: not available on z-slab contexts");
+    ParticleSoA &s = c.soa[c.cur];
+    FaceGrid &f = c.cell;
+    const size_t cells = (size_t)g.I * g.J * g.K;
+    if (!f.wsum) {
+        f.gi = g.I; f.gj = g.J; f.gk = g.K;
+        f.bi = (g.I + kChunk - 1) / kChunk; f.bj = (g.J + kChunk - 1) / kChunk; f.bk = (g.K + kChunk - 1) / kChunk;
+        f.kstore = g.K;
+        f.count = cells;
+        FFB_CUDA(cudaMalloc(&f.wsum, cells * sizeof(float)));
+        FFB_CUDA(cudaMalloc(&f.home, (size_t)f.bi * f.bj * f.bk));
+        FFB_CUDA(cudaMalloc(&f.active, (size_t)f.bi * f.bj * f.bk));
+    }
+    if (c.sort.seam_cell_cap < c.cap) {
+        if (c.sort.seam_cell) FFB_CUDA(cudaFree(c.sort.seam_cell));
+        FFB_CUDA(cudaMalloc(&c.sort.seam_cell, (size_t)c.cap * sizeof(uint32_t)));
+        c.sort.seam_cell_cap = c.cap;
+    }
+    int launches = 0;
+    const float eps = 1e-6f;
+    const int nb = f.bi * f.bj * f.bk;
+    FFB_CUDA(cudaMemsetAsync(f.home, 0, (size_t)nb, c.stream));
+    SeamParams sp;
+    sp.g = g;
+    sp.px = s.p[0]; sp.py = s.p[1]; sp.pz = s.p[2];
+    sp.h = (float)(0.5 * g.dx);
+    sp.sr = (float)(radius + (double)eps);
+    const double chunkdx = g.dx * kChunk;
+    sp.blockdx = (float)chunkdx;
+    sp.inv_blockdx = 1.0 / (double)sp.blockdx;
+    sp.inv_chunkdx = 1.0 / chunkdx;
+    sp.n = c.n;
+    if (c.n > 0) {
+        k_seam_cell<<<(c.n + 255) / 256, 256, 0, c.stream>>>(sp, c.sort.seam_cell, f.home, f.bi, f.bj, f.bk);
+        launches++;
+    }
+    k_dilate26<<<(nb + 127) / 128, 128, 0, c.stream>>>(f.home, f.active, f.bi, f.bj, f.bk);
+    launches++;
+    P2GParams P;
+    P.g = g;
+    P.gi = f.gi; P.gj = f.gj; P.gk = f.gk;
+    P.kstore = f.kstore;
+    P.kw0 = 0; P.kw1 = g.K;
+    P.bi = f.bi; P.bj = f.bj; P.bk = f.bk;
+    P.active = f.active;
+    P.bin_start = c.sort.bin_start;
+    P.px = s.p[0]; P.py = s.p[1]; P.pz = s.p[2];
+    P.ax = P.ay = P.az = nullptr;
+    P.seam = c.sort.seam_cell;
+    P.edge_list = nullptr; P.edge_count = nullptr; P.edge_cap = 0;
+    P.orig = s.orig;
+    P.partial = nullptr; P.cell_flag = nullptr; P.cell_list = nullptr; P.list_count = nullptr; P.list_cap = 0;
+    P.ccx = P.ccy = P.ccz = P.ck0 = 0;
+    P.ovf = nullptr; P.ovf_count = nullptr;
+    P.wsum = f.wsum; P.valid = d_valid;
+    const float h = (float)(0.5 * g.dx);
+    P.off[0] = P.off[1] = P.off[2] = h;                        // gridOffset (dx/2, dx/2, dx/2), e.g. fluidsimulation.cpp:7033
+    P.r = (float)radius;
+    P.sr = sp.sr;
+    P.rsq = P.r * P.r;
+    P.c1 = (4.0f / 9.0f) * (1.0f / (P.r * P.r * P.r * P.r * P.r * P.r));
+    P.c2 = (17.0f / 9.0f) * (1.0f / (P.r * P.r * P.r * P.r));
+    P.c3 = (22.0f / 9.0f) * (1.0f / (P.r * P.r));
+    P.inv_s = (float)(1.0 / (double)(float)g.dx);
+    P.chunk = kChunk * g.dx;
+    P.wm = (int)std::floor(2.0 * (double)P.sr / g.dx + 1e-3) + 1;
+    P.guard_abs = c.guard_abs >= 0.f ? c.guard_abs : 1e-9f;
+    P.guard_per = c.guard_per >= 0.f ? c.guard_per : 1e-12f;
+    P.out_stride = ncomp;
+    P.vec3_norm = ncomp == 3 ? 1 : 0;
+    P.no_norm = normalize ? 0 : 1;
+    dim3 block(32, 4, 2);
+    dim3 grid((P.gi + block.x - 1) / block.x, (P.gj + block.y - 1) / block.y, (P.kstore + block.z - 1) / block.z);
+    for (int ch = 0; ch < ncomp; ch++) {
+        P.vel = s.v[ch];
+        P.out = d_out + ch;
+        k_p2g<3, FFB200_TRANSFER_FLIP><<<grid, block, 0, c.stream>>>(P);
+        launches++;
+    }
     FFB_CUDA(cudaGetLastError());
     return launches;
 }

@@ -89,6 +89,7 @@ SIGNATURES = {
     "ffb200_set_solid_device": [C.c_void_p, C.c_void_p, C.c_void_p],
     "ffb200_set_precision": [C.c_void_p, C.c_int],
     "ffb200_get_tolerance_stats": [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int],
+    "ffb200_attribute_to_grid_transfer": [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int, C.c_double, C.c_int, _f32p, _u8p],
     "ffb200_p2g": [C.c_void_p, C.c_double, C.c_int],
     "ffb200_g2p": [C.c_void_p, C.c_int, C.c_double],
     "ffb200_advect": [C.c_void_p, C.c_double, C.c_double, C.c_int],
@@ -439,6 +440,21 @@ class FlipContext:
         """ffb200_set_solid with device pointers (stored node planes of phi, whole near-solid grid)."""
         self._call("ffb200_set_solid_device", C.c_void_p(int(phi_ptr)), C.c_void_p(int(near_ptr)))
 
+    def attribute_to_grid_transfer(self, pos, attr, radius, normalize=True):
+        """AttributeToGridTransfer<T>::transfer: attr [n] (float) or [n, 3] (vmath::vec3) -> (grid [K, J, I(, 3)], valid [K, J, I])."""
+        pos = _f32(pos)
+        n = pos.shape[0]
+        attr = np.ascontiguousarray(attr, dtype=np.float32)
+        ncomp = 3 if attr.ndim == 2 else 1
+        if attr.shape != ((n, 3) if ncomp == 3 else (n,)):
+            raise ValueError(f"attribute array of shape {attr.shape} for {n} particles")
+        grid = np.zeros((self.K, self.J, self.I) + ((3,) if ncomp == 3 else ()), np.float32)
+        valid = np.zeros((self.K, self.J, self.I), np.uint8)
+        self._call("ffb200_attribute_to_grid_transfer", n, _ptr(pos), _ptr(attr), ncomp, C.c_double(radius), 1 if normalize else 0,
+                   _ptr(grid), _ptr(valid, _u8p))
+        self.n = n
+        return grid, valid
+
     # ---- stages on resident data ----------------------------------------------------------------
     def p2g(self, radius, method):
         self._call("ffb200_p2g", C.c_double(radius), int(method))
@@ -523,19 +539,14 @@ class FlipContext:
 
 
 class AttributeTransfer:
-    """AttributeToGridTransfer<float>::transfer (attributetogridtransfer.h:52-157) by composition, until the P2G kernels
-    get a cell-centred fourth direction: the transfer onto the I x J x K cell-centred grid (offset dx/2 on every axis) is,
-    operation for operation, the U-direction FLIP transfer of VelocityAdvector on an (I-1) x J x K grid with the particle x
-    shifted by float(dx/2) and the attribute in the x velocity (proven bit-exact on the CPU restatements by
-    tests/test_oracle_golden.py::test_attribute_p2g_is_a_shifted_u_transfer). Radii up to the device P2G's limit
-    (below 2 dx: the age / lifetime / density / colour attributes use 1 dx). EXPERIMENTAL in round 1: built from
-    hardware-validated kernels, but this composition itself has not run on hardware yet."""
+    """AttributeToGridTransfer<T>::transfer (attributetogridtransfer.h:52-157) through ffb200_attribute_to_grid_transfer:
+    scalar and vmath::vec3 payloads, radii of 1 to 3 dx, on the cell-centred I x J x K grid. (Round 1 composed this from
+    the U-direction velocity transfer of a grid one cell narrower; the identity behind that is still checked on the CPU,
+    tests/test_oracle_golden.py::test_attribute_p2g_is_a_shifted_u_transfer.)"""
 
     def __init__(self, I, J, K, dx, device=0):
-        if I < 2:
-            raise ValueError("the grid must be at least two cells wide")
         self.I, self.J, self.K, self.dx = I, J, K, dx
-        self.ctx = FlipContext(I - 1, J, K, dx, device)
+        self.ctx = FlipContext(I, J, K, dx, device)
 
     def close(self):
         self.ctx.close()
@@ -546,13 +557,6 @@ class AttributeTransfer:
     def __exit__(self, *exc):
         self.close()
 
-    def transfer(self, pos, attr, radius):
-        """-> (grid[K, J, I] float32, valid[K, J, I] uint8)."""
-        pos = _f32(pos)
-        n = pos.shape[0]
-        shifted = pos.copy()
-        shifted[:, 0] = pos[:, 0] - np.float32(0.5 * self.dx)          # vec3 p = _positions[i] - offset, in float
-        vel = np.zeros((n, 3), np.float32)
-        vel[:, 0] = np.ascontiguousarray(attr, dtype=np.float32).reshape(n)
-        (u, _, _), (vu, _, _) = self.ctx.velocity_advector_advect(shifted, vel, radius=radius, method=FLIP)
-        return u, vu
+    def transfer(self, pos, attr, radius, normalize=True):
+        """-> (grid[K, J, I(, 3)] float32, valid[K, J, I] uint8)."""
+        return self.ctx.attribute_to_grid_transfer(pos, attr, radius, normalize)

@@ -261,6 +261,18 @@ int ffb200_get_tolerance_stats(ffb200_context *ctx, unsigned long long *counts, 
  * ceil(I/3) x ceil(J/3) x ceil(K/3) byte grid. For scenes too large to stage through host arrays per rank. */
 int ffb200_set_solid_device(ffb200_context *ctx, const float *d_phi, const uint8_t *d_near_solid);
 
+/* AttributeToGridTransfer<T>::transfer (attributetogridtransfer.h:52-157, 213-520; the age / lifetime / viscosity /
+ * density / colour / whitewater-proximity grids of fluidsimulation.cpp:6990-7170): the FLIP-kernel splat of one
+ * float (num_components = 1) or one vmath::vec3 (num_components = 3, interleaved, normalised with vec3 /= float)
+ * per particle onto the CELL-CENTRED I x J x K grid (gridOffset (dx/2, dx/2, dx/2) at every call site),
+ * particle_radius = <attribute radius in voxels> * dx (1 to 3 dx in the reference). grid: I*J*K*num_components
+ * floats, valid: I*J*K bytes (weight > 1e-6), both x fastest; normalize = AttributeTransferParameters::normalize
+ * (0: the weighted sums are kept, the whitewater-proximity grid of fluidsimulation.cpp:7083). Valid masks bit for
+ * bit, values to summation order (1e-5), the velocity transfer's contract. Uploads positions and payload (host
+ * order) and REPLACES the resident particle set; whole-grid contexts only. */
+int ffb200_attribute_to_grid_transfer(ffb200_context *ctx, int n, const float *pos, const float *attr, int num_components,
+                                      double particle_radius, int normalize, float *grid, uint8_t *valid);
+
 /* ---- stages on resident data ---------------------------------------------------------------------- */
 
 int ffb200_p2g(ffb200_context *ctx, double particle_radius, int transfer_method);

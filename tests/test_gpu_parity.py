@@ -617,16 +617,51 @@ def test_liquid_sdf_variants_and_postprocess(variant):
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
-def test_attribute_transfer_composition(eng):
-    """AttributeToGridTransfer<float>::transfer through the U-direction FLIP P2G of a grid one cell narrower."""
-    meta, e = load_golden("attribute_24x20x22_r1")
+@pytest.mark.parametrize("name", ["attribute_24x20x22_r1", "attribute_23x21x25_seams_r2"])
+def test_attribute_transfer_golden(eng, name):
+    """AttributeToGridTransfer<float> and <vmath::vec3> (attributetogridtransfer.h:52-157) at radii of 1 dx and 2 dx (the
+    second on the seam-adversarial particle set) against the reference-generated fixtures: valid masks bit-exact, grids
+    1e-5 (summation order), the vec3 flavour with its own normalisation."""
+    meta, e = load_golden(name)
     _, src = load_golden(meta["source"])
     pos = src[meta["key"]]
     attr = (np.random.default_rng(meta["seed"]).random(len(pos)) * 10.0).astype(np.float32)
+    attr3 = np.random.default_rng(meta["seed"] + 1000).random((len(pos), 3)).astype(np.float32)
     with eng.AttributeTransfer(meta["I"], meta["J"], meta["K"], meta["dx"]) as tr:
         grid, valid = tr.transfer(pos, attr, meta["radius"])
-    assert np.array_equal(valid, e["out_valid"])
-    assert close(grid, e["out_grid"])
+        grid3, valid3 = tr.transfer(pos, attr3, meta["radius"])
+        tr.ctx.set_valid_guard(1e30, 0.0)                      # every cell through the reference-order summation
+        exact, valid_e = tr.transfer(pos, attr, meta["radius"])
+        exact3, _ = tr.transfer(pos, attr3, meta["radius"])
+    assert np.array_equal(valid, e["out_valid"]) and np.array_equal(valid3, e["out_valid"]) and np.array_equal(valid_e, e["out_valid"])
+    assert close(grid, e["out_grid"]) and close(grid3, e["out_grid3"])
+    assert bits_equal(exact, e["out_grid"]) and bits_equal(exact3, e["out_grid3"])
+
+
+@pytest.mark.parametrize("radius_cells", [1.0, 2.0, 3.0])
+def test_attribute_transfer_vs_oracle_radii(eng, oracle, radius_cells):
+    """The radii the reference uses (age / lifetime / density / colour 1 dx, whitewater proximity and viscosity solver 2 dx,
+    viscosity 3 dx; fluidsimulation.h:2416-2439) on a non-dyadic grid against the oracle, scalar and vec3, normalised and not."""
+    from blender_flip_fluids_b200 import scenes
+    I, J, K, dx = 22, 19, 21, 0.0137
+    sc = scenes.dam_break(22, dx=dx, vel="zero", dims=(I, J, K), seed=21)
+    rng = np.random.default_rng(5)
+    attr = (rng.random(sc.n) * 4.0 - 1.0).astype(np.float32)
+    attr3 = rng.random((sc.n, 3)).astype(np.float32)
+    radius = float(np.float32(radius_cells) * dx)
+    og, ov = oracle.attribute_p2g(I, J, K, dx, sc.pos, attr, radius)
+    og3, ov3 = oracle.attribute_p2g_vec3(I, J, K, dx, sc.pos, attr3, radius)
+    with eng.AttributeTransfer(I, J, K, dx) as tr:
+        g, v = tr.transfer(sc.pos, attr, radius)
+        g3, v3 = tr.transfer(sc.pos, attr3, radius)
+        raw, vr = tr.transfer(sc.pos, np.ones(sc.n, np.float32), radius, normalize=False)
+        wsum, _ = tr.transfer(sc.pos, np.ones(sc.n, np.float32), radius, normalize=True)
+    assert np.array_equal(v, ov) and np.array_equal(v3, ov3) and np.array_equal(vr, ov)
+    assert close(g, og) and close(g3, og3)
+    assert v.sum() > 1000
+    # unnormalised transfer of a constant 1 is the weight sum itself: above 1e-6 exactly where valid, and its
+    # normalised twin is 1 there
+    assert (raw[ov == 1] > 1e-6).all() and np.abs(wsum[ov == 1] - 1.0).max() < 1e-5
 
 
 # ---- tolerance mode (ffb200_set_precision(FFB200_PRECISION_TOLERANCE)): fp32 gathers, the north star's 1e-5 bar ----
