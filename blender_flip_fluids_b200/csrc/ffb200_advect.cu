@@ -285,9 +285,18 @@ __global__ void FFB_ADV_BOUNDS k_advect(const __grid_constant__ AdvectParams P, 
 //     the boundary box by its 1e-4 margin.
 // Everything else -- the particles that can actually touch a solid -- takes the exact path in full: the reference's
 // fp64 RK3 and _resolveCollision, bit for bit. `stats` counts both populations.
-constexpr float kBand = 4e-3f;            // cells; covers 8 ulps of a coordinate up to 2^11 cells plus the RK3 error
-
-__device__ __forceinline__ bool clear_of_planes(float f, float band) { return f > band && f < 1.0f - band; }
+// floor of a gate-cell coordinate t (units of 3 dx) with a band: false when t is so close to an integer that the few
+// ulps between the approximate and the exact end point (8 ulps of the coordinate, ~5e-7 |t| relative, plus the RK3
+// error, far below 1e-5 cells) could change the floor.
+__device__ __forceinline__ bool gate_cell(float t, int &cell) {
+    const float mm = t + kMagic;
+    float q = t - (mm - kMagic);                           // in [-0.5, 0.5]
+    int i = __float_as_int(mm) - kMagicBits;
+    if (q < 0.0f) { q += 1.0f; i -= 1; }
+    cell = i;
+    const float band = fmaf(fabsf(t), 1e-6f, 2e-5f);
+    return q > band && q < 1.0f - band;
+}
 
 __device__ __noinline__ void exact_advect(const AdvectParams &P, float x0, float y0, float z0, float &x1, float &y1, float &z1,
                                           bool have_k1 = false, float k1x = 0.0f, float k1y = 0.0f, float k1z = 0.0f) {
@@ -326,30 +335,28 @@ __global__ void __launch_bounds__(FFB_ADV_THREADS, FFB_ADV_FAST_MINB) k_advect_f
     bool accept = !P.collide;
     if (P.collide) {
         const GridDesc &g = P.g;
-        // end point: cell and gate cell, both clear of their planes and inside the grid
-        const FastAxis ex = fast_axis(x1, fg), ey = fast_axis(y1, fg), ez = fast_axis(z1, fg);
-        bool sure = clear_of_planes(ex.f, kBand) && clear_of_planes(ey.f, kBand) && clear_of_planes(ez.f, kBand) &&
-                    in_range3(ex.i, ey.i, ez.i, g.I, g.J, g.K);
-        // 3dx gate cells: a float product is enough with the band around it (magic-number floor, no conversion)
-        const float tx = x1 * inv_near, ty = y1 * inv_near, tz = z1 * inv_near;
-        const float mx = tx + kMagic, my = ty + kMagic, mz = tz + kMagic;
-        float qx = tx - (mx - kMagic), qy = ty - (my - kMagic), qz = tz - (mz - kMagic);    // in [-0.5, 0.5]
-        int ni = __float_as_int(mx) - kMagicBits, nj = __float_as_int(my) - kMagicBits, nk = __float_as_int(mz) - kMagicBits;
-        if (qx < 0.0f) { qx += 1.0f; ni -= 1; }
-        if (qy < 0.0f) { qy += 1.0f; nj -= 1; }
-        if (qz < 0.0f) { qz += 1.0f; nk -= 1; }
-        sure = sure && clear_of_planes(qx, kBand) && clear_of_planes(qy, kBand) && clear_of_planes(qz, kBand);
+        // 3dx gate cells of the start and the end point, magic-number floors with a band around the planes: the start is
+        // an exact input, but its reference floor is taken in double; the end differs from the exact one by a few ulps
+        int s3[3], e3[3];
+        bool sure = gate_cell(x0 * inv_near, s3[0]) & gate_cell(y0 * inv_near, s3[1]) & gate_cell(z0 * inv_near, s3[2]) &
+                    gate_cell(x1 * inv_near, e3[0]) & gate_cell(y1 * inv_near, e3[1]) & gate_cell(z1 * inv_near, e3[2]);
+        // the end point's CELL must be inside the grid (the reference clamps it into the boundary box otherwise)
+        const float m = 1e-2f * P.step;                        // 1e-3 dx: above 8 ulps of a coordinate up to 4096 cells
+        sure = sure && x1 > m && y1 > m && z1 > m && x1 < fg.xmax - m && y1 < fg.ymax - m && z1 < fg.zmax - m;
         if (sure) {
-            const bool near_new = !in_range3(ni, nj, nk, P.ni, P.nj, P.nk) || P.near_solid[ni + P.ni * (nj + P.nj * nk)] != 0;
-            if (!near_new && !near_solid(P, x0, y0, z0)) {
+            const bool near_s = !in_range3(s3[0], s3[1], s3[2], P.ni, P.nj, P.nk) || P.near_solid[s3[0] + P.ni * (s3[1] + P.nj * s3[2])] != 0;
+            const bool near_e = !in_range3(e3[0], e3[1], e3[2], P.ni, P.nj, P.nk) || P.near_solid[e3[0] + P.ni * (e3[1] + P.nj * e3[2])] != 0;
+            if (!near_s && !near_e) {
                 accept = true;                                   // the reference returns before looking at the SDF (:7654-7658)
             } else {
-                // clearance shortcut of resolve_collision with one more cell of slack (the start cell comes from the
-                // float-pair floor, which may differ from the double floor within 2^-44 of a plane)
+                // clearance shortcut of resolve_collision with one more cell of slack: the cells come from float-pair
+                // floors (start: within 2^-44 of the double floor; end: a few ulps from the exact end point), so either
+                // may be off by one near a plane
                 const FastAxis sx = fast_axis(x0, fg), sy = fast_axis(y0, fg), sz = fast_axis(z0, fg);
+                const FastAxis ex = fast_axis(x1, fg), ey = fast_axis(y1, fg), ez = fast_axis(z1, fg);
                 if (in_range3(sx.i, sy.i, sz.i - g.kbase, g.I, g.J, g.kloc)) {
-                    const int reach = max(max(abs(ex.i - sx.i), abs(ey.i - sy.i)), abs(ez.i - sz.i)) + 2;
-                    const int c = P.clear[(size_t)sx.i + (size_t)g.I * ((size_t)sy.i + (size_t)g.J * (sz.i - g.kbase))];
+                    const int reach = max(max(abs(ex.i - sx.i), abs(ey.i - sy.i)), abs(ez.i - sz.i)) + 3;
+                    int c = P.clear[(size_t)sx.i + (size_t)g.I * ((size_t)sy.i + (size_t)g.J * (sz.i - g.kbase))];
                     accept = c > reach && box_inside_margin(P.box, x0, y0, z0) && box_inside_margin(P.box, x1, y1, z1);
                 }
             }

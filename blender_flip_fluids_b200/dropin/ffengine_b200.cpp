@@ -12,6 +12,8 @@
 //   FluidSimulation::_advanceMarkerParticles(double)                  fluidsimulation.cpp:7853
 //   ParticleLevelSet::calculateSignedDistanceField(ParticleSystem&, double)   particlelevelset.cpp:161
 //   FluidSimulation::_getMaximumMarkerParticleSpeed()                 fluidsimulation.cpp:10188
+//   AttributeToGridTransfer<float>::transfer, <vmath::vec3>::transfer attributetogridtransfer.h:78 (weak template
+//                                   instantiations the reference calls through the PLT: explicit specialisations here)
 //
 // and two bookkeeping hooks that forward to the reference's own definition (dlsym RTLD_NEXT):
 //
@@ -53,6 +55,9 @@
 #include <vector>
 
 #include "fluidsimulation.h"
+#include "gridutils.h"
+#include "threadutils.h"
+#include "attributetogridtransfer.h"
 #include "particlelevelset.h"
 #include "stopwatch.h"
 #include "velocityadvector.h"
@@ -544,4 +549,62 @@ double FluidSimulation::_getMaximumMarkerParticleSpeed() {
     double speed = 0.0;
     check(ffb200_get_maximum_particle_speed(ctx, &speed));
     return speed;
+}
+
+// ---- attribute transfers ------------------------------------------------------------------------------
+// AttributeToGridTransfer<T>::transfer (attributetogridtransfer.h:78-157): the age / lifetime / viscosity / density /
+// colour / whitewater-proximity grids (fluidsimulation.cpp:4636-4742, 6010, 7011-7170). The transfer uploads its own
+// positions and payload and replaces the device's particle set, so the marker-particle residency ends here (its host
+// copy is brought up to date first); these run once per frame, and only when an attribute is enabled.
+namespace {
+
+template <class T>
+void attribute_transfer_b200(AttributeTransferParameters<T> &params, int ncomp) {
+    run_stage([&] {
+        Array3d<T> *grid = params.attributeGrid;
+        Array3d<bool> *validGrid = params.validGrid;
+        const int I = grid->width, J = grid->height, K = grid->depth;
+        const float h = (float)(0.5 * params.dx);
+        if (params.gridOffset.x != h || params.gridOffset.y != h || params.gridOffset.z != h)
+            throw std::runtime_error("ffengine_b200: attribute transfer with a grid offset other than (dx/2, dx/2, dx/2)");
+        const size_t n = params.positions->size();
+        if (n == 0) return;                                     // no block holds particles: nothing is written (:96-99)
+        inject("attribute");
+        ffb200_context *ctx = context_for(I, J, K, params.dx);
+        flush_pending_field();
+        {
+            std::lock_guard<std::recursive_mutex> lock(g_mutex);
+            sync_host_locked();
+            g_res.ps = nullptr;
+        }
+        const size_t cells = (size_t)I * J * K;
+        std::vector<float> out(cells * ncomp);
+        std::vector<uint8_t> valid(cells);
+        check(ffb200_attribute_to_grid_transfer(ctx, (int)n, raw(params.positions), reinterpret_cast<const float *>(params.attributes->data()),
+                                                ncomp, params.particleRadius, params.normalize ? 1 : 0, out.data(), valid.data()));
+        // the reference writes the cells of the blocks it processed and only ever SETS valid flags (:128-141)
+        float *dst = reinterpret_cast<float *>(grid->getRawArray());
+        bool *vdst = validGrid->getRawArray();
+        for (size_t i = 0; i < cells; i++) {
+            bool touched = valid[i] != 0;
+            for (int q = 0; q < ncomp; q++) touched = touched || out[i * ncomp + q] != 0.0f;
+            if (touched)
+                for (int q = 0; q < ncomp; q++) dst[i * ncomp + q] = out[i * ncomp + q];
+            if (valid[i]) vdst[i] = true;
+        }
+    });
+}
+
+}  // namespace
+
+static_assert(sizeof(Array3d<vmath::vec3>) > 0 && sizeof(vmath::vec3) == 3 * sizeof(float), "interleaved vec3 grid");
+
+template <>
+void AttributeToGridTransfer<float>::transfer(AttributeTransferParameters<float> params) {
+    attribute_transfer_b200(params, 1);
+}
+
+template <>
+void AttributeToGridTransfer<vmath::vec3>::transfer(AttributeTransferParameters<vmath::vec3> params) {
+    attribute_transfer_b200(params, 3);
 }

@@ -1,7 +1,8 @@
 """Run one small simulation through a libffengine-compatible library and dump the particles.
 TEST INFRASTRUCTURE: python tests/dropin_run.py <lib.so> <out.npz> <flip|apic> [frames] [n] [features]
 features: comma list of open (x+ side open), lifetime (fluid-particle lifetime attribute), surfvel (surface
-velocity attribute against obstacles: the second VelocityAdvector call site, fluidsimulation.cpp:6951-6977)."""
+velocity attribute against obstacles: the second VelocityAdvector call site, fluidsimulation.cpp:6951-6977), age /
+viscosity / color (surface attributes: the AttributeToGridTransfer<float | vec3> call sites)."""
 import json
 import os
 import sys
@@ -32,6 +33,12 @@ if "open" in features:
     e.set_fluid_boundary_collisions([1, 0, 1, 1, 1, 1])
 if "lifetime" in features:
     e.enable_fluid_particle_lifetime_attribute()
+if "age" in features:            # AttributeToGridTransfer<float>, radius 1 dx (fluidsimulation.cpp:6991-7015)
+    e.enable_surface_age_attribute()
+if "viscosity" in features:      # AttributeToGridTransfer<float>, radius 3 dx (:7091-7115)
+    e.enable_surface_viscosity_attribute()
+if "color" in features:          # AttributeToGridTransfer<vmath::vec3> (:7148-7172)
+    e.enable_surface_color_attribute()
 if "surfvel" in features:
     e.enable_surface_velocity_attribute()
     e.enable_surface_velocity_attribute_against_obstacles()

@@ -82,6 +82,9 @@ class Engine:
     def enable_surface_velocity_attribute(self): self._void("FluidSimulation_enable_surface_velocity_attribute")      # :1070
     def enable_surface_velocity_attribute_against_obstacles(self):                                     # :1091
         self._void("FluidSimulation_enable_surface_velocity_attribute_against_obstacles")
+    def enable_surface_age_attribute(self): self._void("FluidSimulation_enable_surface_age_attribute")           # :1154
+    def enable_surface_color_attribute(self): self._void("FluidSimulation_enable_surface_color_attribute")       # :1282
+    def enable_surface_viscosity_attribute(self): self._void("FluidSimulation_enable_surface_viscosity_attribute")   # :1389
     def enable_fluid_particle_lifetime_attribute(self): self._void("FluidSimulation_enable_fluid_particle_lifetime_attribute")  # :938
 
     def set_fluid_boundary_collisions(self, active6):                                                  # :226 (x-, x+, y-, y+, z-, z+)

@@ -81,7 +81,7 @@ def test_scene_generators():
 
 
 def test_dropin_reexports_reference_abi():
-    """libffengine_b200.so defines exactly the four interposed C++ members and resolves the
+    """libffengine_b200.so defines exactly the interposed C++ members and resolves the
     reference's whole extern "C" surface through its DT_NEEDED reference library."""
     dropin = os.path.join(ROOT, "blender_flip_fluids_b200", "lib", "libffengine_b200.so")
     ref = os.path.join(ROOT, "oracle", "_ref", "libffengine_ref.so")
@@ -95,6 +95,9 @@ def test_dropin_reexports_reference_abi():
                        "_ZN15FluidSimulation27_extrapolateFluidVelocitiesER16MACVelocityFieldR26ValidVelocityComponentGrid",
                        "_ZN16ParticleLevelSet28calculateSignedDistanceFieldER14ParticleSystemd",
                        "_ZN15FluidSimulation30_getMaximumMarkerParticleSpeedEv",
+                       # explicit specialisations of the weak template instantiations the reference calls through the PLT
+                       "_ZN23AttributeToGridTransferIfE8transferE27AttributeTransferParametersIfE",
+                       "_ZN23AttributeToGridTransferIN5vmath4vec3EE8transferE27AttributeTransferParametersIS1_E",
                        # bookkeeping hooks that forward to the reference's definition (dlsym RTLD_NEXT)
                        "_ZN14ParticleSystem25getAttributeValuesVector3ER23ParticleSystemAttribute",
                        "_ZN15FluidSimulation10initializeEv"}

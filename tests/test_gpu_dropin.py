@@ -67,13 +67,16 @@ def test_dropin_matches_reference(tmp_path, method):
     assert np.abs(fast["vel"].astype(np.float64) - ref["vel"]).max() <= 2e-3 * vscale
 
 
-@pytest.mark.parametrize("features,frames", [("open,surfvel", 3), ("lifetime", 2), ("open,lifetime,surfvel", 2)])
+@pytest.mark.parametrize("features,frames", [("open,surfvel", 3), ("lifetime", 2), ("open,lifetime,surfvel", 2),
+                                             ("age,viscosity,color", 2)])
 def test_dropin_feature_scenes(tmp_path, features, frames):
     """Branches the plain scene never takes: an open domain side (removal planes), the lifetime rule (a host-only
     attribute evaluated by the interposer; loaded particles carry lifetime 0, so the rule removes the whole set at
     once) and the surface-velocity attribute against obstacles -- the SECOND VelocityAdvector::advect +
     _extrapolateFluidVelocities call site (fluidsimulation.cpp:6951-6977), whose host readers also exercise the
-    lazy download through the accessor hook. Bit-identical in exact mode, particle counts included."""
+    lazy download through the accessor hook; and the surface age / viscosity / colour attributes, whose grids come from
+    the interposed AttributeToGridTransfer<float | vec3>::transfer (radii 1 and 3 dx). Bit-identical in exact mode,
+    particle counts included."""
     _libs()
     ref, rs = _run(REF, str(tmp_path / "ref.npz"), "flip", frames=frames, features=features)
     got, gs = _run(DROPIN, str(tmp_path / "got.npz"), "flip", {"FFB200_EXACT_P2G": "1"}, frames=frames, features=features)
