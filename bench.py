@@ -12,8 +12,8 @@ whole scene, ~133 GB of the 180 GB). Particles come from a counter-based hash of
 (blender_flip_fluids_b200/scenes.py), so every decomposition -- and the CPU reference arm -- sees
 bit-identical particles. The batch EVOLVES: every step sorts the particles the previous step advected, ranks
 migrate particles for real. Where the reference's CPU pressure projection would hand back a field, the MAC
-field is overwritten with an analytic divergence-free field (Taylor-Green vortex, tangential at the walls),
-so the set circulates instead of compressing. Same launch mode (eager) at every N.
+field is overwritten with an analytic divergence-free field (two superposed Taylor-Green vortices, tangential at
+the walls, with motion across z), so the set circulates -- and crosses slab faces -- instead of compressing. Same launch mode (eager) at every N.
 
 `value`    device-resident throughput: particles and grids live in HBM, K steps timed with CUDA events on the
            launching stream between barriers, max over ranks.
@@ -59,7 +59,9 @@ PPC = 8
 V0 = 0.5                      # |v| component bound of the synthetic velocities and the amplitude of the analytic field
 SEED = 1234
 RATIO = 0.05
-HALO, GHOST = 7, 2
+HALO = 7
+GHOST = 1                     # ghost particle layers: ceil(radius / dx) -- the P2G kernel reaches 0.866 dx, so 1 (2 for the doubled
+                              # radius of the smooth surface-tension kernel); bit-identity vs the undecomposed run: tests/test_slab_gloo.py
 SAMPLE_PLANES = 16            # fluid cell planes of the CPU reference sample
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
@@ -147,13 +149,20 @@ def reference_arm(n_grid: int, steps: int, warmup: int, threads: int = 0):
     pos[:, 2] = (pos[:, 2].astype(np.float64) - shift * dx).astype(np.float32)
     vel = np.stack(streams[3:6], axis=1)
     aff = [np.stack(streams[6 + 3 * q:9 + 3 * q], axis=1) for q in range(3)] if METHOD == "apic" else None
-    # analytic field (benchscene.taylor_green_field restated with numpy: the same doubles, narrowed once)
-    xu, yu = np.arange(n + 1) * dx, (np.arange(n) + 0.5) * dx
-    u2 = (V0 * np.sin(math.pi * xu)[None, :] * np.cos(math.pi * yu)[:, None]).astype(np.float32)
-    xv, yv = (np.arange(n) + 0.5) * dx, np.arange(n + 1) * dx
-    v2 = (-V0 * np.cos(math.pi * xv)[None, :] * np.sin(math.pi * yv)[:, None]).astype(np.float32)
-    mac = [np.ascontiguousarray(np.broadcast_to(u2[None], (K, n, n + 1))), np.ascontiguousarray(np.broadcast_to(v2[None], (K, n + 1, n))),
-           np.zeros((K + 1, n, n), np.float32)]
+    # analytic field (benchscene.taylor_green_field restated with numpy: the same doubles, narrowed once), on the sample's
+    # planes in SCENE coordinates
+    A = B = 0.5 * V0
+    kz0 = 0 if whole else k0 - 3
+    xf, xc = np.arange(n + 1) * dx, (np.arange(n) + 0.5) * dx
+    yf, yc = np.arange(n + 1) * dx, (np.arange(n) + 0.5) * dx
+    zc, zf = (np.arange(kz0, kz0 + K) + 0.5) * dx, np.arange(kz0, kz0 + K + 1) * dx
+    u2 = (A * np.sin(math.pi * xf)[None, :] * np.cos(math.pi * yc)[:, None]).astype(np.float32)
+    mac = [np.ascontiguousarray(np.broadcast_to(u2[None], (K, n, n + 1))),
+           np.ascontiguousarray(np.broadcast_to((-A * np.cos(math.pi * xc)[None, None, :] * np.sin(math.pi * yf)[None, :, None] +
+                                                 B * np.sin(math.pi * yf)[None, :, None] * np.cos(math.pi * zc)[:, None, None]).astype(np.float32),
+                                                (K, n + 1, n))),
+           np.ascontiguousarray(np.broadcast_to((-B * np.cos(math.pi * yc)[None, :, None] * np.sin(math.pi * zf)[:, None, None]).astype(np.float32),
+                                                (K + 1, n, n)))]
     if whole:
         phi, near = scenes.analytic_solid_sdf(n, n, n, dx)
     else:
@@ -570,6 +579,12 @@ def main():
                "ms_per_step": t_e2e * 1e3, "steps": k_e2e, "path": path,
                "particles": "resident across stages and substeps (uploaded once, outside the timed region); what the host "
                             "pipeline needs every substep crosses PCIe inside it"}
+    if run.sim is not None and getattr(run.sim, "_profile", False):
+        # FFB200_SLAB_PROFILE=1: synchronised wall-clock phases of step_fast (diagnostic; the timed numbers above then
+        # include the synchronisation and are not benchmark figures)
+        ph = run.sim._phase
+        tot = sum(ph.values())
+        sys.stderr.write(f"rank {rank} slab phases, share of {tot:.3f} s: " + ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in ph.items()) + "\n")
     run.close()
 
     # ---- secondary record: BASELINE configs[1], 128^3 APIC (N = 1 only) ----------------------------------------------

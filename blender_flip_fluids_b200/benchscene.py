@@ -75,20 +75,28 @@ def fill_dam_break(ctx, I, J, K, dx, k_begin, k_end, apic, v0, seed, device, hea
 
 
 def taylor_green_field(I, J, K, dx, kbase, kloc, amp, device):
-    """A divergence-free MAC field that is tangential to the unit-box walls: u = A sin(pi x) cos(pi y),
-    v = -A cos(pi x) sin(pi y), w = 0, sampled at the face centres (stored planes [kbase, kbase + kloc (+1))).
-    Stand-in for the pressure-projected field in the evolving-batch benchmark: particles circulate, the set
-    does not compress."""
+    """A divergence-free MAC field that is tangential to the unit-box walls, sampled at the face centres of the
+    stored planes [kbase, kbase + kloc (+1)): two superposed Taylor-Green vortices,
+        u =  A sin(pi x) cos(pi y)
+        v = -A cos(pi x) sin(pi y) + B sin(pi y) cos(pi z)
+        w =                        - B cos(pi y) sin(pi z),      A = B = amp / 2
+    (its discrete divergence on the MAC grid vanishes identically). Stand-in for the pressure-projected field in the
+    evolving-batch benchmark: particles circulate in x-y AND across z -- they cross slab faces, so ranks really
+    migrate them -- and the set does not compress."""
     f64 = dict(dtype=torch.float64, device=device)
-    xu = torch.arange(I + 1, **f64) * dx
-    yu = (torch.arange(J, **f64) + 0.5) * dx
-    u2 = (amp * torch.sin(math.pi * xu)[None, :] * torch.cos(math.pi * yu)[:, None]).to(torch.float32)
-    xv = (torch.arange(I, **f64) + 0.5) * dx
-    yv = torch.arange(J + 1, **f64) * dx
-    v2 = (-amp * torch.cos(math.pi * xv)[None, :] * torch.sin(math.pi * yv)[:, None]).to(torch.float32)
+    A = B = 0.5 * amp
+    pi = math.pi
+    xf = torch.arange(I + 1, **f64) * dx                       # face / centre coordinates per axis
+    xc = (torch.arange(I, **f64) + 0.5) * dx
+    yf = torch.arange(J + 1, **f64) * dx
+    yc = (torch.arange(J, **f64) + 0.5) * dx
+    zc = (torch.arange(kbase, kbase + kloc, **f64) + 0.5) * dx
+    zf = torch.arange(kbase, kbase + kloc + 1, **f64) * dx
+    u2 = (A * torch.sin(pi * xf)[None, :] * torch.cos(pi * yc)[:, None]).to(torch.float32)
     u = u2[None].expand(kloc, J, I + 1).contiguous()
-    v = v2[None].expand(kloc, J + 1, I).contiguous()
-    w = torch.zeros((kloc + 1, J, I), dtype=torch.float32, device=device)
+    v = (-A * torch.cos(pi * xc)[None, None, :] * torch.sin(pi * yf)[None, :, None] +
+         B * torch.sin(pi * yf)[None, :, None] * torch.cos(pi * zc)[:, None, None]).to(torch.float32).expand(kloc, J + 1, I).contiguous()
+    w = (-B * torch.cos(pi * yc)[None, :, None] * torch.sin(pi * zf)[:, None, None]).to(torch.float32).expand(kloc + 1, J, I).contiguous()
     return u, v, w
 
 
