@@ -147,9 +147,15 @@ __global__ void k_route_mark_ghosts(Streams cur, Streams dat, int n, double inv_
     }
     if (gup) write_record(cur, j, block_up + (size_t)caps.up_m * rows, caps.up_g, sgu);
     if (gdown) write_record(cur, j, block_down + (size_t)caps.dn_m * rows, caps.dn_g, sgd);
-    if (keep) cur.ids[j] |= kGhostBit;                        // after its record (with the clean id) was written
+    // `keep` (sent, and kept here as the new owner's ghost copy) is only FLAGGED: the ghost bit is set by
+    // launch_route_end, so that the marking can be repeated with larger capacities when a section overflowed
     if (leave) holes[sh] = (uint32_t)j;
-    if (j < n) leave_flag[j] = leave ? 1 : 0;
+    if (j < n) leave_flag[j] = leave ? 1 : (keep ? 2 : 0);
+}
+
+__global__ void k_apply_keep(uint32_t *__restrict__ ids, const uint8_t *__restrict__ leave_flag, int n) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && leave_flag[j] == 2) ids[j] |= kGhostBit;
 }
 
 __global__ void k_write_header2(const int *counters, int which_m, int which_g, int cap, int cap_g, int rows, float *block) {
@@ -172,7 +178,7 @@ __global__ void k_fill_collect(int n, int n_new, int nholes, const uint8_t *leav
         is_front = h < (uint32_t)n_new;
     }
     const int j = n_new + t;
-    const bool is_tail_stay = t < nholes && j < n && !leave_flag[j];
+    const bool is_tail_stay = t < nholes && j < n && leave_flag[j] != 1;
     const int sa = warp_slot(is_front, counters + 0);
     const int sb = warp_slot(is_tail_stay, counters + 1);
     if (is_front) front_hole[sa] = h;
@@ -241,7 +247,7 @@ int launch_pack_layers(Context &c, int lo_a, int hi_a, float *block_a, int lo_b,
 // launch_route_begin packs the migrants and lists the holes (asynchronous); launch_route_end
 // reads the counts (synchronises the stream), fills the holes and sets the new particle count.
 struct RouteState {
-    int k_begin, k_end, has_up, has_down, n;
+    int k_begin, k_end, has_up, has_down, n, ghosts;
 };
 static RouteState g_route;      // one routing in flight per process (one context per rank)
 
@@ -274,7 +280,7 @@ int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, floa
         if (block_up) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, cap, rows, block_up); launches++; }
         if (block_down) { k_write_header<<<1, 1, 0, c.stream>>>(c.slab_counters, 2, cap, rows, block_down); launches++; }
     }
-    g_route = RouteState{k_begin, k_end, block_up != nullptr, block_down != nullptr, n};
+    g_route = RouteState{k_begin, k_end, block_up != nullptr, block_down != nullptr, n, ghost_layers > 0 ? 1 : 0};
     FFB_CUDA(cudaGetLastError());
     return launches;
 }
@@ -293,6 +299,10 @@ int launch_route_end(Context &c, int counts_host[3], int known_holes) {
         FFB_CUDA(cudaStreamSynchronize(c.stream));
     }
     const int nholes = h[3], n_new = n - nholes;
+    if (g_route.ghosts && n > 0) {                             // migrants kept as ghost copies get their ghost bit now
+        k_apply_keep<<<(n + 255) / 256, 256, 0, c.stream>>>(cur.ids, leave_flag, n);
+        launches++;
+    }
     if (nholes > 0 && n_new > 0) {
         FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 2 * sizeof(int), c.stream));
         k_fill_collect<<<(nholes + 255) / 256, 256, 0, c.stream>>>(n, n_new, nholes, leave_flag, holes, c.slab_counters,

@@ -411,27 +411,39 @@ class SlabSimulation:
         #    dropped; the end ranks keep whatever strayed past the domain
         kb = self.kb if self.down is not None else self.INT_MIN
         ke = self.ke if self.up is not None else self.INT_MAX
-        caps, b2 = self._blocks2()
-        be.route_ghosts_begin(kb, ke, g, b2["up_send"] if self.up is not None else None,
-                              b2["dn_send"] if self.down is not None else None, caps)
-        hdr = self._swap_blocks2(caps, b2)            # one synchronisation serves the exchange and the routing
         up, dn = self.up is not None, self.down is not None
-        n_owned, _, _ = be.route_end(int(hdr[0, 4]) if up else (int(hdr[1, 4]) if dn else None))
-        # true counts of both directions per face (identical knowledge on both ranks of the face)
-        self._face_counts = {"up": (max(int(hdr[0, 0]), int(hdr[2, 0])), max(int(hdr[0, 2]), int(hdr[2, 2]))),
-                             "dn": (max(int(hdr[1, 0]), int(hdr[3, 0])), max(int(hdr[1, 2]), int(hdr[3, 2])))}
-        if (up and (hdr[0, 3] or hdr[2, 3])) or (dn and (hdr[1, 3] or hdr[3, 3])):
-            raise RuntimeError("slab exchange: the ghost copies near a face grew by more than 15 %% + 8192 within one substep "
-                               "(rank %d, capacities %s, headers %s)" % (self.rank, caps, hdr.tolist()))
-        # a migrant that did not fit its section stays with its sender, OUTSIDE the sender's slab and unknown to its
-        # new owner: the next P2G would silently lose its contributions. Like the ghost sections, fail loudly
-        # (capacities are twice the previous substep's traffic + 4096; the fixed-batch benchmark never applies
-        # the migration, so there it only costs a counter).
-        if int(hdr[:, 1].max()) != 0:
+        caps, b2 = self._blocks2()
+        faces, hdr = ("up", "dn"), None
+        for attempt in range(3):
+            be.route_ghosts_begin(kb, ke, g, b2["up_send"] if up else None, b2["dn_send"] if dn else None, caps)
+            h = self._swap_blocks2(caps, b2, faces)   # one synchronisation serves the exchange and the routing
+            if hdr is None:
+                hdr = h
+            else:
+                # rows 0, 1 (our send headers) always describe the LAST marking -- what route_end applies; rows 2, 3 (what
+                # the neighbours sent) change only on the faces that were exchanged again
+                hdr[0], hdr[1] = h[0], h[1]
+                if "up" in faces:
+                    hdr[2] = h[2]
+                if "dn" in faces:
+                    hdr[3] = h[3]
+            # true counts of both directions per face (identical knowledge on both ranks of the face)
+            self._face_counts = {"up": (max(int(hdr[0, 0]), int(hdr[2, 0])), max(int(hdr[0, 2]), int(hdr[2, 2]))),
+                                 "dn": (max(int(hdr[1, 0]), int(hdr[3, 0])), max(int(hdr[1, 2]), int(hdr[3, 2])))}
+            # a section that overflowed (migrants or ghost copies; both ranks of the face read it in the same two
+            # headers) is exchanged again on that face alone, with capacities sized from the true counts the headers
+            # carry: the marking is repeatable (the ghost bits of kept migrants are only applied by route_end)
+            over = tuple(f for f, rows in (("up", (0, 2)), ("dn", (1, 3)))
+                         if (up if f == "up" else dn) and any(int(hdr[r, 1]) or int(hdr[r, 3]) for r in rows))
+            if not over or not apply_migration:
+                break
             self.overflows = getattr(self, "overflows", 0) + 1
-            if apply_migration:
-                raise RuntimeError("slab exchange: the migrants across a face more than doubled (+4096) within one substep "
-                                   "(rank %d, capacities %s, headers %s)" % (self.rank, caps, hdr.tolist()))
+            faces = over
+            caps, b2 = self._blocks2(resize=over)
+        else:
+            raise RuntimeError("slab exchange: sections still overflow after two resized exchanges (rank %d, capacities %s, "
+                               "headers %s)" % (self.rank, caps, hdr.tolist()))
+        n_owned, _, _ = be.route_end(int(hdr[0, 4]) if up else (int(hdr[1, 4]) if dn else None))
         mig_up, gh_up = (min(int(hdr[2, 0]), caps[0]), int(hdr[2, 2])) if up else (0, 0)
         mig_dn, gh_dn = (min(int(hdr[3, 0]), caps[2]), int(hdr[3, 2])) if dn else (0, 0)
         if apply_migration:
@@ -447,28 +459,42 @@ class SlabSimulation:
     def _bucket(x):
         return (int(x) + 4095) // 4096 * 4096
 
-    def _blocks2(self):
+    def _blocks2(self, resize=None):
         """Per-face section capacities (up migrants, up ghosts, down migrants, down ghosts) and buffers,
-        derived from the previous exchange's counts on that face: twice the migrants + 4096, 1.15x the ghost
-        copies + 8192, rounded up to 4096. Everything in a buffer travels, so the fit is kept tight; a
-        migrant that does not fit stays with its sender for one substep, the counts adapt the next."""
+        derived from the previous exchange's counts on that face: twice the migrants (never below a quarter of a
+        ghost layer: migrants arrive in bursts, a lattice layer reaches the face at once) + 4096, 1.15x the ghost
+        copies + 8192, rounded up to 4096. Everything in a buffer travels, so the fit is kept tight. `resize` names the
+        faces whose sections overflowed in this substep's exchange: their capacities are taken from the true counts
+        (now in _face_counts), the other faces keep their buffers -- and what they received -- untouched."""
         (mu, gu), (md, gd) = self._face_counts["up"], self._face_counts["dn"]
-        caps = (self._bucket(2 * mu + 4096), self._bucket(1.15 * gu + 8192), self._bucket(2 * md + 4096), self._bucket(1.15 * gd + 8192))
-        if getattr(self, "_block2_caps", None) != caps:
-            self._block2_caps = caps
+        if resize is None and getattr(self, "force_initial_caps", None):
+            caps = tuple(self.force_initial_caps)            # tests: undersized sections, so that every exchange is repeated
+        elif resize is None:
+            caps = (self._bucket(max(2 * mu, gu // 4) + 4096), self._bucket(1.15 * gu + 8192),
+                    self._bucket(max(2 * md, gd // 4) + 4096), self._bucket(1.15 * gd + 8192))
+        else:
+            old = self._block2_caps
+            caps = ((max(old[0], self._bucket(mu + 4096)), max(old[1], self._bucket(gu + 4096))) if "up" in resize else old[:2]) + \
+                   ((max(old[2], self._bucket(md + 4096)), max(old[3], self._bucket(gd + 4096))) if "dn" in resize else old[2:])
+        old_caps = getattr(self, "_block2_caps", None)
+        if old_caps != caps:
             nb = self.backend.new_block2
-            self._blk2 = {"up_send": nb(caps[0], caps[1]), "up_recv": nb(caps[0], caps[1]),
-                          "dn_send": nb(caps[2], caps[3]), "dn_recv": nb(caps[2], caps[3])}
+            blk = dict(getattr(self, "_blk2", {}))
+            if old_caps is None or old_caps[:2] != caps[:2]:
+                blk["up_send"], blk["up_recv"] = nb(caps[0], caps[1]), nb(caps[0], caps[1])
+            if old_caps is None or old_caps[2:] != caps[2:]:
+                blk["dn_send"], blk["dn_recv"] = nb(caps[2], caps[3]), nb(caps[2], caps[3])
+            self._block2_caps, self._blk2 = caps, blk
         return caps, self._blk2
 
-    def _swap_blocks2(self, caps, b):
-        """Exchange the two-section buffers with both neighbours; returns the four 8-int headers
+    def _swap_blocks2(self, caps, b, faces=("up", "dn")):
+        """Exchange the two-section buffers with the neighbours on `faces`; returns the four 8-int headers
         [up_send, dn_send, up_recv, dn_recv] (rows of absent neighbours are zero)."""
         rows = self.backend.record_floats()
         items = []
-        if self.up is not None:
+        if self.up is not None and "up" in faces:
             items.append((b["up_send"], b["up_recv"], self.up))
-        if self.down is not None:
+        if self.down is not None and "dn" in faces:
             items.append((b["dn_send"], b["dn_recv"], self.down))
         _sendrecv(items)
         off = {"up_send": (caps[0] + caps[1]) * rows, "up_recv": (caps[0] + caps[1]) * rows,

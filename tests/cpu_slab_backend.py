@@ -172,14 +172,17 @@ class CpuOracleFastBackend(CpuOracleBackend):
             nm, ng = int(mig.sum()), int(gh.sum())
             blk[(cap_m + cap_g) * rows:].view(torch.int32)[:] = torch.tensor([nm, int(nm > cap_m), ng, int(ng > cap_g), int(leave.sum()), 0, 0, 0],
                                                                                dtype=torch.int32)
-        ids = ids.copy()
-        ids[keep] |= self.GHOST                                  # sent, and kept here as the new owner's ghost copy
-        self.ids = torch.from_numpy(ids)
+        self._keep = keep                                        # ghost bit applied by route_end (the marking may be repeated)
         self._leave = leave
         self._counts = (int((up & sent).sum()), int((down & sent).sum()))
 
     def route_end(self, leaving=None):
         assert leaving is None or leaving == int(self._leave.sum())
+        if getattr(self, "_keep", None) is not None:
+            ids = self.ids.numpy().copy()
+            ids[self._keep] |= self.GHOST                        # sent, and kept here as the new owner's ghost copy
+            self.ids = torch.from_numpy(ids)
+            self._keep = None
         stay = torch.from_numpy(np.nonzero(~self._leave)[0])
         self.streams = [s.index_select(0, stay) for s in self.streams]
         self.ids = self.ids.index_select(0, stay)

@@ -36,7 +36,9 @@ phi, near = scenes.analytic_solid_sdf(I, J, K, dx)
 kb, ke = slab.slab_range(K, world, rank)
 be = slab.GpuBackend(I, J, K, dx, kb, ke, 7, lr, apic)
 be.set_solid(phi, near)
-sim = slab.SlabSimulation(I, J, K, dx, rank, world, be, halo=7, ghost=2)
+sim = slab.SlabSimulation(I, J, K, dx, rank, world, be, halo=7, ghost=1 if sys.argv[4] == "fast-tiny" else 2)
+if sys.argv[4] == "fast-tiny":
+    sim.force_initial_caps = (8, 16, 8, 16)       # every merged exchange overflows and is repeated with resized sections
 kz = np.floor(sc.pos[:, 2].astype(np.float64) * (1.0 / dx)).astype(np.int64)
 sel = np.nonzero((kz >= kb) & (kz < ke))[0]
 cols = [sc.pos[sel, 0], sc.pos[sel, 1], sc.pos[sel, 2], sc.vel[sel, 0], sc.vel[sel, 1], sc.vel[sel, 2]]
@@ -46,11 +48,12 @@ if apic:
 dev = torch.device("cuda", lr)
 sim.set_particles([torch.from_numpy(np.ascontiguousarray(c)).to(dev) for c in cols], torch.from_numpy(sel.astype(np.int32)).to(dev))
 dt = 1.5 * dx / 0.9
-if sys.argv[4] == "fast":
+if sys.argv[4].startswith("fast"):
     sim.load_resident()
     for _ in range(2):
         sim.step_fast(sc.radius, 0.05, dt)
     sim.sync_from_backend()
+    assert sys.argv[4] != "fast-tiny" or getattr(sim, "overflows", 0) >= 2
 else:
     for _ in range(2):
         sim.step(sc.radius, 0.05, dt)
@@ -73,7 +76,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("plumbing", ["fast", "generic"])
+@pytest.mark.parametrize("plumbing", ["fast", "generic", "fast-tiny"])
 @pytest.mark.parametrize("method", ["flip", "apic"])
 def test_two_gpu_slab_matches_single_gpu(tmp_path, method, plumbing):
     import torch
