@@ -62,6 +62,7 @@ RATIO = 0.05
 HALO = 7
 GHOST = 1                     # ghost particle layers: ceil(radius / dx) -- the P2G kernel reaches 0.866 dx, so 1 (2 for the doubled
                               # radius of the smooth surface-tension kernel); bit-identity vs the undecomposed run: tests/test_slab_gloo.py
+OVERLAP = os.environ.get("FFB200_BENCH_OVERLAP", "1") != "0"     # N > 1: neighbour exchange overlapped with the interior particles
 SAMPLE_PLANES = 16            # fluid cell planes of the CPU reference sample
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
@@ -273,7 +274,7 @@ class Runner:
     def step(self):
         if self.sim is not None:
             self.sim.step_fast(self.radius, RATIO, self.dt, apply_migration=not self.fixed,
-                               projected_field=None if self.fixed else self.tg)
+                               projected_field=None if self.fixed else self.tg, overlap=OVERLAP)
             return
         c = self.ctx
         c.p2g(self.radius, self.m)            # bins + sort + seam words + U, V, W transfers
@@ -447,6 +448,8 @@ def main():
     for _ in range(warmup):
         run.step()
     barrier()
+    if run.sim is not None and getattr(run.sim, "_profile", False):
+        run.sim._phase = {}                   # FFB200_SLAB_PROFILE=1: steady-state phases only
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_per_step = run.time_steps(steps, barrier)
@@ -551,7 +554,8 @@ def main():
             h_in = [t.cpu().pin_memory() for t in run.tg]
 
             def e2e_step():
-                run.sim.step_fast(run.radius, RATIO, run.dt, apply_migration=True, projected_field=h_in, p2g_download=h_out)
+                run.sim.step_fast(run.radius, RATIO, run.dt, apply_migration=True, projected_field=h_in, p2g_download=h_out,
+                                  overlap=OVERLAP)
                 return run.ctx.maximum_particle_speed()
 
             h2d = sum(t.numel() for t in h_in) * 4
@@ -583,8 +587,11 @@ def main():
         # FFB200_SLAB_PROFILE=1: synchronised wall-clock phases of step_fast (diagnostic; the timed numbers above then
         # include the synchronisation and are not benchmark figures)
         ph = run.sim._phase
-        tot = sum(ph.values())
-        sys.stderr.write(f"rank {rank} slab phases, share of {tot:.3f} s: " + ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in ph.items()) + "\n")
+        nst = steps + 3
+        sys.stderr.write(f"rank {rank} slab phases, ms per step (synchronised): " + ", ".join(f"{k} {1e3 * v / nst:.3f}" for k, v in ph.items()) +
+                         f"; total {1e3 * sum(ph.values()) / nst:.3f}; exchange repeats {getattr(run.sim, 'overflows', 0)}\n")
+    class run_sim_overflows:                  # exchanges repeated because a section overflowed (slab.step_fast), this rank
+        v = getattr(run.sim, "overflows", 0) if run.sim is not None else None
     run.close()
 
     # ---- secondary record: BASELINE configs[1], 128^3 APIC (N = 1 only) ----------------------------------------------
@@ -632,11 +639,13 @@ def main():
     if rank == 0:
         cfg = dict(base_config,
                    parallelism="single GPU" if world == 1 else f"z-slab x{world} ({n // world} planes per rank, halo {HALO}, ghost "
-                               f"particle layers {GHOST}), face halo + particle migration over NCCL, one process per GPU",
+                               f"particle layers {GHOST}), face halo + particle migration over NCCL, one process per GPU" +
+                               (", migrant/ghost exchange overlapped with the interior particles' G2P + advection" if OVERLAP else ""),
                    l2="inputs larger than L2 (particle streams + grids >> 126 MB per step)",
                    batch="evolving: each step sorts and transfers the particles the previous step advected (ranks migrate them); "
                          "the MAC field is replaced by an analytic divergence-free field where the CPU projection would return one",
-                   launch="eager launches (every N)")
+                   launch="eager launches (every N)",
+                   exchange_repeats=(getattr(run_sim_overflows, "v", None)))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 (fp64 index/gather arithmetic)", "data": "synthetic", "config": cfg,

@@ -52,6 +52,7 @@ struct AdvectParams {
     double buffer;          // (double)_solidBufferWidth * _dx
     int collide;
     int n;
+    Window win;
 };
 
 __device__ __forceinline__ bool box_inside(const Box &b, float x, float y, float z) {
@@ -238,7 +239,7 @@ __device__ __noinline__ void resolve_collision(const AdvectParams &P, float ox, 
 __global__ void FFB_ADV_BOUNDS k_advect(const __grid_constant__ AdvectParams P, uint32_t *__restrict__ list,
                                         unsigned long long *__restrict__ stats) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
+    if (j >= P.n || window_skip(P.win, j)) return;
     const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
     float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
     if (P.k1x) {
@@ -319,7 +320,7 @@ __device__ __noinline__ void exact_advect(const AdvectParams &P, float x0, float
 __global__ void __launch_bounds__(FFB_ADV_THREADS, FFB_ADV_FAST_MINB) k_advect_fast(const __grid_constant__ AdvectParams P, const __grid_constant__ FastGrid fg,
                                              float inv_near, uint32_t *__restrict__ list, unsigned long long *__restrict__ stats) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
+    if (j >= P.n || window_skip(P.win, j)) return;
     const float x0 = P.px[j], y0 = P.py[j], z0 = P.pz[j];
     float k1x, k1y, k1z, k2x, k2y, k2z, k3x, k3y, k3z;
     if (P.k1x) {
@@ -488,6 +489,7 @@ int launch_advect(Context &c, double dt, double cfl, int collide) {
     P.buffer = (double)0.2f * g.dx;
     P.collide = collide;
     P.n = c.n;
+    P.win = c.window;
     if (c.precision == FFB200_PRECISION_TOLERANCE) c.tol_advected += (unsigned long long)c.n;
     if (c.precision == FFB200_PRECISION_TOLERANCE) {
         unsigned long long *stats = tolerance_stats(c);

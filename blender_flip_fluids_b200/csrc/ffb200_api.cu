@@ -479,6 +479,22 @@ int ffb200_set_precision(ffb200_context *ctx, int mode) {
     });
 }
 
+int ffb200_set_particle_window(ffb200_context *ctx, int k_lo, int k_hi, int mode) {
+    return guarded("ffb200_set_particle_window", ctx, [&](Context &c) {
+        if (mode < 0 || mode > 2) throw std::domain_error("window mode must be 0 (off), 1 (inside) or 2 (outside)");
+        const GridDesc &g = c.g;
+        auto bin_of_plane = [&](long long k) -> uint32_t {          // first bin of cell plane k (clamped to the bin grid)
+            long long hz = 2 * (k - g.kbase) + kApron;
+            hz = hz < 0 ? 0 : (hz > g.HZ ? g.HZ : hz);
+            return (uint32_t)((unsigned long long)hz * (unsigned long long)g.HY * (unsigned long long)g.HX);
+        };
+        c.window.bin_start = c.sort.bin_start;
+        c.window.lo_bin = bin_of_plane(k_lo);
+        c.window.hi_bin = bin_of_plane(k_hi);
+        c.window.mode = mode;
+    }, false);
+}
+
 int ffb200_get_tolerance_stats(ffb200_context *ctx, unsigned long long *counts, int reset) {
     return guarded("ffb200_get_tolerance_stats", ctx, [&](Context &c) {
         if (!counts) throw std::invalid_argument("null output pointer");

@@ -50,6 +50,24 @@ __device__ __forceinline__ float vlen3(float x, float y, float z) { return sqrtf
 // 1.0 / s evaluated in double and narrowed: the `float inv = 1.0 / s;` of vmath.cpp:100-103.
 __device__ __forceinline__ float finv(float s) { return (float)(1.0 / (double)s); }
 
+// ---- particle window ------------------------------------------------------------------------
+// A contiguous range of the SORTED particle streams, given by two entries of the bin table (bins are z-major, so
+// "all particles of the cell planes [k_lo, k_hi)" is such a range). The per-particle kernels take it as a predicate,
+// so the host can split a stage into "near the slab faces" and "interior" launches without knowing the indices
+// (no device-to-host read): the z-slab driver overlaps its neighbour exchange with the interior part.
+struct Window {
+    const uint32_t *bin_start = nullptr;
+    uint32_t lo_bin = 0, hi_bin = 0;
+    int mode = 0;                   // 0: every particle; 1: inside [bin_start[lo_bin], bin_start[hi_bin]); 2: outside it
+};
+
+__device__ __forceinline__ bool window_skip(const Window &w, int j) {
+    if (w.mode == 0) return false;
+    const uint32_t r0 = __ldg(w.bin_start + w.lo_bin), r1 = __ldg(w.bin_start + w.hi_bin);
+    const bool inside = (uint32_t)j >= r0 && (uint32_t)j < r1;
+    return w.mode == 1 ? !inside : inside;
+}
+
 // ---- MAC field view -------------------------------------------------------------------------
 
 struct MacView {

@@ -115,6 +115,7 @@ struct Context {
     int k1s_cap = 0;
     unsigned resident_next = 0;          // ffb200_declare_resident: inputs the next host-buffer call may skip uploading
     unsigned resident_arg = 0;           // ... as latched for the call in progress (cleared for every other call)
+    Window window;                            // ffb200_set_particle_window: the particles the next G2P / advection / routing touch
     int precision = FFB200_PRECISION_EXACT;   // ffb200_set_precision: exact (reference arithmetic) or tolerance (fp32 gathers, 1e-5)
     unsigned long long tol_advected = 0;      // particles advected in tolerance mode since the last reset (host-side count)
     unsigned long long *tol_stats = nullptr;  // device: {particles advected on the fp32 path, particles sent to the exact code, ...}

@@ -36,11 +36,12 @@ struct G2PParams {
     float inv_s;        // (float)(1.0 / (float)_dx)   (vec3 / _dx)
     float invdx;        // 1.0f / _dx
     int n;
+    Window win;
 };
 
 __global__ void FFB_G2P_BOUNDS k_g2p_flip(const __grid_constant__ G2PParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
+    if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const GridDesc &g = P.g;
     const double x = px, y = py, z = pz;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void apic_component(const G2PParams &P, const float *
 
 __global__ void FFB_G2P_BOUNDS k_g2p_apic(const __grid_constant__ G2PParams P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
+    if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const GridDesc &g = P.g;
     const double x = px, y = py, z = pz;
@@ -229,7 +230,7 @@ __device__ __noinline__ bool g2p_apic_fast_generic(const G2PParams &P, const Fas
 __global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FAST_MINB)
     k_g2p_apic_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg, unsigned long long *__restrict__ stats) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
+    if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const FastAxis xu = fast_axis(px, fg), yu = fast_axis(py, fg), zu = fast_axis(pz, fg);
     const FastAxis xs = fast_shift(xu), ys = fast_shift(yu), zs = fast_shift(zu);
@@ -285,7 +286,7 @@ __device__ __noinline__ void g2p_flip_fast_generic(const G2PParams &P, const Fas
 __global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FAST_MINB)
     k_g2p_flip_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n) return;
+    if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const float v0 = P.vx[j], v1 = P.vy[j], v2 = P.vz[j];
     const FastAxis xu = fast_axis(px, fg), yu = fast_axis(py, fg), zu = fast_axis(pz, fg);
@@ -365,6 +366,7 @@ int launch_g2p(Context &c, int method, double ratio) {
     P.inv_s = (float)(1.0 / (double)(float)c.g.dx);
     P.invdx = (float)(1.0f / c.g.dx);
     P.n = c.n;
+    P.win = c.window;
     const int blocks = (c.n + FFB_G2P_THREADS - 1) / FFB_G2P_THREADS;
     if (c.precision == FFB200_PRECISION_TOLERANCE) {
         const FastGrid fg = make_fast_grid(c.g);

@@ -115,10 +115,13 @@ __global__ void k_route_mark(Streams cur, Streams dat, int n, double inv_dx, int
 // from the resident (pristine) batch, exactly what a start-of-substep exchange would send.
 __global__ void k_route_mark_ghosts(Streams cur, Streams dat, int n, double inv_dx, int k_begin, int k_end, int g,
                                     float *block_up, float *block_down, FaceCaps caps, int remove_migrants, int *counters,
-                                    uint32_t *holes, uint8_t *leave_flag) {
+                                    uint32_t *holes, uint8_t *leave_flag, Window win) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     bool ghost = false, up = false, down = false, gup = false, gdown = false, keep = false;
-    if (j < n) {
+    // with a window only the particles near the slab faces (and the ghost copies) are looked at: the others can neither
+    // leave nor be ghost copies (their flags were cleared by the launcher). Whole warps drop out together almost always.
+    const bool look = j < n && !window_skip(win, j);
+    if (look) {
         const int kd = __double2int_rd((double)dat.s[2][j] * inv_dx);      // where the particle is going
         const int kc = __double2int_rd((double)cur.s[2][j] * inv_dx);      // where the resident copy is
         ghost = (cur.ids[j] & kGhostBit) != 0u;
@@ -150,7 +153,7 @@ __global__ void k_route_mark_ghosts(Streams cur, Streams dat, int n, double inv_
     // `keep` (sent, and kept here as the new owner's ghost copy) is only FLAGGED: the ghost bit is set by
     // launch_route_end, so that the marking can be repeated with larger capacities when a section overflowed
     if (leave) holes[sh] = (uint32_t)j;
-    if (j < n) leave_flag[j] = leave ? 1 : (keep ? 2 : 0);
+    if (look) leave_flag[j] = leave ? 1 : (keep ? 2 : 0);
 }
 
 __global__ void k_apply_keep(uint32_t *__restrict__ ids, const uint8_t *__restrict__ leave_flag, int n) {
@@ -264,9 +267,10 @@ int launch_route_begin(Context &c, int k_begin, int k_end, float *block_up, floa
     FFB_CUDA(cudaMemsetAsync(c.slab_counters, 0, 8 * sizeof(int), c.stream));
     if (ghost_layers > 0) {
         if (n > 0) {
+            if (c.window.mode != 0) FFB_CUDA(cudaMemsetAsync(leave_flag, 0, (size_t)n, c.stream));
             k_route_mark_ghosts<<<(n + 255) / 256, 256, 0, c.stream>>>(cur, dat, n, c.g.inv_dx, k_begin, k_end, ghost_layers,
                                                                        block_up, block_down, FaceCaps{caps[0], caps[1], caps[2], caps[3]},
-                                                                       fixed ? 0 : 1, c.slab_counters, holes, leave_flag);
+                                                                       fixed ? 0 : 1, c.slab_counters, holes, leave_flag, c.window);
             launches++;
         }
         if (block_up) { k_write_header2<<<1, 1, 0, c.stream>>>(c.slab_counters, 1, 4, caps[0], caps[1], rows, block_up); launches++; }

@@ -88,6 +88,7 @@ SIGNATURES = {
     "ffb200_set_solid": [C.c_void_p, _f32p, _u8p],
     "ffb200_set_solid_device": [C.c_void_p, C.c_void_p, C.c_void_p],
     "ffb200_set_precision": [C.c_void_p, C.c_int],
+    "ffb200_set_particle_window": [C.c_void_p, C.c_int, C.c_int, C.c_int],
     "ffb200_get_tolerance_stats": [C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int],
     "ffb200_attribute_to_grid_transfer": [C.c_void_p, C.c_int, _f32p, _f32p, C.c_int, C.c_double, C.c_int, _f32p, _u8p],
     "ffb200_p2g": [C.c_void_p, C.c_double, C.c_int],
@@ -425,6 +426,10 @@ class FlipContext:
             raise ValueError(f"near-solid mask must have shape {self.near_dims}, got {near.shape}")
         self._call("ffb200_set_solid", _ptr(phi), _ptr(near, _u8p))
         self.synchronize()
+
+    def set_particle_window(self, k_lo, k_hi, mode):
+        """ffb200_set_particle_window: mode 0 off, 1 inside the planes [k_lo, k_hi), 2 outside."""
+        self._call("ffb200_set_particle_window", int(k_lo), int(k_hi), int(mode))
 
     def set_precision(self, tolerance):
         """ffb200_set_precision: False = exact (bit-identical gathers), True = tolerance (fp32 gathers, 1e-5)."""

@@ -54,8 +54,9 @@ def _staged(t):
     return t.is_cuda and dist.get_backend() == "gloo"
 
 
-def _sendrecv(items):
-    """One batched neighbour exchange. items: (send tensor or None, recv tensor or None, peer)."""
+def _sendrecv(items, wait=True):
+    """One batched neighbour exchange. items: (send tensor or None, recv tensor or None, peer). wait=False (NCCL only)
+    returns the outstanding requests: kernels launched meanwhile on the current stream overlap the transfer."""
     ops, staged = [], []
     for send, recv, peer in items:
         if send is not None:
@@ -69,10 +70,14 @@ def _sendrecv(items):
             else:
                 ops.append(dist.P2POp(dist.irecv, recv, peer))
     if ops:
-        for r in dist.batch_isend_irecv(ops):
+        reqs = dist.batch_isend_irecv(ops)
+        if not wait and not staged:
+            return reqs
+        for r in reqs:
             r.wait()
     for recv, buf in staged:
         recv.copy_(buf)
+    return []
 
 
 def _all_gather(outs, t):
@@ -149,6 +154,9 @@ class GpuBackend:
 
     def synchronize(self):
         torch.cuda.synchronize(self.device)
+
+    def set_window(self, k_lo, k_hi, mode):
+        self.ctx.set_particle_window(k_lo, k_hi, mode)
 
     # ---- device-side plumbing (ffb200_slab.cu) ---------------------------------------------------
     fast = True
@@ -352,7 +360,8 @@ class SlabSimulation:
         self._ghosts_ready = False
         self._n_owned = int(n_owned)
 
-    def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True, apply_migration=True, projected_field=None, p2g_download=None):
+    def step_fast(self, radius, ratio, dt, cfl=5.0, collide=True, apply_migration=True, projected_field=None, p2g_download=None,
+                  overlap=False):
         """One substep with device-side plumbing. apply_migration=False is the fixed-batch
         benchmark mode (context in ffb200_set_fixed_batch): ghosts are added and removed and
         migrants are selected, packed and exchanged as usual, but the resident batch itself is
@@ -393,6 +402,7 @@ class SlabSimulation:
         self._tick("p2g")
         # 3. face halos (zero copy, straight into the halo planes), saved copy
         self._halo_exchange_fast()
+        self._tick("halo")
         be.save_field()
         if p2g_download is not None:
             # e2e: the owned planes of the transferred field go to (pinned) host memory -- the CPU pressure solve's input
@@ -402,8 +412,15 @@ class SlabSimulation:
             # the field the host's projection would hand back (stored planes incl. halo; device or pinned host tensors)
             for dst, src in zip(self._stored_field_views(), projected_field):
                 dst.copy_(src.view(-1), non_blocking=True)
-        self._tick("halo+save")
-        # 4. G2P + advection; the marked ghost copies ride along (a few %) and are dropped below
+        self._tick("save+field")
+        # 4. G2P + advection; the marked ghost copies ride along (a few %) and are dropped below.
+        #    overlap: only the particles within `halo` planes of a slab face (and the ghost copies) can leave the slab or
+        #    become ghost copies -- a substep moves a particle by at most CFL cells -- so they go first, the exchange of
+        #    step 5 is started, and the interior particles are advanced while it is in flight.
+        inner = (self.kb + self.halo if self.down is not None else -(2 ** 30), self.ke - self.halo if self.up is not None else 2 ** 30)
+        overlap = overlap and getattr(be, "set_window", None) is not None and self.world > 1
+        if overlap:
+            be.set_window(inner[0], inner[1], 2)
         be.g2p(ratio)
         be.advect(dt, cfl, collide)
         self._tick("g2p+advect")
@@ -415,8 +432,25 @@ class SlabSimulation:
         caps, b2 = self._blocks2()
         faces, hdr = ("up", "dn"), None
         for attempt in range(3):
+            if overlap and attempt > 0:
+                be.set_window(inner[0], inner[1], 2)          # a repeated marking looks at the same particles
             be.route_ghosts_begin(kb, ke, g, b2["up_send"] if up else None, b2["dn_send"] if dn else None, caps)
-            h = self._swap_blocks2(caps, b2, faces)   # one synchronisation serves the exchange and the routing
+            self._tick("route-mark")
+            if overlap and attempt == 0:
+                pending = self._swap_blocks2_start(b2, faces)
+                be.set_window(inner[0], inner[1], 1)          # the interior, while the blocks travel
+                be.g2p(ratio)
+                be.advect(dt, cfl, collide)
+                be.set_window(0, 0, 0)
+                self._tick("interior g2p+advect")
+                for r in pending:
+                    r.wait()
+                h = self._swap_blocks2_headers(caps, b2)
+            else:
+                h = self._swap_blocks2(caps, b2, faces)   # one synchronisation serves the exchange and the routing
+                if overlap:
+                    be.set_window(0, 0, 0)
+            self._tick("exchange")
             if hdr is None:
                 hdr = h
             else:
@@ -453,7 +487,7 @@ class SlabSimulation:
         self._n_owned = n_owned
         be.append_records(b2["dn_recv"], caps[2], gh_dn, as_ghost=True)
         be.append_records(b2["up_recv"], caps[0], gh_up, as_ghost=True)
-        self._tick("migrate")
+        self._tick("route-end+append")
 
     @staticmethod
     def _bucket(x):
@@ -487,16 +521,26 @@ class SlabSimulation:
             self._block2_caps, self._blk2 = caps, blk
         return caps, self._blk2
 
-    def _swap_blocks2(self, caps, b, faces=("up", "dn")):
-        """Exchange the two-section buffers with the neighbours on `faces`; returns the four 8-int headers
-        [up_send, dn_send, up_recv, dn_recv] (rows of absent neighbours are zero)."""
-        rows = self.backend.record_floats()
+    def _swap_items(self, b, faces):
         items = []
         if self.up is not None and "up" in faces:
             items.append((b["up_send"], b["up_recv"], self.up))
         if self.down is not None and "dn" in faces:
             items.append((b["dn_send"], b["dn_recv"], self.down))
-        _sendrecv(items)
+        return items
+
+    def _swap_blocks2_start(self, b, faces=("up", "dn")):
+        """Start the exchange of the two-section buffers without waiting (NCCL; gloo staging completes it at once)."""
+        return _sendrecv(self._swap_items(b, faces), wait=False)
+
+    def _swap_blocks2(self, caps, b, faces=("up", "dn")):
+        """Exchange the two-section buffers with the neighbours on `faces`; returns the four 8-int headers
+        [up_send, dn_send, up_recv, dn_recv] (rows of absent neighbours are zero)."""
+        _sendrecv(self._swap_items(b, faces))
+        return self._swap_blocks2_headers(caps, b)
+
+    def _swap_blocks2_headers(self, caps, b):
+        rows = self.backend.record_floats()
         off = {"up_send": (caps[0] + caps[1]) * rows, "up_recv": (caps[0] + caps[1]) * rows,
                "dn_send": (caps[2] + caps[3]) * rows, "dn_recv": (caps[2] + caps[3]) * rows}
         hdr = torch.stack([b[k][off[k]:].view(torch.int32) for k in ("up_send", "dn_send", "up_recv", "dn_recv")]).cpu()

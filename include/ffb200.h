@@ -256,6 +256,13 @@ int ffb200_postprocess_liquid_sdf(ffb200_context *ctx);
 int ffb200_set_precision(ffb200_context *ctx, int mode);
 int ffb200_get_tolerance_stats(ffb200_context *ctx, unsigned long long *counts, int reset);
 
+/* Restricts the NEXT ffb200_g2p / ffb200_advect / ffb200_slab_route_ghosts_begin calls to the particles whose (sorted)
+ * cell plane lies inside (mode 1) or outside (mode 2) the global plane range [k_lo, k_hi); mode 0 lifts the
+ * restriction. Valid while the particle order is the one of the last sort (ffb200_p2g ... ffb200_advect of one
+ * substep). The range is resolved on the device from the bin table, so no size crosses PCIe: the z-slab driver
+ * advects the particles near its faces first, starts the neighbour exchange, and runs the interior meanwhile. */
+int ffb200_set_particle_window(ffb200_context *ctx, int k_lo, int k_hi, int mode);
+
 /* ffb200_set_solid with DEVICE pointers: d_phi holds the context's stored node planes only
  * ((I+1)(J+1)(kloc+1) floats, first plane = the context's first stored cell plane), d_near_solid the whole
  * ceil(I/3) x ceil(J/3) x ceil(K/3) byte grid. For scenes too large to stage through host arrays per rank. */

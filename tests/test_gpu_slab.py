@@ -1,6 +1,7 @@
 """Two-rank z-slab parity (-m gpu): the slab driver with the CUDA plumbing kernels on two ranks
 against ONE single-GPU context on the same particles -- ids, positions, velocities and affine rows
-bit-identical after two substeps with migration. With two or more devices the ranks use one GPU each
+bit-identical after two substeps with migration (also with undersized exchange sections, which are repeated, and with
+the exchange overlapped with the interior particles' G2P + advection). With two or more devices the ranks use one GPU each
 over NCCL; on a single-GPU box both ranks share device 0 and exchange over gloo (staged through
 host memory by slab._sendrecv), which still runs every slab kernel."""
 import os
@@ -51,7 +52,7 @@ dt = 1.5 * dx / 0.9
 if sys.argv[4].startswith("fast"):
     sim.load_resident()
     for _ in range(2):
-        sim.step_fast(sc.radius, 0.05, dt)
+        sim.step_fast(sc.radius, 0.05, dt, overlap=(sys.argv[4] == "fast-overlap"))
     sim.sync_from_backend()
     assert sys.argv[4] != "fast-tiny" or getattr(sim, "overflows", 0) >= 2
 else:
@@ -76,7 +77,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("plumbing", ["fast", "generic", "fast-tiny"])
+@pytest.mark.parametrize("plumbing", ["fast", "generic", "fast-tiny", "fast-overlap"])
 @pytest.mark.parametrize("method", ["flip", "apic"])
 def test_two_gpu_slab_matches_single_gpu(tmp_path, method, plumbing):
     import torch
