@@ -400,8 +400,13 @@ class SlabSimulation:
         # 2. P2G on owned + ghost particles
         be.p2g(radius)
         self._tick("p2g")
-        # 3. face halos (zero copy, straight into the halo planes), saved copy
-        self._halo_exchange_fast()
+        # 3. face halos, saved copy. overlap: the halo exchange is only STARTED here; the particles at least `halo` planes
+        #    away from every face never sample a halo plane (CFL + stagger + trilinear < halo), so the first half of them
+        #    is advanced while the planes travel (step 4a)
+        inner = (self.kb + self.halo if self.down is not None else -(2 ** 30), self.ke - self.halo if self.up is not None else 2 ** 30)
+        overlap = overlap and getattr(be, "set_window", None) is not None and self.world > 1
+        mid = (max(inner[0], self.kb) + min(inner[1], self.ke)) // 2
+        halo_pending = self._halo_exchange_fast(start_only=overlap)
         self._tick("halo")
         be.save_field()
         if p2g_download is not None:
@@ -417,10 +422,19 @@ class SlabSimulation:
         #    overlap: only the particles within `halo` planes of a slab face (and the ghost copies) can leave the slab or
         #    become ghost copies -- a substep moves a particle by at most CFL cells -- so they go first, the exchange of
         #    step 5 is started, and the interior particles are advanced while it is in flight.
-        inner = (self.kb + self.halo if self.down is not None else -(2 ** 30), self.ke - self.halo if self.up is not None else 2 ** 30)
-        overlap = overlap and getattr(be, "set_window", None) is not None and self.world > 1
         if overlap:
-            be.set_window(inner[0], inner[1], 2)
+            be.set_window(inner[0], mid, 1)                   # 4a. interior, lower half: overlaps the halo exchange
+            be.g2p(ratio)
+            be.advect(dt, cfl, collide)
+            self._tick("interior-A g2p+advect")
+            for r in halo_pending:
+                r.wait()
+            self._halo_unpack(also_saved=True)
+            if projected_field is not None:                   # the stand-in projection also covers the halo planes
+                for dst, src in zip(self._stored_field_views(), projected_field):
+                    dst.copy_(src.view(-1), non_blocking=True)
+            self._tick("halo wait+unpack")
+            be.set_window(inner[0], inner[1], 2)              # 4b. the particles near the faces + the ghost copies
         be.g2p(ratio)
         be.advect(dt, cfl, collide)
         self._tick("g2p+advect")
@@ -438,7 +452,7 @@ class SlabSimulation:
             self._tick("route-mark")
             if overlap and attempt == 0:
                 pending = self._swap_blocks2_start(b2, faces)
-                be.set_window(inner[0], inner[1], 1)          # the interior, while the blocks travel
+                be.set_window(mid, inner[1], 1)               # 4c. interior, upper half, while the blocks travel
                 be.g2p(ratio)
                 be.advect(dt, cfl, collide)
                 be.set_window(0, 0, 0)
@@ -568,7 +582,7 @@ class SlabSimulation:
             self._owned_views = v
         return v
 
-    def _halo_exchange_fast(self):
+    def _halo_exchange_fast(self, start_only=False):
         """Face halos of u, v, w: ONE message per face and direction (the three fields' plane ranges packed into one
         buffer; 12 separate NCCL point-to-point operations per middle rank cost more in latency than the 21 MB per
         face cost in bandwidth)."""
@@ -593,12 +607,30 @@ class SlabSimulation:
                 o += m
             items.append((sbuf, rbuf, peer))
             self.exchanged_bytes += sbuf.numel() * 4
-        _sendrecv(items)
-        for side, (peer, pairs, ns, nr, sbuf, rbuf) in plan.items():
+        pending = _sendrecv(items, wait=not start_only)
+        if start_only:
+            return pending
+        self._halo_unpack()
+        return []
+
+    def _halo_unpack(self, also_saved=False):
+        """Received halo planes -> the halo planes of u, v, w (and of the saved copy, when the copy was taken before
+        they arrived)."""
+        for side, (peer, pairs, ns, nr, sbuf, rbuf) in self._halo_plan.items():
             o = 0
-            for (_, recv), m in zip(pairs, nr):
+            for d, ((_, recv), m) in enumerate(zip(pairs, nr)):
                 recv.copy_(rbuf[o:o + m].view(recv.shape))
                 o += m
+        if also_saved:
+            for d in range(3):
+                f, kbase = self.backend.field_planes(d)
+                sv, _ = self.backend.field_planes(d, saved=True)
+                extra = 1 if d == 2 else 0
+                o0, o1 = self.kb - kbase, self.ke - kbase
+                if self.up is not None:
+                    sv[o1:o1 + self.halo + extra].copy_(f[o1:o1 + self.halo + extra])
+                if self.down is not None:
+                    sv[o0 - self.halo:o0].copy_(f[o0 - self.halo:o0])
 
     def sync_from_backend(self):
         """Pull the resident streams back into self.streams / self.ids (tests, gather)."""
