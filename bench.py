@@ -62,7 +62,10 @@ RATIO = 0.05
 HALO = 7
 GHOST = 1                     # ghost particle layers: ceil(radius / dx) -- the P2G kernel reaches 0.866 dx, so 1 (2 for the doubled
                               # radius of the smooth surface-tension kernel); bit-identity vs the undecomposed run: tests/test_slab_gloo.py
-OVERLAP = os.environ.get("FFB200_BENCH_OVERLAP", "1") != "0"     # N > 1: neighbour exchange overlapped with the interior particles
+# N > 1: neighbour exchanges overlapped with the interior particles' G2P + advection. It pays once the slabs are thin (the
+# windowed launches cost a few % on thick slabs: 32.5 vs 30.8 ms at N = 2, 9.55 vs 10.14 ms at N = 8, 512^3); "auto" = slabs of
+# at most 128 planes
+OVERLAP_ENV = os.environ.get("FFB200_BENCH_OVERLAP", "auto")
 SAMPLE_PLANES = 16            # fluid cell planes of the CPU reference sample
 HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
@@ -249,6 +252,7 @@ class Runner:
         self.radius = 0.5 * self.dx * math.sqrt(3.0)
         self.dt = self.dx / V0            # ~1 cell per substep at the velocity bound (CFL limit is 5)
         self.kb, self.ke = slab.slab_range(n, world, rank)
+        self.overlap = world > 1 and ((n // world) <= 128 if OVERLAP_ENV == "auto" else OVERLAP_ENV != "0")
         if world > 1:
             self.backend = slab.GpuBackend(n, n, n, self.dx, self.kb, self.ke, HALO, local_rank, self.apic)
             self.ctx = self.backend.ctx
@@ -274,7 +278,7 @@ class Runner:
     def step(self):
         if self.sim is not None:
             self.sim.step_fast(self.radius, RATIO, self.dt, apply_migration=not self.fixed,
-                               projected_field=None if self.fixed else self.tg, overlap=OVERLAP)
+                               projected_field=None if self.fixed else self.tg, overlap=self.overlap)
             return
         c = self.ctx
         c.p2g(self.radius, self.m)            # bins + sort + seam words + U, V, W transfers
@@ -555,7 +559,7 @@ def main():
 
             def e2e_step():
                 run.sim.step_fast(run.radius, RATIO, run.dt, apply_migration=True, projected_field=h_in, p2g_download=h_out,
-                                  overlap=OVERLAP)
+                                  overlap=run.overlap)
                 return run.ctx.maximum_particle_speed()
 
             h2d = sum(t.numel() for t in h_in) * 4
@@ -590,6 +594,7 @@ def main():
         nst = steps + 3
         sys.stderr.write(f"rank {rank} slab phases, ms per step (synchronised): " + ", ".join(f"{k} {1e3 * v / nst:.3f}" for k, v in ph.items()) +
                          f"; total {1e3 * sum(ph.values()) / nst:.3f}; exchange repeats {getattr(run.sim, 'overflows', 0)}\n")
+    run_overlap = run.overlap
     class run_sim_overflows:                  # exchanges repeated because a section overflowed (slab.step_fast), this rank
         v = getattr(run.sim, "overflows", 0) if run.sim is not None else None
     run.close()
@@ -640,7 +645,7 @@ def main():
         cfg = dict(base_config,
                    parallelism="single GPU" if world == 1 else f"z-slab x{world} ({n // world} planes per rank, halo {HALO}, ghost "
                                f"particle layers {GHOST}), face halo + particle migration over NCCL, one process per GPU" +
-                               (", migrant/ghost exchange overlapped with the interior particles' G2P + advection" if OVERLAP else ""),
+                               (", halo and migrant/ghost exchanges overlapped with the interior particles' G2P + advection" if run_overlap else ""),
                    l2="inputs larger than L2 (particle streams + grids >> 126 MB per step)",
                    batch="evolving: each step sorts and transfers the particles the previous step advected (ranks migrate them); "
                          "the MAC field is replaced by an analytic divergence-free field where the CPU projection would return one",

@@ -525,6 +525,11 @@ class SlabSimulation:
             caps = ((max(old[0], self._bucket(mu + 4096)), max(old[1], self._bucket(gu + 4096))) if "up" in resize else old[:2]) + \
                    ((max(old[2], self._bucket(md + 4096)), max(old[3], self._bucket(gd + 4096))) if "dn" in resize else old[2:])
         old_caps = getattr(self, "_block2_caps", None)
+        if resize is None and old_caps is not None and not getattr(self, "force_initial_caps", None):
+            # hysteresis: a buffer is kept while it is large enough and not more than twice what is needed (reallocating
+            # -- and zero-filling -- 60 MB blocks because a count crossed a 4096 boundary costs more than the spare
+            # bytes cost on NVLink)
+            caps = tuple(o if n <= o <= 2 * n else n for o, n in zip(old_caps, caps))
         if old_caps != caps:
             nb = self.backend.new_block2
             blk = dict(getattr(self, "_blk2", {}))
