@@ -13,7 +13,8 @@ whole scene, ~133 GB of the 180 GB). Particles come from a counter-based hash of
 bit-identical particles. The batch EVOLVES: every step sorts the particles the previous step advected, ranks
 migrate particles for real. Where the reference's CPU pressure projection would hand back a field, the MAC
 field is overwritten with an analytic divergence-free field (two superposed Taylor-Green vortices, tangential at
-the walls, with motion across z), so the set circulates -- and crosses slab faces -- instead of compressing. Same launch mode (eager) at every N.
+the walls of the inner box the fluid lives in, with motion across z), so the set circulates -- and crosses slab
+faces -- instead of compressing or piling up against the solid. Same launch mode (eager) at every N.
 
 `value`    device-resident throughput: particles and grids live in HBM, K steps timed with CUDA events on the
            launching stream between barriers, max over ranks.
@@ -157,9 +158,11 @@ def reference_arm(n_grid: int, steps: int, warmup: int, threads: int = 0):
     # planes in SCENE coordinates
     A = B = 0.5 * V0
     kz0 = 0 if whole else k0 - 3
-    xf, xc = np.arange(n + 1) * dx, (np.arange(n) + 0.5) * dx
-    yf, yc = np.arange(n + 1) * dx, (np.arange(n) + 0.5) * dx
-    zc, zf = (np.arange(kz0, kz0 + K) + 0.5) * dx, np.arange(kz0, kz0 + K + 1) * dx
+    a_in, L_in = 3.0 * dx, dx * n - 6.0 * dx
+    inner = lambda t: np.clip((t - a_in) / L_in, 0.0, 1.0)
+    xf, xc = inner(np.arange(n + 1) * dx), inner((np.arange(n) + 0.5) * dx)
+    yf, yc = inner(np.arange(n + 1) * dx), inner((np.arange(n) + 0.5) * dx)
+    zc, zf = inner((np.arange(kz0, kz0 + K) + 0.5) * dx), inner(np.arange(kz0, kz0 + K + 1) * dx)
     u2 = (A * np.sin(math.pi * xf)[None, :] * np.cos(math.pi * yc)[:, None]).astype(np.float32)
     mac = [np.ascontiguousarray(np.broadcast_to(u2[None], (K, n, n + 1))),
            np.ascontiguousarray(np.broadcast_to((-A * np.cos(math.pi * xc)[None, None, :] * np.sin(math.pi * yf)[None, :, None] +

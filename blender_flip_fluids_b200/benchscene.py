@@ -75,23 +75,29 @@ def fill_dam_break(ctx, I, J, K, dx, k_begin, k_end, apic, v0, seed, device, hea
 
 
 def taylor_green_field(I, J, K, dx, kbase, kloc, amp, device):
-    """A divergence-free MAC field that is tangential to the unit-box walls, sampled at the face centres of the
-    stored planes [kbase, kbase + kloc (+1)): two superposed Taylor-Green vortices,
-        u =  A sin(pi x) cos(pi y)
-        v = -A cos(pi x) sin(pi y) + B sin(pi y) cos(pi z)
-        w =                        - B cos(pi y) sin(pi z),      A = B = amp / 2
-    (its discrete divergence on the MAC grid vanishes identically). Stand-in for the pressure-projected field in the
-    evolving-batch benchmark: particles circulate in x-y AND across z -- they cross slab faces, so ranks really
-    migrate them -- and the set does not compress."""
+    """A divergence-free MAC field whose normal component vanishes on the walls of the INNER box [a, 1 - a]^3,
+    a = 3 dx (the fluid's margin; the collision surface of the wall solid sits at 1.7 dx), sampled at the face centres
+    of the stored planes [kbase, kbase + kloc (+1)): two superposed Taylor-Green vortices in the inner coordinates
+    s = clamp((x - a) / (1 - 2a), 0, 1),
+        u =  A sin(pi sx) cos(pi sy)
+        v = -A cos(pi sx) sin(pi sy) + B sin(pi sy) cos(pi sz)
+        w =                          - B cos(pi sy) sin(pi sz),      A = B = amp / 2
+    (inside the inner box its discrete divergence on the MAC grid vanishes identically). Stand-in for the
+    pressure-projected field in the evolving-batch benchmark: particles circulate in x-y AND across z -- they cross
+    slab faces, so ranks really migrate them --, the set does not compress, and nothing is driven into the walls (a
+    field tangential only at the DOMAIN boundary packs hundreds of particles per cell against the solid within a few
+    steps, which no projected field of the real pipeline does)."""
     f64 = dict(dtype=torch.float64, device=device)
     A = B = 0.5 * amp
     pi = math.pi
-    xf = torch.arange(I + 1, **f64) * dx                       # face / centre coordinates per axis
-    xc = (torch.arange(I, **f64) + 0.5) * dx
-    yf = torch.arange(J + 1, **f64) * dx
-    yc = (torch.arange(J, **f64) + 0.5) * dx
-    zc = (torch.arange(kbase, kbase + kloc, **f64) + 0.5) * dx
-    zf = torch.arange(kbase, kbase + kloc + 1, **f64) * dx
+    a, L = 3.0 * dx, dx * max(I, J, K) - 6.0 * dx
+    inner = lambda t: torch.clamp((t - a) / L, 0.0, 1.0)
+    xf = inner(torch.arange(I + 1, **f64) * dx)                  # face / centre coordinates per axis, inner-box units
+    xc = inner((torch.arange(I, **f64) + 0.5) * dx)
+    yf = inner(torch.arange(J + 1, **f64) * dx)
+    yc = inner((torch.arange(J, **f64) + 0.5) * dx)
+    zc = inner((torch.arange(kbase, kbase + kloc, **f64) + 0.5) * dx)
+    zf = inner(torch.arange(kbase, kbase + kloc + 1, **f64) * dx)
     u2 = (A * torch.sin(pi * xf)[None, :] * torch.cos(pi * yc)[:, None]).to(torch.float32)
     u = u2[None].expand(kloc, J, I + 1).contiguous()
     v = (-A * torch.cos(pi * xc)[None, None, :] * torch.sin(pi * yf)[None, :, None] +

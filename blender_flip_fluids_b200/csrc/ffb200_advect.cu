@@ -31,7 +31,7 @@ struct Box {
 #ifdef FFB_ADV_MINB
 #define FFB_ADV_BOUNDS FFB_ADV_BOUNDS
 #else
-#define FFB_ADV_BOUNDS __launch_bounds__(FFB_ADV_THREADS)
+#define FFB_ADV_BOUNDS __launch_bounds__(FFB_ADV_THREADS, 3)
 #endif
 
 struct AdvectParams {

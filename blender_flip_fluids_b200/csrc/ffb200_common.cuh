@@ -177,19 +177,50 @@ __device__ __forceinline__ void mac_lerp_pair(const GridDesc &g, const float *__
     rb = trilerp8(pb, cx.f, cy.f, cz.f);
 }
 
+// eight faces at p + {0,1} + {0,sj} + {0,sk} in trilerp8's corner order {000,100,010,001,101,011,110,111};
+// unconditional (interior cells only)
+__device__ __forceinline__ void load8t(const float *__restrict__ p, int sj, int sk, float v[8]) {
+    v[0] = __ldg(p);           v[1] = __ldg(p + 1);
+    v[2] = __ldg(p + sj);      v[3] = __ldg(p + sk);
+    v[4] = __ldg(p + sk + 1);  v[5] = __ldg(p + sk + sj);
+    v[6] = __ldg(p + sj + 1);  v[7] = __ldg(p + sk + sj + 1);
+}
+
+__device__ __forceinline__ double trilerp8f(const float v[8], double x, double y, double z) {
+    const double p[8] = {(double)v[0], (double)v[1], (double)v[2], (double)v[3], (double)v[4], (double)v[5], (double)v[6], (double)v[7]};
+    return trilerp8(p, x, y, z);
+}
+
 // MACVelocityField::evaluateVelocityAtPositionLinear(vec3) (macvelocityfield.cpp:631-645):
 // float position widened to double, zero outside the grid, components narrowed to float.
 // Each axis needs its index/fraction twice only: in the unshifted frame (the component
-// normal to it) and shifted by half a cell (the two other components).
+// normal to it) and shifted by half a cell (the two other components). A point whose (unshifted) cell has its whole
+// 3 x 3 x 3 neighbourhood inside the grid touches only existing faces in every frame: its 24 loads need no range test,
+// use 32-bit offsets (face counts below 2^31, checked by the host) and are issued back to back; the arithmetic is the
+// same either way.
 __device__ __forceinline__ void mac_eval(const GridDesc &g, const MacView &m, float px, float py, float pz,
                                          float &ox, float &oy, float &oz) {
     const double x = px, y = py, z = pz;
+    const double hdx = 0.5 * g.dx;
+    const AxisCoord xu = axis_coord(x, g), yu = axis_coord(y, g), zu = axis_coord(z, g);
+    if ((unsigned)(xu.i - 1) < (unsigned)(g.I - 2) && (unsigned)(yu.i - 1) < (unsigned)(g.J - 2) &&
+        (unsigned)(zu.i - 1) < (unsigned)(g.K - 2)) {
+        const AxisCoord xs = axis_coord(x - hdx, g), ys = axis_coord(y - hdx, g), zs = axis_coord(z - hdx, g);
+        const int sju = g.I + 1, sku = (g.I + 1) * g.J, sjv = g.I, skv = g.I * (g.J + 1), sjw = g.I, skw = g.I * g.J;
+        const int ks = zs.i - g.kbase, kk = zu.i - g.kbase;
+        float a[8], b[8], c[8];                                  // all 24 loads in flight, then the three fp64 blends
+        load8t(m.u + (xu.i + sju * ys.i + sku * ks), sju, sku, a);
+        load8t(m.v + (xs.i + sjv * yu.i + skv * ks), sjv, skv, b);
+        load8t(m.w + (xs.i + sjw * ys.i + skw * kk), sjw, skw, c);
+        ox = (float)trilerp8f(a, xu.f, ys.f, zs.f);
+        oy = (float)trilerp8f(b, xs.f, yu.f, zs.f);
+        oz = (float)trilerp8f(c, xs.f, ys.f, zu.f);
+        return;
+    }
     if (!pos_in_grid(x, y, z, g)) {
         ox = oy = oz = 0.0f;
         return;
     }
-    const double hdx = 0.5 * g.dx;
-    const AxisCoord xu = axis_coord(x, g), yu = axis_coord(y, g), zu = axis_coord(z, g);
     const AxisCoord xs = axis_coord(x - hdx, g), ys = axis_coord(y - hdx, g), zs = axis_coord(z - hdx, g);
     ox = (float)mac_lerp<0>(g, m.u, xu, ys, zs);
     oy = (float)mac_lerp<1>(g, m.v, xs, yu, zs);

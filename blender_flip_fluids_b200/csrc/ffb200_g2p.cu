@@ -73,6 +73,9 @@ __global__ void FFB_G2P_BOUNDS k_g2p_flip(const __grid_constant__ G2PParams P) {
 // interpolated velocity (mac_lerp, double arithmetic). Both read the same 8 faces whenever the
 // float and the double index arithmetic agree on the cell -- always, except within an ulp of a
 // cell plane -- so they are loaded once.
+__device__ __forceinline__ void apic_math(const G2PParams &P, const float v[8], float ix, float iy, float iz, float &ox, float &oy,
+                                          float &oz);
+
 template <int DIR>
 __device__ __forceinline__ void apic_component(const G2PParams &P, const float *__restrict__ f, float px, float py, float pz,
                                                bool in_grid, const AxisCoord &cx, const AxisCoord &cy, const AxisCoord &cz,
@@ -84,9 +87,6 @@ __device__ __forceinline__ void apic_component(const G2PParams &P, const float *
     const float ix = (x - idx2posf(gi, g.dx)) * P.inv_s;
     const float iy = (y - idx2posf(gj, g.dx)) * P.inv_s;
     const float iz = (z - idx2posf(gk, g.dx)) * P.inv_s;
-    const float invdx = P.invdx;
-    const float mx = 1.0f - ix, my = 1.0f - iy, mz = 1.0f - iz;
-
     // faces in the order c = di + 2 dj + 4 dk; out-of-range faces read 0 (skipping a term and adding
     // w * 0 give the same sum)
     const long long sj = gw, sk = (long long)gw * gh;
@@ -105,6 +105,26 @@ __device__ __forceinline__ void apic_component(const G2PParams &P, const float *
         }
     }
 
+    apic_math(P, v, ix, iy, iz, ox, oy, oz);
+
+    // velocity component (zero outside the grid, macvelocityfield.cpp:631-645)
+    if (!in_grid) {
+        vel = 0.0f;
+    } else if (gi == cx.i && gj == cy.i && gk == cz.i) {
+        // trilerp8 corner order {000,100,010,001,101,011,110,111}
+        const double p[8] = {(double)v[0], (double)v[1], (double)v[2], (double)v[4],
+                             (double)v[5], (double)v[6], (double)v[3], (double)v[7]};
+        vel = (float)trilerp8(p, cx.f, cy.f, cz.f);
+    } else {
+        vel = (float)mac_lerp<DIR>(g, f, cx, cy, cz);
+    }
+}
+
+// The affine row from the eight faces v (index c = di + 2 dj + 4 dk) and the float fractions of the gradient frame.
+__device__ __forceinline__ void apic_math(const G2PParams &P, const float v[8], float ix, float iy, float iz, float &ox, float &oy,
+                                          float &oz) {
+    const float invdx = P.invdx;
+    const float mx = 1.0f - ix, my = 1.0f - iy, mz = 1.0f - iz;
     // gradient weights (fluidsimulation.cpp:6737-6768). The reference's 24 three-factor products
     // reduce to 21 multiplications: (-a)*b == -(a*b) exactly, and factors are shared where the
     // reference associates them the same way. Signs are applied in the sums below.
@@ -124,18 +144,12 @@ __device__ __forceinline__ void apic_component(const G2PParams &P, const float *
     sx -= xw[3] * v[6]; sy += yw[2] * v[6]; sz += z2 * v[6];
     sx += xw[3] * v[7]; sy += yw[3] * v[7]; sz += z3 * v[7];
     ox = sx; oy = sy; oz = sz;
+}
 
-    // velocity component (zero outside the grid, macvelocityfield.cpp:631-645)
-    if (!in_grid) {
-        vel = 0.0f;
-    } else if (gi == cx.i && gj == cy.i && gk == cz.i) {
-        // trilerp8 corner order {000,100,010,001,101,011,110,111}
-        const double p[8] = {(double)v[0], (double)v[1], (double)v[2], (double)v[4],
-                             (double)v[5], (double)v[6], (double)v[3], (double)v[7]};
-        vel = (float)trilerp8(p, cx.f, cy.f, cz.f);
-    } else {
-        vel = (float)mac_lerp<DIR>(g, f, cx, cy, cz);
-    }
+// trilerp8 of faces given in the c = di + 2 dj + 4 dk order (reordered to the reference's corner order)
+__device__ __forceinline__ float trilerp_c(const float v[8], double fx, double fy, double fz) {
+    const double p[8] = {(double)v[0], (double)v[1], (double)v[2], (double)v[4], (double)v[5], (double)v[6], (double)v[3], (double)v[7]};
+    return (float)trilerp8(p, fx, fy, fz);
 }
 
 __global__ void FFB_G2P_BOUNDS k_g2p_apic(const __grid_constant__ G2PParams P) {
@@ -144,10 +158,42 @@ __global__ void FFB_G2P_BOUNDS k_g2p_apic(const __grid_constant__ G2PParams P) {
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const GridDesc &g = P.g;
     const double x = px, y = py, z = pz;
-    const bool in_grid = pos_in_grid(x, y, z, g);
     const double hdx = 0.5 * g.dx;
     const AxisCoord xu = axis_coord(x, g), yu = axis_coord(y, g), zu = axis_coord(z, g);
     const AxisCoord xs = axis_coord(x - hdx, g), ys = axis_coord(y - hdx, g), zs = axis_coord(z - hdx, g);
+    // Interior cell (its 3 x 3 x 3 neighbourhood is inside the grid: every face of every frame exists) whose gradient
+    // frames -- the reference's FLOAT-shifted coordinates, floored in double (:6717-6735) -- pick the same cells as
+    // the velocity frames: the 24 faces are loaded once, back to back, with 32-bit offsets; same arithmetic as below.
+    if ((unsigned)(xu.i - 1) < (unsigned)(g.I - 2) && (unsigned)(yu.i - 1) < (unsigned)(g.J - 2) &&
+        (unsigned)(zu.i - 1) < (unsigned)(g.K - 2)) {
+        const float fxs = px - P.h, fys = py - P.h, fzs = pz - P.h;
+        const int gxs = pos2idx(fxs, g.inv_dx), gys = pos2idx(fys, g.inv_dx), gzs = pos2idx(fzs, g.inv_dx);
+        if (gxs == xs.i && gys == ys.i && gzs == zs.i) {
+            const int sju = g.I + 1, sku = (g.I + 1) * g.J, sjv = g.I, skv = g.I * (g.J + 1), sjw = g.I, skw = g.I * g.J;
+            const int ks = zs.i - g.kbase, kk = zu.i - g.kbase;
+            float a[8], b[8], c[8];
+            load8(P.cur.u + (xu.i + sju * ys.i + sku * ks), sju, sku, a);
+            load8(P.cur.v + (xs.i + sjv * yu.i + skv * ks), sjv, skv, b);
+            load8(P.cur.w + (xs.i + sjw * ys.i + skw * kk), sjw, skw, c);
+            // float fractions of the gradient frames: (x - GridIndexToPosition(g)) * (float)(1 / (float)dx)
+            const float ixu = (px - idx2posf(xu.i, g.dx)) * P.inv_s, iyu = (py - idx2posf(yu.i, g.dx)) * P.inv_s,
+                        izu = (pz - idx2posf(zu.i, g.dx)) * P.inv_s;
+            const float ixs = (fxs - idx2posf(gxs, g.dx)) * P.inv_s, iys = (fys - idx2posf(gys, g.dx)) * P.inv_s,
+                        izs = (fzs - idx2posf(gzs, g.dx)) * P.inv_s;
+            float g0, g1, g2;
+            apic_math(P, a, ixu, iys, izs, g0, g1, g2);
+            P.a[0][j] = g0; P.a[1][j] = g1; P.a[2][j] = g2;
+            P.ovx[j] = trilerp_c(a, xu.f, ys.f, zs.f);
+            apic_math(P, b, ixs, iyu, izs, g0, g1, g2);
+            P.a[3][j] = g0; P.a[4][j] = g1; P.a[5][j] = g2;
+            P.ovy[j] = trilerp_c(b, xs.f, yu.f, zs.f);
+            apic_math(P, c, ixs, iys, izu, g0, g1, g2);
+            P.a[6][j] = g0; P.a[7][j] = g1; P.a[8][j] = g2;
+            P.ovz[j] = trilerp_c(c, xs.f, ys.f, zu.f);
+            return;
+        }
+    }
+    const bool in_grid = pos_in_grid(x, y, z, g);
     float v0, v1, v2, ax, ay, az;
     apic_component<0>(P, P.cur.u, px, py, pz, in_grid, xu, ys, zs, v0, ax, ay, az);
     P.a[0][j] = ax; P.a[1][j] = ay; P.a[2][j] = az;
