@@ -61,9 +61,14 @@ struct StageEvents {
 };
 
 // Context plus the bookkeeping that only this file needs.
+constexpr int kUploadChunks = 8;
+
 struct ContextImpl : Context {
     StageEvents evs;
     int launches[kNumStages] = {};
+    // pipelined field upload (g2p_upload_pipelined): copy stream, its fork event, one event per plane chunk
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_fork = nullptr, chunk_done[kUploadChunks] = {};
 };
 
 // Stage timing events are skipped while the stream is being captured into a CUDA graph (a caller may
@@ -181,6 +186,10 @@ void destroy_impl(ContextImpl *c) {
     dev_free(c->sort.seam_cell);
     dev_free(c->sort.edge_count);
     for (int q = 0; q < 3; q++) dev_free(c->k1s[q]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_fork) cudaEventDestroy(c->copy_fork);
+    for (auto &e : c->chunk_done)
+        if (e) cudaEventDestroy(e);
     for (auto &cs : c->sort.cell) {
         if (cs.partial) cudaFree(cs.partial);
         if (cs.cell_list) cudaFree(cs.cell_list);
@@ -355,7 +364,7 @@ void set_solid_impl(ContextImpl &c, const float *phi, const uint8_t *near_solid)
     c.has_solid = true;
 }
 
-void p2g_impl(ContextImpl &c, double radius, int method) {
+void p2g_impl(ContextImpl &c, double radius, int method, const HostFieldOut *host = nullptr) {
     if (method != FFB200_TRANSFER_FLIP && method != FFB200_TRANSFER_APIC) throw std::domain_error("unknown transfer method");
     if (!(radius > 0.0)) throw std::domain_error("particle radius must be positive");
     if (method == FFB200_TRANSFER_APIC && !c.has_affine) throw std::logic_error("APIC transfer needs affine particle data");
@@ -377,11 +386,16 @@ void p2g_impl(ContextImpl &c, double radius, int method) {
     int lp = launch_p2g_prepare(c, radius, seam_done);
     tp.done(lp);
     StageTimer t(c, kP2G);
-    int l = launch_p2g(c, radius, method);
+    int l = launch_p2g(c, radius, method, host);
     t.done(l);
+    if (host) FFB_CUDA(cudaStreamSynchronize(c.stream));      // the copies were enqueued behind each direction's kernels
 }
 
-void g2p_impl(ContextImpl &c, int method, double ratio) {
+bool g2p_upload_pipelined(ContextImpl &c, int method, double ratio, const float *const cur[3], const float *const saved[3]);
+
+// upload_cur / upload_saved: host fields to bring in first (null: the device copies are current)
+void g2p_impl(ContextImpl &c, int method, double ratio, const float *const *upload_cur = nullptr,
+              const float *const *upload_saved = nullptr) {
     if (method != FFB200_TRANSFER_FLIP && method != FFB200_TRANSFER_APIC) throw std::domain_error("unknown transfer method");
     if (method == FFB200_TRANSFER_APIC) {
         ensure_capacity(c, c.n, true);
@@ -395,9 +409,17 @@ void g2p_impl(ContextImpl &c, int method, double ratio) {
         }
         c.k1s_cap = c.cap;
     }
-    StageTimer t(c, kG2P);
-    int l = launch_g2p(c, method, ratio);
-    t.done(l);
+    if (!upload_cur || !g2p_upload_pipelined(c, method, ratio, upload_cur, upload_saved)) {
+        if (upload_cur) {
+            StageTimer th(c, kH2D);
+            upload_field(c, false, upload_cur[0], upload_cur[1], upload_cur[2]);
+            th.done(0);
+            if (upload_saved) upload_field(c, true, upload_saved[0], upload_saved[1], upload_saved[2]);
+        }
+        StageTimer t(c, kG2P);
+        int l = launch_g2p(c, method, ratio);
+        t.done(l);
+    }
     if (method == FFB200_TRANSFER_FLIP) {
         c.k1_epoch = c.epoch;
         c.k1_buf = 2;
@@ -408,6 +430,69 @@ void g2p_impl(ContextImpl &c, int method, double ratio) {
         c.k1_epoch = c.epoch;
         c.k1_buf = c.nondestructive ? (c.cur ^ 1) : c.cur;
     }
+}
+
+// G2P with the field(s) coming from the host: the stored planes travel in kUploadChunks chunks on a copy stream, and
+// behind each chunk the gather runs over the sorted particles (z-major bins) whose support lies wholly in the planes
+// that have arrived -- the upload of a 512^3 field (1.6 GB, ~32 ms over PCIe) then hides the gather instead of
+// preceding it. A particle of cell plane k reads planes k-1 .. k+1 of u and v (staggered half a cell in z) and k, k+1
+// of w, in every kernel variant; ranges end two planes short of the uploaded extent. Needs sorted resident particles
+// (their bin table gives the range bounds: one small read) and no active particle window; false = not applicable.
+bool g2p_upload_pipelined(ContextImpl &c, int method, double ratio, const float *const cur[3], const float *const saved[3]) {
+    static const bool on = [] { const char *e = std::getenv("FFB200_PIPELINED_UPLOAD"); return e ? std::atoi(e) != 0 : true; }();
+    const GridDesc &g = c.g;
+    if (!on || !c.sorted || c.n == 0 || c.window.mode != 0 || g.kloc < 8 * kUploadChunks) return false;
+    if ((size_t)c.face[0].count * 4 < ((size_t)8 << 20)) return false;   // small fields: one copy, one launch
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(c.stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return false;
+    if (!c.copy_stream) {
+        FFB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        FFB_CUDA(cudaEventCreateWithFlags(&c.copy_fork, cudaEventDisableTiming));
+        for (int q = 0; q < kUploadChunks; q++) FFB_CUDA(cudaEventCreateWithFlags(&c.chunk_done[q], cudaEventDisableTiming));
+    }
+    // particle index where each range ends: the first particle of cell plane kbase + z_end - 2
+    int zend[kUploadChunks];
+    uint32_t bound[kUploadChunks];
+    for (int q = 0; q < kUploadChunks; q++) {
+        zend[q] = (int)((long long)g.kloc * (q + 1) / kUploadChunks);
+        if (q + 1 < kUploadChunks) {
+            const unsigned long long hz = (unsigned long long)(2 * (zend[q] - 2) + kApron);
+            const unsigned long long bin = hz * (unsigned long long)g.HY * (unsigned long long)g.HX;
+            FFB_CUDA(cudaMemcpyAsync(&bound[q], c.sort.bin_start + bin, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+        }
+    }
+    FFB_CUDA(cudaEventRecord(c.copy_fork, c.stream));          // the copies overwrite fields earlier work may still read
+    FFB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_fork, 0));
+    FFB_CUDA(cudaStreamSynchronize(c.stream));
+    bound[kUploadChunks - 1] = (uint32_t)c.n;
+    StageTimer t(c, kG2P);
+    int launches = 0, z0 = 0;
+    uint32_t first = 0;
+    for (int q = 0; q < kUploadChunks; q++) {
+        for (int pass = 0; pass < 2; pass++) {
+            const float *const *h = pass == 0 ? saved : cur;
+            if (!h) continue;
+            for (int d = 0; d < 3; d++) {
+                FaceGrid &f = c.face[d];
+                const size_t plane = (size_t)f.gi * f.gj;
+                // w stores kloc + 1 planes: the extra one goes with the last chunk
+                const int z1 = (q + 1 == kUploadChunks) ? f.kstore : zend[q];
+                float *dst = pass == 0 ? f.saved : f.vel;
+                FFB_CUDA(cudaMemcpyAsync(dst + plane * z0, h[d] + plane * ((size_t)g.kbase + z0), plane * (size_t)(z1 - z0) * 4,
+                                         cudaMemcpyHostToDevice, c.copy_stream));
+            }
+        }
+        FFB_CUDA(cudaEventRecord(c.chunk_done[q], c.copy_stream));
+        FFB_CUDA(cudaStreamWaitEvent(c.stream, c.chunk_done[q], 0));
+        const uint32_t end = std::min(std::max(bound[q], first), (uint32_t)c.n);
+        launches += launch_g2p(c, method, ratio, (int)first, (int)(end - first));
+        first = end;
+        z0 = zend[q];
+    }
+    t.done(launches);
+    // the caller's buffers are free again when this returns, whether or not a download follows
+    FFB_CUDA(cudaEventSynchronize(c.chunk_done[kUploadChunks - 1]));
+    return true;
 }
 
 void advect_impl(ContextImpl &c, double dt, double cfl, int collide) {
@@ -854,9 +939,13 @@ int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos
         } else {
             set_particles_impl(c, n, pos, vel, affx, affy, affz);
         }
-        p2g_impl(c, particle_radius, transfer_method);
-        // null outputs stay on the device (ffb200_get_velocity_field fetches them later)
-        if (u || v || w || validu || validv || validw) get_field_impl(c, u, v, w, validu, validv, validw);
+        // null outputs stay on the device (ffb200_get_velocity_field fetches them later); the others are copied out
+        // direction by direction behind the transfer kernels
+        HostFieldOut host;
+        host.vel[0] = u; host.vel[1] = v; host.vel[2] = w;
+        host.valid[0] = validu; host.valid[1] = validv; host.valid[2] = validw;
+        const bool any = u || v || w || validu || validv || validw;
+        p2g_impl(c, particle_radius, transfer_method, any ? &host : nullptr);
     });
 }
 
@@ -900,14 +989,12 @@ int ffb200_update_marker_particle_velocities(ffb200_context *ctx, int n, const f
         } else {
             set_particles_impl(c, n, pos, vel, nullptr, nullptr, nullptr);
         }
-        if (!(res & FFB200_RESIDENT_FIELD)) {
-            StageTimer t(c, kH2D);
-            upload_field(c, false, u, v, w);
-            t.done(0);
-        }
-        if (!apic && !(res & FFB200_RESIDENT_SAVED_FIELD)) upload_field(c, true, su, sv, sw);
         sort_impl(c);                                          // spatial order for the gathers (no-op if still sorted)
-        g2p_impl(c, transfer_method, ratio_pic_flip);
+        const float *const h_cur[3] = {u, v, w}, *const h_saved[3] = {su, sv, sw};
+        const bool up_cur = !(res & FFB200_RESIDENT_FIELD), up_saved = !apic && !(res & FFB200_RESIDENT_SAVED_FIELD);
+        if (up_cur && (!u || !v || !w)) throw std::invalid_argument("null velocity field pointer");
+        if (up_saved && !up_cur) upload_field(c, true, su, sv, sw);
+        g2p_impl(c, transfer_method, ratio_pic_flip, up_cur ? h_cur : nullptr, up_cur && up_saved ? h_saved : nullptr);
         // resident particles with null outputs: the results stay on the device until ffb200_get_particles asks
         if (vel || !(res & FFB200_RESIDENT_PARTICLES))
             get_particles_impl(c, nullptr, vel, apic ? affx : nullptr, apic ? affy : nullptr, apic ? affz : nullptr);

@@ -146,11 +146,17 @@ int launch_extrapolate(Context &c, int layers);          // GridUtils::extrapola
 // ffb200_p2g.cu
 void p2g_seam_begin(Context &c, double radius, SeamParams &sp);   // clears marks / counters, fills sp
 int launch_p2g_prepare(Context &c, double radius, bool seam_done);   // [membership words +] block masks
-int launch_p2g(Context &c, double radius, int method);  // the three transfer kernels
+// host destinations of a transfer (reference layouts, whole-grid extents): each direction's faces and valid bytes are
+// copied out on the stream that produced them, so the copies of one direction overlap the kernels of the others
+struct HostFieldOut {
+    float *vel[3] = {nullptr, nullptr, nullptr};
+    uint8_t *valid[3] = {nullptr, nullptr, nullptr};
+};
+int launch_p2g(Context &c, double radius, int method, const HostFieldOut *host = nullptr);  // the three transfer kernels
 int launch_attribute_p2g(Context &c, double radius, int ncomp, int normalize, float *d_out, uint8_t *d_valid);   // AttributeToGridTransfer<T>
 
 // ffb200_g2p.cu
-int launch_g2p(Context &c, int method, double ratio);
+int launch_g2p(Context &c, int method, double ratio, int first = 0, int count = -1);   // [first, first + count) of the sorted particles
 
 // ffb200_advect.cu
 int launch_solid_clearance(Context &c);                  // after every change of the solid SDF

@@ -35,12 +35,13 @@ struct G2PParams {
     float h;            // 0.5f * _dx
     float inv_s;        // (float)(1.0 / (float)_dx)   (vec3 / _dx)
     float invdx;        // 1.0f / _dx
-    int n;
+    int n;              // end of the particle range of this launch ...
+    int first = 0;      // ... and its start (a pipelined upload launches the sorted particles range by range)
     Window win;
 };
 
 __global__ void FFB_G2P_BOUNDS k_g2p_flip(const __grid_constant__ G2PParams P) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = P.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const GridDesc &g = P.g;
@@ -153,7 +154,7 @@ __device__ __forceinline__ float trilerp_c(const float v[8], double fx, double f
 }
 
 __global__ void FFB_G2P_BOUNDS k_g2p_apic(const __grid_constant__ G2PParams P) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = P.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const GridDesc &g = P.g;
@@ -275,7 +276,7 @@ __device__ __noinline__ bool g2p_apic_fast_generic(const G2PParams &P, const Fas
 #endif
 __global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FAST_MINB)
     k_g2p_apic_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg, unsigned long long *__restrict__ stats) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = P.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const FastAxis xu = fast_axis(px, fg), yu = fast_axis(py, fg), zu = fast_axis(pz, fg);
@@ -331,7 +332,7 @@ __device__ __noinline__ void g2p_flip_fast_generic(const G2PParams &P, const Fas
 
 __global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FAST_MINB)
     k_g2p_flip_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = P.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];
     const float v0 = P.vx[j], v1 = P.vy[j], v2 = P.vz[j];
@@ -393,8 +394,9 @@ int launch_max_speed_sq(Context &c, uint32_t *out_bits) {
     return 1;
 }
 
-int launch_g2p(Context &c, int method, double ratio) {
-    if (c.n == 0) return 0;
+int launch_g2p(Context &c, int method, double ratio, int first, int count) {
+    if (count < 0) count = c.n - first;
+    if (count <= 0) return 0;
     ParticleSoA &s = c.soa[c.cur];
     G2PParams P;
     P.g = c.g;
@@ -411,9 +413,10 @@ int launch_g2p(Context &c, int method, double ratio) {
     P.h = (float)(0.5f * c.g.dx);
     P.inv_s = (float)(1.0 / (double)(float)c.g.dx);
     P.invdx = (float)(1.0f / c.g.dx);
-    P.n = c.n;
+    P.first = first;
+    P.n = first + count;
     P.win = c.window;
-    const int blocks = (c.n + FFB_G2P_THREADS - 1) / FFB_G2P_THREADS;
+    const int blocks = (count + FFB_G2P_THREADS - 1) / FFB_G2P_THREADS;
     if (c.precision == FFB200_PRECISION_TOLERANCE) {
         const FastGrid fg = make_fast_grid(c.g);
         if (method == FFB200_TRANSFER_APIC)

@@ -959,19 +959,20 @@ constexpr int kListThreads = 256;
 constexpr uint32_t kEmptyCell = 0xffffffffu;              // padding entry of the cell list
 constexpr int kListRounds = 4;                             // cells per thread: a CTA lists a region of 1024 cells
 template <int DIR>
-__device__ __forceinline__ void cell_list_body(const P2GParams &P, uint32_t bx, int iz) {
+__global__ void __launch_bounds__(kListThreads) k_p2g_cell_list(const __grid_constant__ P2GParams P) {
     constexpr int kWarps = kListThreads / 32;
     __shared__ uint32_t warp_cnt[2][kListRounds][kWarps];
     __shared__ uint32_t cta_cnt[2];
     __shared__ uint32_t cta_base;
     const uint32_t nxy = (uint32_t)P.ccx * (uint32_t)P.ccy;
+    const int iz = (int)blockIdx.y;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, below = (1u << lane) - 1u;
     int cls[kListRounds];                                     // 0 empty, 1 plain, 2 seam
     uint4 ra[kListRounds], rb[kListRounds];                   // the CellRec of this thread's cell of round r
     uint32_t rank[kListRounds];                               // rank inside its warp's class group
 #pragma unroll
     for (int r = 0; r < kListRounds; r++) {
-        const uint32_t xy = (bx * (uint32_t)kListRounds + r) * (uint32_t)kListThreads + threadIdx.x;
+        const uint32_t xy = (blockIdx.x * (uint32_t)kListRounds + r) * (uint32_t)kListThreads + threadIdx.x;
         cls[r] = 0;
         ra[r] = make_uint4(0u, 0u, 0u, 0u);
         rb[r] = make_uint4(0u, 0u, 0u, 0u);
@@ -1028,28 +1029,6 @@ __device__ __forceinline__ void cell_list_body(const P2GParams &P, uint32_t bx, 
         reinterpret_cast<uint4 *>(P.cell_list + cta_base + np + threadIdx.x)[0] = make_uint4(kEmptyCell, 0u, 0u, 0u);
     if (threadIdx.x < ns32 - ns)
         reinterpret_cast<uint4 *>(P.cell_list + seam_base + ns + threadIdx.x)[0] = make_uint4(kEmptyCell, 0u, 0u, 0u);
-}
-
-template <int DIR>
-__global__ void __launch_bounds__(kListThreads) k_p2g_cell_list(const __grid_constant__ P2GParams P) {
-    cell_list_body<DIR>(P, blockIdx.x, (int)blockIdx.y);
-}
-
-// The three MAC directions in ONE launch (blockIdx.z = direction): the directions are independent, and as separate
-// launches on three streams they barely overlapped (each grid fills the GPU); one grid keeps the directions of a
-// region adjacent in time, so positions and membership words fetched for one are L2 hits for the other two.
-struct P2GParams3 {
-    P2GParams p[3];
-};
-
-__global__ void __launch_bounds__(kListThreads) k_p2g_cell_list3(const __grid_constant__ P2GParams3 Q) {
-    const int dir = (int)blockIdx.z;
-    const P2GParams &P = Q.p[dir];
-    const uint32_t nxy = (uint32_t)P.ccx * (uint32_t)P.ccy;
-    if ((int)blockIdx.y >= P.ccz || blockIdx.x * (uint32_t)(kListThreads * kListRounds) >= nxy) return;    // block-uniform
-    if (dir == 0) cell_list_body<0>(P, blockIdx.x, (int)blockIdx.y);
-    else if (dir == 1) cell_list_body<1>(P, blockIdx.x, (int)blockIdx.y);
-    else cell_list_body<2>(P, blockIdx.x, (int)blockIdx.y);
 }
 
 // APIC "edge" particle (within a few ulps of a cell plane) of shifted cell b: the reference's own
@@ -1302,10 +1281,11 @@ __device__ __forceinline__ void splat_cell(const P2GParams &P, const uint4 r0, c
 #define FFB_CELLS_MINB 6
 #endif
 template <int DIR, int METHOD>
-__device__ __forceinline__ void cells_body(const P2GParams &P, CellStage<METHOD> &S, uint32_t block, uint32_t nblocks) {
-    const uint32_t stride = nblocks * (uint32_t)kCellThreads;         // a multiple of 32: warps stay aligned to the list
+__global__ void __launch_bounds__(kCellThreads, FFB_CELLS_MINB) k_p2g_cells(const __grid_constant__ P2GParams P) {
+    __shared__ CellStage<METHOD> S;
+    const uint32_t stride = gridDim.x * (uint32_t)kCellThreads;       // a multiple of 32: warps stay aligned to the list
     const uint32_t count = __ldg(P.list_count);
-    for (uint32_t e = block * (uint32_t)kCellThreads + threadIdx.x; e < count; e += stride) {
+    for (uint32_t e = blockIdx.x * (uint32_t)kCellThreads + threadIdx.x; e < count; e += stride) {
         const uint4 *rec = reinterpret_cast<const uint4 *>(P.cell_list + e);
         const uint4 r0 = __ldg(rec);
         if (r0.x == kEmptyCell) continue;                      // padding
@@ -1317,27 +1297,12 @@ __device__ __forceinline__ void cells_body(const P2GParams &P, CellStage<METHOD>
     }
 }
 
-template <int DIR, int METHOD>
-__global__ void __launch_bounds__(kCellThreads, FFB_CELLS_MINB) k_p2g_cells(const __grid_constant__ P2GParams P) {
-    __shared__ CellStage<METHOD> S;
-    cells_body<DIR, METHOD>(P, S, blockIdx.x, gridDim.x);
-}
-
-template <int METHOD>
-__global__ void __launch_bounds__(kCellThreads, FFB_CELLS_MINB) k_p2g_cells3(const __grid_constant__ P2GParams3 Q) {
-    __shared__ CellStage<METHOD> S;
-    const uint32_t dir = blockIdx.x % 3u, block = blockIdx.x / 3u, nblocks = gridDim.x / 3u;   // gridDim.x is a multiple of 3
-    if (dir == 0) cells_body<0, METHOD>(Q.p[0], S, block, nblocks);
-    else if (dir == 1) cells_body<1, METHOD>(Q.p[1], S, block, nblocks);
-    else cells_body<2, METHOD>(Q.p[2], S, block, nblocks);
-}
-
 // APIC edge particles, one thread each. (1) An edge particle whose exact cell (the reference's
 // double floor in some block frame) differs from its bin cell also reaches nodes outside the 8
 // corners of its cell: list those contributions (almost always none). (2) Its contributions to its
 // own cell's corners, see below.
 template <int DIR, int METHOD>
-__device__ __forceinline__ void edge_body(const P2GParams &P) {
+__global__ void k_p2g_edge(const __grid_constant__ P2GParams P) {
     const uint32_t nedge = min(__ldg(P.edge_count), P.edge_cap);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nedge) return;
@@ -1406,26 +1371,14 @@ __device__ __forceinline__ void edge_body(const P2GParams &P) {
     for (int c = 0; c < 8; c++) P.partial[(size_t)c * plane + cell] = acc[c];
 }
 
-template <int DIR, int METHOD>
-__global__ void k_p2g_edge(const __grid_constant__ P2GParams P) {
-    edge_body<DIR, METHOD>(P);
-}
-
-template <int METHOD>
-__global__ void k_p2g_edge3(const __grid_constant__ P2GParams3 Q) {
-    if (blockIdx.y == 0) edge_body<0, METHOD>(Q.p[0]);
-    else if (blockIdx.y == 1) edge_body<1, METHOD>(Q.p[1]);
-    else edge_body<2, METHOD>(Q.p[2]);
-}
-
 #ifndef FFB_NODES_BY
 #define FFB_NODES_BY 4
 #endif
 template <int DIR, int METHOD>
-__device__ __forceinline__ void nodes_body(const P2GParams &P, int bz) {
+__global__ void __launch_bounds__(32 * FFB_NODES_BY) k_p2g_nodes(const __grid_constant__ P2GParams P) {
     const int ni = blockIdx.x * blockDim.x + threadIdx.x;
     const int nj = blockIdx.y * blockDim.y + threadIdx.y;
-    const int nk = bz * blockDim.z + threadIdx.z + P.kw0;
+    const int nk = blockIdx.z * blockDim.z + threadIdx.z + P.kw0;
     if (ni >= P.gi || nj >= P.gj || nk >= P.kw1) return;
     // face and cell counts fit 32 bits (checked by the launcher): 32-bit index arithmetic
     const uint32_t fidx = (uint32_t)ni + (uint32_t)P.gi * ((uint32_t)nj + (uint32_t)P.gj * (uint32_t)(nk - P.g.kbase));
@@ -1506,50 +1459,6 @@ __device__ __forceinline__ void nodes_body(const P2GParams &P, int bz) {
     P.out[fidx] = s;                                           // write-out :155-162
     P.wsum[fidx] = sw;
     P.valid[fidx] = sw > eps ? 1 : 0;
-}
-
-template <int DIR, int METHOD>
-__global__ void __launch_bounds__(32 * FFB_NODES_BY) k_p2g_nodes(const __grid_constant__ P2GParams P) {
-    nodes_body<DIR, METHOD>(P, (int)blockIdx.z);
-}
-
-template <int METHOD>
-__global__ void __launch_bounds__(32 * FFB_NODES_BY) k_p2g_nodes3(const __grid_constant__ P2GParams3 Q, int nz) {
-    const int dir = (int)blockIdx.z / nz, bz = (int)blockIdx.z % nz;      // nz planes per direction (the largest of the three)
-    if (dir == 0) nodes_body<0, METHOD>(Q.p[0], bz);
-    else if (dir == 1) nodes_body<1, METHOD>(Q.p[1], bz);
-    else nodes_body<2, METHOD>(Q.p[2], bz);
-}
-
-// The default transfer of all three directions: four launches on the context's stream.
-template <int METHOD>
-int launch_cells3(Context &c, const P2GParams3 &Q) {
-    cudaStream_t st = c.stream;
-    unsigned nx = 0, nz = 0, gx = 0, gy = 0, gz = 0;
-    long long ncell = 0;
-    for (int d = 0; d < 3; d++) {
-        const P2GParams &P = Q.p[d];
-        FFB_CUDA(cudaMemsetAsync(P.ovf_count, 0, sizeof(int), st));
-        FFB_CUDA(cudaMemsetAsync(P.list_count, 0, 2 * sizeof(uint32_t), st));
-        const unsigned nxy = (unsigned)P.ccx * (unsigned)P.ccy;
-        nx = std::max(nx, (nxy + kListThreads * kListRounds - 1) / (kListThreads * kListRounds));
-        nz = std::max(nz, (unsigned)P.ccz);
-        ncell = std::max(ncell, (long long)P.ccx * P.ccy * P.ccz);
-        gx = std::max(gx, (unsigned)(P.gi + 31) / 32);
-        gy = std::max(gy, (unsigned)(P.gj + FFB_NODES_BY - 1) / FFB_NODES_BY);
-        gz = std::max(gz, (unsigned)(P.kw1 - P.kw0));
-    }
-    k_p2g_cell_list3<<<dim3(nx, nz, 3), kListThreads, 0, st>>>(Q);
-    const long long want = (ncell + kCellThreads - 1) / kCellThreads;
-    const unsigned ctas = (unsigned)std::min<long long>(want, (long long)c.sm_count * FFB_CELLS_MINB * 8);
-    k_p2g_cells3<METHOD><<<3 * ctas, kCellThreads, 0, st>>>(Q);
-    int launches = 2;
-    if (METHOD == FFB200_TRANSFER_APIC) {
-        k_p2g_edge3<METHOD><<<dim3((Q.p[0].edge_cap + 127) / 128, 3), 128, 0, st>>>(Q);
-        launches++;
-    }
-    k_p2g_nodes3<METHOD><<<dim3(gx, gy, 3 * gz), dim3(32, FFB_NODES_BY, 1), 0, st>>>(Q, (int)gz);
-    return launches + 1;
 }
 
 template <int DIR, int METHOD>
@@ -1679,7 +1588,7 @@ int launch_p2g_prepare(Context &c, double radius, bool seam_done) {
     return launches;
 }
 
-int launch_p2g(Context &c, double radius, int method) {
+int launch_p2g(Context &c, double radius, int method, const HostFieldOut *host) {
     int launches = 0;
     const GridDesc &g = c.g;
     ParticleSoA &s = c.soa[c.cur];
@@ -1688,12 +1597,16 @@ int launch_p2g(Context &c, double radius, int method) {
     // FFB200_P2G_VARIANT: 0 cell-partial splat (default), 3 coloured block splat, 1 brick gather, 2 global gather
     static const int variant = [] { const char *e = std::getenv("FFB200_P2G_VARIANT"); return e ? std::atoi(e) : 0; }();
     static const bool multi_stream = [] { const char *e = std::getenv("FFB200_P2G_STREAMS"); return e ? std::atoi(e) != 0 : true; }();
-    // FFB200_P2G_MERGED (default 1): the default transfer runs the three directions in shared launches
-    static const bool merged_on = [] { const char *e = std::getenv("FFB200_P2G_MERGED"); return e ? std::atoi(e) != 0 : true; }();
+    static const bool prioritised = [] { const char *e = std::getenv("FFB200_P2G_PRIORITY"); return e ? std::atoi(e) != 0 : true; }();
+    auto copy_out = [&](int d, cudaStream_t st) {
+        if (!host) return;
+        FaceGrid &f = c.face[d];
+        const size_t off = (size_t)f.gi * f.gj * g.kbase;
+        if (host->vel[d]) FFB_CUDA(cudaMemcpyAsync(host->vel[d] + off, f.vel, f.count * 4, cudaMemcpyDeviceToHost, st));
+        if (host->valid[d]) FFB_CUDA(cudaMemcpyAsync(host->valid[d] + off, f.valid, f.count, cudaMemcpyDeviceToHost, st));
+    };
     bool forked = false;
-    bool merged = false;
     P2GParams deferred;
-    P2GParams3 Q;
     for (int d = 0; d < 3; d++) {
         FaceGrid &f = c.face[d];
         P2GParams P;
@@ -1769,10 +1682,15 @@ int launch_p2g(Context &c, double radius, int method) {
             P.list_cap = (uint32_t)cells;
             // the three directions are independent: 1 and 2 run on auxiliary streams, forked from and
             // joined back into the context stream with events (FFB200_P2G_STREAMS=0: one stream)
-            merged = merged_on;
-            if (d > 0 && multi_stream && !merged) {
+            if (d > 0 && multi_stream) {
                 if (!cs.stream) {
-                    FFB_CUDA(cudaStreamCreateWithFlags(&cs.stream, cudaStreamNonBlocking));
+                    // direction 1 above direction 2 above the context stream: the directions then FINISH one after
+                    // the other instead of together, and a finished direction's device-to-host copy (host outputs)
+                    // runs under the kernels of the next
+                    int least = 0, greatest = 0;
+                    FFB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+                    const int prio = prioritised ? std::max(greatest, std::min(least, greatest + (d - 1))) : least;
+                    FFB_CUDA(cudaStreamCreateWithPriority(&cs.stream, cudaStreamNonBlocking, prio));
                     FFB_CUDA(cudaEventCreateWithFlags(&cs.done, cudaEventDisableTiming));
                 }
                 if (!c.sort.fork) FFB_CUDA(cudaEventCreateWithFlags(&c.sort.fork, cudaEventDisableTiming));
@@ -1784,19 +1702,14 @@ int launch_p2g(Context &c, double radius, int method) {
                 st = cs.stream;
             }
         }
-        if (merged) {
-            Q.p[d] = P;
-            continue;
-        }
         if (d == 0) deferred = P;                              // direction 0 is enqueued last, after the forks
         if (d == 1) launches += launch_dir<1>(c, P, method, variant, st);
         if (d == 2) launches += launch_dir<2>(c, P, method, variant, st);
+        if (d > 0) copy_out(d, st);
         if (st != c.stream) FFB_CUDA(cudaEventRecord(c.sort.cell[d].done, st));
     }
-    if (merged)
-        launches += method == FFB200_TRANSFER_APIC ? launch_cells3<FFB200_TRANSFER_APIC>(c, Q) : launch_cells3<FFB200_TRANSFER_FLIP>(c, Q);
-    else
-        launches += launch_dir<0>(c, deferred, method, variant, c.stream);
+    launches += launch_dir<0>(c, deferred, method, variant, c.stream);
+    copy_out(0, c.stream);
     if (forked)
         for (int d = 1; d < 3; d++) FFB_CUDA(cudaStreamWaitEvent(c.stream, c.sort.cell[d].done, 0));
     FFB_CUDA(cudaGetLastError());

@@ -157,3 +157,51 @@ def test_config3_fill_box_256_flip_obstacle(eng):
     assert sc.n > 30_000_000
     moved = _run_properties(eng, sc, eng.FLIP, phi, near, 0.02)
     assert moved > 0                                     # the collision projection really fired
+
+
+@pytest.mark.parametrize("method_name", ["flip", "apic"])
+def test_pipelined_host_field_io_matches_device_path(eng, method_name):
+    """The host-buffer entry points move a large field in pieces under the kernels (ffb200_velocity_advector_advect:
+    each direction's faces and masks leave behind that direction's kernels; ffb200_update_marker_particle_velocities:
+    the field arrives in plane chunks, the gather follows range by range over the sorted particles). Same bits as the
+    plain sequence set field -> kernel -> get, on a random (not smooth) field so that a particle launched before its
+    planes arrived cannot go unnoticed; some particles sit outside the grid in z (clamped bins, zero velocity)."""
+    from blender_flip_fluids_b200 import scenes
+    method = eng.APIC if method_name == "apic" else eng.FLIP
+    apic = method == eng.APIC
+    sc = scenes.dam_break(128, apic=apic, vel="random", v0=0.5, seed=4321)
+    rng = np.random.default_rng(99)
+    pos = sc.pos.copy()
+    pos[:50, 2] = -0.5 * sc.dx                                  # below the grid
+    pos[50:100, 2] = (128 + 0.5) * sc.dx                         # above it
+    aff = [sc.affx, sc.affy, sc.affz] if apic else [None] * 3
+    mac = [rng.standard_normal(s).astype(np.float32) for s in eng.mac_shapes(128, 128, 128)]
+    saved = [rng.standard_normal(s).astype(np.float32) for s in eng.mac_shapes(128, 128, 128)]
+    with eng.FlipContext(128, 128, 128, sc.dx) as ctx:
+        ctx.set_particles(pos, sc.vel, *aff)
+        ctx.p2g(sc.radius, method)
+        f_want, m_want = ctx.get_velocity_field()
+        ctx.set_velocity_field(*mac)
+        ctx.set_velocity_field(*saved, saved=True)
+        ctx.sort_particles()
+        ctx.g2p(method, 0.05)
+        _, v_want, *a_want = ctx.get_particles(pos=False, vel=True, affine=apic)
+    with eng.FlipContext(128, 128, 128, sc.dx) as ctx:
+        f_got, m_got = ctx.velocity_advector_advect(pos, sc.vel, *aff, radius=sc.radius, method=method)
+        for a, b in zip(list(f_want) + list(m_want), list(f_got) + list(m_got)):
+            assert a.tobytes() == b.tobytes()
+        got = ctx.update_marker_particle_velocities(pos, sc.vel, mac, saved=None if apic else saved, method=method, ratio_pic_flip=0.05)
+        if apic:
+            assert got[0].tobytes() == v_want.tobytes()
+            for a, b in zip(a_want, got[1:]):
+                assert a.tobytes() == b.tobytes()
+        else:
+            assert got.tobytes() == v_want.tobytes()
+        # resident particles (the drop-in's protocol): the same call with null particle pointers
+        ctx.declare_resident(particles=True)
+        ctx.update_marker_particle_velocities(None, None, mac, saved=None if apic else saved, method=method, ratio_pic_flip=0.05)
+        _, v_res, *a_res = ctx.get_particles(pos=False, vel=True, affine=apic)
+        if apic:       # APIC output does not depend on the old velocity; FLIP's does (v_old was just replaced)
+            assert v_res.tobytes() == v_want.tobytes()
+            for a, b in zip(a_want, a_res):
+                assert a.tobytes() == b.tobytes()
