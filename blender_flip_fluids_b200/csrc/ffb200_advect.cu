@@ -28,11 +28,13 @@ struct Box {
 #ifndef FFB_ADV_THREADS
 #define FFB_ADV_THREADS 256
 #endif
-#ifdef FFB_ADV_MINB
-#define FFB_ADV_BOUNDS FFB_ADV_BOUNDS
-#else
-#define FFB_ADV_BOUNDS __launch_bounds__(FFB_ADV_THREADS, 3)
+// resident CTAs per SM the exact gathers are compiled for. They are latency-bound (L1/L2-hit gathers feeding long fp64
+// chains), so occupancy beats register comfort: measured at 512^3, G2P + advection take 21.5 ms unbounded / at 3 CTAs
+// (68-80 registers, no spills), 19.6 ms at 4 (64 registers), 18.9 ms at 5 (48 registers, 72-160 B of spills), 19.4 ms at 6
+#ifndef FFB_ADV_MINB
+#define FFB_ADV_MINB 5
 #endif
+#define FFB_ADV_BOUNDS __launch_bounds__(FFB_ADV_THREADS, FFB_ADV_MINB)
 
 struct AdvectParams {
     GridDesc g;
@@ -315,7 +317,7 @@ __device__ __noinline__ void exact_advect(const AdvectParams &P, float x0, float
 // list (warp-aggregated slot allocation) for pass 2 -- running the exact code inline instead leaves the warps of a
 // near-wall region with a handful of active lanes each (13.8 of 32 measured), which cost more than the whole exact kernel.
 #ifndef FFB_ADV_FAST_MINB
-#define FFB_ADV_FAST_MINB 4
+#define FFB_ADV_FAST_MINB 5
 #endif
 __global__ void __launch_bounds__(FFB_ADV_THREADS, FFB_ADV_FAST_MINB) k_advect_fast(const __grid_constant__ AdvectParams P, const __grid_constant__ FastGrid fg,
                                              float inv_near, uint32_t *__restrict__ list, unsigned long long *__restrict__ stats) {

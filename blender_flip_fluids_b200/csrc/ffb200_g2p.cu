@@ -17,11 +17,13 @@ namespace {
 #ifndef FFB_G2P_THREADS
 #define FFB_G2P_THREADS 256
 #endif
-#ifdef FFB_G2P_MINB
-#define FFB_G2P_BOUNDS FFB_G2P_BOUNDS
-#else
-#define FFB_G2P_BOUNDS __launch_bounds__(FFB_G2P_THREADS)
+// resident CTAs per SM the exact gathers are compiled for. They are latency-bound (L1/L2-hit gathers feeding long fp64
+// chains), so occupancy beats register comfort: measured at 512^3, G2P + advection take 21.5 ms unbounded / at 3 CTAs
+// (68-80 registers, no spills), 19.6 ms at 4 (64 registers), 18.9 ms at 5 (48 registers, 72-160 B of spills), 19.4 ms at 6
+#ifndef FFB_G2P_MINB
+#define FFB_G2P_MINB 5
 #endif
+#define FFB_G2P_BOUNDS __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_MINB)
 
 struct G2PParams {
     GridDesc g;
@@ -272,7 +274,7 @@ __device__ __noinline__ bool g2p_apic_fast_generic(const G2PParams &P, const Fas
 }
 
 #ifndef FFB_G2P_FAST_MINB
-#define FFB_G2P_FAST_MINB 4
+#define FFB_G2P_FAST_MINB 5
 #endif
 __global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FAST_MINB)
     k_g2p_apic_fast(const __grid_constant__ G2PParams P, const __grid_constant__ FastGrid fg, unsigned long long *__restrict__ stats) {

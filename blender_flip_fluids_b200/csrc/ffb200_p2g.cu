@@ -593,270 +593,6 @@ __device__ __forceinline__ void accumulate_global(const P2GParams &P, const Face
         }
 }
 
-// ---- coloured splat kernel ------------------------------------------------------------------------
-//
-// One CTA owns ONE reference 10^3-node block and keeps its 1000 (sum w, sum w*v) pairs in shared
-// memory. This is the reference's own per-block algorithm (each particle of the block is splat
-// onto its 2x2x2 nodes in the block-local frame, velocityadvector.cpp:467-623), parallelised
-// without atomics: the block's particles are grouped by "shifted cell" (the cell of the staggered
-// frame whose corner nodes are base + {0,1}^3); two shifted cells of the same parity class touch
-// disjoint node sets, so the 8 parity classes ("colours") are processed one after the other,
-// one thread per shifted cell, with a barrier in between. Every node receives exactly one cell
-// per colour, so the accumulation order is fixed: colour order, then the sorted particle order
-// inside the cell. Per particle the separable per-axis factors are computed once (6 instead of
-// 24 evaluations) and combined in the reference's operand order, so every weight is
-// bit-identical; only the summation order differs from the reference (guard band + exact_face).
-//
-// Particles on the 11^3 shifted cells around the block are read straight from the sorted
-// streams (each once per CTA, 1.33x redundancy between neighbouring blocks). APIC "edge"
-// particles (within a few ulps of a cell plane, flagged by k_seam_home) are left out of the fast
-// path, collected from the 13^3 cells around the block, sorted, and given exact_contribution().
-constexpr int kSplatThreads = 256;
-#ifndef FFB_SPLAT_MINB
-#define FFB_SPLAT_MINB 4
-#endif
-constexpr int kSplatFlagCap = 192;
-
-struct SplatShared {
-    float sw[kChunk * kChunk * kChunk];
-    float swv[kChunk * kChunk * kChunk];
-    uint32_t flagged[kSplatFlagCap];
-    int nflag;
-};
-
-template <int DIR, int METHOD>
-__global__ void __launch_bounds__(kSplatThreads, FFB_SPLAT_MINB) k_p2g_splat(const __grid_constant__ P2GParams P) {
-    __shared__ SplatShared S;
-    const int tid = threadIdx.x;
-    const int nbv[3] = {(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + P.kw0 / kChunk};
-    const int n0[3] = {nbv[0] * kChunk, nbv[1] * kChunk, nbv[2] * kChunk};
-    const int H[3] = {P.g.HX, P.g.HY, P.g.HZ};
-    const int dims[3] = {P.gi, P.gj, P.gk};
-    const bool active = P.active[nbv[0] + P.bi * (nbv[1] + P.bj * nbv[2])] != 0;
-
-    for (int t = tid; t < kChunk * kChunk * kChunk; t += kSplatThreads) { S.sw[t] = 0.0f; S.swv[t] = 0.0f; }
-    if (tid == 0) S.nflag = 0;
-    __syncthreads();
-
-    float bpos[3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) bpos[a] = idx2posf(nbv[a], P.chunk);
-
-    if (active) {
-        for (int colour = 0; colour < 8; colour++) {
-            const int par[3] = {colour & 1, (colour >> 1) & 1, colour >> 2};
-            const int ci[3] = {tid % 6, (tid / 6) % 6, tid / 36};
-            int brel[3];
-            bool mine = tid < 216;
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                brel[a] = par[a] + 2 * ci[a];            // 0..10: shifted cell relative to (block origin - 1)
-                mine = mine && brel[a] <= kChunk;
-            }
-            float aw[8], awv[8];
-#pragma unroll
-            for (int c = 0; c < 8; c++) { aw[c] = 0.0f; awv[c] = 0.0f; }
-            if (mine) {
-                int hb[3];
-                float gpos0[3], gpos1[3];
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const int lo0 = brel[a] - 1;          // local index of the cell's lower node, -1..9
-                    gpos0[a] = idx2posf(lo0, P.g.dx);
-                    gpos1[a] = idx2posf(lo0 + 1, P.g.dx);
-                    hb[a] = 2 * (n0[a] + lo0) + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
-                }
-                // the cell's particles: 2 bins x (2 x 2) rows = four runs of the sorted streams. All
-                // eight bounds are fetched up front, then the runs are walked as one list with the
-                // next particle's loads in flight while the current one is splat.
-                const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
-                uint32_t rs[4], re[4];
-#pragma unroll
-                for (int rr = 0; rr < 4; rr++) {
-                    const int hz = hb[2] + (rr >> 1), hy = hb[1] + (rr & 1);
-                    rs[rr] = 0; re[rr] = 0;
-                    if (hx0 <= hx1 && hz >= 0 && hz < H[2] && hy >= 0 && hy < H[1]) {
-                        const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
-                        rs[rr] = __ldg(P.bin_start + row + hx0);
-                        re[rr] = __ldg(P.bin_start + row + hx1 + 1);
-                    }
-                }
-                int run = 0;
-                uint32_t q = rs[0];
-                while (run < 4 && q >= re[run]) { run++; if (run < 4) q = rs[run]; }
-                uint32_t word = 0;
-                float px = 0.f, py = 0.f, pz = 0.f, vel = 0.f, a0 = 0.f, a1 = 0.f, a2 = 0.f;
-                if (run < 4) {
-                    word = __ldg(P.seam + q);
-                    px = __ldg(P.px + q); py = __ldg(P.py + q); pz = __ldg(P.pz + q); vel = __ldg(P.vel + q);
-                    if (METHOD == FFB200_TRANSFER_APIC) { a0 = __ldg(P.ax + q); a1 = __ldg(P.ay + q); a2 = __ldg(P.az + q); }
-                }
-                while (run < 4) {
-                    // advance to the next particle and start its loads
-                    int nrun = run;
-                    uint32_t nq = q + 1;
-                    while (nrun < 4 && nq >= re[nrun]) { nrun++; if (nrun < 4) nq = rs[nrun]; }
-                    uint32_t nword = 0;
-                    float npx = 0.f, npy = 0.f, npz = 0.f, nvel = 0.f, na0 = 0.f, na1 = 0.f, na2 = 0.f;
-                    if (nrun < 4) {
-                        nword = __ldg(P.seam + nq);
-                        npx = __ldg(P.px + nq); npy = __ldg(P.py + nq); npz = __ldg(P.pz + nq); nvel = __ldg(P.vel + nq);
-                        if (METHOD == FFB200_TRANSFER_APIC) { na0 = __ldg(P.ax + nq); na1 = __ldg(P.ay + nq); na2 = __ldg(P.az + nq); }
-                    }
-                    const bool use = seam_member(word, nbv[0], nbv[1], nbv[2]) &&
-                                     !(METHOD == FFB200_TRANSFER_APIC && (word & kEdgeBit));   // edge: exact path below
-                    if (use) {
-                        const float xl0 = (px - P.off[0]) - bpos[0];
-                        const float xl1 = (py - P.off[1]) - bpos[1];
-                        const float xl2 = (pz - P.off[2]) - bpos[2];
-                        // node - particle, per axis and per node (0: lower, 1: upper)
-                        const float vx[2] = {gpos0[0] - xl0, gpos1[0] - xl0};
-                        const float vy[2] = {gpos0[1] - xl1, gpos1[1] - xl1};
-                        const float vz[2] = {gpos0[2] - xl2, gpos1[2] - xl2};
-                        if (METHOD == FFB200_TRANSFER_FLIP) {
-                            const float xx[2] = {vx[0] * vx[0], vx[1] * vx[1]};
-                            const float yy[2] = {vy[0] * vy[0], vy[1] * vy[1]};
-                            const float zz[2] = {vz[0] * vz[0], vz[1] * vz[1]};
-#pragma unroll
-                            for (int c = 0; c < 8; c++) {
-                                const float d2 = xx[c & 1] + yy[(c >> 1) & 1] + zz[c >> 2];
-                                if (d2 < P.rsq) {
-                                    const float w = 1.0f - P.c1 * d2 * d2 * d2 + P.c2 * d2 * d2 - P.c3 * d2;
-                                    awv[c] += w * vel;
-                                    aw[c] += w;
-                                }
-                            }
-                        } else {
-                            // ipos = (p - gpos) / dx and the (1 - ipos, ipos) factors of :574-592
-                            const float t0 = (xl0 - gpos0[0]) * P.inv_s, t1 = (xl1 - gpos0[1]) * P.inv_s,
-                                        t2 = (xl2 - gpos0[2]) * P.inv_s;
-                            const float fx[2] = {1.0f - t0, t0}, fy[2] = {1.0f - t1, t1}, fz[2] = {1.0f - t2, t2};
-                            const float ax[2] = {a0 * vx[0], a0 * vx[1]};
-                            const float ay[2] = {a1 * vy[0], a1 * vy[1]};
-                            const float az[2] = {a2 * vz[0], a2 * vz[1]};
-#pragma unroll
-                            for (int c = 0; c < 8; c++) {
-                                const float w = fx[c & 1] * fy[(c >> 1) & 1] * fz[c >> 2];
-                                const float apic = ax[c & 1] + ay[(c >> 1) & 1] + az[c >> 2];
-                                awv[c] += w * (vel + apic);
-                                aw[c] += w;
-                            }
-                        }
-                    }
-                    run = nrun; q = nq; word = nword;
-                    px = npx; py = npy; pz = npz; vel = nvel; a0 = na0; a1 = na1; a2 = na2;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const int lx = brel[0] - 1 + (c & 1), ly = brel[1] - 1 + ((c >> 1) & 1), lz = brel[2] - 1 + (c >> 2);
-                    if ((unsigned)lx < (unsigned)kChunk && (unsigned)ly < (unsigned)kChunk && (unsigned)lz < (unsigned)kChunk) {
-                        const int idx = lx + kChunk * (ly + kChunk * lz);
-                        S.sw[idx] += aw[c];               // one shifted cell per colour touches a node: no race
-                        S.swv[idx] += awv[c];
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        if (METHOD == FFB200_TRANSFER_APIC) {
-            // edge particles that are members of this block: from the global list k_seam_home built
-            // (a few hundred entries per direction); if that list overflowed, from the 13^3 shifted
-            // cells around the block instead
-            const uint32_t nedge = __ldg(P.edge_count);
-            if (nedge <= P.edge_cap) {
-                for (uint32_t t = tid; t < nedge; t += kSplatThreads) {
-                    const uint32_t q = __ldg(P.edge_list + t);
-                    if (seam_member(__ldg(P.seam + q), nbv[0], nbv[1], nbv[2])) {
-                        const int slot = atomicAdd(&S.nflag, 1);
-                        if (slot < kSplatFlagCap) S.flagged[slot] = q;
-                    }
-                }
-            } else {
-                for (int t = tid; t < 13 * 13 * 13; t += kSplatThreads) {
-                    const int cr[3] = {t % 13, (t / 13) % 13, t / 169};
-                    int hb[3];
-#pragma unroll
-                    for (int a = 0; a < 3; a++)
-                        hb[a] = 2 * (n0[a] - 2 + cr[a]) + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
-                    const int hx0 = max(hb[0], 0), hx1 = min(hb[0] + 1, H[0] - 1);
-                    if (hx0 > hx1) continue;
-                    for (int dz = 0; dz < 2; dz++) {
-                        const int hz = hb[2] + dz;
-                        if (hz < 0 || hz >= H[2]) continue;
-                        for (int dy = 0; dy < 2; dy++) {
-                            const int hy = hb[1] + dy;
-                            if (hy < 0 || hy >= H[1]) continue;
-                            const size_t row = ((size_t)hz * P.g.HY + hy) * P.g.HX;
-                            const uint32_t s = __ldg(P.bin_start + row + hx0), e = __ldg(P.bin_start + row + hx1 + 1);
-                            for (uint32_t q = s; q < e; q++) {
-                                const uint32_t word = __ldg(P.seam + q);
-                                if ((word & kEdgeBit) && seam_member(word, nbv[0], nbv[1], nbv[2])) {
-                                    const int slot = atomicAdd(&S.nflag, 1);
-                                    if (slot < kSplatFlagCap) S.flagged[slot] = q;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {   // slots were claimed in arbitrary order: put the few entries in sorted order
-                const int m = min(S.nflag, kSplatFlagCap);
-                for (int i = 1; i < m; i++) {
-                    const uint32_t key = S.flagged[i];
-                    int j = i - 1;
-                    while (j >= 0 && S.flagged[j] > key) { S.flagged[j + 1] = S.flagged[j]; j--; }
-                    S.flagged[j + 1] = key;
-                }
-            }
-            __syncthreads();
-        }
-    }
-
-    // ---- epilogue: one pass over the block's nodes -------------------------------------------------
-    const int nflag = S.nflag;
-    for (int t = tid; t < kChunk * kChunk * kChunk; t += kSplatThreads) {
-        const int l[3] = {t % kChunk, (t / kChunk) % kChunk, t / (kChunk * kChunk)};
-        const int n[3] = {n0[0] + l[0], n0[1] + l[1], n0[2] + l[2]};
-        const int ks = n[2] - P.g.kbase;
-        if (n[0] >= P.gi || n[1] >= P.gj || n[2] >= P.gk || n[2] < P.kw0 || n[2] >= P.kw1) continue;
-        const size_t fidx = (size_t)n[0] + (size_t)P.gi * ((size_t)n[1] + (size_t)P.gj * ks);
-        float sw = S.sw[t], swv = S.swv[t];
-        if (active) {
-            FaceFrame f;
-#pragma unroll
-            for (int a = 0; a < 3; a++) {
-                f.nb[a] = nbv[a];
-                f.lo[a] = l[a];
-                f.bpos[a] = bpos[a];
-                f.gpos[a] = idx2posf(l[a], P.g.dx);
-                f.gposm[a] = idx2posf(l[a] - 1, P.g.dx);
-                const int c = 2 * n[a] + (a == DIR ? 0 : 1) + kApron - (a == 2 ? 2 * P.g.kbase : 0);
-                f.h0[a] = max(c - P.wm, 0);
-                f.h1[a] = min(c + P.wm - 1, H[a] - 1);
-            }
-            bool redo = nflag > kSplatFlagCap;            // pathological: more edge particles than the list holds
-            if (!redo) {
-                for (int i = 0; i < nflag; i++) {
-                    float w, wv;
-                    if (exact_contribution<DIR, METHOD>(P, f, S.flagged[i], w, wv)) {
-                        swv += wv;
-                        sw += w;
-                    }
-                }
-            }
-            const float eps = 1e-6f;
-            if (redo || fabsf(sw - eps) <= P.guard_abs + P.guard_per * 512.0f) exact_face<DIR, METHOD>(P, f, sw, swv);
-        }
-        const float eps = 1e-6f;
-        float s = swv;
-        if (sw > eps) s /= sw;                                 // :527-531
-        P.out[fidx] = s;                                       // write-out :155-162
-        P.wsum[fidx] = sw;
-        P.valid[fidx] = sw > eps ? 1 : 0;
-    }
-}
-
 // ---- cell-partial splat (default) -------------------------------------------------------------------
 //
 // The splat again, but with no CTA structure at all, so every particle is visited exactly once
@@ -1487,13 +1223,6 @@ int launch_cells(Context &c, P2GParams &P, cudaStream_t st) {
 }
 
 template <int DIR, int METHOD>
-void launch_splat(Context &c, P2GParams &P) {
-    const int zb0 = P.kw0 / kChunk, zb1 = (P.kw1 - 1) / kChunk;
-    dim3 grid(P.bi, P.bj, zb1 - zb0 + 1);
-    k_p2g_splat<DIR, METHOD><<<grid, kSplatThreads, 0, c.stream>>>(P);
-}
-
-template <int DIR, int METHOD>
 void launch_brick(Context &c, P2GParams &P) {
     constexpr int CAP = BrickCap<METHOD>::value;
     const size_t smem = sizeof(float4) * CAP * (METHOD == FFB200_TRANSFER_APIC ? 2 : 1) + sizeof(BrickShared);
@@ -1509,19 +1238,12 @@ void launch_brick(Context &c, P2GParams &P) {
 
 template <int DIR>
 int launch_dir(Context &c, P2GParams &P, int method, int variant, cudaStream_t st) {
-    // variant 0: cell-partial splat (support of one cell: default radius and APIC); 3: coloured block
-    // splat (same support); 1: brick gather (any radius up to 2 dx); 2: first-generation global
-    // gather. FFB200_P2G_VARIANT overrides; radii above dx always take the brick gather.
+    // variant 0: cell-partial splat (support of one cell: default radius and APIC); 1: brick gather (any
+    // radius up to 2 dx); 2: whole-grid gather (also the attribute transfer's kernel). FFB200_P2G_VARIANT
+    // overrides; radii above dx always take the brick gather.
     if (variant == 0 && P.wm == 2) {
         if (method == FFB200_TRANSFER_APIC) return launch_cells<DIR, FFB200_TRANSFER_APIC>(c, P, st);
         return launch_cells<DIR, FFB200_TRANSFER_FLIP>(c, P, st);
-    }
-    if (variant == 3 && P.wm == 2) {
-        if (method == FFB200_TRANSFER_APIC)
-            launch_splat<DIR, FFB200_TRANSFER_APIC>(c, P);
-        else
-            launch_splat<DIR, FFB200_TRANSFER_FLIP>(c, P);
-        return 1;
     }
     if (variant <= 1) {
         if (method == FFB200_TRANSFER_APIC)
@@ -1594,7 +1316,7 @@ int launch_p2g(Context &c, double radius, int method, const HostFieldOut *host) 
     ParticleSoA &s = c.soa[c.cur];
     const float eps = 1e-6f;
     const float sr = (float)(radius + (double)eps);            // float sr = _particleRadius + eps;
-    // FFB200_P2G_VARIANT: 0 cell-partial splat (default), 3 coloured block splat, 1 brick gather, 2 global gather
+    // FFB200_P2G_VARIANT: 0 cell-partial splat (default), 1 brick gather, 2 whole-grid gather
     static const int variant = [] { const char *e = std::getenv("FFB200_P2G_VARIANT"); return e ? std::atoi(e) : 0; }();
     static const bool multi_stream = [] { const char *e = std::getenv("FFB200_P2G_STREAMS"); return e ? std::atoi(e) != 0 : true; }();
     static const bool prioritised = [] { const char *e = std::getenv("FFB200_P2G_PRIORITY"); return e ? std::atoi(e) != 0 : true; }();

@@ -85,27 +85,60 @@ __global__ void k_keys(GridDesc g, const float *__restrict__ px, const float *__
     atomicAdd(bin_count + k, 1u);
 }
 
-// Counting-sort flavour: besides the key, keep the particle's arrival rank in its bin.
+// Counting-sort flavour: besides the key, keep the particle's arrival rank in its bin. Both kernels are bound by the
+// latency of dependent scattered accesses (atomic with return value; bin_start[key] then a scattered store), at full
+// occupancy already: each thread handles kSortIlp particles, a block stride apart, with the independent accesses of all
+// of them issued before the first dependent one.
+constexpr int kSortIlp = 4;
+
 __global__ void k_keys_rank(GridDesc g, const float *__restrict__ px, const float *__restrict__ py,
                             const float *__restrict__ pz, uint32_t *__restrict__ key, uint32_t *__restrict__ rank,
                             uint32_t *__restrict__ bin_count, int n) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t k = half_cell_key(g, px[j], py[j], pz[j]);
-    key[j] = k;
-    rank[j] = atomicAdd(bin_count + k, 1u);
+    const int base = blockIdx.x * (blockDim.x * kSortIlp) + threadIdx.x;
+    uint32_t k[kSortIlp], r[kSortIlp];
+#pragma unroll
+    for (int q = 0; q < kSortIlp; q++) {
+        const int j = base + q * blockDim.x;
+        if (j < n) k[q] = half_cell_key(g, px[j], py[j], pz[j]);
+    }
+#pragma unroll
+    for (int q = 0; q < kSortIlp; q++)
+        if (base + q * (int)blockDim.x < n) r[q] = atomicAdd(bin_count + k[q], 1u);
+#pragma unroll
+    for (int q = 0; q < kSortIlp; q++) {
+        const int j = base + q * blockDim.x;
+        if (j < n) {
+            key[j] = k[q];
+            rank[j] = r[q];
+        }
+    }
 }
 
 // slot = bin_start[key] + rank; sorted position -> (key, source slot).
 __global__ void k_place(const uint32_t *__restrict__ key, const uint32_t *__restrict__ rank,
                         const uint32_t *__restrict__ bin_start, uint32_t *__restrict__ key_out,
                         uint32_t *__restrict__ val_out, int n) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint32_t k = key[j];
-    const uint32_t dst = bin_start[k] + rank[j];
-    key_out[dst] = k;
-    val_out[dst] = (uint32_t)j;
+    const int base = blockIdx.x * (blockDim.x * kSortIlp) + threadIdx.x;
+    uint32_t k[kSortIlp], dst[kSortIlp];
+#pragma unroll
+    for (int q = 0; q < kSortIlp; q++) {
+        const int j = base + q * blockDim.x;
+        if (j < n) {
+            k[q] = key[j];
+            dst[q] = rank[j];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kSortIlp; q++)
+        if (base + q * (int)blockDim.x < n) dst[q] += bin_start[k[q]];
+#pragma unroll
+    for (int q = 0; q < kSortIlp; q++) {
+        const int j = base + q * blockDim.x;
+        if (j < n) {
+            key_out[dst[q]] = k[q];
+            val_out[dst[q]] = (uint32_t)j;
+        }
+    }
 }
 
 // ---- exclusive scan (reduce / scan partials / apply) ---------------------------------------------------
@@ -402,7 +435,7 @@ int launch_sort(Context &c, const SeamParams *seam) {
         if (use_radix)
             k_keys<<<blocks_for(n, 256), 256, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
         else
-            k_keys_rank<<<blocks_for(n, FFB_KEYS_THREADS), FFB_KEYS_THREADS, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
+            k_keys_rank<<<blocks_for(n, FFB_KEYS_THREADS * kSortIlp), FFB_KEYS_THREADS, 0, c.stream>>>(g, src.p[0], src.p[1], src.p[2], s.key[0], s.val[0], s.bin_start, n);
         launches++;
     }
     launches += exclusive_scan_inplace(c, s.bin_start, (size_t)g.nbins + 2);
@@ -415,7 +448,7 @@ int launch_sort(Context &c, const SeamParams *seam) {
         // slot = bin_start[key] + arrival rank. The arrival order inside a bin is arbitrary (integer
         // atomics); k_reorder re-ranks the members of every multi-particle bin by original index,
         // so the final order is the deterministic (key, original index) order all the same.
-        k_place<<<blocks_for(n, FFB_KEYS_THREADS), FFB_KEYS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.bin_start, s.key[1], s.val[1], n);
+        k_place<<<blocks_for(n, FFB_KEYS_THREADS * kSortIlp), FFB_KEYS_THREADS, 0, c.stream>>>(s.key[0], s.val[0], s.bin_start, s.key[1], s.val[1], n);
         launches++;
         std::swap(s.key[0], s.key[1]);
         std::swap(s.val[0], s.val[1]);

@@ -288,7 +288,9 @@ int ffb200_advect(ffb200_context *ctx, double dt, double cfl_condition_number, i
 
 /* ---- one-call host-buffer entry points (what the libffengine interposer calls) ---------------------- */
 
-/* VelocityAdvector::advect: upload particles, sort, transfer, download faces + valid masks. */
+/* VelocityAdvector::advect: upload particles, sort, transfer, download faces + valid masks. Each direction's
+ * faces and mask leave the device behind that direction's kernels, under the kernels of the other two (the copies
+ * overlap when the host arrays are page-locked: ffb200_pin_host_memory). All outputs are complete on return. */
 int ffb200_velocity_advector_advect(ffb200_context *ctx, int n, const float *pos, const float *vel,
                                     const float *affx, const float *affy, const float *affz,
                                     double particle_radius, int transfer_method,
@@ -366,7 +368,9 @@ int ffb200_extrapolate_fluid_velocities(ffb200_context *ctx, float *u, float *v,
 
 /* _updateMarkerParticleVelocitiesThread: upload particles and both fields, gather, download.
  * vel is updated in place; affx/affy/affz are outputs for APIC (ignored for FLIP);
- * su/sv/sw (the saved field) may be NULL for APIC. */
+ * su/sv/sw (the saved field) may be NULL for APIC. Large fields arrive in plane chunks on a copy stream with the
+ * gather following range by range over the sorted particles, so the upload hides the kernel (page-locked host
+ * arrays); the host field arrays may be reused as soon as the call returns. */
 int ffb200_update_marker_particle_velocities(ffb200_context *ctx, int n, const float *pos, float *vel,
                                              float *affx, float *affy, float *affz,
                                              const float *u, const float *v, const float *w,

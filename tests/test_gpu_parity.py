@@ -243,11 +243,11 @@ print("ok")
 '''
 
 
-@pytest.mark.parametrize("env", [{"FFB200_P2G_VARIANT": "1"}, {"FFB200_P2G_VARIANT": "2"}, {"FFB200_P2G_VARIANT": "3"},
+@pytest.mark.parametrize("env", [{"FFB200_P2G_VARIANT": "1"}, {"FFB200_P2G_VARIANT": "2"},
                                  {"FFB200_SORT": "radix"}, {"FFB200_P2G_STREAMS": "0", "FFB200_FUSE_SEAM": "0"},
                                  {"FFB200_REUSE_G2P": "0"}])
 def test_alternate_kernel_paths(env, tmp_path):
-    """The earlier-generation P2G kernels, the LSD radix sort and the switched-off fusions (single P2G
+    """The gather formulations of the P2G (brick: radii up to 2 dx; whole grid: the attribute transfer's kernel), the LSD radix sort and the switched-off fusions (single P2G
     stream, stand-alone membership pass, no RK3 stage-1 reuse) stay selectable and correct."""
     import os
     import subprocess
