@@ -45,7 +45,8 @@ for r in rows[2:]:
         v, u = r[idx[k]], units[idx[k]]
         try:
             f = float(v.replace(",", ""))
-            if m == "time us" and u in ("ns", "nsecond"): f /= 1e3
+            if m == "time us":
+                f *= {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(u, 1.0)
             if m == "warp-instr M": f /= 1e6
             if m.startswith("DRAM") and m.endswith("MB"):
                 f = {"byte": f / 1e6, "Kbyte": f / 1e3, "Mbyte": f, "Gbyte": f * 1e3}.get(u, f)
