@@ -408,10 +408,11 @@ def main():
         if rank != 0:
             return 0
         model, cores = host_cpu()
-        ref_steps = min(steps, 6)                 # each rep is seconds of CPU work; the rate does not depend on the count
-        value, info = reference_arm(n, ref_steps, 1)
+        # every step is ~2 s of CPU work on the 16-plane sample: K steps are timed as asked, up to 40 (a run of minutes)
+        ref_steps = min(steps, 40)
+        value, info = reference_arm(n, ref_steps, min(warmup, 2))
         cfg = dict(base_config, cpu_model=model, timed_reps=ref_steps)
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": ref_steps,
                 "warmup": warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32 (fp64 gathers)", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "reference",
