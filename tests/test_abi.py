@@ -170,3 +170,25 @@ e.close()
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert "ERR FluidSimulation_update - ffb200_create" in r.stdout and "UPDATED" not in r.stdout, r.stdout[-1500:]
     assert "ALIVE 2160 2160" in r.stdout
+
+
+def test_header_compiles_as_plain_c_and_cxx(tmp_path):
+    """include/ffb200.h is the boundary: it must be consumable by a C compiler (cgo / JNI / ctypes generators read it
+    as C) and by C++ (the interposer), with no CUDA or torch types in any signature."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = os.path.join(root, "include")
+    src = tmp_path / "use.c"
+    src.write_text('#include "ffb200.h"\nint main(void) { ffb200_context *c = 0; int a, b, r; (void)c; return ffb200_get_version(&a, &b, &r) ? 0 : 1; }\n')
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", f"-I{inc}", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cxx = tmp_path / "use.cpp"
+    cxx.write_text(src.read_text())
+    r = subprocess.run([shutil.which("g++"), "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", f"-I{inc}", str(cxx)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, "ffb200.h")).read(), flags=re.S)      # declarations only
+    for banned in ("cuda", "torch", "at::", "std::", "Tensor"):
+        assert banned not in code.replace("void *cuda_stream", ""), banned
