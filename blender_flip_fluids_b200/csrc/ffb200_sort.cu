@@ -192,16 +192,26 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const uint32_t *__
     if (threadIdx.x == 0) partial[blockIdx.x] = total;
 }
 
-// one CTA, sequential over chunks of blockDim
+// one CTA, sequential over chunks of blockDim * kPartialItems (a 512^3 bin table has 262 K tile totals: 32 rounds)
+constexpr int kPartialItems = 8;
 __global__ void __launch_bounds__(1024) k_scan_partials(uint32_t *partial, int m) {
     __shared__ uint32_t ws[33];
     uint32_t carry = 0;
-    for (int base = 0; base < m; base += blockDim.x) {
-        int i = base + threadIdx.x;
-        uint32_t v = i < m ? partial[i] : 0u;
+    for (int base = 0; base < m; base += blockDim.x * kPartialItems) {
+        const int i0 = base + threadIdx.x * kPartialItems;
+        uint32_t v[kPartialItems], s = 0;
+#pragma unroll
+        for (int q = 0; q < kPartialItems; q++) {
+            v[q] = i0 + q < m ? partial[i0 + q] : 0u;
+            s += v[q];
+        }
         uint32_t total;
-        uint32_t ex = block_exclusive_scan(v, ws, total);
-        if (i < m) partial[i] = ex + carry;
+        uint32_t run = block_exclusive_scan(s, ws, total) + carry;
+#pragma unroll
+        for (int q = 0; q < kPartialItems; q++) {
+            if (i0 + q < m) partial[i0 + q] = run;
+            run += v[q];
+        }
         carry += total;
     }
 }
@@ -430,6 +440,8 @@ int launch_sort(Context &c, const SeamParams *seam) {
     static const bool use_radix = [] { const char *e = std::getenv("FFB200_SORT"); return e && std::string(e) == "radix"; }();
 
     // bin histogram + keys
+    // (accumulating the scan's tile totals in the key pass -- one warp-aggregated atomic per tile -- to drop the scan's
+    // reduce pass over the table was measured: +1.2 ms at 512^3, the match/atomic costs more than the 0.6 ms pass)
     FFB_CUDA(cudaMemsetAsync(s.bin_start, 0, ((size_t)g.nbins + 2) * sizeof(uint32_t), c.stream));
     if (n > 0) {
         if (use_radix)
