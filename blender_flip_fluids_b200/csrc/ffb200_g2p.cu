@@ -24,6 +24,10 @@ namespace {
 #define FFB_G2P_MINB 5
 #endif
 #define FFB_G2P_BOUNDS __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_MINB)
+// the FLIP gather samples two fields per component and keeps more state live: 4 CTAs (64 registers, no spills)
+#ifndef FFB_G2P_FLIP_MINB
+#define FFB_G2P_FLIP_MINB 4
+#endif
 
 struct G2PParams {
     GridDesc g;
@@ -42,7 +46,7 @@ struct G2PParams {
     Window win;
 };
 
-__global__ void FFB_G2P_BOUNDS k_g2p_flip(const __grid_constant__ G2PParams P) {
+__global__ void __launch_bounds__(FFB_G2P_THREADS, FFB_G2P_FLIP_MINB) k_g2p_flip(const __grid_constant__ G2PParams P) {
     const int j = P.first + blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.n || window_skip(P.win, j)) return;
     const float px = P.px[j], py = P.py[j], pz = P.pz[j];

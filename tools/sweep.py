@@ -21,6 +21,9 @@ cases = [(128, 8, "apic", "dam"), (128, 8, "flip", "dam"), (64, 8, "flip", "dam"
          (256, 8, "flip", "fill")]
 if not quick:
     cases += [(256, 27, "flip", "dam"), (256, 27, "apic", "dam")]
+only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--method=")]
+if only:
+    cases = [c for c in cases if c[2] in only]
 
 
 def balg(method, ppc):
